@@ -1,0 +1,335 @@
+// a7 + a9 + a11 + a12: granularity index selection and the five-stream bit packer.
+//
+//   reference: CGIC/models/model.py:217-260 (selection, which streams exist per mode, bpp),
+//              HuffmanCoding.compress  CGIC/tools/indices_coding.py:113-126 (78-82, 91-98, 101-110),
+//              BinaryCoding.compress   CGIC/tools/mask_coding.py:40-55.
+//
+// One CTA per (stream, image).  An index stream walks its level's grid in row-major order in
+// tiles of 1024 positions: mask test + symbol fetch (the block's top-left token), a block-wide
+// exclusive scan of the code lengths gives every symbol its bit offset, the codes are OR-ed into
+// a shared-memory staging window (atomicOr on 32-bit words), and complete words leave as
+// coalesced big-endian 32-bit stores.  The partial last word is carried into the next tile, so
+// global memory sees every output word exactly once and needs no pre-zeroing.
+// Framing (must be byte exact): [pad count byte][payload, MSB first][pad zero bits],
+// pad = 8 - nbits % 8 in 1..8, empty symbol list -> 0 bytes.
+#include "common.cuh"
+
+namespace cgic {
+namespace {
+
+constexpr int PK_THREADS = 256;
+constexpr int PK_ITEMS = 4;
+constexpr int PK_TILE = PK_THREADS * PK_ITEMS;
+
+struct PackArgs {
+    const int64_t *idx;  // [B,h,w]  (or the symbol list for the single-stream entry point)
+    const int32_t *mask[3];
+    int h, w, mode;
+    int64_t n_direct;  // >= 0: single stream of n_direct symbols taken from idx, no mask
+    DevTable T;
+    uint8_t *out;
+    int64_t image_stride;
+    int64_t slot_off[5];
+    int64_t slot_cap[5];
+    int32_t *sizes;
+};
+
+__device__ __forceinline__ uint32_t to_big_endian(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+
+// block-wide exclusive scan of one int per thread; returns the exclusive prefix, total in *total
+__device__ __forceinline__ int block_exscan(int v, int *s_warp, int *total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int ws = lane < PK_THREADS / 32 ? s_warp[lane] : 0;
+        int winc = ws;
+#pragma unroll
+        for (int o = 1; o < PK_THREADS / 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += n;
+        }
+        if (lane < PK_THREADS / 32) s_warp[lane] = winc - ws;
+        if (lane == PK_THREADS / 32 - 1) s_warp[PK_THREADS / 32] = winc;
+    }
+    __syncthreads();
+    const int r = s_warp[wid] + inc - v;
+    *total = s_warp[PK_THREADS / 32];
+    __syncthreads();
+    return r;
+}
+
+__device__ void pack_index_stream(const PackArgs &a, int s, int b, uint32_t *stage)
+{
+    __shared__ int s_warp[PK_THREADS / 32 + 1];
+    __shared__ uint32_t s_carry;
+    __shared__ int s_bad;
+    const int tid = threadIdx.x;
+    int gw, step;
+    int64_t n_pos;
+    const int32_t *mask = nullptr;
+    const int64_t *src;
+    uint8_t *out;
+    int32_t *size_out;
+    int64_t cap;
+    if (a.n_direct >= 0) {
+        gw = 1;
+        step = 1;
+        n_pos = a.n_direct;
+        src = a.idx;
+        out = a.out;
+        size_out = a.sizes;
+        cap = a.slot_cap[0];
+    } else {
+        step = 4 >> s;
+        gw = a.w / step;
+        n_pos = (int64_t)(a.h / step) * gw;
+        mask = a.mask[s] + (int64_t)b * n_pos;
+        src = a.idx + (int64_t)b * a.h * a.w;
+        out = a.out + (int64_t)b * a.image_stride + a.slot_off[s];
+        size_out = a.sizes + b * 5 + s;
+        cap = a.slot_cap[s];
+    }
+    uint32_t *out32 = reinterpret_cast<uint32_t *>(out);
+    if (tid == 0) {
+        s_carry = 0;
+        s_bad = 0;
+    }
+    __syncthreads();
+    int64_t P = 8;  // stream bit position (header byte first)
+    for (int64_t tile = 0; tile < n_pos; tile += PK_TILE) {
+        int sym[PK_ITEMS], len[PK_ITEMS];
+        int tsum = 0;
+#pragma unroll
+        for (int i = 0; i < PK_ITEMS; ++i) {
+            const int64_t pos = tile + (int64_t)tid * PK_ITEMS + i;
+            len[i] = 0;
+            sym[i] = 0;
+            if (pos < n_pos) {
+                bool on = true;
+                int64_t at = pos;
+                if (mask) {
+                    on = mask[pos] == 1;
+                    const int y = (int)(pos / gw), x = (int)(pos - (int64_t)y * gw);
+                    at = (int64_t)(y * step) * a.w + x * step;
+                }
+                if (on) {
+                    const int64_t v = src[at];
+                    if (v < 0 || v >= a.T.K) {
+                        s_bad = 1;
+                    } else {
+                        sym[i] = (int)v;
+                        len[i] = a.T.len[v];
+                    }
+                }
+            }
+            tsum += len[i];
+        }
+        int tot;
+        int o = block_exscan(tsum, s_warp, &tot);
+        const int r0 = (int)(P & 31);
+        const int nwords = (r0 + tot + 31) >> 5;
+        for (int j = tid; j < nwords; j += PK_THREADS) stage[j] = (j == 0 && r0) ? s_carry : 0u;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < PK_ITEMS; ++i) {
+            if (len[i]) {
+                const uint32_t *code = a.T.pool + a.T.off[sym[i]];
+                int q = r0 + o;
+                for (int rem = len[i]; rem > 0; rem -= 32, q += 32, ++code) {
+                    const uint32_t cw = *code;
+                    const int sh = q & 31, wi = q >> 5;
+                    atomicOr(&stage[wi], cw >> sh);
+                    if (sh && (sh + min(rem, 32) > 32)) atomicOr(&stage[wi + 1], cw << (32 - sh));
+                }
+                o += len[i];
+            }
+        }
+        __syncthreads();
+        const int full = (r0 + tot) >> 5;
+        const int64_t w0 = P >> 5;
+        if ((w0 + full) * 4 <= cap)
+            for (int j = tid; j < full; j += PK_THREADS) out32[w0 + j] = to_big_endian(stage[j]);
+        if (tid == 0) s_carry = ((r0 + tot) & 31) ? stage[full] : 0u;
+        P += tot;
+        __syncthreads();
+    }
+    // tail: bytes not yet written, pad, header
+    const int64_t nbits = P - 8;
+    if (nbits == 0 || s_bad) {
+        if (tid == 0) *size_out = s_bad ? -1 : 0;
+        return;
+    }
+    const int64_t total = nbits / 8 + 2;
+    const int64_t written = (P >> 5) * 4;
+    const uint32_t carry = (P & 31) ? s_carry : 0u;
+    if (total > cap) {
+        if (tid == 0) *size_out = -2;
+        return;
+    }
+    if (tid < 8) {
+        const int64_t i = written + tid;
+        if (i < total) out[i] = tid < 4 ? (uint8_t)(carry >> (24 - 8 * tid)) : (uint8_t)0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        out[0] = (uint8_t)(8 - (int)(nbits & 7));
+        *size_out = (int32_t)total;
+    }
+}
+
+// mask / raw bit stream: one output byte per thread
+__device__ void pack_bit_stream(const int32_t *v, int64_t n, uint8_t *out, int64_t cap, int32_t *size_out)
+{
+    if (n == 0) {
+        if (threadIdx.x == 0) *size_out = 0;
+        return;
+    }
+    const int64_t total = n / 8 + 2;
+    if (total > cap) {
+        if (threadIdx.x == 0) *size_out = -2;
+        return;
+    }
+    const int64_t nbytes = total - 1;  // payload bytes incl. the (possibly all-pad) last one
+    for (int64_t j = threadIdx.x; j < nbytes; j += blockDim.x) {
+        uint32_t byte = 0;
+        const int64_t base = j * 8;
+        if (base + 8 <= n) {
+            const int4 lo = *reinterpret_cast<const int4 *>(v + base);
+            const int4 hi = *reinterpret_cast<const int4 *>(v + base + 4);
+            byte = ((lo.x != 0) << 7) | ((lo.y != 0) << 6) | ((lo.z != 0) << 5) | ((lo.w != 0) << 4) | ((hi.x != 0) << 3) |
+                   ((hi.y != 0) << 2) | ((hi.z != 0) << 1) | (hi.w != 0);
+        } else {
+            for (int i = 0; i < 8 && base + i < n; ++i) byte |= (uint32_t)(v[base + i] != 0) << (7 - i);
+        }
+        out[1 + j] = (uint8_t)byte;
+    }
+    if (threadIdx.x == 0) {
+        out[0] = (uint8_t)(8 - (int)(n & 7));
+        *size_out = (int32_t)total;
+    }
+}
+
+__global__ void __launch_bounds__(PK_THREADS) pack_kernel(const PackArgs a)
+{
+    extern __shared__ __align__(16) uint32_t stage[];
+    const int s = blockIdx.x, b = blockIdx.y;
+    if (!stream_present(a.mode, s)) {
+        if (threadIdx.x == 0) a.sizes[b * 5 + s] = 0;
+        return;
+    }
+    if (s < 3) {
+        pack_index_stream(a, s, b, stage);
+    } else {
+        const int lvl = s - 3;  // 0 coarse, 1 medium
+        const int div = lvl == 0 ? 4 : 2;
+        const int64_t n = (int64_t)(a.h / div) * (a.w / div);
+        pack_bit_stream(a.mask[lvl] + (int64_t)b * n, n, a.out + (int64_t)b * a.image_stride + a.slot_off[s], a.slot_cap[s],
+                        a.sizes + b * 5 + s);
+    }
+}
+
+__global__ void __launch_bounds__(PK_THREADS) pack_single_kernel(const PackArgs a)
+{
+    extern __shared__ __align__(16) uint32_t stage[];
+    pack_index_stream(a, 0, 0, stage);
+}
+
+__global__ void __launch_bounds__(PK_THREADS)
+bits_single_kernel(const int32_t *v, int64_t n, uint8_t *out, int64_t cap, int32_t *size_out)
+{
+    pack_bit_stream(v, n, out, cap, size_out);
+}
+
+size_t stage_bytes(int max_len) { return ((size_t)PK_TILE * max_len / 32 + 4) * 4; }
+
+int ensure_smem(const void *fn, size_t bytes)
+{
+    if (bytes > 48 * 1024) CGIC_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return CGIC_OK;
+}
+
+}  // namespace
+}  // namespace cgic
+
+using namespace cgic;
+
+extern "C" int cgic_pack(const int64_t *idx, const int32_t *m_c, const int32_t *m_m, const int32_t *m_f, int B, int h, int w,
+                         int mode, const cgic_table *t, uint8_t *bytes_out, int32_t *sizes_out, cgic_stream_t stream)
+{
+    CGIC_REQUIRE(idx && m_c && m_m && m_f && bytes_out && sizes_out, CGIC_EINVAL, "cgic_pack: null argument");
+    CGIC_REQUIRE(B >= 0 && h > 0 && w > 0 && h % 4 == 0 && w % 4 == 0, CGIC_EINVAL, "cgic_pack: token grid %dx%d must be multiples of 4", h, w);
+    CGIC_REQUIRE(mode >= 0 && mode <= 6, CGIC_EINVAL, "cgic_pack: mode %d", mode);
+    CGIC_REQUIRE((reinterpret_cast<uintptr_t>(bytes_out) & 15) == 0 && (reinterpret_cast<uintptr_t>(m_c) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(m_m) & 15) == 0,
+                 CGIC_EINVAL, "cgic_pack: bytes_out and masks must be 16-byte aligned");
+    if (B == 0) return CGIC_OK;
+    PackArgs a{};
+    int rc = table_device_view(t, &a.T);
+    if (rc) return rc;
+    const PackLayout L = make_pack_layout(a.T.max_len, h, w);
+    a.idx = idx;
+    a.mask[0] = m_c;
+    a.mask[1] = m_m;
+    a.mask[2] = m_f;
+    a.h = h;
+    a.w = w;
+    a.mode = mode;
+    a.n_direct = -1;
+    a.out = bytes_out;
+    a.image_stride = L.stride;
+    for (int s = 0; s < 5; ++s) {
+        a.slot_off[s] = L.off[s];
+        a.slot_cap[s] = L.cap[s];
+    }
+    a.sizes = sizes_out;
+    const size_t smem = stage_bytes(a.T.max_len);
+    CGIC_REQUIRE(smem <= 200 * 1024, CGIC_EINVAL, "cgic_pack: code length %d needs %zu bytes of staging", a.T.max_len, smem);
+    rc = ensure_smem((const void *)pack_kernel, smem);
+    if (rc) return rc;
+    // the coarse-mask payload must stay int4-loadable per image: (h/4)*(w/4) ints per image
+    CGIC_REQUIRE(((int64_t)(h / 4) * (w / 4)) % 4 == 0 || B == 1, CGIC_EINVAL,
+                 "cgic_pack: (h/4)*(w/4) must be a multiple of 4 for batched masks");
+    pack_kernel<<<dim3(5, B), PK_THREADS, smem, as_stream(stream)>>>(a);
+    CGIC_LAUNCH_CHECK();
+    return CGIC_OK;
+}
+
+extern "C" int cgic_huff_encode(const int64_t *symbols, int64_t n, const cgic_table *t, uint8_t *out, int64_t cap,
+                                int32_t *size_out, cgic_stream_t stream)
+{
+    CGIC_REQUIRE(out && size_out && n >= 0 && (symbols || n == 0), CGIC_EINVAL, "cgic_huff_encode: bad argument");
+    CGIC_REQUIRE((reinterpret_cast<uintptr_t>(out) & 3) == 0, CGIC_EINVAL, "cgic_huff_encode: out must be 4-byte aligned");
+    PackArgs a{};
+    int rc = table_device_view(t, &a.T);
+    if (rc) return rc;
+    a.idx = symbols;
+    a.n_direct = n;
+    a.out = out;
+    a.slot_cap[0] = cap;
+    a.sizes = size_out;
+    const size_t smem = stage_bytes(a.T.max_len);
+    CGIC_REQUIRE(smem <= 200 * 1024, CGIC_EINVAL, "cgic_huff_encode: code length %d too long", a.T.max_len);
+    rc = ensure_smem((const void *)pack_single_kernel, smem);
+    if (rc) return rc;
+    pack_single_kernel<<<1, PK_THREADS, smem, as_stream(stream)>>>(a);
+    CGIC_LAUNCH_CHECK();
+    return CGIC_OK;
+}
+
+extern "C" int cgic_bits_encode(const int32_t *values, int64_t n, uint8_t *out, int64_t cap, int32_t *size_out,
+                                cgic_stream_t stream)
+{
+    CGIC_REQUIRE(out && size_out && n >= 0 && (values || n == 0), CGIC_EINVAL, "cgic_bits_encode: bad argument");
+    CGIC_REQUIRE((reinterpret_cast<uintptr_t>(values) & 15) == 0, CGIC_EINVAL, "cgic_bits_encode: values must be 16-byte aligned");
+    bits_single_kernel<<<1, PK_THREADS, 0, as_stream(stream)>>>(values, n, out, cap, size_out);
+    CGIC_LAUNCH_CHECK();
+    return CGIC_OK;
+}

@@ -1,0 +1,190 @@
+// a5  TripleGrainFixedEntropyRouter.forward  (CGIC/modules/vqvae/RouterTriple.py:15-96)
+// a6  mask-mix tail of Encoder.forward        (CGIC/modules/vqvae/vqvae_blocks.py:361-366)
+//
+// The reference sorts the flattened entropy map and thresholds on `<` against the k-th smallest
+// value.  Only that one order statistic is needed, so the kernel runs an exact 4-pass radix
+// select (8 bits per pass, shared-memory histogram) over order-preserving integer keys: the
+// threshold VALUE is identical to sorted[k-1], hence so are the masks.  The ranks k_c / k_m and
+// the mode come from the host (Python round() on doubles, banker's rounding).
+//   per_image = 1 : one CTA per image, thresholds per image (B independent B == 1 calls)
+//   per_image = 0 : one CTA, thresholds over the whole batch (reference behaviour for B > 1)
+#include "common.cuh"
+
+namespace cgic {
+namespace {
+
+constexpr int RT_THREADS = 512;
+
+__device__ __forceinline__ uint32_t float_key(float v)
+{
+    if (v != v) return 0xFFFFFFFFu;  // torch.sort places NaN last
+    const uint32_t u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k)
+{
+    if (k == 0xFFFFFFFFu) return __int_as_float(0x7fc00000);
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+// value of rank `rank` (0-based) among fetch(0..n-1); whole CTA must call.
+template <typename Fetch>
+__device__ float select_rank(Fetch fetch, int64_t n, int64_t rank, uint32_t *s_hist, uint32_t *s_state)
+{
+    uint32_t prefix = 0, mask = 0;
+    if (rank > n - 1) rank = n - 1;
+    if (rank < 0) rank = 0;
+    if (threadIdx.x == 0) {
+        s_state[0] = 0;
+        s_state[1] = (uint32_t)rank;
+        s_state[2] = (uint32_t)((uint64_t)rank >> 32);
+    }
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+        __syncthreads();
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t k = float_key(fetch(i));
+            if ((k & mask) == prefix) atomicAdd(&s_hist[(k >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint64_t r = ((uint64_t)s_state[2] << 32) | s_state[1];
+            uint32_t d = 0;
+            for (; d < 255; ++d) {
+                if (r < s_hist[d]) break;
+                r -= s_hist[d];
+            }
+            s_state[0] = prefix | (d << shift);
+            s_state[1] = (uint32_t)r;
+            s_state[2] = (uint32_t)(r >> 32);
+        }
+        __syncthreads();
+        prefix = s_state[0];
+        mask |= 0xFFu << shift;
+        __syncthreads();
+    }
+    return key_float(prefix);
+}
+
+// grid = B (per_image) or 1; writes m_c and m_m.
+__global__ void __launch_bounds__(RT_THREADS)
+router_select_kernel(const float *__restrict__ e16, const float *__restrict__ e8, int B, int h16, int w16, int mode,
+                     int64_t k_c, int64_t k_m, int per_image, int32_t *__restrict__ m_c, int32_t *__restrict__ m_m)
+{
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_state[4];
+    const int h8 = 2 * h16, w8 = 2 * w16;
+    const int64_t n16_img = (int64_t)h16 * w16, n8_img = (int64_t)h8 * w8;
+    const int nb = per_image ? 1 : B;
+    const int64_t img0 = per_image ? blockIdx.x : 0;
+    const float *a16 = e16 + img0 * n16_img;
+    const float *a8 = e8 + img0 * n8_img;
+    int32_t *c = m_c + img0 * n16_img;
+    int32_t *m = m_m + img0 * n8_img;
+    const int64_t n16 = nb * n16_img, n8 = nb * n8_img;
+    const bool use_c = mode == 0 || mode == 2 || mode == 3;
+
+    if (use_c) {
+        const float thr = select_rank([&](int64_t i) { return a16[i]; }, n16, k_c != 0 ? k_c - 1 : 0, s_hist, s_state);
+        for (int64_t i = threadIdx.x; i < n16; i += blockDim.x) c[i] = a16[i] < thr;
+    } else {
+        for (int64_t i = threadIdx.x; i < n16; i += blockDim.x) c[i] = (mode == 4);
+    }
+    __syncthreads();  // c[] (global) is re-read below by other threads of this CTA
+    auto parent = [&](int64_t i) -> int64_t {  // coarse cell above medium cell i
+        const int64_t img = i / n8_img, p = i - img * n8_img;
+        const int y = (int)(p / w8), x = (int)(p - (int64_t)y * w8);
+        return img * n16_img + (int64_t)(y >> 1) * w16 + (x >> 1);
+    };
+    if (mode == 0) {
+        // entropy of cells under a coarse patch is zeroed before the sort (RouterTriple.py:27)
+        const float thr = select_rank(
+            [&](int64_t i) { return __fmul_rn(a8[i], __fsub_rn(1.0f, (float)c[parent(i)])); }, n8,
+            k_m != 0 ? k_m - 1 : 0, s_hist, s_state);
+        for (int64_t i = threadIdx.x; i < n8; i += blockDim.x) m[i] = (a8[i] < thr) && !c[parent(i)];
+    } else if (mode == 1) {
+        const float thr = select_rank([&](int64_t i) { return a8[i]; }, n8, k_m != 0 ? k_m - 1 : 0, s_hist, s_state);
+        for (int64_t i = threadIdx.x; i < n8; i += blockDim.x) m[i] = a8[i] < thr;
+    } else if (mode == 3) {
+        for (int64_t i = threadIdx.x; i < n8; i += blockDim.x) m[i] = 1 - c[parent(i)];
+    } else {
+        for (int64_t i = threadIdx.x; i < n8; i += blockDim.x) m[i] = (mode == 5);
+    }
+}
+
+// one thread per fine token: m_f and the optional gate tensor [B,1,h,3w]
+__global__ void router_fine_kernel(const int32_t *__restrict__ m_c, const int32_t *__restrict__ m_m, int64_t n_tokens, int h,
+                                   int w, int mode, int32_t *__restrict__ m_f, float *__restrict__ gate)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tokens) return;
+    const int64_t plane = (int64_t)h * w;
+    const int64_t b = t / plane, p = t - b * plane;
+    const int y = (int)(p / w), x = (int)(p - (int64_t)y * w);
+    const int c = m_c[b * (plane / 16) + (int64_t)(y >> 2) * (w / 4) + (x >> 2)];
+    const int m = m_m[b * (plane / 4) + (int64_t)(y >> 1) * (w / 2) + (x >> 1)];
+    int f;
+    if (mode <= 2) f = (1 - c - m) != 0;
+    else f = (mode == 6);
+    m_f[t] = f;
+    if (gate) {
+        float *row = gate + (b * h + y) * (int64_t)(3 * w);
+        row[x] = (float)c;
+        row[w + x] = (float)m;
+        row[2 * w + x] = (mode <= 2) ? (float)(1 - c - m) : (float)f;
+    }
+}
+
+__global__ void mask_mix_kernel(const float *__restrict__ h_c, const float *__restrict__ h_m, const float *__restrict__ h_f,
+                                const int32_t *__restrict__ m_c, const int32_t *__restrict__ m_m,
+                                const int32_t *__restrict__ m_f, int64_t n, int C, int h, int w, float *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = (int)(i % w);
+    const int y = (int)((i / w) % h);
+    const int64_t bc = i / ((int64_t)w * h);  // b*C + c
+    const int64_t b = bc / C;
+    const int h8 = h / 2, w8 = w / 2, h16 = h / 4, w16 = w / 4;
+    const float a = __fmul_rn(h_c[(bc * h16 + (y >> 2)) * w16 + (x >> 2)], (float)m_c[(b * h16 + (y >> 2)) * w16 + (x >> 2)]);
+    const float m = __fmul_rn(h_m[(bc * h8 + (y >> 1)) * w8 + (x >> 1)], (float)m_m[(b * h8 + (y >> 1)) * w8 + (x >> 1)]);
+    const float f = __fmul_rn(h_f[i], (float)m_f[(b * h + y) * (int64_t)w + x]);
+    out[i] = __fadd_rn(__fadd_rn(a, m), f);
+}
+
+}  // namespace
+}  // namespace cgic
+
+using namespace cgic;
+
+extern "C" size_t cgic_router_workspace_bytes(int, int, int) { return 256; }
+
+extern "C" int cgic_router(const float *e16, const float *e8, int B, int h16, int w16, int mode, int64_t k_c, int64_t k_m,
+                           int per_image, int32_t *m_c, int32_t *m_m, int32_t *m_f, float *gate_out, void *, size_t,
+                           cgic_stream_t stream_)
+{
+    CGIC_REQUIRE(e16 && e8 && m_c && m_m && m_f, CGIC_EINVAL, "cgic_router: null argument");
+    CGIC_REQUIRE(B >= 0 && h16 > 0 && w16 > 0 && mode >= 0 && mode <= 6 && k_c >= 0 && k_m >= 0, CGIC_EINVAL,
+                 "cgic_router: bad argument B=%d h16=%d w16=%d mode=%d", B, h16, w16, mode);
+    if (B == 0) return CGIC_OK;
+    cudaStream_t stream = as_stream(stream_);
+    router_select_kernel<<<per_image ? B : 1, RT_THREADS, 0, stream>>>(e16, e8, B, h16, w16, mode, k_c, k_m, per_image, m_c, m_m);
+    CGIC_LAUNCH_CHECK();
+    const int64_t n = (int64_t)B * 16 * h16 * w16;
+    router_fine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(m_c, m_m, n, 4 * h16, 4 * w16, mode, m_f, gate_out);
+    CGIC_LAUNCH_CHECK();
+    return CGIC_OK;
+}
+
+extern "C" int cgic_mask_mix(const float *h_c, const float *h_m, const float *h_f, const int32_t *m_c, const int32_t *m_m,
+                             const int32_t *m_f, int B, int C, int h, int w, float *out, cgic_stream_t stream)
+{
+    CGIC_REQUIRE(h_c && h_m && h_f && m_c && m_m && m_f && out, CGIC_EINVAL, "cgic_mask_mix: null argument");
+    CGIC_REQUIRE(B >= 0 && C > 0 && h > 0 && w > 0 && h % 4 == 0 && w % 4 == 0, CGIC_EINVAL, "cgic_mask_mix: bad shape");
+    const int64_t n = (int64_t)B * C * h * w;
+    if (n == 0) return CGIC_OK;
+    mask_mix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(h_c, h_m, h_f, m_c, m_m, m_f, n, C, h, w, out);
+    CGIC_LAUNCH_CHECK();
+    return CGIC_OK;
+}

@@ -1,0 +1,395 @@
+"""Tensor-level wrappers over the C-ABI (include/cgic_b200.h).
+
+PyTorch is only plumbing here: it owns device memory and the stream; every op below enqueues
+hand-written sm_100a kernels from libcgic_b200.so on torch's current stream and returns torch
+tensors.  Inputs must be CUDA tensors -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+STREAM_NAMES = ("indices_coarse", "indices_medium", "indices_fine", "mask_coarse", "mask_medium")
+_STREAM_BITS = (0x1F, 0x16, 0x0D, 0x0B, 0x01, 0x02, 0x04)
+
+
+def stream_present(mode: int, s: int) -> bool:
+    """Which of the five files exist per compression mode (CGIC/models/model.py:225-260)."""
+    return bool((_STREAM_BITS[mode] >> s) & 1)
+
+
+def _cuda(t: torch.Tensor, dtype: torch.dtype, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (the B200 path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# --------------------------------------------------------------------------------------------
+# a8  Huffman table
+# --------------------------------------------------------------------------------------------
+class HuffTable:
+    """Owns a `cgic_table*`.  freq[s] = int count of symbol s, order = push order (None: 0..K-1)."""
+
+    def __init__(self, freq: Sequence[int], order: Optional[Sequence[int]] = None):
+        f = np.ascontiguousarray(np.asarray(freq, dtype=np.int64))
+        o = None if order is None else np.ascontiguousarray(np.asarray(order, dtype=np.int32))
+        if o is not None and o.shape != f.shape:
+            raise ValueError("order must list every symbol once")
+        handle = C.c_void_p()
+        check(lib().cgic_huff_build(f.ctypes.data, None if o is None else o.ctypes.data, int(f.shape[0]), C.byref(handle)),
+              "cgic_huff_build")
+        self._h = handle
+        self._free = lib().cgic_huff_free          # bound now: module globals may be gone at interpreter exit
+        self.K = int(f.shape[0])
+        self.max_len = lib().cgic_huff_max_len(self._h)
+        self._uploaded_on = None
+        self._layouts = {}
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._free(h)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def code(self, sym: int) -> str:
+        buf = C.create_string_buffer(self.max_len + 1)
+        n = lib().cgic_huff_code(self._h, int(sym), buf, self.max_len + 1)
+        if n < 0:
+            check(n, "cgic_huff_code")
+        return buf.value.decode()
+
+    def codes(self) -> dict:
+        return {s: self.code(s) for s in range(self.K)}
+
+    def lengths(self) -> np.ndarray:
+        return np.asarray([lib().cgic_huff_code_len(self._h, s) for s in range(self.K)], np.int32)
+
+    def upload(self) -> "HuffTable":
+        dev = torch.cuda.current_device()
+        if self._uploaded_on != dev:
+            check(lib().cgic_huff_upload(self._h), "cgic_huff_upload")
+            self._uploaded_on = dev
+        return self
+
+    def stream_capacity(self, n_symbols: int) -> int:
+        return int(lib().cgic_huff_stream_capacity(self._h, int(n_symbols)))
+
+    def layout(self, h: int, w: int) -> Tuple[np.ndarray, np.ndarray, int]:
+        """(slot_off[5], slot_cap[5], image_stride) of the packed-image layout for an h x w token grid."""
+        key = (h, w)
+        if key not in self._layouts:
+            off = np.zeros(5, np.int64)
+            cap = np.zeros(5, np.int64)
+            stride = C.c_int64(0)
+            check(lib().cgic_pack_layout(self._h, h, w, off.ctypes.data, cap.ctypes.data, C.addressof(stride)), "cgic_pack_layout")
+            self._layouts[key] = (off, cap, int(stride.value))
+        return self._layouts[key]
+
+
+# --------------------------------------------------------------------------------------------
+# a1  VQ
+# --------------------------------------------------------------------------------------------
+_ws_cache = {}
+
+
+def _workspace(tag: str, nbytes: int, device: torch.device) -> torch.Tensor:
+    """Grow-only scratch buffer per (tag, device, stream); allocation happens off the hot path after warm-up."""
+    key = (tag, device.index, _stream())
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def vq_assign(z: torch.Tensor, codebook: torch.Tensor, want_zq: bool = True, want_sqerr: bool = True):
+    """quantize.py:69-98 -> (idx int64 [B*h*w], z_q fp32 NCHW or None, sqerr float64[1] or None)."""
+    z = _cuda(z, torch.float32, "z")
+    cb = _cuda(codebook, torch.float32, "codebook")
+    if z.dim() != 4 or z.shape[1] != 4 or cb.dim() != 2 or cb.shape[1] != 4:
+        raise ValueError(f"vq_assign supports e_dim == 4 (z {tuple(z.shape)}, codebook {tuple(cb.shape)})")
+    B, _, h, w = z.shape
+    n = B * h * w
+    idx = torch.empty(n, dtype=torch.int64, device=z.device)
+    zq = torch.empty_like(z) if want_zq else None
+    sq = torch.empty(1, dtype=torch.float64, device=z.device) if want_sqerr else None
+    nbytes = lib().cgic_vq_workspace_bytes(n)
+    ws = _workspace("vq", nbytes, z.device)
+    check(lib().cgic_vq_assign(z.data_ptr(), B, h, w, cb.data_ptr(), cb.shape[0], idx.data_ptr(), _p(zq), _p(sq),
+                               ws.data_ptr(), ws.numel(), _stream()), "cgic_vq_assign")
+    return idx, zq, sq
+
+
+def vq_count(idx: torch.Tensor, counters: torch.Tensor) -> None:
+    """quantize.py:79-81: counters[idx[i]] += 1, counters fp32 [K] (in place)."""
+    idx = _cuda(idx, torch.int64, "idx")
+    if not (counters.is_cuda and counters.dtype == torch.float32 and counters.is_contiguous()):
+        raise TypeError("counters must be a contiguous fp32 CUDA tensor")
+    check(lib().cgic_vq_count(idx.data_ptr(), idx.numel(), counters.data_ptr(), counters.numel(), _stream()), "cgic_vq_count")
+
+
+# --------------------------------------------------------------------------------------------
+# a4 entropy, a5 router, a6 mask-mix
+# --------------------------------------------------------------------------------------------
+_BINS = None
+
+
+def linspace_bins() -> np.ndarray:
+    """The 32 fp32 values of torch.linspace(-1, 1, 32) (model.py:480), computed by torch on the host."""
+    global _BINS
+    if _BINS is None:
+        _BINS = np.ascontiguousarray(torch.linspace(-1, 1, 32).numpy().astype(np.float32))
+    return _BINS
+
+
+def entropy_maps(x: torch.Tensor, want8: bool = True, want16: bool = True):
+    """model.py:440-483 for patch sizes 8 and 16 in one pass -> (e8 [B,H/8,W/8], e16 [B,H/16,W/16])."""
+    x = _cuda(x, torch.float32, "x")
+    if x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError("entropy_maps expects [B,3,H,W]")
+    B, _, H, W = x.shape
+    e8 = torch.empty(B, H // 8, W // 8, dtype=torch.float32, device=x.device) if want8 else None
+    e16 = torch.empty(B, H // 16, W // 16, dtype=torch.float32, device=x.device) if want16 else None
+    check(lib().cgic_entropy_maps(x.data_ptr(), B, H, W, linspace_bins().ctypes.data, _p(e8), _p(e16), _stream()),
+          "cgic_entropy_maps")
+    return e8, e16
+
+
+def router_mode(coarse_ratio: float, medium_ratio: float) -> int:
+    """Mode from which ratios are exactly 0.0 in Python doubles (RouterTriple.py:8-13,19,36,72)."""
+    fine_ratio = 1 - coarse_ratio - medium_ratio
+    zeros = (fine_ratio == 0) + (medium_ratio == 0) + (coarse_ratio == 0)
+    if zeros == 0:
+        return 0
+    if zeros == 1:
+        return 1 if coarse_ratio == 0 else (2 if medium_ratio == 0 else 3)
+    return 4 if coarse_ratio != 0 else (5 if medium_ratio != 0 else 6)
+
+
+def router_ranks(coarse_ratio: float, medium_ratio: float, n16: int, n8: int, mode: int) -> Tuple[int, int]:
+    """k_coarse, k_medium: Python round() (banker's) on double products (RouterTriple.py:23,30,42,54,66)."""
+    k_c = round(n16 * coarse_ratio)
+    k_m = round(4 * n16 * coarse_ratio + n8 * medium_ratio) if mode == 0 else round(n8 * medium_ratio)
+    return int(k_c), int(k_m)
+
+
+def router(e16: torch.Tensor, e8: torch.Tensor, coarse_ratio: float, medium_ratio: float, per_image: bool = False,
+           want_gate: bool = False):
+    """RouterTriple.py:15-96 -> (m_c, m_m, m_f int32 [B,1,.,.], gate fp32 [B,1,h,3w] or None, mode)."""
+    e16 = _cuda(e16, torch.float32, "e16")
+    e8 = _cuda(e8, torch.float32, "e8")
+    B, h16, w16 = e16.shape
+    if tuple(e8.shape) != (B, 2 * h16, 2 * w16):
+        raise ValueError(f"e8 {tuple(e8.shape)} does not match e16 {tuple(e16.shape)}")
+    mode = router_mode(coarse_ratio, medium_ratio)
+    nimg = 1 if per_image else B
+    k_c, k_m = router_ranks(coarse_ratio, medium_ratio, nimg * h16 * w16, nimg * 4 * h16 * w16, mode)
+    dev = e16.device
+    m_c = torch.empty(B, 1, h16, w16, dtype=torch.int32, device=dev)
+    m_m = torch.empty(B, 1, 2 * h16, 2 * w16, dtype=torch.int32, device=dev)
+    m_f = torch.empty(B, 1, 4 * h16, 4 * w16, dtype=torch.int32, device=dev)
+    gate = torch.empty(B, 1, 4 * h16, 12 * w16, dtype=torch.float32, device=dev) if want_gate else None
+    check(lib().cgic_router(e16.data_ptr(), e8.data_ptr(), B, h16, w16, mode, k_c, k_m, int(per_image), m_c.data_ptr(),
+                            m_m.data_ptr(), m_f.data_ptr(), _p(gate), None, 0, _stream()), "cgic_router")
+    return m_c, m_m, m_f, gate, mode
+
+
+def mask_mix(h_c, h_m, h_f, m_c, m_m, m_f) -> torch.Tensor:
+    """vqvae_blocks.py:361-366: up4(h_c)*up4(m_c) + up2(h_m)*up2(m_m) + h_f*m_f."""
+    h_c, h_m, h_f = (_cuda(t, torch.float32, n) for t, n in ((h_c, "h_c"), (h_m, "h_m"), (h_f, "h_f")))
+    m_c, m_m, m_f = (_cuda(t, torch.int32, n) for t, n in ((m_c, "m_c"), (m_m, "m_m"), (m_f, "m_f")))
+    B, Cc, h, w = h_f.shape
+    out = torch.empty_like(h_f)
+    check(lib().cgic_mask_mix(h_c.data_ptr(), h_m.data_ptr(), h_f.data_ptr(), m_c.data_ptr(), m_m.data_ptr(), m_f.data_ptr(),
+                              B, Cc, h, w, out.data_ptr(), _stream()), "cgic_mask_mix")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# a7/a9/a11/a12 pack and a10/a13/a14 unpack (batched, B independent images)
+# --------------------------------------------------------------------------------------------
+def pack(idx: torch.Tensor, m_c, m_m, m_f, mode: int, table: HuffTable, h: int, w: int):
+    """model.py:217-260 for B images -> (bytes uint8 [B, image_stride], sizes int32 [B,5])."""
+    idx = _cuda(idx, torch.int64, "idx")
+    m_c, m_m, m_f = (_cuda(t, torch.int32, n) for t, n in ((m_c, "m_c"), (m_m, "m_m"), (m_f, "m_f")))
+    B = idx.numel() // (h * w)
+    table.upload()
+    _, _, stride = table.layout(h, w)
+    out = torch.empty(B, stride, dtype=torch.uint8, device=idx.device)
+    sizes = torch.empty(B, 5, dtype=torch.int32, device=idx.device)
+    check(lib().cgic_pack(idx.data_ptr(), m_c.data_ptr(), m_m.data_ptr(), m_f.data_ptr(), B, h, w, mode, table.handle,
+                          out.data_ptr(), sizes.data_ptr(), _stream()), "cgic_pack")
+    return out, sizes
+
+
+def unpack(bytes_: torch.Tensor, sizes: torch.Tensor, mode: int, table: HuffTable, codebook: torch.Tensor, h: int, w: int):
+    """model.py:269-392 for B images -> (mc, mm, mf int64, ind int64 [B,h,w], quant fp32 [B,4,h,w], status int32 [B])."""
+    bytes_ = _cuda(bytes_, torch.uint8, "bytes")
+    sizes = _cuda(sizes, torch.int32, "sizes")
+    cb = _cuda(codebook, torch.float32, "codebook")
+    B = sizes.shape[0]
+    table.upload()
+    _, _, stride = table.layout(h, w)
+    if bytes_.numel() != B * stride:
+        raise ValueError(f"bytes has {bytes_.numel()} elements, expected {B}*{stride}")
+    dev = bytes_.device
+    mc = torch.empty(B, h // 4, w // 4, dtype=torch.int64, device=dev)
+    mm = torch.empty(B, h // 2, w // 2, dtype=torch.int64, device=dev)
+    mf = torch.empty(B, h, w, dtype=torch.int64, device=dev)
+    ind = torch.empty(B, h, w, dtype=torch.int64, device=dev)
+    quant = torch.empty(B, 4, h, w, dtype=torch.float32, device=dev)
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+    nbytes = lib().cgic_unpack_workspace_bytes(B, h, w)
+    ws = _workspace("unpack", nbytes, dev)
+    check(lib().cgic_unpack(bytes_.data_ptr(), sizes.data_ptr(), B, h, w, mode, table.handle, cb.data_ptr(), mc.data_ptr(),
+                            mm.data_ptr(), mf.data_ptr(), ind.data_ptr(), quant.data_ptr(), status.data_ptr(), ws.data_ptr(),
+                            ws.numel(), _stream()), "cgic_unpack")
+    return mc, mm, mf, ind, quant, status
+
+
+# --------------------------------------------------------------------------------------------
+# single-stream codec ops (a9, a10, a11)
+# --------------------------------------------------------------------------------------------
+def huff_encode(symbols: torch.Tensor, table: HuffTable) -> bytes:
+    """indices_coding.py:113-126 payload: 1-D integer CUDA tensor -> bytes (b'' if empty)."""
+    s = _cuda(symbols.reshape(-1), symbols.dtype, "symbols")
+    if s.dtype != torch.int64:
+        s = s.to(torch.int64)
+    n = s.numel()
+    if n == 0:
+        return b""
+    table.upload()
+    cap = (table.stream_capacity(n) + 15) // 16 * 16
+    out = torch.empty(cap, dtype=torch.uint8, device=s.device)
+    size = torch.empty(1, dtype=torch.int32, device=s.device)
+    check(lib().cgic_huff_encode(s.data_ptr(), n, table.handle, out.data_ptr(), cap, size.data_ptr(), _stream()), "cgic_huff_encode")
+    nb = int(size.item())
+    if nb < 0:
+        raise KeyError("symbol outside the code table")  # the reference raises KeyError from self.codes[character]
+    return bytes(out[:nb].cpu().numpy())
+
+
+def huff_decode(data: bytes, table: HuffTable, device) -> Optional[list]:
+    """indices_coding.py:153-168: bytes -> list of symbols, None for the empty file."""
+    if len(data) == 0:
+        return None
+    table.upload()
+    buf = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(device)
+    cap = len(data) * 8
+    out = torch.empty(cap, dtype=torch.int32, device=device)
+    cnt = torch.empty(1, dtype=torch.int32, device=device)
+    check(lib().cgic_huff_decode(buf.data_ptr(), len(data), table.handle, out.data_ptr(), cap, cnt.data_ptr(), _stream()),
+          "cgic_huff_decode")
+    n = int(cnt.item())
+    if n < 0:
+        raise RuntimeError(f"cgic_huff_decode: status {n}")
+    return out[:n].cpu().tolist()
+
+
+def bits_encode(values: torch.Tensor) -> bytes:
+    """mask_coding.py:40-55 payload."""
+    v = _cuda(values.reshape(-1), values.dtype, "values")
+    if v.dtype != torch.int32:
+        v = v.to(torch.int32)
+    n = v.numel()
+    if n == 0:
+        return b""
+    if v.data_ptr() % 16:
+        v = v.clone()
+    cap = n // 8 + 2
+    out = torch.empty(cap, dtype=torch.uint8, device=v.device)
+    size = torch.empty(1, dtype=torch.int32, device=v.device)
+    check(lib().cgic_bits_encode(v.data_ptr(), n, out.data_ptr(), cap, size.data_ptr(), _stream()), "cgic_bits_encode")
+    return bytes(out[: int(size.item())].cpu().numpy())
+
+
+def bits_decode(data: bytes, device) -> Optional[list]:
+    """mask_coding.py:81-96."""
+    if len(data) == 0:
+        return None
+    buf = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(device)
+    cap = len(data) * 8
+    out = torch.empty(cap, dtype=torch.int32, device=device)
+    cnt = torch.empty(1, dtype=torch.int32, device=device)
+    check(lib().cgic_bits_decode(buf.data_ptr(), len(data), out.data_ptr(), cap, cnt.data_ptr(), _stream()), "cgic_bits_decode")
+    return out[: int(cnt.item())].cpu().tolist()
+
+
+# --------------------------------------------------------------------------------------------
+# host-buffer session (the e2e call)
+# --------------------------------------------------------------------------------------------
+class Session:
+    """cgic_session: device arena + stream created once; compress/decompress take HOST tensors
+    (pin them for full PCIe speed), copy in, run the kernels, copy out, synchronise."""
+
+    def __init__(self, B: int, h: int, w: int, mode: int, table: HuffTable, codebook: torch.Tensor):
+        cb = np.ascontiguousarray(codebook.detach().cpu().numpy().astype(np.float32))
+        handle = C.c_void_p()
+        table.upload()
+        check(lib().cgic_session_create(B, h, w, mode, table.handle, cb.ctypes.data, cb.shape[0], C.byref(handle)),
+              "cgic_session_create")
+        self._s = handle
+        self._destroy = lib().cgic_session_destroy
+        self._table = table
+        self.B, self.h, self.w, self.mode = B, h, w, mode
+        self.image_stride = int(lib().cgic_session_image_stride(self._s))
+        pin = dict(pin_memory=True)
+        n4 = B * h * w
+        self.bytes = torch.empty(B, self.image_stride, dtype=torch.uint8, **pin)
+        self.sizes = torch.empty(B, 5, dtype=torch.int32, **pin)
+        self.idx = torch.empty(n4, dtype=torch.int64, **pin)
+        self.mc = torch.empty(B, h // 4, w // 4, dtype=torch.int64, **pin)
+        self.mm = torch.empty(B, h // 2, w // 2, dtype=torch.int64, **pin)
+        self.mf = torch.empty(B, h, w, dtype=torch.int64, **pin)
+        self.ind = torch.empty(B, h, w, dtype=torch.int64, **pin)
+        self.quant = torch.empty(B, 4, h, w, dtype=torch.float32, **pin)
+        self.status = torch.empty(B, dtype=torch.int32, **pin)
+
+    def close(self):
+        s, self._s = getattr(self, "_s", None), None
+        if s:
+            self._destroy(s)
+
+    __del__ = close
+
+    @staticmethod
+    def _host(t: torch.Tensor, dtype, name):
+        if t.is_cuda or t.dtype != dtype or not t.is_contiguous():
+            raise TypeError(f"{name}: expected a contiguous host tensor of {dtype}")
+        return t.data_ptr()
+
+    def compress(self, z, m_c, m_m, m_f, want_idx: bool = False):
+        """host z fp32 [B,4,h,w] + int32 masks -> (bytes [B,stride] uint8, sizes [B,5] int32[, idx]) (pinned host)."""
+        check(lib().cgic_session_compress_host(self._s, self._host(z, torch.float32, "z"), self._host(m_c, torch.int32, "m_c"),
+                                               self._host(m_m, torch.int32, "m_m"), self._host(m_f, torch.int32, "m_f"),
+                                               self.bytes.data_ptr(), self.sizes.data_ptr(),
+                                               self.idx.data_ptr() if want_idx else None, None, None),
+              "cgic_session_compress_host")
+        return (self.bytes, self.sizes, self.idx) if want_idx else (self.bytes, self.sizes)
+
+    def decompress(self, bytes_, sizes):
+        """host bytes/sizes -> (mc, mm, mf, ind int64, quant fp32, status) (pinned host)."""
+        check(lib().cgic_session_decompress_host(self._s, self._host(bytes_, torch.uint8, "bytes"),
+                                                 self._host(sizes, torch.int32, "sizes"), self.mc.data_ptr(), self.mm.data_ptr(),
+                                                 self.mf.data_ptr(), self.ind.data_ptr(), self.quant.data_ptr(),
+                                                 self.status.data_ptr()), "cgic_session_decompress_host")
+        return self.mc, self.mm, self.mf, self.ind, self.quant, self.status

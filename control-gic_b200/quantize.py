@@ -1,0 +1,95 @@
+"""VectorQuantize2 -- drop-in for CGIC/modules/vqvae/quantize.py:9-98 backed by cgic_vq_assign.
+
+Same constructor, attributes (`embedding`, `embedding_counter`, n_e, e_dim, beta, legacy) and
+state-dict keys (`embedding.weight`, `embedding_counter.<i>` with shape [1]); forward returns
+(z_q, loss, z_indices) with z_indices int64 flat [B*h*w] exactly like the reference.
+Differences, all deliberate: the counters are not moved to CUDA at construction (the reference's
+`.cuda()` at quantize.py:28 makes CPU construction impossible); `remap` / `sane_index_shape`
+are accepted and, as in the reference's forward, unused.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import ops
+
+
+class _VQFunction(torch.autograd.Function):
+    """Forward = the CUDA kernels; backward = straight-through for z_q (quantize.py:93) plus the
+    analytic gradient of the commitment loss (quantize.py:85-90)."""
+
+    @staticmethod
+    def forward(ctx, z, weight, beta, legacy):
+        idx, zq, sq = ops.vq_assign(z.detach(), weight.detach())
+        mean = (sq / z.numel()).to(torch.float32)[0]
+        loss = mean + beta * mean if legacy else beta * mean + mean
+        ctx.save_for_backward(z, weight, idx)
+        ctx.beta, ctx.legacy = beta, legacy
+        ctx.mark_non_differentiable(idx)
+        return zq, loss, idx
+
+    @staticmethod
+    def backward(ctx, g_zq, g_loss, _g_idx):
+        z, weight, idx = ctx.saved_tensors
+        B, C, h, w = z.shape
+        e = weight[idx].view(B, h, w, C).permute(0, 3, 1, 2)
+        diff = (z - e) * (2.0 / z.numel())
+        wz, we = (1.0, ctx.beta) if ctx.legacy else (ctx.beta, 1.0)
+        g_z = g_w = None
+        if ctx.needs_input_grad[0]:
+            g_z = g_zq + g_loss * wz * diff
+        if ctx.needs_input_grad[1]:
+            g_w = torch.zeros_like(weight).index_add_(0, idx, (-g_loss * we * diff).permute(0, 2, 3, 1).reshape(-1, C))
+        return g_z, g_w, None, None
+
+
+class VectorQuantize2(nn.Module):
+    def __init__(self, n_e, e_dim, beta, remap=None, unknown_index="random", sane_index_shape=False, legacy=True):
+        super().__init__()
+        if e_dim != 4:
+            raise ValueError("the B200 VQ kernel implements e_dim == 4 (the only value Control-GIC uses)")
+        self.n_e = n_e
+        self.e_dim = e_dim
+        self.beta = beta
+        self.legacy = legacy
+        self.embedding = nn.Embedding(n_e, e_dim)
+        self.embedding.weight.data.uniform_(-1.0 / n_e, 1.0 / n_e)                      # quantize.py:25-26
+        # plain dict -> torch sorts the keys: iteration order "0","1","10","100",... (quantize.py:28)
+        self.embedding_counter = nn.ParameterDict(
+            {str(i): nn.Parameter(torch.zeros(1)) for i in range(n_e)}).requires_grad_(False)
+        self.remap = remap
+        self.unknown_index = unknown_index
+        self.re_embed = n_e
+        self.sane_index_shape = sane_index_shape
+
+    # -- counters as one tensor (the reference touches them one .item() at a time) ---------
+    def counter_order(self):
+        """Symbols in the ParameterDict's iteration order = the Huffman heap push order."""
+        return [int(k) for k in self.embedding_counter.keys()]
+
+    def counters_flat(self) -> torch.Tensor:
+        """fp32 [n_e] indexed by symbol."""
+        vals = torch.cat([p.detach().reshape(1) for p in self.embedding_counter.values()])
+        flat = torch.empty_like(vals)
+        flat[torch.as_tensor(self.counter_order(), device=vals.device)] = vals
+        return flat
+
+    @torch.no_grad()
+    def _bump_counters(self, idx: torch.Tensor) -> None:                                 # quantize.py:79-81
+        flat = self.counters_flat().to(idx.device).contiguous()
+        ops.vq_count(idx, flat)
+        for k, p in self.embedding_counter.items():
+            p.copy_(flat[int(k): int(k) + 1])
+
+    def forward(self, z):
+        w = self.embedding.weight
+        if torch.is_grad_enabled() and (z.requires_grad or w.requires_grad):
+            z_q, loss, idx = _VQFunction.apply(z, w, self.beta, self.legacy)
+        else:
+            idx, z_q, sq = ops.vq_assign(z, w)
+            mean = (sq / z.numel()).to(torch.float32)[0]
+            loss = mean + self.beta * mean if self.legacy else self.beta * mean + mean
+        if self.training:
+            self._bump_counters(idx)
+        return z_q, loss, idx

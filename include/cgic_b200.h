@@ -1,0 +1,189 @@
+/*
+ * cgic_b200.h -- C ABI of the B200-native VQ + entropy-coding hot path of Control-GIC.
+ *
+ * This is the drop-in boundary: every entry point replaces one function (or one inlined block)
+ * of the reference's Python hot path and is what a binding on the reference side would call
+ * (ctypes stub: INTEGRATION.md).  Reference citations are relative to the reference repo root.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, a stream handle; no torch / C++ types.
+ *   - every `*_dev` / unqualified data pointer is DEVICE memory owned by the caller (torch
+ *     allocates); the library never allocates or frees on the hot path and never synchronises
+ *     unless the function name says `_host`.  Work is enqueued on `stream` (a cudaStream_t,
+ *     e.g. torch.cuda.current_stream().cuda_stream).  `cgic_table` and `cgic_session` are the
+ *     only library-owned handles.
+ *   - return value: CGIC_OK (0) or a negative CGIC_E* code; cgic_last_error() returns a
+ *     thread-local description.  Nothing ever calls exit() (the reference does, at
+ *     CGIC/tools/indices_coding.py:102-104).
+ *   - layouts are the reference's: latents / images NCHW fp32, indices int64, router masks
+ *     int32 [B,1,h,w], decoded masks int64.  h, w below are the FINE token grid (image H/4, W/4)
+ *     and must be multiples of 4 for the pack / unpack / router entry points.
+ *   - stream order inside a packed image: 0 indices_coarse, 1 indices_medium, 2 indices_fine,
+ *     3 mask_coarse, 4 mask_medium (the five files of CGIC/models/model.py:226-232).
+ */
+#ifndef CGIC_B200_H
+#define CGIC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGIC_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define CGIC_API __attribute__((visibility("default")))
+#else
+#define CGIC_API
+#endif
+
+#define CGIC_OK 0
+#define CGIC_EINVAL (-1)  /* bad argument */
+#define CGIC_ENOMEM (-2)  /* host or device allocation failed (init-time calls only) */
+#define CGIC_ESPACE (-3)  /* caller buffer / workspace too small */
+#define CGIC_ECUDA (-4)   /* CUDA runtime error, see cgic_last_error() */
+#define CGIC_EFORMAT (-5) /* corrupt bitstream */
+
+typedef void *cgic_stream_t;          /* cudaStream_t */
+typedef struct cgic_table cgic_table; /* static Huffman code table (host + device copy) */
+typedef struct cgic_session cgic_session;
+
+CGIC_API int cgic_abi_version(void);
+CGIC_API const char *cgic_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * a8  HuffmanCoding.__init__ / make_heap / merge_nodes / make_codes
+ *     CGIC/tools/indices_coding.py:10-17, 46-75.  Host-side, init time, heapq-exact.
+ *     freq[s]  = int(counter) of symbol s;   order[i] = symbol pushed i-th, i.e. the iteration
+ *     order of the reference's `frequency` mapping (NULL = 0..K-1).  The model's
+ *     nn.ParameterDict iterates its keys in lexicographic string order (quantize.py:28).
+ *     The table is immutable after build and may be shared between threads.
+ * ------------------------------------------------------------------------------------------ */
+CGIC_API int cgic_huff_build(const int64_t *freq, const int32_t *order, int K, cgic_table **out);
+CGIC_API void cgic_huff_free(cgic_table *t);
+CGIC_API int cgic_huff_num_symbols(const cgic_table *t);
+CGIC_API int cgic_huff_max_len(const cgic_table *t);
+CGIC_API int cgic_huff_code_len(const cgic_table *t, int sym);
+/* writes the code of `sym` as a NUL-terminated '0'/'1' string (HuffmanCoding.codes[sym]);
+ * returns its length or CGIC_ESPACE. */
+CGIC_API int cgic_huff_code(const cgic_table *t, int sym, char *buf, int cap);
+/* copies the table to the CURRENT device (once; synchronous; init time). */
+CGIC_API int cgic_huff_upload(cgic_table *t);
+
+/* ------------------------------------------------------------------------------------------
+ * a1  VectorQuantize2.forward      CGIC/modules/vqvae/quantize.py:69-98   (e_dim == 4)
+ *     z [B,4,h,w] fp32 NCHW, codebook [K,4] fp32 (16-byte aligned)
+ *     idx_out  int64 [B*h*w]   nearest code, reference rounding sequence, first index on ties
+ *     zq_out   fp32 [B,4,h,w]  fl(z + fl(e - z))            (nullable)
+ *     sqerr_out double[1]      sum over all elements of (e - z)^2; loss = (1+beta)*sqerr/numel
+ *                              (nullable)
+ *     Tokens whose latent is bit-identical to the top-left token of their 4x4 / 2x2 block (the
+ *     structure the mask-mix of vqvae_blocks.py:364-366 creates) share that token's search.
+ * ------------------------------------------------------------------------------------------ */
+CGIC_API size_t cgic_vq_workspace_bytes(int64_t n_tokens);
+CGIC_API int cgic_vq_assign(const float *z, int B, int h, int w, const float *codebook, int K, int64_t *idx_out,
+                   float *zq_out, double *sqerr_out, void *workspace, size_t workspace_bytes,
+                   cgic_stream_t stream);
+
+/* a3  training-mode counter update, quantize.py:79-81: counters[idx[i]] += 1 (fp32 counters). */
+CGIC_API int cgic_vq_count(const int64_t *idx, int64_t n, float *counters, int K, cgic_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a4  Entropy.forward              CGIC/models/model.py:440-483
+ *     x [B,3,H,W] fp32; bins32_host = the 32 values of torch.linspace(-1,1,32) (HOST pointer);
+ *     e8_out [B,H/8,W/8], e16_out [B,H/16,W/16] fp32 (either nullable).  H, W multiples of 16.
+ * ------------------------------------------------------------------------------------------ */
+CGIC_API int cgic_entropy_maps(const float *x, int B, int H, int W, const float *bins32_host, float *e8_out,
+                      float *e16_out, cgic_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a5  TripleGrainFixedEntropyRouter.forward   CGIC/modules/vqvae/RouterTriple.py:15-96
+ *     e16 [B,h16,w16], e8 [B,2*h16,2*w16] fp32.  mode 0..6 and the ranks k_c, k_m are computed
+ *     by the caller in Python doubles with round() exactly as RouterTriple.py:19-30,36-90 does.
+ *     per_image = 0: thresholds over the whole batch (what the reference does for B > 1);
+ *     per_image = 1: B independent B == 1 calls (k_c, k_m then refer to ONE image).
+ *     m_c int32 [B,1,h16,w16], m_m int32 [B,1,2h16,2w16], m_f int32 [B,1,4h16,4w16];
+ *     gate_out fp32 [B,1,4h16,3*4w16] = cat(up4(c), up2(m), f) on the last dim (nullable).
+ * ------------------------------------------------------------------------------------------ */
+CGIC_API size_t cgic_router_workspace_bytes(int B, int h16, int w16);
+CGIC_API int cgic_router(const float *e16, const float *e8, int B, int h16, int w16, int mode, int64_t k_c,
+                int64_t k_m, int per_image, int32_t *m_c, int32_t *m_m, int32_t *m_f, float *gate_out,
+                void *workspace, size_t workspace_bytes, cgic_stream_t stream);
+
+/* a6  mask-mix, CGIC/modules/vqvae/vqvae_blocks.py:361-366:
+ *     out = up4(h_c)*up4(m_c) + up2(h_m)*up2(m_m) + h_f*m_f       [B,C,h,w] fp32 */
+CGIC_API int cgic_mask_mix(const float *h_c, const float *h_m, const float *h_f, const int32_t *m_c,
+                  const int32_t *m_m, const int32_t *m_f, int B, int C, int h, int w, float *out,
+                  cgic_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a7 + a9 + a11 + a12  index selection + 5-stream pack     CGIC/models/model.py:217-260,
+ *     HuffmanCoding.compress indices_coding.py:113-126, BinaryCoding.compress mask_coding.py:40-55.
+ *     Per image: slot s of image b starts at bytes_out + b*image_stride + slot_off[s] and holds
+ *     sizes_out[b*5+s] bytes (0 = stream absent in this mode, or empty: the reference's 0-byte
+ *     file).  bpp = 8 * sum(sizes) / (H*W).  sizes_out < 0 flags an out-of-range symbol.
+ *     cgic_pack_layout fills the worst-case slot offsets / capacities for a table and grid.
+ * ------------------------------------------------------------------------------------------ */
+CGIC_API int cgic_pack_layout(const cgic_table *t, int h, int w, int64_t slot_off[5], int64_t slot_cap[5],
+                     int64_t *image_stride);
+CGIC_API int cgic_pack(const int64_t *idx, const int32_t *m_c, const int32_t *m_m, const int32_t *m_f, int B, int h,
+              int w, int mode, const cgic_table *t, uint8_t *bytes_out, int32_t *sizes_out,
+              cgic_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a10 + a11 + a13 + a14  unpack + mask / index re-assembly + codebook gather
+ *     CGIC/models/model.py:269-392, decompress_string indices_coding.py:153-168, mask_coding.py:81-96.
+ *     bytes / sizes use the cgic_pack layout.  Outputs (all device, caller-allocated):
+ *     mc_out int64 [B,h/4,w/4], mm_out int64 [B,h/2,w/2], mf_out int64 [B,h,w]   (grain masks)
+ *     ind_out int64 [B,h,w], quant_out fp32 [B,4,h,w] = codebook[ind] (exact rows, NCHW)
+ *     status_out int32 [B]: 0 ok, else CGIC_EFORMAT (symbol count != mask population, bad
+ *     framing, ...) -- the cases in which the reference raises.
+ * ------------------------------------------------------------------------------------------ */
+CGIC_API size_t cgic_unpack_workspace_bytes(int B, int h, int w);
+CGIC_API int cgic_unpack(const uint8_t *bytes, const int32_t *sizes, int B, int h, int w, int mode,
+                const cgic_table *t, const float *codebook, int64_t *mc_out, int64_t *mm_out,
+                int64_t *mf_out, int64_t *ind_out, float *quant_out, int32_t *status_out, void *workspace,
+                size_t workspace_bytes, cgic_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Single-stream codec entry points (what HuffmanCoding / BinaryCoding objects bind to).
+ *     a9  HuffmanCoding.compress           indices_coding.py:113-126
+ *     a10 HuffmanCoding.decompress_string  indices_coding.py:153-168
+ *     a11 BinaryCoding.compress / decompress_string   mask_coding.py:40-55, 81-96
+ *     size_out / count_out are device int32[1].  Decoders: nbytes == 0 -> count -1 (the
+ *     reference returns None).  cap is in bytes (encode) or symbols (decode).
+ * ------------------------------------------------------------------------------------------ */
+CGIC_API int64_t cgic_huff_stream_capacity(const cgic_table *t, int64_t n_symbols);
+CGIC_API int cgic_huff_encode(const int64_t *symbols, int64_t n, const cgic_table *t, uint8_t *out, int64_t cap,
+                     int32_t *size_out, cgic_stream_t stream);
+CGIC_API int cgic_huff_decode(const uint8_t *bytes, int64_t nbytes, const cgic_table *t, int32_t *symbols_out,
+                     int64_t cap, int32_t *count_out, cgic_stream_t stream);
+CGIC_API int cgic_bits_encode(const int32_t *values, int64_t n, uint8_t *out, int64_t cap, int32_t *size_out,
+                     cgic_stream_t stream);
+CGIC_API int cgic_bits_decode(const uint8_t *bytes, int64_t nbytes, int32_t *values_out, int64_t cap,
+                     int32_t *count_out, cgic_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-buffer session: the call a reference-side plugin makes per batch when its tensors live
+ * in host memory (pinned for full PCIe speed).  Owns its device buffers, workspace and stream
+ * (allocated at create time, never on the hot path).  compress = a1 + a7 + a12 for B
+ * independent images; decompress = a13 + a14.  Both copy host->device, run, copy device->host
+ * and synchronise before returning.
+ * ------------------------------------------------------------------------------------------ */
+CGIC_API int cgic_session_create(int B, int h, int w, int mode, const cgic_table *t, const float *codebook_host, int K,
+                        cgic_session **out);
+CGIC_API void cgic_session_destroy(cgic_session *s);
+CGIC_API int64_t cgic_session_image_stride(const cgic_session *s);
+CGIC_API int cgic_session_compress_host(cgic_session *s, const float *z, const int32_t *m_c, const int32_t *m_m,
+                               const int32_t *m_f, uint8_t *bytes_out, int32_t *sizes_out, int64_t *idx_out,
+                               float *zq_out, double *sqerr_out);
+CGIC_API int cgic_session_decompress_host(cgic_session *s, const uint8_t *bytes, const int32_t *sizes, int64_t *mc_out,
+                                 int64_t *mm_out, int64_t *mf_out, int64_t *ind_out, float *quant_out,
+                                 int32_t *status_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGIC_B200_H */
