@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""bench.py -- Mpixels/s of the VQ + entropy-coding hot path (encode + decode) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of synthetic images:
+    encode = VectorQuantize2.forward (a1) + index selection + 5-stream Huffman/binary pack (a7,a9,a11,a12)
+    decode = 5-stream unpack + mask/index re-assembly + codebook gather (a10,a11,a13,a14)
+Workload at every N: 64 images of 256x256 per GPU (BASELINE.json configs[1]; configs[3] is the
+same thing at N = 8), ratio (0.1, 0.8, 0.1), K = 1024 codebook; images are sharded contiguously
+over ranks with no data-path collective, one all-reduce of {bytes, pixels, sqerr} at the end
+("scaling": "weak").
+
+    value     device-resident: inputs already in HBM, each step timed by a CUDA-event pair on the
+              launching stream, L2 flushed (256 MiB memset) between steps outside the pairs.
+    e2e       the host-buffer C-ABI call (cgic_session_compress_host + _decompress_host): pinned
+              host inputs -> H2D -> kernels -> D2H of every result, wall clock, per step.
+    roofline  dominant kernel, its duration measured live with the library's per-launch CUDA
+              events (cgic_prof_*), against the algorithmic bytes of DESIGN.md and the measured
+              HBM peak of MEASURED_PEAKS.json.
+    cpu_baseline  the reference-shaped Python/torch CPU port (oracle/refport.py) on a bounded
+              sample of the same images, on this box's host cores (rank 0, N = 1 only).
+--impl reference times that CPU port alone (the reference is pure Python and cannot travel to
+the GPU box) and prints the same line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Mpixels/s encode+decode (VQ+entropy)"
+UNIT = "Mpixels/s"
+WORKLOADS = {
+    # name: (images per GPU, H, W, coarse ratio, medium ratio)
+    "c2_b64_256x256_r0.1-0.8-0.1": (64, 256, 256, 0.1, 0.8),
+    "c3_b24_512x768_r0.3-0.6-0.1": (24, 512, 768, 0.3, 0.6),
+    "c3_b24_512x768_r0.1-0.8-0.1": (24, 512, 768, 0.1, 0.8),
+    "c3_b24_512x768_r0.05-0.05-0.9": (24, 512, 768, 0.05, 0.05),
+}
+DEFAULT_WORKLOAD = "c2_b64_256x256_r0.1-0.8-0.1"
+
+_SAMPLER = r"""
+import sys, time
+import pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+out = open(sys.argv[2], "w")
+while True:
+    try:
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+    except Exception:
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+    out.write("%.6f %d %d %d %.1f\n" % (time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), mx, r,
+                                        nv.nvmlDeviceGetPowerUsage(h) / 1000.0))
+    out.flush()
+    time.sleep(0.005)
+"""
+_REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+            0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+
+class ClockSampler:
+    """nvml samples of SM clock / throttle reasons in a side process (no GIL contention with the launch loop)."""
+
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.mktemp(prefix="cgic_clocks_")
+        try:
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER, str(gpu_index), self.path],
+                                         stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = [l.split() for l in open(self.path) if l.strip()]
+            os.unlink(self.path)
+        except OSError:
+            return None
+        rows = [(float(a), int(b), int(c), int(d), float(e)) for a, b, c, d, e in (r for r in rows if len(r) == 5)]
+        if not rows:
+            return None
+        inside = [r for r in rows if t0 <= r[0] <= t1] or rows
+        bits = 0
+        for r in inside:
+            bits |= r[3]
+        reasons = [n for b, n in _REASONS.items() if bits & b and n != "gpu_idle"]
+        return {"sm_mhz": statistics.median(r[1] for r in inside), "sm_max_mhz": inside[0][2], "reasons": reasons,
+                "samples": len(inside), "power_w_max": max(r[4] for r in inside)}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def config_of(args, world):
+    B, H, W, c, m = WORKLOADS[args.workload]
+    return {"workload": args.workload, "images_per_gpu": B, "global_images": B * world, "height": H, "width": W,
+            "ratio": [c, m, round(1 - c - m, 6)], "codebook": 1024, "parallelism": f"image-sharded dp{world}",
+            "l2": "flushed between timed steps (256 MiB memset outside the event pairs)"}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the reference-shaped port on host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_inputs(B, H, W, c, m, seed):
+    """Same seeded inputs as the GPU arm, built on the CPU with the oracle's router / mask-mix."""
+    import numpy as np
+    import torch
+
+    import workload
+    from oracle import oracle as orc
+    cbk, counts = workload.codebook_and_counts()
+    e16, e8 = workload.entropy_maps(B, H, W, seed)
+    hc, hm, hf = workload.heads(B, H, W, cbk, seed)
+    zs, masks = [], []
+    for b in range(B):
+        mc, mm, mf, mode = orc.router(e16[b:b + 1].numpy(), e8[b:b + 1].numpy(), c, m)
+        z = orc.mask_mix(hc[b:b + 1].numpy(), hm[b:b + 1].numpy(), hf[b:b + 1].numpy(), mc, mm, mf)
+        zs.append(torch.from_numpy(z))
+        masks.append(tuple(torch.from_numpy(np.ascontiguousarray(t)) for t in (mc, mm, mf)))   # [1,1,.,.] like grain_mask
+    return cbk, counts, zs, masks
+
+
+def cpu_run(args, n_images_cap, seconds, steps=None, warmup=0):
+    """Times refport.roundtrip_mode0 (VQ -> select -> 5 files -> read back -> re-assemble -> gather) per image.
+    steps=None: repeat passes over the sample until `seconds` have elapsed."""
+    import torch
+
+    import workload
+    from oracle import refport
+    B, H, W, c, m = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = min(B, n_images_cap)
+    cbk, counts, zs, masks = cpu_inputs(n, H, W, c, m, seed=1000)
+    table = refport.huffman_codes(counts.tolist(), workload.lexicographic_order())
+    reverse = {v: k for k, v in table.items()}
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    sizes_all = []
+    with tempfile.TemporaryDirectory(dir=shm) as tmp:
+        def one_pass():
+            out = []
+            for b in range(n):
+                ind, bpp, ind_dec, quant, sizes = refport.roundtrip_mode0(zs[b], cbk, masks[b], table, reverse, tmp)
+                out.append(sizes)
+            return out
+        for _ in range(warmup):
+            one_pass()
+        t0 = time.perf_counter()
+        passes = 0
+        while True:
+            sizes_all = one_pass()
+            passes += 1
+            if steps is not None and passes >= steps:
+                break
+            if steps is None and time.perf_counter() - t0 >= seconds:
+                break
+        dt = time.perf_counter() - t0
+    mpix = passes * n * H * W / 1e6
+    return {"value": mpix / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} of the {B} images of one step x {passes} passes, {dt:.1f} s, torch threads = {cores}, files on {shm or 'tmp'}",
+            "ms_per_image": 1e3 * dt / (passes * n)}, sizes_all, dt / passes
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    B, H, W, c, m = WORKLOADS[args.workload]
+    # calibrate on one image, then size the per-step sample so that the whole run stays within ~2 minutes
+    cal, _, t_img = cpu_run(args, 1, 0, steps=1, warmup=1)
+    budget = 120.0
+    n = max(1, min(B, int(budget / max(1, args.steps + args.warmup) / max(t_img, 1e-4))))
+    res, _, t_step = cpu_run(args, n, 0, steps=args.steps, warmup=args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_of(args, world),
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import cgic_b200 as cg
+    import workload
+    from cgic_b200 import dist as cdist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, H, W, c, m = WORKLOADS[args.workload]
+    h, w = H // 4, W // 4
+    seed, first = 1000, rank * B                  # every rank owns its own contiguous range of the global image list
+    cbk, counts = workload.codebook_and_counts()
+    table = cg.ops.HuffTable(counts.numpy(), workload.lexicographic_order()).upload()
+    cb = cbk.to(dev)
+    e16, e8 = workload.entropy_maps(B, H, W, seed, first)
+    mc, mm, mf, _, mode = cg.ops.router(e16.to(dev), e8.to(dev), c, m, per_image=True)
+    hc, hm, hf = (t.to(dev) for t in workload.heads(B, H, W, cbk, seed, first))
+    z = cg.ops.mask_mix(hc, hm, hf, mc, mm, mf)
+    del hc, hm, hf
+    pixels = B * H * W
+
+    def step():
+        idx, zq, sq = cg.ops.vq_assign(z, cb)
+        packed, sizes = cg.ops.pack(idx, mc, mm, mf, mode, table, h, w)
+        dmc, dmm, dmf, ind, quant, status = cg.ops.unpack(packed, sizes, mode, table, cb, h, w)
+        return idx, sq, sizes, ind, quant, status
+    kernels_per_step = 6    # vq_classify, vq_search, vq_finalize, pack, unpack_decode, unpack_assemble
+
+    # correctness gate of the run itself (round trip + status), before any timing
+    idx, sq, sizes, ind, quant, status = step()
+    torch.cuda.synchronize()
+    assert int(status.abs().sum()) == 0 and int(sizes.min()) >= 0
+    assert torch.equal(ind.view(-1), idx), "decode(encode(idx)) != idx"
+    sizes_first = sizes.cpu()
+
+    runner = step
+    graph = None
+    if not args.no_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            g_out = step()
+        runner = graph.replay
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        runner()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_begin = time.time()
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        runner()
+        b.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    if graph is not None:
+        idx, sq, sizes, ind, quant, status = g_out
+    else:
+        idx, sq, sizes, ind, quant, status = step()
+    torch.cuda.synchronize()
+    assert torch.equal(sizes.cpu(), sizes_first) and torch.equal(ind.view(-1), idx)
+    # the path's only collective: {bytes, pixels, squared error} summed over ranks
+    tot_bytes, tot_pix, tot_sq, bpp = cdist.reduce_rate_distortion(float(sizes_first.sum()), float(pixels), float(sq.item()), device=dev)
+
+    # ---- e2e: host buffers through the C-ABI session (H2D + kernels + D2H inside the timed region)
+    sess = cg.ops.Session(B, h, w, mode, table, cbk)
+    zh = z.cpu().pin_memory()
+    mh = [t_.cpu().pin_memory() for t_ in (mc, mm, mf)]
+    for _ in range(3):
+        by, sz = sess.compress(zh, *mh)
+        out = sess.decompress(by, sz)
+    assert torch.equal(sz, sizes_first) and torch.equal(out[3].view(-1), idx.cpu()) and int(out[5].abs().sum()) == 0
+    n_e2e = max(10, min(args.steps, 100))
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        by, sz = sess.compress(zh, *mh)
+        sess.decompress(by, sz)
+    e2e_s = time.perf_counter() - t0
+    t_end = time.time()
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    n4, n8, n16 = B * h * w, B * h * w // 4, B * h * w // 16
+    blob = B * sess.image_stride
+    h2d = n4 * 16 + (n4 + n8 + n16) * 4 + blob + B * 20
+    d2h = blob + B * 20 + n4 * 8 + n4 * 16 + (n4 + n8 + n16) * 8 + B * 4
+    sess.close()
+    clocks = sampler.stop(t_begin, t_end) if sampler else None
+
+    # ---- roofline of the dominant kernel: per-launch CUDA events inside the library, eager launches
+    lib = cg._lib.lib()
+    prof_steps = 20
+    lib.cgic_prof_enable(1)
+    for _ in range(prof_steps):
+        flush.zero_()
+        step()
+    import ctypes
+    buf = ctypes.create_string_buffer(8192)
+    cg._lib.check(min(lib.cgic_prof_report(buf, 8192), 0), "cgic_prof_report")
+    lib.cgic_prof_enable(0)
+    kern = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split()
+        kern[name] = {"launches_per_step": int(cnt) / prof_steps, "us_per_launch": 1e3 * float(ms) / int(cnt)}
+    step_us = sum(k["us_per_launch"] * k["launches_per_step"] for k in kern.values())
+    for k in kern.values():
+        k["share"] = k["us_per_launch"] * k["launches_per_step"] / step_us
+    top = max(kern, key=lambda n: kern[n]["share"])
+    stream_bytes = float(sizes_first.sum())
+    alg = algorithmic_bytes(B, h, w, stream_bytes)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg[top] / (kern[top]["us_per_launch"] * 1e-6) / 1e9
+    roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "traffic": NCU_TRAFFIC.get(top), "algorithmic_bytes_per_launch": alg[top],
+                "us_per_launch": kern[top]["us_per_launch"], "kernels": kern,
+                "step_algorithmic_bytes": alg["step"],
+                "step_achieved_gbs": alg["step"] / (dev_ms / args.steps * 1e-3) / 1e9,
+                "step_frac": alg["step"] / (dev_ms / args.steps * 1e-3) / 1e9 / peak}
+
+    value = world * pixels * args.steps / 1e6 / (dev_ms * 1e-3)
+    e2e_value = world * pixels * n_e2e / 1e6 / e2e_s
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_of(args, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e,
+                    "ms_per_step": 1e3 * e2e_s / n_e2e},
+            "gpu_launches": kernels_per_step * args.steps, "cuda_graph": graph is not None,
+            "bpp": bpp, "stream_bytes_per_step": tot_bytes, "clocks": clocks, "roofline": roofline}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu, cpu_sizes, _ = cpu_run(args, 16, args.cpu_seconds)
+        # parity gate in the same run: the port's five file sizes == the GPU's stream sizes, image by image
+        for b, s in enumerate(cpu_sizes):
+            assert list(s) == sizes_first[b].tolist(), f"CPU port and GPU stream sizes differ on image {b}"
+        cpu["parity"] = f"stream sizes of {len(cpu_sizes)} images identical to the GPU's (bpp bit-exact)"
+        line["cpu_baseline"] = cpu
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
+# capture (profiles/), filled in after each capture; None = not captured yet.
+NCU_TRAFFIC = {}
+
+
+def algorithmic_bytes(B, h, w, stream_bytes):
+    """Algorithmic HBM bytes per launch of each kernel and of the whole step:
+    per fine token: z 16 B in, z_q 16 B out, idx 8 B out (a1); idx 8 B in + masks 5.25 B in + streams out (pack);
+    streams in + masks 5.25*2 B (int64) out + ind 8 B out + quant 16 B out (unpack)."""
+    n4 = B * h * w
+    masks32 = n4 * 4 * (1 + 0.25 + 0.0625)
+    masks64 = masks32            # SURVEY 8d counts the decoded masks at 5.25 B/token (we write them as int64 like the reference)
+    consts = 1024 * 16
+    out = {
+        "vq_classify_kernel": n4 * 16,                       # reads z
+        "vq_search_kernel": n4 * 16 + consts,                # reads (at most) z + codebook
+        "vq_finalize_kernel": n4 * (16 + 16 + 8) + consts,   # reads z, writes z_q + idx
+        "pack_kernel": n4 * 8 + masks32 + stream_bytes,
+        "unpack_decode_kernel": stream_bytes,
+        "unpack_assemble_kernel": masks64 + n4 * (8 + 16) + consts,
+    }
+    out["step"] = n4 * (16 + 16 + 8) + masks32 + 2 * stream_bytes + masks64 + n4 * (8 + 16) + 2 * consts
+    return out
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

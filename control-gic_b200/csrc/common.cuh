@@ -64,4 +64,15 @@ PackLayout make_pack_layout(int max_len, int h, int w);
 
 static inline cudaStream_t as_stream(cgic_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Per-kernel device timing (cgic_prof_*): while enabled, every kernel launch of the library is
+// bracketed by two CUDA events recorded on the launching stream.  Off by default; costs one
+// relaxed load per launch when off.
+struct ProfScope {
+    ProfScope(const char *name, cudaStream_t stream);
+    ~ProfScope();
+    int slot;
+    cudaStream_t stream;
+};
+#define CGIC_PROF(name, stream) ::cgic::ProfScope prof_scope__(name, stream)
+
 }  // namespace cgic

@@ -114,7 +114,10 @@ extern "C" int cgic_entropy_maps(const float *x, int B, int H, int W, const floa
     if (B == 0) return CGIC_OK;
     Bins bins;
     for (int i = 0; i < 32; ++i) bins.v[i] = bins32_host[i];
-    entropy_kernel<<<dim3(W / 16, H / 16, B), 256, 0, as_stream(stream)>>>(x, H, W, bins, e8_out, e16_out);
+    {
+        CGIC_PROF("entropy_kernel", as_stream(stream));
+        entropy_kernel<<<dim3(W / 16, H / 16, B), 256, 0, as_stream(stream)>>>(x, H, W, bins, e8_out, e16_out);
+    }
     CGIC_LAUNCH_CHECK();
     return CGIC_OK;
 }

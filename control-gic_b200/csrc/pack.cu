@@ -297,7 +297,10 @@ extern "C" int cgic_pack(const int64_t *idx, const int32_t *m_c, const int32_t *
     // the coarse-mask payload must stay int4-loadable per image: (h/4)*(w/4) ints per image
     CGIC_REQUIRE(((int64_t)(h / 4) * (w / 4)) % 4 == 0 || B == 1, CGIC_EINVAL,
                  "cgic_pack: (h/4)*(w/4) must be a multiple of 4 for batched masks");
-    pack_kernel<<<dim3(5, B), PK_THREADS, smem, as_stream(stream)>>>(a);
+    {
+        CGIC_PROF("pack_kernel", as_stream(stream));
+        pack_kernel<<<dim3(5, B), PK_THREADS, smem, as_stream(stream)>>>(a);
+    }
     CGIC_LAUNCH_CHECK();
     return CGIC_OK;
 }

@@ -169,10 +169,16 @@ extern "C" int cgic_router(const float *e16, const float *e8, int B, int h16, in
                  "cgic_router: bad argument B=%d h16=%d w16=%d mode=%d", B, h16, w16, mode);
     if (B == 0) return CGIC_OK;
     cudaStream_t stream = as_stream(stream_);
-    router_select_kernel<<<per_image ? B : 1, RT_THREADS, 0, stream>>>(e16, e8, B, h16, w16, mode, k_c, k_m, per_image, m_c, m_m);
+    {
+        CGIC_PROF("router_select_kernel", stream);
+        router_select_kernel<<<per_image ? B : 1, RT_THREADS, 0, stream>>>(e16, e8, B, h16, w16, mode, k_c, k_m, per_image, m_c, m_m);
+    }
     CGIC_LAUNCH_CHECK();
     const int64_t n = (int64_t)B * 16 * h16 * w16;
-    router_fine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(m_c, m_m, n, 4 * h16, 4 * w16, mode, m_f, gate_out);
+    {
+        CGIC_PROF("router_fine_kernel", stream);
+        router_fine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(m_c, m_m, n, 4 * h16, 4 * w16, mode, m_f, gate_out);
+    }
     CGIC_LAUNCH_CHECK();
     return CGIC_OK;
 }
@@ -184,7 +190,10 @@ extern "C" int cgic_mask_mix(const float *h_c, const float *h_m, const float *h_
     CGIC_REQUIRE(B >= 0 && C > 0 && h > 0 && w > 0 && h % 4 == 0 && w % 4 == 0, CGIC_EINVAL, "cgic_mask_mix: bad shape");
     const int64_t n = (int64_t)B * C * h * w;
     if (n == 0) return CGIC_OK;
-    mask_mix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(h_c, h_m, h_f, m_c, m_m, m_f, n, C, h, w, out);
+    {
+        CGIC_PROF("mask_mix_kernel", as_stream(stream));
+        mask_mix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(h_c, h_m, h_f, m_c, m_m, m_f, n, C, h, w, out);
+    }
     CGIC_LAUNCH_CHECK();
     return CGIC_OK;
 }

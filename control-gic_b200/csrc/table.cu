@@ -12,6 +12,8 @@
 // Nodes are pushed in the caller-given order; the two nodes popped for a merge become the
 // '0' and '1' child in pop order.
 #include <algorithm>
+#include <atomic>
+#include <map>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -29,6 +31,35 @@ void set_error(const char *fmt, ...)
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// ---- per-kernel event timing ---------------------------------------------------------------
+namespace {
+struct ProfRecord {
+    const char *name;
+    cudaEvent_t e0, e1;
+};
+std::mutex g_prof_mu;
+std::vector<ProfRecord> g_prof;
+std::atomic<int> g_prof_on{0};
+}  // namespace
+
+ProfScope::ProfScope(const char *name, cudaStream_t st) : slot(-1), stream(st)
+{
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    ProfRecord r{name, nullptr, nullptr};
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+    cudaEventRecord(r.e0, st);
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    g_prof.push_back(r);
+    slot = (int)g_prof.size() - 1;
+}
+
+ProfScope::~ProfScope()
+{
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    cudaEventRecord(g_prof[slot].e1, stream);
 }
 
 PackLayout make_pack_layout(int max_len, int h, int w)
@@ -115,6 +146,42 @@ extern "C" {
 int cgic_abi_version(void) { return CGIC_ABI_VERSION; }
 
 const char *cgic_last_error(void) { return cgic::g_err; }
+
+int cgic_prof_enable(int on)
+{
+    std::lock_guard<std::mutex> lock(cgic::g_prof_mu);
+    for (auto &r : cgic::g_prof) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    cgic::g_prof.clear();
+    cgic::g_prof_on.store(on ? 1 : 0);
+    return CGIC_OK;
+}
+
+int cgic_prof_report(char *buf, int cap)
+{
+    CGIC_REQUIRE(buf && cap > 0, CGIC_EINVAL, "cgic_prof_report: bad buffer");
+    CGIC_CUDA_CHECK(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lock(cgic::g_prof_mu);
+    std::map<std::string, std::pair<long, double>> acc;
+    for (auto &r : cgic::g_prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) continue;
+        auto &a = acc[r.name];
+        a.first += 1;
+        a.second += ms;
+    }
+    std::string out;
+    char line[160];
+    for (auto &kv : acc) {
+        snprintf(line, sizeof(line), "%s %ld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += line;
+    }
+    CGIC_REQUIRE((int)out.size() + 1 <= cap, CGIC_ESPACE, "cgic_prof_report: buffer of %d too small for %zu", cap, out.size());
+    std::memcpy(buf, out.c_str(), out.size() + 1);
+    return (int)out.size();
+}
 
 int cgic_huff_build(const int64_t *freq, const int32_t *order, int K, cgic_table **out)
 {

@@ -388,9 +388,15 @@ extern "C" int cgic_unpack(const uint8_t *bytes, const int32_t *sizes, int B, in
     a.status = status_out;
     cudaStream_t stream = as_stream(stream_);
     CGIC_CUDA_CHECK(cudaMemsetAsync(status_out, 0, (size_t)B * 4, stream));
-    unpack_decode_kernel<<<dim3(5, B), UP_THREADS, 0, stream>>>(a);
+    {
+        CGIC_PROF("unpack_decode_kernel", stream);
+        unpack_decode_kernel<<<dim3(5, B), UP_THREADS, 0, stream>>>(a);
+    }
     CGIC_LAUNCH_CHECK();
-    unpack_assemble_kernel<<<dim3((unsigned)((a.g.n4 + 255) / 256), B), 256, 0, stream>>>(a);
+    {
+        CGIC_PROF("unpack_assemble_kernel", stream);
+        unpack_assemble_kernel<<<dim3((unsigned)((a.g.n4 + 255) / 256), B), 256, 0, stream>>>(a);
+    }
     CGIC_LAUNCH_CHECK();
     return CGIC_OK;
 }

@@ -439,16 +439,25 @@ extern "C" int cgic_vq_assign(const float *z, int B, int h, int w, const float *
     const int blocks = (int)((n + VQ_THREADS - 1) / VQ_THREADS);
 
     CGIC_CUDA_CHECK(cudaMemsetAsync(c.counters, 0, 64, stream));
-    vq_classify_kernel<<<blocks, VQ_THREADS, 0, stream>>>(z, n, h, w, c.leader_of, c.list, c.best, c.counters);
+    {
+        CGIC_PROF("vq_classify_kernel", stream);
+        vq_classify_kernel<<<blocks, VQ_THREADS, 0, stream>>>(z, n, h, w, c.leader_of, c.list, c.best, c.counters);
+    }
     CGIC_LAUNCH_CHECK();
     // persistent grid: 2 CTAs per SM, never more CTAs than there is work for in the worst case
     const int64_t max_units = ((n + 32 * VQ_T - 1) / (32 * VQ_T)) * (Kpad / VQ_CHUNK);
     const int64_t want = (max_units + VQ_THREADS / 32 - 1) / (VQ_THREADS / 32);
     const int grid = (int)(want < 2 * (int64_t)n_sm ? (want < 1 ? 1 : want) : 2 * (int64_t)n_sm);
-    vq_search_kernel<<<grid, VQ_THREADS, smem, stream>>>(z, h, w, codebook, K, Kpad, c.list, c.counters, c.best);
+    {
+        CGIC_PROF("vq_search_kernel", stream);
+        vq_search_kernel<<<grid, VQ_THREADS, smem, stream>>>(z, h, w, codebook, K, Kpad, c.list, c.counters, c.best);
+    }
     CGIC_LAUNCH_CHECK();
-    vq_finalize_kernel<<<blocks, VQ_THREADS, 0, stream>>>(z, n, h, w, codebook, c.leader_of, c.best, idx_out, zq_out,
-                                                          c.partials, c.counters, sqerr_out);
+    {
+        CGIC_PROF("vq_finalize_kernel", stream);
+        vq_finalize_kernel<<<blocks, VQ_THREADS, 0, stream>>>(z, n, h, w, codebook, c.leader_of, c.best, idx_out, zq_out,
+                                                              c.partials, c.counters, sqerr_out);
+    }
     CGIC_LAUNCH_CHECK();
     return CGIC_OK;
 }

@@ -53,6 +53,13 @@ typedef struct cgic_session cgic_session;
 CGIC_API int cgic_abi_version(void);
 CGIC_API const char *cgic_last_error(void);
 
+/* Per-kernel device timing for bench.py's roofline: while enabled, every kernel the library
+ * launches is bracketed by CUDA events on the launching stream.  cgic_prof_report synchronises
+ * the device and writes one "kernel_name launches total_ms" line per kernel; returns the text
+ * length.  (No reference counterpart: the reference has no timing code) */
+CGIC_API int cgic_prof_enable(int on);
+CGIC_API int cgic_prof_report(char *buf, int cap);
+
 /* ------------------------------------------------------------------------------------------
  * a8  HuffmanCoding.__init__ / make_heap / merge_nodes / make_codes
  *     CGIC/tools/indices_coding.py:10-17, 46-75.  Host-side, init time, heapq-exact.

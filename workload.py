@@ -26,21 +26,32 @@ def lexicographic_order(k: int = K):
     return sorted(range(k), key=str)
 
 
-def entropy_maps(B: int, H: int, W: int, seed: int):
-    g = torch.Generator().manual_seed(seed)
-    return torch.rand(B, H // 16, W // 16, generator=g), torch.rand(B, H // 8, W // 8, generator=g)
+def _image_generator(seed: int, image: int) -> torch.Generator:
+    return torch.Generator().manual_seed(seed * 1_000_003 + image)
 
 
-def heads(B: int, H: int, W: int, codebook: torch.Tensor, seed: int):
+def entropy_maps(B: int, H: int, W: int, seed: int, first_image: int = 0):
+    """(e16 [B,H/16,W/16], e8 [B,H/8,W/8]); image i depends on (seed, first_image + i) only, so any
+    sub-batch (a rank's shard, the CPU baseline's sample) sees the same images."""
+    e16, e8 = [], []
+    for i in range(B):
+        g = _image_generator(seed, first_image + i)
+        e16.append(torch.rand(H // 16, W // 16, generator=g))
+        e8.append(torch.rand(H // 8, W // 8, generator=g))
+    return torch.stack(e16), torch.stack(e8)
+
+
+def heads(B: int, H: int, W: int, codebook: torch.Tensor, seed: int, first_image: int = 0):
     """Three latent heads [B,4,H/16,W/16], [B,4,H/8,W/8], [B,4,H/4,W/4] near codebook entries."""
-    g = torch.Generator().manual_seed(seed + 1)
-    out = []
-    for div in (16, 8, 4):
-        h, w = H // div, W // div
-        idx = torch.randint(0, codebook.shape[0], (B * h * w,), generator=g)
-        v = codebook[idx] + 1e-4 * torch.randn(B * h * w, 4, generator=g) / K
-        out.append(v.view(B, h, w, 4).permute(0, 3, 1, 2).contiguous())
-    return out
+    out = [[], [], []]
+    for i in range(B):
+        g = _image_generator(seed + 1, first_image + i)
+        for lvl, div in enumerate((16, 8, 4)):
+            h, w = H // div, W // div
+            idx = torch.randint(0, codebook.shape[0], (h * w,), generator=g)
+            v = codebook[idx] + 1e-4 * torch.randn(h * w, 4, generator=g) / K
+            out[lvl].append(v.view(h, w, 4).permute(2, 0, 1))
+    return [torch.stack(v).contiguous() for v in out]
 
 
 def mix(hc, hm, hf, mc, mm, mf):
