@@ -40,7 +40,11 @@ struct DevTable {
     const uint16_t *len;   // [K] code length in bits
     const uint32_t *off;   // [K] first word of the code in `pool`
     const uint32_t *pool;  // code bits, MSB first, left aligned, ceil(len/32) words per symbol
-    const uint32_t *lut;   // [1 << lut_bits]: (sym << 8) | len, or (node << 8) | 0xFF to keep walking
+    const uint32_t *lut;   // [1 << lut_bits]: (sym << 8) | len, (lut2 offset << 8) | 0x80 | height, or (node << 8) | 0xFF to keep walking
+    const uint32_t *lut2;  // second-level tables: (sym << 8) | bits used beyond lut_bits; == lut + lut_pad
+    uint32_t lut_pad;          // words from lut to lut2 (16-byte multiple)
+    uint32_t dec_stage_words;  // words a decoder CTA stages in shared memory: lut (+ lut2 when small)
+    const uint2 *enc;          // [K] (code left aligned, length) when max_len <= 32, else null
     const int32_t *child;  // [2 * (2K-1)]: child[2*node + bit]; ids < K are leaves (= symbols)
 };
 
@@ -50,10 +54,38 @@ int table_max_len(const cgic_table *t);
 // which of the five streams exist per compression mode (CGIC/models/model.py:225-260)
 __host__ __device__ inline bool stream_present(int mode, int s)
 {
-    // bit s of the entry: 0 ic, 1 im, 2 if, 3 mc, 4 mm
-    const unsigned char tab[7] = {0x1F, 0x16, 0x0D, 0x0B, 0x01, 0x02, 0x04};
-    return (tab[mode] >> s) & 1;
+    // byte `mode` of the constant, bit s: 0 ic, 1 im, 2 if, 3 mc, 4 mm  (modes 0..6: 1F 16 0D 0B 01 02 04)
+    return (0x0402010B0D161FULL >> (8 * mode + s)) & 1;
 }
+
+#ifdef __CUDACC__
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) global -> shared with mbarrier completion ----
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// one thread: init the barrier for a single arrival
+__device__ __forceinline__ void mbar_init(unsigned long long *mbar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// one thread: announce `bytes` and start the copy; dst / src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *mbar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(mbar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_addr(mbar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *mbar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(smem_addr(mbar)), "r"(parity)
+                     : "memory");
+}
+#endif
 
 struct PackLayout {
     int64_t off[5];

@@ -88,6 +88,10 @@ struct cgic_table {
     std::vector<uint32_t> off;
     std::vector<uint32_t> pool;
     std::vector<uint32_t> lut;
+    std::vector<uint32_t> lut2;  // second-level decode tables (codes a little longer than lut_bits)
+    std::vector<uint32_t> dec;   // lut ++ lut2, each padded to 16 bytes: one bulk copy stages both in shared memory
+    std::vector<uint2> enc;      // [K] (code bits left aligned, length) when max_len <= 32, else empty
+    size_t lut_pad = 0;
     std::vector<int32_t> child;  // 2 * (2K-1)
     std::vector<std::string> code;
     // device copy (one device per process in this design)
@@ -257,6 +261,39 @@ int cgic_huff_build(const int64_t *freq, const int32_t *order, int K, cgic_table
         }
         t->lut[v] = node < K ? ((uint32_t)node << 8) | (uint32_t)used : ((uint32_t)node << 8) | 0xFFu;
     }
+    // second level: an internal node reached after lut_bits bits whose subtree is at most 8 deep
+    // gets a 2^height table indexed by the next `height` bits; entry = (sym << 8) | bits used.
+    // First-level entry becomes (offset << 8) | 0x80 | height.  Deeper subtrees keep the tree walk.
+    {
+        std::vector<int> height(nn, 0);
+        for (int node = K; node < nn; ++node)  // children are always created before their parent
+            height[node] = 1 + std::max(height[t->child[2 * (size_t)node]], height[t->child[2 * (size_t)node + 1]]);
+        for (uint32_t v = 0; v < t->lut.size(); ++v) {
+            if ((t->lut[v] & 0xFFu) != 0xFFu) continue;
+            const int top = (int)(t->lut[v] >> 8);
+            const int hgt = height[top];
+            if (hgt > 8 || t->lut2.size() + ((size_t)1 << hgt) >= ((size_t)1 << 24)) continue;
+            const uint32_t base = (uint32_t)t->lut2.size();
+            for (uint32_t u = 0; u < (1u << hgt); ++u) {
+                int node = top, used = 0;
+                while (node >= K) {
+                    node = t->child[2 * (size_t)node + ((u >> (hgt - 1 - used)) & 1)];
+                    ++used;
+                }
+                t->lut2.push_back(((uint32_t)node << 8) | (uint32_t)used);
+            }
+            t->lut[v] = (base << 8) | 0x80u | (uint32_t)hgt;
+        }
+        if (t->lut2.empty()) t->lut2.push_back(0);
+    }
+    t->lut_pad = (t->lut.size() + 3) / 4 * 4;
+    t->dec.assign(t->lut_pad + (t->lut2.size() + 3) / 4 * 4, 0u);
+    std::copy(t->lut.begin(), t->lut.end(), t->dec.begin());
+    std::copy(t->lut2.begin(), t->lut2.end(), t->dec.begin() + t->lut_pad);
+    if (t->max_len <= 32) {
+        t->enc.resize((size_t)(K + 1) / 2 * 2);
+        for (int s = 0; s < K; ++s) t->enc[s] = make_uint2(t->pool[t->off[s]], t->len[s]);
+    }
     *out = t;
     return CGIC_OK;
 }
@@ -296,8 +333,8 @@ int cgic_huff_upload(cgic_table *t)
     CGIC_REQUIRE(!t->dev_blob, CGIC_EINVAL, "cgic_huff_upload: table already lives on device %d", t->device);
     auto pad = [](size_t n) { return (n + 255) / 256 * 256; };
     const size_t b_len = pad(t->len.size() * 2), b_off = pad(t->off.size() * 4), b_pool = pad(t->pool.size() * 4),
-                 b_lut = pad(t->lut.size() * 4), b_child = pad(t->child.size() * 4);
-    const size_t total = b_len + b_off + b_pool + b_lut + b_child;
+                 b_lut = pad(t->dec.size() * 4), b_child = pad(t->child.size() * 4), b_lut2 = pad(t->enc.size() * 8);
+    const size_t total = b_len + b_off + b_pool + b_lut + b_child + b_lut2;
     std::vector<unsigned char> host(total, 0);
     size_t o = 0;
     std::memcpy(host.data() + o, t->len.data(), t->len.size() * 2);
@@ -309,11 +346,14 @@ int cgic_huff_upload(cgic_table *t)
     std::memcpy(host.data() + o, t->pool.data(), t->pool.size() * 4);
     const size_t o_pool = o;
     o += b_pool;
-    std::memcpy(host.data() + o, t->lut.data(), t->lut.size() * 4);
+    std::memcpy(host.data() + o, t->dec.data(), t->dec.size() * 4);
     const size_t o_lut = o;
     o += b_lut;
     std::memcpy(host.data() + o, t->child.data(), t->child.size() * 4);
     const size_t o_child = o;
+    o += b_child;
+    if (!t->enc.empty()) std::memcpy(host.data() + o, t->enc.data(), t->enc.size() * 8);
+    const size_t o_lut2 = o;
     void *blob = nullptr;
     CGIC_CUDA_CHECK(cudaMalloc(&blob, total));
     cudaError_t e = cudaMemcpy(blob, host.data(), total, cudaMemcpyHostToDevice);
@@ -332,6 +372,11 @@ int cgic_huff_upload(cgic_table *t)
     t->view.pool = reinterpret_cast<const uint32_t *>(base + o_pool);
     t->view.lut = reinterpret_cast<const uint32_t *>(base + o_lut);
     t->view.child = reinterpret_cast<const int32_t *>(base + o_child);
+    t->view.lut2 = t->view.lut + t->lut_pad;
+    t->view.lut_pad = (uint32_t)t->lut_pad;
+    // stage lut + lut2 together when that stays small, else only the first level
+    t->view.dec_stage_words = (uint32_t)(t->dec.size() * 4 <= 64 * 1024 ? t->dec.size() : t->lut_pad);
+    t->view.enc = t->enc.empty() ? nullptr : reinterpret_cast<const uint2 *>(base + o_lut2);
     t->dev_blob = blob;
     t->device = dev;
     return CGIC_OK;

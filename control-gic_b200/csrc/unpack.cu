@@ -16,12 +16,14 @@
 //   the set cells of its level = prefix[word] + popc(bits below) -> the decoded symbol that the
 //   reference's masked assignment puts there (row-major order); ind = fine + up2(medium) +
 //   up4(coarse); quant = codebook[ind] written NCHW; masks written as int64 like the reference.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace cgic {
 namespace {
 
-constexpr int UP_THREADS = 128;
+constexpr int UP_THREADS = 512;  // == DEC_THREADS
 
 struct UnpackWs {
     uint16_t *sym;     // [B][n16 + n8 + n4]
@@ -89,73 +91,396 @@ struct UnpackArgs {
     int64_t *mc_out, *mm_out, *mf_out, *ind_out;
     float *quant_out;
     int32_t *status;
+    int mask_stage;  // 1: mask CTAs copy the mask streams to shared memory first
 };
 
-// ---- serial prefix decoder (one thread).  Returns the number of symbols, -1 for an empty
-// stream (the reference returns None), -2 on overflow of `cap`.
-template <typename Out>
-__device__ int decode_stream(const uint8_t *in, int64_t nbytes, const DevTable &T, Out *out, int64_t cap)
+// ---- parallel prefix decoder (whole CTA, one stream) ------------------------------------------
+// A Huffman stream carries no synchronisation points, but prefix codes self-synchronise: a decoder
+// started at a wrong bit falls into step with the true codeword sequence after a few codewords.
+// The stream is cut into 128-bit subsequences, one per thread.  Every thread decodes the
+// codewords that START inside its subsequence, first from a guessed start (the subsequence
+// boundary), then again from the end position its left neighbour reports, until no start
+// changes any more; thread 0 always starts from a known codeword boundary, so after k rounds
+// the first k subsequences are exact whatever the data -- typically everything settles in 2-4
+// rounds.  Counts are then prefix-summed and a last pass writes the symbols in stream order.
+// Streams longer than one CTA-load of subsequences are processed chunk by chunk, the exact end
+// of a chunk seeding the next.  Result = the reference's greedy decode (indices_coding.py:140-151),
+// including its dropping of a trailing incomplete code.
+constexpr int DEC_THREADS = 512;
+constexpr int DEC_SUB_BITS = 128;
+constexpr int64_t DEC_STOP = (int64_t)1 << 60;  // "decoding ended": beyond every subsequence
+
+struct BitWindow {
+    const uint8_t *in;  // 4-byte aligned stream start (the header byte is bit 0..7)
+    int64_t nbytes;
+    int64_t wi;         // index of the cached word pair
+    uint32_t w0, w1;
+    __device__ __forceinline__ uint32_t word(int64_t i) const
+    {
+        const int64_t b = i * 4;
+        if (b + 4 <= nbytes) return __byte_perm(*reinterpret_cast<const uint32_t *>(in + b), 0, 0x0123);
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (b + k < nbytes) v |= (uint32_t)in[b + k] << (24 - 8 * k);
+        return v;
+    }
+    // the 32 stream bits starting at bit q, MSB first
+    __device__ __forceinline__ uint32_t peek(int64_t q)
+    {
+        const int64_t i = q >> 5;
+        if (i != wi) {
+            w0 = (i == wi + 1) ? w1 : word(i);
+            w1 = word(i + 1);
+            wi = i;
+        }
+        return __funnelshift_l(w1, w0, (int)(q & 31));
+    }
+};
+
+// Decodes the codewords starting in [q, q_sub_end) (and before q_end = end of the payload).
+// Returns their number; *q_next = start of the next codeword (DEC_STOP when decoding is over).
+// s_lut: first-level table in shared memory; lut2: second-level tables (shared or global).
+template <bool WRITE, typename Out>
+__device__ __forceinline__ int decode_range(BitWindow &bw, int64_t q, int64_t q_sub_end, int64_t q_end, const uint32_t *s_lut,
+                                            const uint32_t *lut2, const DevTable &T, Out *out, int64_t *q_next)
 {
+    int cnt = 0;
+    const int L = T.lut_bits;
+    while (q < q_sub_end) {
+        if (q >= q_end) {
+            q = DEC_STOP;
+            break;
+        }
+        const uint32_t win = bw.peek(q);
+        const uint32_t e = s_lut[win >> (32 - L)];
+        int len = (int)(e & 0xFFu);
+        int sym = (int)(e >> 8);
+        if (len & 0x80) {
+            if (len != 0xFF) {  // second-level table on the next `hgt` bits (L + hgt <= 20 window bits)
+                const int hgt = len & 0x7F;
+                const uint32_t e2 = lut2[sym + ((win << L) >> (32 - hgt))];
+                sym = (int)(e2 >> 8);
+                len = L + (int)(e2 & 0xFFu);
+            } else {            // long code: walk the tree bit by bit
+                int node = sym;
+                int64_t qq = q + L;
+                while (node >= T.K && qq < q_end) {
+                    const uint32_t bit = bw.peek(qq) >> 31;
+                    node = __ldg(&T.child[2 * node + (int)bit]);
+                    ++qq;
+                }
+                if (node >= T.K) {  // trailing incomplete code: dropped, decoding ends
+                    q = DEC_STOP;
+                    break;
+                }
+                sym = node;
+                len = (int)(qq - q);
+            }
+        }
+        if (q + len > q_end) {  // completed only by bits past the payload: not a symbol
+            q = DEC_STOP;
+            break;
+        }
+        if (WRITE) out[cnt] = (Out)sym;
+        ++cnt;
+        q += len;
+    }
+    *q_next = q;
+    return cnt;
+}
+
+// Whole CTA (DEC_THREADS threads).  Returns (same value in every thread) the number of symbols,
+// -1 for an empty stream (the reference returns None), -2 when `cap` would overflow.
+// `in` must be 4-byte aligned.
+template <typename Out>
+__device__ int decode_stream_cta(const uint8_t *in, int64_t nbytes, const DevTable &T, const uint32_t *s_lut, const uint32_t *lut2,
+                                 Out *out, int64_t cap)
+{
+    __shared__ int64_t s_start[DEC_THREADS + 1];
+    __shared__ int s_wsum[DEC_THREADS / 32];
     if (nbytes <= 0) return -1;
+    const int tid = threadIdx.x;
     const int pad = in[0];
     int64_t nbits = (nbytes - 1) * 8 - pad;
     if (pad == 0 || nbits < 0) nbits = 0;  // text[:-0] is empty in the reference
-    const uint8_t *p = in + 1;
-    const int64_t npay = nbytes - 1;
-    unsigned long long buf = 0;  // MSB-aligned window
-    int avail = 0;
-    int64_t next = 0;  // next payload byte to load
-    int64_t pos = 0;   // consumed bits
+    const int64_t q_end = 8 + nbits;
+    BitWindow bw{in, nbytes, -2, 0u, 0u};
+    int64_t chunk_q0 = 8;     // first bit of this chunk's first subsequence
+    int64_t chunk_start = 8;  // exact start of the first codeword at or after chunk_q0
+    int64_t total = 0;
+    while (chunk_q0 < q_end && chunk_start < DEC_STOP) {
+        const int64_t sub0 = chunk_q0 + (int64_t)tid * DEC_SUB_BITS;
+        const int64_t sub1 = sub0 + DEC_SUB_BITS;
+        const bool live = sub0 < q_end;
+        int64_t my_start = tid == 0 ? chunk_start : sub0;
+        int64_t my_end = my_start;
+        int cnt = 0;
+        if (live) cnt = decode_range<false, Out>(bw, my_start, sub1, q_end, s_lut, lut2, T, nullptr, &my_end);
+        for (;;) {
+            s_start[tid + 1] = my_end;
+            __syncthreads();
+            const int64_t s = tid == 0 ? chunk_start : s_start[tid];
+            const bool changed = live && s != my_start;
+            if (!__syncthreads_or(changed)) break;
+            if (changed) {
+                my_start = s;
+                my_end = s;  // a start beyond this subsequence passes through unchanged
+                cnt = decode_range<false, Out>(bw, my_start, sub1, q_end, s_lut, lut2, T, nullptr, &my_end);
+            }
+        }
+        // exclusive scan of the counts
+        const int lane = tid & 31, wid = tid >> 5;
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += n;
+        }
+        if (lane == 31) s_wsum[wid] = inc;
+        __syncthreads();
+        int woff = 0, ctot = 0;
+#pragma unroll
+        for (int i = 0; i < DEC_THREADS / 32; ++i) {
+            const int v = s_wsum[i];
+            if (i < wid) woff += v;
+            ctot += v;
+        }
+        if (total + ctot > cap) return -2;
+        if (live && cnt) {
+            int64_t dummy;
+            decode_range<true, Out>(bw, my_start, sub1, q_end, s_lut, lut2, T, out + total + woff + inc - cnt, &dummy);
+        }
+        total += ctot;
+        // dead threads hold my_end == their sub0 (no codeword can start there), so the last
+        // slot is exact only when the last thread was live; otherwise decoding is finished
+        const int64_t next_start = s_start[DEC_THREADS];
+        __syncthreads();
+        chunk_q0 += (int64_t)DEC_THREADS * DEC_SUB_BITS;
+        chunk_start = next_start;
+    }
+    return (int)total;
+}
+
+// ---- candidate-start decoder (codes of at most DEC_MAX_D bits) --------------------------------
+// Near-uniform code lengths (a trained codebook used evenly: lengths 9..12) barely
+// self-synchronise, and the rounds above then degenerate into a serial walk.  The first codeword
+// of a subsequence can only start at one of D = max_len offsets (the codeword straddling the
+// boundary is at most max_len bits long), so instead of guessing:
+//   A  every (subsequence, candidate offset) pair is decoded independently -> (end offset in the
+//      next subsequence, number of codewords): a table f[sub][offset], D x redundant work but
+//      perfectly parallel and data independent;
+//   B  the true start offsets follow by composing the f[sub] along the stream -- blocks of
+//      subsequences are composed per candidate in parallel, one thread chains the block results,
+//      then every block replays its subsequences from its now known start;
+//   C  counts are prefix-summed and each subsequence is decoded once more from its true start,
+//      writing its symbols.
+// Chunks of `ch` subsequences (shared-memory capacity) are processed in sequence.
+constexpr int DEC_MAX_D = 128;       // candidate path handles max_len <= 128 (== DEC_SUB_BITS)
+constexpr int DEC_MAX_CH = 1024;     // subsequences per chunk
+constexpr int DEC_LOOKAHEAD_WORDS = 16;  // staged words past the chunk: straddling codeword + a 64-bit window
+constexpr uint32_t DEC_OFF_STOP = 0xFF;
+constexpr uint32_t DEC_QSTOP = 0x7FFFFFFFu;
+
+// Decode loop over a chunk staged in shared memory as native-endian words (bit 31 of word 0 is
+// stream bit 0 of the chunk; words past the stream are zero).  32-bit positions local to the chunk.
+// Codewords starting in [q, q_sub_end); returns their number, *q_next = start of the next
+// codeword or DEC_QSTOP once the payload end q_end is reached.
+template <bool WRITE, typename Out>
+__device__ __forceinline__ int decode_range_smem(const uint32_t *s_words, uint32_t q, uint32_t q_sub_end, uint32_t q_end,
+                                                 const uint32_t *s_lut, const uint32_t *lut2, const DevTable &T, Out *out,
+                                                 uint32_t *q_next)
+{
     int cnt = 0;
     const int L = T.lut_bits;
-    while (pos < nbits) {
-        while (avail <= 56) {
-            const unsigned long long byte = next < npay ? p[next] : 0;
-            ++next;
-            buf |= byte << (56 - avail);
-            avail += 8;
-        }
-        const uint32_t e = __ldg(&T.lut[(uint32_t)(buf >> (64 - L))]);
-        int len = e & 0xFF;
-        int sym;
-        if (len != 0xFF) {
-            sym = e >> 8;
-        } else {
-            // long code: continue bit by bit from the tree node reached after L bits
-            if (pos + L >= nbits) break;
-            int node = e >> 8;
-            buf <<= L;
-            avail -= L;
-            pos += L;
-            len = 0;
-            for (;;) {
-                if (pos + len >= nbits) return cnt;  // trailing incomplete code is dropped
-                if (avail == 0) {
-                    const unsigned long long byte = next < npay ? p[next] : 0;
-                    ++next;
-                    buf = byte << 56;
-                    avail = 8;
+    while (q < q_sub_end) {
+        const uint32_t i = q >> 5;
+        const uint32_t win = __funnelshift_l(s_words[i + 1], s_words[i], q & 31);
+        const uint32_t e = s_lut[win >> (32 - L)];
+        uint32_t len = e & 0xFFu;
+        uint32_t sym = e >> 8;
+        if (len & 0x80u) {
+            if (len != 0xFFu) {  // second-level table on the next `hgt` bits
+                const uint32_t hgt = len & 0x7Fu;
+                const uint32_t e2 = lut2[sym + ((win << L) >> (32 - hgt))];
+                sym = e2 >> 8;
+                len = L + (e2 & 0xFFu);
+            } else {             // long code (<= DEC_MAX_D bits): walk the tree; bits past the payload read as 0
+                int node = (int)sym;
+                uint32_t qq = q + L;
+                while (node >= T.K) {
+                    const uint32_t bit = (s_words[qq >> 5] >> (31 - (qq & 31))) & 1u;
+                    node = __ldg(&T.child[2 * node + (int)bit]);
+                    ++qq;
                 }
-                const int bit = (int)(buf >> 63);
-                buf <<= 1;
-                --avail;
-                ++len;
-                node = __ldg(&T.child[2 * node + bit]);
-                if (node < T.K) break;
+                sym = (uint32_t)node;
+                len = qq - q;
             }
-            if (cnt >= cap) return -2;
-            out[cnt++] = (Out)node;
-            pos += len;
-            continue;
         }
-        if (pos + len > nbits) break;  // code completed only thanks to pad bits: not a symbol
-        if (cnt >= cap) return -2;
-        out[cnt++] = (Out)sym;
-        buf <<= len;
-        avail -= len;
-        pos += len;
+        if (q + len > q_end) {  // incomplete, or completed only by bits past the payload: dropped, decoding ends
+            q = DEC_QSTOP;
+            break;
+        }
+        if (WRITE) out[cnt] = (Out)sym;
+        ++cnt;
+        q += len;
     }
+    *q_next = q;
     return cnt;
+}
+
+// dynamic shared memory behind the staged tables: f[ch * D] (uint16) then the chunk's words
+template <typename Out>
+__device__ int decode_stream_cta_cand(const uint8_t *in, int64_t nbytes, const DevTable &T, const uint32_t *s_lut, const uint32_t *lut2,
+                                      uint16_t *s_fn, uint32_t *s_words, int ch, Out *out, int64_t cap)
+{
+    __shared__ uint8_t s_blockfn[32 * DEC_MAX_D];
+    __shared__ uint8_t s_blkstart[32];
+    __shared__ uint8_t s_substart[DEC_MAX_CH];
+    __shared__ int s_wsum[DEC_THREADS / 32];
+    __shared__ uint32_t s_next;
+    if (nbytes <= 0) return -1;
+    const int tid = threadIdx.x;
+    const int pad = in[0];
+    int64_t nbits = (nbytes - 1) * 8 - pad;
+    if (pad == 0 || nbits < 0) nbits = 0;
+    const int64_t q_end_abs = 8 + nbits;  // stream bit coordinates (header byte = bits 0..7)
+    const int D = T.max_len;
+    const int64_t nsub_total = (nbits + DEC_SUB_BITS - 1) / DEC_SUB_BITS;
+    const int nwords_stage = ch * (DEC_SUB_BITS / 32) + DEC_LOOKAHEAD_WORDS;
+    uint32_t start_off = 0;
+    int64_t total = 0;
+    for (int64_t c0 = 0; c0 < nsub_total && start_off != DEC_OFF_STOP; c0 += ch) {
+        const int nsub = (int)min((int64_t)ch, nsub_total - c0);
+        // ---- stage the chunk: bytes [c0 * 16, ...) of the stream as big-endian words, zero past the end
+        {
+            const int64_t byte0 = c0 * (DEC_SUB_BITS / 8);
+            const int nw = nsub * (DEC_SUB_BITS / 32) + DEC_LOOKAHEAD_WORDS;
+            for (int wi = tid; wi < nw; wi += DEC_THREADS) {
+                const int64_t bo = byte0 + (int64_t)wi * 4;
+                uint32_t v = 0;
+                if (bo + 4 <= nbytes) {
+                    v = __byte_perm(__ldg(reinterpret_cast<const uint32_t *>(in + bo)), 0, 0x0123);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (bo + k < nbytes) v |= (uint32_t)in[bo + k] << (24 - 8 * k);
+                }
+                s_words[wi] = v;
+            }
+            (void)nwords_stage;
+        }
+        __syncthreads();
+        const int64_t rel_end = q_end_abs - c0 * DEC_SUB_BITS;  // payload end, local to the chunk
+        const uint32_t q_end = (uint32_t)min(rel_end, (int64_t)(nsub * DEC_SUB_BITS + 8 + DEC_MAX_D + 64));
+        // ---- A: every (subsequence, candidate) pair
+        for (int pair = tid; pair < nsub * D; pair += DEC_THREADS) {
+            const int i = pair / D, c = pair - i * D;
+            const uint32_t sub0 = 8u + (uint32_t)i * DEC_SUB_BITS;
+            uint32_t qn;
+            const int n = decode_range_smem<false, Out>(s_words, sub0 + c, sub0 + DEC_SUB_BITS, q_end, s_lut, lut2, T, nullptr, &qn);
+            const uint32_t e = qn == DEC_QSTOP ? DEC_OFF_STOP : qn - (sub0 + DEC_SUB_BITS);
+            s_fn[pair] = (uint16_t)((e << 8) | (uint32_t)n);
+        }
+        __syncthreads();
+        // ---- B: true start offset of every subsequence
+        const int bs = nsub <= 128 ? 8 : 32;  // subsequences per block; at most 32 blocks either way
+        const int nblk = (nsub + bs - 1) / bs;
+        for (int item = tid; item < nblk * D; item += DEC_THREADS) {
+            const int blk = item / D, c = item - blk * D;
+            uint32_t x = (uint32_t)c;
+            const int j1 = min(nsub, (blk + 1) * bs);
+            for (int j = blk * bs; j < j1 && x != DEC_OFF_STOP; ++j) x = s_fn[j * D + x] >> 8;
+            s_blockfn[item] = (uint8_t)x;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t x = start_off;
+            for (int blk = 0; blk < nblk; ++blk) {
+                s_blkstart[blk] = (uint8_t)x;
+                if (x != DEC_OFF_STOP) x = s_blockfn[blk * D + x];
+            }
+            s_next = x;
+        }
+        __syncthreads();
+        if (tid < nblk) {
+            uint32_t x = s_blkstart[tid];
+            const int j1 = min(nsub, (tid + 1) * bs);
+            for (int j = tid * bs; j < j1; ++j) {
+                s_substart[j] = (uint8_t)x;
+                if (x != DEC_OFF_STOP) x = s_fn[j * D + x] >> 8;
+            }
+        }
+        __syncthreads();
+        // ---- C: counts -> offsets -> symbols
+        for (int base = 0; base < nsub; base += DEC_THREADS) {
+            const int i = base + tid;
+            uint32_t st = DEC_OFF_STOP;
+            int cnt = 0;
+            if (i < nsub) {
+                st = s_substart[i];
+                if (st != DEC_OFF_STOP) cnt = s_fn[i * D + st] & 0xFF;
+            }
+            const int lane = tid & 31, wid = tid >> 5;
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += n;
+            }
+            if (lane == 31) s_wsum[wid] = inc;
+            __syncthreads();
+            int woff = 0, ctot = 0;
+#pragma unroll
+            for (int k = 0; k < DEC_THREADS / 32; ++k) {
+                const int v = s_wsum[k];
+                if (k < wid) woff += v;
+                ctot += v;
+            }
+            if (total + ctot > cap) return -2;
+            if (cnt) {
+                const uint32_t sub0 = 8u + (uint32_t)i * DEC_SUB_BITS;
+                uint32_t dummy;
+                decode_range_smem<true, Out>(s_words, sub0 + st, sub0 + DEC_SUB_BITS, q_end, s_lut, lut2, T, out + total + woff + inc - cnt, &dummy);
+            }
+            total += ctot;
+            __syncthreads();
+        }
+        start_off = s_next;
+    }
+    return (int)total;
+}
+
+// subsequences per chunk for a table: f[] takes ch * D * 2 bytes of shared memory (<= 40 KB)
+__host__ __device__ inline int cand_chunk_subs(int max_len)
+{
+    int ch = (40 * 1024 / (max_len * 2)) & ~31;
+    return ch > DEC_MAX_CH ? DEC_MAX_CH : ch;
+}
+
+template <typename Out>
+__device__ __forceinline__ int decode_stream_any(const uint8_t *in, int64_t nbytes, const DevTable &T, const uint32_t *s_dec,
+                                                 const uint32_t *lut2, Out *out, int64_t cap)
+{
+    if (T.max_len <= DEC_MAX_D) {
+        // f[] lives right behind the staged tables in dynamic shared memory
+        const int ch = cand_chunk_subs(T.max_len);
+        uint32_t *s_words = const_cast<uint32_t *>(s_dec) + T.dec_stage_words;
+        uint16_t *s_fn = reinterpret_cast<uint16_t *>(s_words + ch * (DEC_SUB_BITS / 32) + DEC_LOOKAHEAD_WORDS);
+        return decode_stream_cta_cand<Out>(in, nbytes, T, s_dec, lut2, s_fn, s_words, ch, out, cap);
+    }
+    return decode_stream_cta<Out>(in, nbytes, T, s_dec, lut2, out, cap);
+}
+
+// Stages the decode tables with one TMA bulk copy; every thread of the CTA must call.
+// Returns the second-level table pointer (shared when it was staged, else global).
+__device__ __forceinline__ const uint32_t *stage_decode_tables(const DevTable &T, uint32_t *s_dec, unsigned long long *mbar)
+{
+    if (threadIdx.x == 0) mbar_init(mbar);
+    __syncthreads();
+    if (threadIdx.x == 0) tma_load_1d(s_dec, T.lut, T.dec_stage_words * 4u, mbar);
+    mbar_wait(mbar, 0);
+    return T.dec_stage_words > T.lut_pad ? s_dec + T.lut_pad : T.lut2;
 }
 
 // mask cell value per mode (model.py:278-280, 301-303, 319-321, 338-340, 360-387)
@@ -178,27 +503,20 @@ __device__ __forceinline__ int fine_cell(const UnpackArgs &a, const uint8_t *mc,
     return a.mode == 6;
 }
 
-// bitmap + exclusive popcount prefix of one level, by the whole CTA
+// bitmap + exclusive popcount prefix of one level, by the whole CTA; wordfn(wi) = the 32 cells
+// wi*32 .. wi*32+31 (bit i = cell wi*32+i; bits past n are masked here)
 template <typename F>
-__device__ void build_level(int gw, int64_t n, int nw, uint32_t *bits, uint32_t *prefix, int32_t *pop_out, F cell)
+__device__ void build_level(int64_t n, int nw, uint32_t *bits, uint32_t *prefix, int32_t *pop_out, F wordfn)
 {
-    __shared__ int s_warp[UP_THREADS / 32 + 1];
-    __shared__ int s_run;
-    if (threadIdx.x == 0) s_run = 0;
-    __syncthreads();
+    __shared__ int s_warp[UP_THREADS / 32];
+    int run = 0;
     for (int base = 0; base < nw; base += UP_THREADS) {
         const int wi = base + threadIdx.x;
         uint32_t word = 0;
         if (wi < nw) {
-            const int64_t p0 = (int64_t)wi * 32;
-            int y = (int)(p0 / gw), x = (int)(p0 - (int64_t)y * gw);
-            for (int i = 0; i < 32 && p0 + i < n; ++i) {
-                word |= (uint32_t)cell(y, x) << i;
-                if (++x == gw) {
-                    x = 0;
-                    ++y;
-                }
-            }
+            word = wordfn(wi);
+            const int64_t left = n - (int64_t)wi * 32;
+            if (left < 32) word &= (1u << left) - 1u;
             bits[wi] = word;
         }
         const int v = __popc(word);
@@ -211,118 +529,258 @@ __device__ void build_level(int gw, int64_t n, int nw, uint32_t *bits, uint32_t 
         }
         if (lane == 31) s_warp[wid] = inc;
         __syncthreads();
-        int woff = 0;
-        for (int i = 0; i < wid; ++i) woff += s_warp[i];
-        int tot = 0;
-        for (int i = 0; i < UP_THREADS / 32; ++i) tot += s_warp[i];
-        const int run = s_run;
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int i = 0; i < UP_THREADS / 32; ++i) {
+            const int t = s_warp[i];
+            if (i < wid) woff += t;
+            tot += t;
+        }
         if (wi < nw) prefix[wi] = (uint32_t)(run + woff + inc - v);
-        __syncthreads();
-        if (threadIdx.x == 0) s_run = run + tot;
+        run += tot;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *pop_out = s_run;
+    if (threadIdx.x == 0) *pop_out = run;
 }
 
+// 32 cells of a level from its per-cell function (any geometry)
+template <typename F>
+__device__ __forceinline__ uint32_t word_from_cells(int wi, int gw, int64_t n, F cell)
+{
+    const int64_t p0 = (int64_t)wi * 32;
+    int y = (int)(p0 / gw), x = (int)(p0 - (int64_t)y * gw);
+    const int lim = (int)min((int64_t)32, n - p0);
+    uint32_t word = 0;
+    for (int i = 0; i < lim; ++i) {
+        word |= (uint32_t)cell(y, x) << i;
+        if (++x == gw) {
+            x = 0;
+            ++y;
+        }
+    }
+    return word;
+}
+
+// 32 consecutive cells straight from a mask stream (cell j = payload bit j, MSB first): bit i = cell wi*32+i
+__device__ __forceinline__ uint32_t word_from_stream(const uint8_t *in, int cap, int wi)
+{
+    uint32_t be = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int o = 1 + 4 * wi + k;
+        if (o < cap) be |= (uint32_t)in[o] << (24 - 8 * k);
+    }
+    return __brev(be);
+}
+
+// every bit of the low 16 bits doubled into 2 adjacent bits
+__device__ __forceinline__ uint32_t spread2(uint32_t x)
+{
+    x &= 0xFFFFu;
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x | (x << 1);
+}
+
+// copies a 16-byte aligned slot prefix into shared memory (whole CTA); returns the shared pointer
+__device__ __forceinline__ const uint8_t *stage_bytes(const uint8_t *src, int nbytes, unsigned char *dst)
+{
+    const int n16 = (nbytes + 15) >> 4;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) reinterpret_cast<uint4 *>(dst)[i] = __ldg(reinterpret_cast<const uint4 *>(src) + i);
+    return dst;
+}
+
+// grid (5, B): CTAs 0..2 decode the index streams, CTA 3 builds the coarse level, CTA 4 the medium
+// and fine levels.  Dynamic shared memory: decode tables (CTAs 0..2) / mask stream bytes (3, 4).
 __global__ void __launch_bounds__(UP_THREADS) unpack_decode_kernel(const UnpackArgs a)
 {
+    extern __shared__ __align__(128) unsigned char dyn[];
+    __shared__ __align__(8) unsigned long long mbar;
     const int s = blockIdx.x, b = blockIdx.y;
     const Geo &g = a.g;
     const uint8_t *img = a.bytes + (int64_t)b * a.image_stride;
     const int32_t *sz = a.sizes + b * 5;
     const int nwt = g.nw16 + g.nw8 + g.nw4;
     if (s < 3) {
-        if (threadIdx.x != 0) return;
         const int64_t soff = s == 0 ? 0 : (s == 1 ? g.n16 : g.n16 + g.n8);
         const int64_t cap = s == 0 ? g.n16 : (s == 1 ? g.n8 : g.n4);
         int cnt = -1;
-        if (stream_present(a.mode, s))
-            cnt = decode_stream<uint16_t>(img + a.slot_off[s], sz[s], a.T, a.ws.sym + (int64_t)b * (g.n16 + g.n8 + g.n4) + soff, cap);
-        a.ws.count[b * 3 + s] = cnt;
-        if (cnt == -2) atomicExch(&a.status[b], CGIC_EFORMAT);
+        const int nbytes = stream_present(a.mode, s) ? sz[s] : 0;
+        if (nbytes > 0) {
+            uint32_t *s_dec = reinterpret_cast<uint32_t *>(dyn);
+            const uint32_t *lut2 = stage_decode_tables(a.T, s_dec, &mbar);
+            cnt = decode_stream_any<uint16_t>(img + a.slot_off[s], nbytes, a.T, s_dec, lut2,
+                                              a.ws.sym + (int64_t)b * (g.n16 + g.n8 + g.n4) + soff, cap);
+        }
+        if (threadIdx.x == 0) {
+            a.ws.count[b * 3 + s] = cnt;
+            if (cnt == -2) atomicExch(&a.status[b], CGIC_EFORMAT);
+        }
         return;
     }
+    const bool need_c = a.mode == 0 || a.mode == 2 || a.mode == 3;
+    const bool need_m = a.mode == 0 || a.mode == 1;
+    const int cap_c = (int)(g.n16 / 8 + 2), cap_m = (int)(g.n8 / 8 + 2);
+    // framing check of the mask streams this mode reads
+    bool ok_c = true, ok_m = true;
+    if (need_c) ok_c = sz[3] == cap_c && img[a.slot_off[3]] == 8 - (int)(g.n16 & 7);
+    if (need_m && s == 4) ok_m = sz[4] == cap_m && img[a.slot_off[4]] == 8 - (int)(g.n8 & 7);
+    if (threadIdx.x == 0 && ((s == 3 && !ok_c) || (s == 4 && !ok_m))) atomicExch(&a.status[b], CGIC_EFORMAT);
+    // mask bytes: shared copies when they fit (a.mask_stage), else straight from global
     const uint8_t *mc = img + a.slot_off[3];
     const uint8_t *mm = img + a.slot_off[4];
-    // framing check of the mask streams this mode reads
-    if (threadIdx.x == 0) {
-        const bool need_c = a.mode == 0 || a.mode == 2 || a.mode == 3;
-        const bool need_m = a.mode == 0 || a.mode == 1;
-        if (s == 3 && need_c && (sz[3] != g.n16 / 8 + 2 || mc[0] != 8 - (int)(g.n16 & 7))) atomicExch(&a.status[b], CGIC_EFORMAT);
-        if (s == 4 && need_m && (sz[4] != g.n8 / 8 + 2 || mm[0] != 8 - (int)(g.n8 & 7))) atomicExch(&a.status[b], CGIC_EFORMAT);
+    if (a.mask_stage) {
+        const int off_m = (cap_c + 15) & ~15;
+        if (need_c && ok_c) mc = stage_bytes(mc, cap_c, dyn);
+        if (need_m && ok_m && s == 4) mm = stage_bytes(mm, cap_m, dyn + off_m);
+        __syncthreads();
     }
     uint32_t *bits = a.ws.bits + (int64_t)b * nwt;
     uint32_t *prefix = a.ws.prefix + (int64_t)b * nwt;
     int32_t *pop = a.ws.pop + b * 3;
     if (s == 3) {
-        build_level(g.w16, g.n16, g.nw16, bits, prefix, pop + 0, [&](int y, int x) { return coarse_cell(a, mc, y, x); });
+        if (need_c)
+            build_level(g.n16, g.nw16, bits, prefix, pop + 0, [&](int wi) { return word_from_stream(mc, cap_c, wi); });
+        else
+            build_level(g.n16, g.nw16, bits, prefix, pop + 0, [&](int) { return a.mode == 4 ? 0xFFFFFFFFu : 0u; });
     } else {
-        build_level(g.w8, g.n8, g.nw8, bits + g.nw16, prefix + g.nw16, pop + 1,
-                    [&](int y, int x) { return medium_cell(a, mc, mm, y, x); });
-        build_level(g.w, g.n4, g.nw4, bits + g.nw16 + g.nw8, prefix + g.nw16 + g.nw8, pop + 2,
-                    [&](int y, int x) { return fine_cell(a, mc, mm, y, x); });
+        if (need_m)
+            build_level(g.n8, g.nw8, bits + g.nw16, prefix + g.nw16, pop + 1, [&](int wi) { return word_from_stream(mm, cap_m, wi); });
+        else if (a.mode == 3)
+            build_level(g.n8, g.nw8, bits + g.nw16, prefix + g.nw16, pop + 1, [&](int wi) {
+                return word_from_cells(wi, g.w8, g.n8, [&](int y, int x) { return medium_cell(a, mc, mm, y, x); });
+            });
+        else
+            build_level(g.n8, g.nw8, bits + g.nw16, prefix + g.nw16, pop + 1, [&](int) { return a.mode == 5 ? 0xFFFFFFFFu : 0u; });
+        uint32_t *fb = bits + g.nw16 + g.nw8, *fp = prefix + g.nw16 + g.nw8;
+        if (a.mode > 2) {
+            build_level(g.n4, g.nw4, fb, fp, pop + 2, [&](int) { return a.mode == 6 ? 0xFFFFFFFFu : 0u; });
+        } else if (g.w % 32 == 0) {
+            // a bitmap word = 32 cells of one row = 16 medium cells (2 stream bytes) and 8 coarse cells (1 byte)
+            build_level(g.n4, g.nw4, fb, fp, pop + 2, [&](int wi) {
+                const int64_t p0 = (int64_t)wi * 32;
+                const int y = (int)(p0 / g.w), x0 = (int)(p0 - (int64_t)y * g.w);
+                uint32_t m16 = 0, c8 = 0;
+                if (need_m) {
+                    const int64_t p8 = (int64_t)(y >> 1) * g.w8 + (x0 >> 1);
+                    const uint8_t *q = mm + 1 + (p8 >> 3);
+                    m16 = __brev(((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16));
+                }
+                if (need_c) {
+                    const int64_t p16 = (int64_t)(y >> 2) * g.w16 + (x0 >> 2);
+                    c8 = __brev((uint32_t)mc[1 + (p16 >> 3)] << 24);
+                }
+                return ~(spread2(m16) | spread2(spread2(c8)));
+            });
+        } else {
+            build_level(g.n4, g.nw4, fb, fp, pop + 2, [&](int wi) {
+                return word_from_cells(wi, g.w, g.n4, [&](int y, int x) { return fine_cell(a, mc, mm, y, x); });
+            });
+        }
     }
 }
 
+// One thread per 4 consecutive fine tokens of a row (w is a multiple of 4): they share one coarse
+// cell, two medium cells and one bitmap word per level.  16-byte stores throughout.
 __global__ void __launch_bounds__(256) unpack_assemble_kernel(const UnpackArgs a)
 {
     const Geo &g = a.g;
     const int b = blockIdx.y;
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t quad = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int nwt = g.nw16 + g.nw8 + g.nw4;
     const uint32_t *bits = a.ws.bits + (int64_t)b * nwt;
     const uint32_t *prefix = a.ws.prefix + (int64_t)b * nwt;
-    const int32_t *cnt = a.ws.count + b * 3;
-    const int32_t *pop = a.ws.pop + b * 3;
-    if (p == 0) {
+    const int32_t *cntp = a.ws.count + b * 3;
+    if (quad == 0) {
         // the reference's masked assignment raises unless #symbols == #set cells (an empty
         // coarse / medium stream stands for zeros, model.py:284-290)
+        const int32_t *pop = a.ws.pop + b * 3;
         for (int s = 0; s < 3; ++s) {
             if (!stream_present(a.mode, s)) continue;
-            const bool empty_ok = cnt[s] == -1 && (s < 2 || pop[s] == 0);
-            if (!empty_ok && cnt[s] != pop[s]) atomicExch(&a.status[b], CGIC_EFORMAT);
+            const bool empty_ok = cntp[s] == -1 && (s < 2 || pop[s] == 0);
+            if (!empty_ok && cntp[s] != pop[s]) atomicExch(&a.status[b], CGIC_EFORMAT);
         }
     }
+    const int64_t p = quad * 4;
     if (p >= g.n4) return;
     const int y = (int)(p / g.w), x = (int)(p - (int64_t)y * g.w);
     const uint16_t *sym = a.ws.sym + (int64_t)b * (g.n16 + g.n8 + g.n4);
+    const int cnt0 = cntp[0], cnt1 = cntp[1], cnt2 = cntp[2];
     const int64_t p16 = (int64_t)(y >> 2) * g.w16 + (x >> 2);
-    const int64_t p8 = (int64_t)(y >> 1) * g.w8 + (x >> 1);
+    const int64_t p8 = (int64_t)(y >> 1) * g.w8 + (x >> 1);  // even: p8 and p8 + 1 share a word
     const uint32_t wc = bits[p16 >> 5], wm = bits[g.nw16 + (p8 >> 5)], wf = bits[g.nw16 + g.nw8 + (p >> 5)];
-    const int cbit = (wc >> (p16 & 31)) & 1, mbit = (wm >> (p8 & 31)) & 1, fbit = (wf >> (p & 31)) & 1;
-    int64_t ind = 0;
-    if (cbit && cnt[0] > 0) {
-        const int r = prefix[p16 >> 5] + __popc(wc & ((1u << (p16 & 31)) - 1u));
-        if (r < cnt[0]) ind += sym[r];
+    const int sc = (int)(p16 & 31), sm = (int)(p8 & 31), sf = (int)(p & 31);
+    const int cbit = (wc >> sc) & 1;
+    int64_t base = 0;
+    if (cbit && cnt0 > 0) {
+        const int r = prefix[p16 >> 5] + __popc(wc & ((1u << sc) - 1u));
+        if (r < cnt0) base = sym[r];
     }
-    if (mbit && cnt[1] > 0) {
-        const int r = prefix[g.nw16 + (p8 >> 5)] + __popc(wm & ((1u << (p8 & 31)) - 1u));
-        if (r < cnt[1]) ind += sym[g.n16 + r];
+    int mbit[2];
+    int64_t mval[2] = {0, 0};
+    {
+        const uint32_t pre = prefix[g.nw16 + (p8 >> 5)];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            mbit[j] = (wm >> (sm + j)) & 1;
+            if (mbit[j] && cnt1 > 0) {
+                const int r = pre + __popc(wm & ((1u << (sm + j)) - 1u));
+                if (r < cnt1) mval[j] = sym[g.n16 + r];
+            }
+        }
     }
-    if (fbit && cnt[2] > 0) {
-        const int r = prefix[g.nw16 + g.nw8 + (p >> 5)] + __popc(wf & ((1u << (p & 31)) - 1u));
-        if (r < cnt[2]) ind += sym[g.n16 + g.n8 + r];
+    int fbit[4];
+    int64_t ind[4];
+    {
+        const uint32_t pre = prefix[g.nw16 + g.nw8 + (p >> 5)];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            fbit[i] = (wf >> (sf + i)) & 1;
+            int64_t v = base + mval[i >> 1];
+            if (fbit[i] && cnt2 > 0) {
+                const int r = pre + __popc(wf & ((1u << (sf + i)) - 1u));
+                if (r < cnt2) v += sym[g.n16 + g.n8 + r];
+            }
+            ind[i] = v;
+        }
     }
-    a.ind_out[(int64_t)b * g.n4 + p] = ind;
-    a.mf_out[(int64_t)b * g.n4 + p] = fbit;
-    if (((y | x) & 1) == 0) a.mm_out[(int64_t)b * g.n8 + p8] = mbit;
-    if (((y | x) & 3) == 0) a.mc_out[(int64_t)b * g.n16 + p16] = cbit;
+    longlong2 *ind_o = reinterpret_cast<longlong2 *>(a.ind_out + (int64_t)b * g.n4 + p);
+    ind_o[0] = make_longlong2(ind[0], ind[1]);
+    ind_o[1] = make_longlong2(ind[2], ind[3]);
+    longlong2 *mf_o = reinterpret_cast<longlong2 *>(a.mf_out + (int64_t)b * g.n4 + p);
+    mf_o[0] = make_longlong2(fbit[0], fbit[1]);
+    mf_o[1] = make_longlong2(fbit[2], fbit[3]);
+    if ((y & 1) == 0) *reinterpret_cast<longlong2 *>(a.mm_out + (int64_t)b * g.n8 + p8) = make_longlong2(mbit[0], mbit[1]);
+    if ((y & 3) == 0) a.mc_out[(int64_t)b * g.n16 + p16] = cbit;
     if (a.quant_out) {
-        const int64_t k = ind < a.T.K ? ind : 0;  // sums of overlapping levels cannot occur with valid masks
-        const float4 e = __ldg(reinterpret_cast<const float4 *>(a.codebook) + k);
-        float *q = a.quant_out + (int64_t)b * 4 * g.n4 + p;
-        q[0] = e.x;
-        q[g.n4] = e.y;
-        q[2 * g.n4] = e.z;
-        q[3 * g.n4] = e.w;
-        if (ind >= a.T.K) atomicExch(&a.status[b], CGIC_EFORMAT);
+        float4 e[4];
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            bad |= ind[i] >= a.T.K;  // sums of overlapping levels cannot occur with valid masks
+            e[i] = __ldg(reinterpret_cast<const float4 *>(a.codebook) + (ind[i] < a.T.K ? ind[i] : 0));
+        }
+        float4 *q = reinterpret_cast<float4 *>(a.quant_out + (int64_t)b * 4 * g.n4 + p);
+        const int64_t plane4 = g.n4 / 4;
+        q[0] = make_float4(e[0].x, e[1].x, e[2].x, e[3].x);
+        q[plane4] = make_float4(e[0].y, e[1].y, e[2].y, e[3].y);
+        q[2 * plane4] = make_float4(e[0].z, e[1].z, e[2].z, e[3].z);
+        q[3 * plane4] = make_float4(e[0].w, e[1].w, e[2].w, e[3].w);
+        if (bad) atomicExch(&a.status[b], CGIC_EFORMAT);
     }
 }
 
-__global__ void huff_decode_single_kernel(const uint8_t *bytes, int64_t nbytes, DevTable T, int32_t *out, int64_t cap,
-                                          int32_t *count_out)
+__global__ void __launch_bounds__(DEC_THREADS)
+huff_decode_single_kernel(const uint8_t *bytes, int64_t nbytes, DevTable T, int32_t *out, int64_t cap, int32_t *count_out)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0) *count_out = decode_stream<int32_t>(bytes, nbytes, T, out, cap);
+    extern __shared__ __align__(128) unsigned char dyn[];
+    __shared__ __align__(8) unsigned long long mbar;
+    uint32_t *s_dec = reinterpret_cast<uint32_t *>(dyn);
+    const uint32_t *lut2 = stage_decode_tables(T, s_dec, &mbar);
+    const int cnt = decode_stream_any<int32_t>(bytes, nbytes, T, s_dec, lut2, out, cap);
+    if (threadIdx.x == 0) *count_out = cnt;
 }
 
 __global__ void bits_decode_single_kernel(const uint8_t *bytes, int64_t nbytes, int32_t *out, int64_t cap, int32_t *count_out)
@@ -341,6 +799,16 @@ __global__ void bits_decode_single_kernel(const uint8_t *bytes, int64_t nbytes, 
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbits; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = stream_bit(bytes, i);
     if (threadIdx.x == 0 && blockIdx.x == 0) *count_out = (int32_t)nbits;
+}
+
+size_t decode_smem_bytes(const DevTable &T)
+{
+    size_t b = (size_t)T.dec_stage_words * 4;
+    if (T.max_len <= DEC_MAX_D) {
+        const size_t ch = (size_t)cand_chunk_subs(T.max_len);
+        b += ch * T.max_len * 2 + (ch * (DEC_SUB_BITS / 32) + DEC_LOOKAHEAD_WORDS) * 4;
+    }
+    return b;
 }
 
 }  // namespace
@@ -387,15 +855,27 @@ extern "C" int cgic_unpack(const uint8_t *bytes, const int32_t *sizes, int B, in
     a.quant_out = quant_out;
     a.status = status_out;
     cudaStream_t stream = as_stream(stream_);
+    for (const void *ptr : {(const void *)mm_out, (const void *)mf_out, (const void *)ind_out, (const void *)quant_out, (const void *)bytes})
+        CGIC_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, CGIC_EINVAL, "cgic_unpack: buffers must be 16-byte aligned");
+    // dynamic shared memory: decode tables for the stream CTAs, mask stream bytes for the mask CTAs
+    const size_t dec_bytes = decode_smem_bytes(a.T);
+    const size_t mask_bytes = (size_t)(((a.g.n16 / 8 + 2 + 15) & ~15) + ((a.g.n8 / 8 + 2 + 15) & ~15));
+    a.mask_stage = mask_bytes <= 96 * 1024;
+    const size_t smem = std::max(dec_bytes, a.mask_stage ? mask_bytes : (size_t)0);
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        CGIC_CUDA_CHECK(cudaFuncSetAttribute(unpack_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
     CGIC_CUDA_CHECK(cudaMemsetAsync(status_out, 0, (size_t)B * 4, stream));
     {
         CGIC_PROF("unpack_decode_kernel", stream);
-        unpack_decode_kernel<<<dim3(5, B), UP_THREADS, 0, stream>>>(a);
+        unpack_decode_kernel<<<dim3(5, B), UP_THREADS, smem, stream>>>(a);
     }
     CGIC_LAUNCH_CHECK();
     {
         CGIC_PROF("unpack_assemble_kernel", stream);
-        unpack_assemble_kernel<<<dim3((unsigned)((a.g.n4 + 255) / 256), B), 256, 0, stream>>>(a);
+        unpack_assemble_kernel<<<dim3((unsigned)((a.g.n4 / 4 + 255) / 256), B), 256, 0, stream>>>(a);
     }
     CGIC_LAUNCH_CHECK();
     return CGIC_OK;
@@ -406,10 +886,17 @@ extern "C" int cgic_huff_decode(const uint8_t *bytes, int64_t nbytes, const cgic
 {
     CGIC_REQUIRE(count_out && nbytes >= 0 && (bytes || nbytes == 0) && (symbols_out || cap == 0), CGIC_EINVAL,
                  "cgic_huff_decode: bad argument");
+    CGIC_REQUIRE((reinterpret_cast<uintptr_t>(bytes) & 3) == 0, CGIC_EINVAL, "cgic_huff_decode: bytes must be 4-byte aligned");
     DevTable T;
     int rc = table_device_view(t, &T);
     if (rc) return rc;
-    huff_decode_single_kernel<<<1, 32, 0, as_stream(stream)>>>(bytes, nbytes, T, symbols_out, cap, count_out);
+    const size_t smem = decode_smem_bytes(T);
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        CGIC_CUDA_CHECK(cudaFuncSetAttribute(huff_decode_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    huff_decode_single_kernel<<<1, DEC_THREADS, smem, as_stream(stream)>>>(bytes, nbytes, T, symbols_out, cap, count_out);
     CGIC_LAUNCH_CHECK();
     return CGIC_OK;
 }
