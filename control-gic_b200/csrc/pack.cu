@@ -12,14 +12,15 @@
 // global memory sees every output word exactly once and needs no pre-zeroing.
 // Framing (must be byte exact): [pad count byte][payload, MSB first][pad zero bits],
 // pad = 8 - nbits % 8 in 1..8, empty symbol list -> 0 bytes.
+#include <map>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace cgic {
 namespace {
 
-constexpr int PK_THREADS = 256;
-constexpr int PK_ITEMS = 4;
-constexpr int PK_TILE = PK_THREADS * PK_ITEMS;
+constexpr int PK_THREADS = 512;
 
 struct PackArgs {
     const int64_t *idx;  // [B,h,w]  (or the symbol list for the single-stream entry point)
@@ -48,27 +49,26 @@ __device__ __forceinline__ int block_exscan(int v, int *s_warp, int *total)
     }
     if (lane == 31) s_warp[wid] = inc;
     __syncthreads();
-    if (wid == 0) {
-        int ws = lane < PK_THREADS / 32 ? s_warp[lane] : 0;
-        int winc = ws;
+    int woff = 0, tot = 0;
 #pragma unroll
-        for (int o = 1; o < PK_THREADS / 32; o <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, winc, o);
-            if (lane >= o) winc += n;
-        }
-        if (lane < PK_THREADS / 32) s_warp[lane] = winc - ws;
-        if (lane == PK_THREADS / 32 - 1) s_warp[PK_THREADS / 32] = winc;
+    for (int i = 0; i < PK_THREADS / 32; ++i) {
+        const int t = s_warp[i];
+        if (i < wid) woff += t;
+        tot += t;
     }
+    *total = tot;
     __syncthreads();
-    const int r = s_warp[wid] + inc - v;
-    *total = s_warp[PK_THREADS / 32];
-    __syncthreads();
-    return r;
+    return woff + inc - v;
 }
 
-__device__ void pack_index_stream(const PackArgs &a, int s, int b, uint32_t *stage)
+// One index stream by the whole CTA.  ITEMS consecutive grid positions per thread and tile; the
+// code table is read from shared memory (s_enc: (code bits left aligned, length) per symbol) when
+// every code fits 32 bits, else from the global code pool.  `stage` holds one tile of output bits.
+template <int ITEMS>
+__device__ void pack_index_stream(const PackArgs &a, int s, int b, uint32_t *stage, const uint2 *s_enc)
 {
-    __shared__ int s_warp[PK_THREADS / 32 + 1];
+    constexpr int TILE = PK_THREADS * ITEMS;
+    __shared__ int s_warp[PK_THREADS / 32];
     __shared__ uint32_t s_carry;
     __shared__ int s_bad;
     const int tid = threadIdx.x;
@@ -104,33 +104,63 @@ __device__ void pack_index_stream(const PackArgs &a, int s, int b, uint32_t *sta
     }
     __syncthreads();
     int64_t P = 8;  // stream bit position (header byte first)
-    for (int64_t tile = 0; tile < n_pos; tile += PK_TILE) {
-        int sym[PK_ITEMS], len[PK_ITEMS];
+    for (int64_t tile = 0; tile < n_pos; tile += TILE) {
+        int sym[ITEMS];
+        uint32_t len[ITEMS], code[ITEMS];
+        const int64_t pos0 = tile + (int64_t)tid * ITEMS;
+        // ---- which positions emit a symbol (vector loads of the mask where possible)
+        bool on[ITEMS];
+        if (!mask) {
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) on[i] = pos0 + i < n_pos;
+        } else if (ITEMS % 4 == 0 && pos0 + ITEMS <= n_pos) {
+#pragma unroll
+            for (int v = 0; v < ITEMS / 4; ++v) {
+                const int4 m = __ldg(reinterpret_cast<const int4 *>(mask + pos0) + v);
+                on[4 * v] = m.x == 1;
+                on[4 * v + 1] = m.y == 1;
+                on[4 * v + 2] = m.z == 1;
+                on[4 * v + 3] = m.w == 1;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) on[i] = pos0 + i < n_pos && mask[pos0 + i] == 1;
+        }
+        // ---- symbols: the block's top-left token (model.py:219-221)
+        int y = 0, x = 0;
+        if (mask) {
+            y = (int)(pos0 / gw);
+            x = (int)(pos0 - (int64_t)y * gw);
+        }
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            sym[i] = -1;
+            if (on[i]) {
+                const int64_t at = mask ? (int64_t)(y * step) * a.w + x * step : pos0 + i;
+                const int64_t v = src[at];
+                if (v < 0 || v >= a.T.K) s_bad = 1;
+                else sym[i] = (int)v;
+            }
+            if (++x == gw) {
+                x = 0;
+                ++y;
+            }
+        }
         int tsum = 0;
 #pragma unroll
-        for (int i = 0; i < PK_ITEMS; ++i) {
-            const int64_t pos = tile + (int64_t)tid * PK_ITEMS + i;
+        for (int i = 0; i < ITEMS; ++i) {
             len[i] = 0;
-            sym[i] = 0;
-            if (pos < n_pos) {
-                bool on = true;
-                int64_t at = pos;
-                if (mask) {
-                    on = mask[pos] == 1;
-                    const int y = (int)(pos / gw), x = (int)(pos - (int64_t)y * gw);
-                    at = (int64_t)(y * step) * a.w + x * step;
-                }
-                if (on) {
-                    const int64_t v = src[at];
-                    if (v < 0 || v >= a.T.K) {
-                        s_bad = 1;
-                    } else {
-                        sym[i] = (int)v;
-                        len[i] = a.T.len[v];
-                    }
+            code[i] = 0;
+            if (sym[i] >= 0) {
+                if (s_enc) {
+                    const uint2 e = s_enc[sym[i]];
+                    code[i] = e.x;
+                    len[i] = e.y;
+                } else {
+                    len[i] = a.T.len[sym[i]];
                 }
             }
-            tsum += len[i];
+            tsum += (int)len[i];
         }
         int tot;
         int o = block_exscan(tsum, s_warp, &tot);
@@ -139,17 +169,23 @@ __device__ void pack_index_stream(const PackArgs &a, int s, int b, uint32_t *sta
         for (int j = tid; j < nwords; j += PK_THREADS) stage[j] = (j == 0 && r0) ? s_carry : 0u;
         __syncthreads();
 #pragma unroll
-        for (int i = 0; i < PK_ITEMS; ++i) {
+        for (int i = 0; i < ITEMS; ++i) {
             if (len[i]) {
-                const uint32_t *code = a.T.pool + a.T.off[sym[i]];
                 int q = r0 + o;
-                for (int rem = len[i]; rem > 0; rem -= 32, q += 32, ++code) {
-                    const uint32_t cw = *code;
+                if (s_enc) {
                     const int sh = q & 31, wi = q >> 5;
-                    atomicOr(&stage[wi], cw >> sh);
-                    if (sh && (sh + min(rem, 32) > 32)) atomicOr(&stage[wi + 1], cw << (32 - sh));
+                    atomicOr(&stage[wi], code[i] >> sh);
+                    if (sh + (int)len[i] > 32) atomicOr(&stage[wi + 1], code[i] << (32 - sh));
+                } else {
+                    const uint32_t *cw_p = a.T.pool + a.T.off[sym[i]];
+                    for (int rem = (int)len[i]; rem > 0; rem -= 32, q += 32, ++cw_p) {
+                        const uint32_t cw = *cw_p;
+                        const int sh = q & 31, wi = q >> 5;
+                        atomicOr(&stage[wi], cw >> sh);
+                        if (sh && (sh + min(rem, 32) > 32)) atomicOr(&stage[wi + 1], cw << (32 - sh));
+                    }
                 }
-                o += len[i];
+                o += (int)len[i];
             }
         }
         __syncthreads();
@@ -217,16 +253,36 @@ __device__ void pack_bit_stream(const int32_t *v, int64_t n, uint8_t *out, int64
     }
 }
 
+// dynamic shared memory: [code table K x 8 bytes when max_len <= 32][one tile of output bits]
+template <int ITEMS>
+__device__ __forceinline__ void pack_stream_entry(const PackArgs &a, int s, int b, unsigned char *dyn, unsigned long long *mbar)
+{
+    const uint2 *s_enc = nullptr;
+    uint32_t *stage = reinterpret_cast<uint32_t *>(dyn);
+    if (a.T.enc) {  // stage the code table with one TMA bulk copy
+        const uint32_t bytes = (uint32_t)((a.T.K + 1) / 2 * 2) * 8u;
+        if (threadIdx.x == 0) mbar_init(mbar);
+        __syncthreads();
+        if (threadIdx.x == 0) tma_load_1d(dyn, a.T.enc, bytes, mbar);
+        mbar_wait(mbar, 0);
+        s_enc = reinterpret_cast<const uint2 *>(dyn);
+        stage = reinterpret_cast<uint32_t *>(dyn + bytes);
+    }
+    pack_index_stream<ITEMS>(a, s, b, stage, s_enc);
+}
+
+template <int ITEMS>
 __global__ void __launch_bounds__(PK_THREADS) pack_kernel(const PackArgs a)
 {
-    extern __shared__ __align__(16) uint32_t stage[];
+    extern __shared__ __align__(128) unsigned char dyn[];
+    __shared__ __align__(8) unsigned long long mbar;
     const int s = blockIdx.x, b = blockIdx.y;
     if (!stream_present(a.mode, s)) {
         if (threadIdx.x == 0) a.sizes[b * 5 + s] = 0;
         return;
     }
     if (s < 3) {
-        pack_index_stream(a, s, b, stage);
+        pack_stream_entry<ITEMS>(a, s, b, dyn, &mbar);
     } else {
         const int lvl = s - 3;  // 0 coarse, 1 medium
         const int div = lvl == 0 ? 4 : 2;
@@ -236,10 +292,12 @@ __global__ void __launch_bounds__(PK_THREADS) pack_kernel(const PackArgs a)
     }
 }
 
+template <int ITEMS>
 __global__ void __launch_bounds__(PK_THREADS) pack_single_kernel(const PackArgs a)
 {
-    extern __shared__ __align__(16) uint32_t stage[];
-    pack_index_stream(a, 0, 0, stage);
+    extern __shared__ __align__(128) unsigned char dyn[];
+    __shared__ __align__(8) unsigned long long mbar;
+    pack_stream_entry<ITEMS>(a, 0, 0, dyn, &mbar);
 }
 
 __global__ void __launch_bounds__(PK_THREADS)
@@ -248,11 +306,25 @@ bits_single_kernel(const int32_t *v, int64_t n, uint8_t *out, int64_t cap, int32
     pack_bit_stream(v, n, out, cap, size_out);
 }
 
-size_t stage_bytes(int max_len) { return ((size_t)PK_TILE * max_len / 32 + 4) * 4; }
+// tile of PK_THREADS * items positions: output bits + 2 words, plus the staged code table
+size_t pack_smem_bytes(const DevTable &T, int items)
+{
+    size_t b = ((size_t)PK_THREADS * items * T.max_len / 32 + 4) * 4;
+    if (T.enc) b += (size_t)((T.K + 1) / 2 * 2) * 8;
+    return b;
+}
 
 int ensure_smem(const void *fn, size_t bytes)
 {
-    if (bytes > 48 * 1024) CGIC_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    static std::mutex mu;
+    static std::map<const void *, size_t> granted;
+    if (bytes <= 48 * 1024) return CGIC_OK;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &g = granted[fn];
+    if (bytes > g) {
+        CGIC_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        g = bytes;
+    }
     return CGIC_OK;
 }
 
@@ -268,7 +340,7 @@ extern "C" int cgic_pack(const int64_t *idx, const int32_t *m_c, const int32_t *
     CGIC_REQUIRE(B >= 0 && h > 0 && w > 0 && h % 4 == 0 && w % 4 == 0, CGIC_EINVAL, "cgic_pack: token grid %dx%d must be multiples of 4", h, w);
     CGIC_REQUIRE(mode >= 0 && mode <= 6, CGIC_EINVAL, "cgic_pack: mode %d", mode);
     CGIC_REQUIRE((reinterpret_cast<uintptr_t>(bytes_out) & 15) == 0 && (reinterpret_cast<uintptr_t>(m_c) & 15) == 0 &&
-                     (reinterpret_cast<uintptr_t>(m_m) & 15) == 0,
+                     (reinterpret_cast<uintptr_t>(m_m) & 15) == 0 && (reinterpret_cast<uintptr_t>(m_f) & 15) == 0,
                  CGIC_EINVAL, "cgic_pack: bytes_out and masks must be 16-byte aligned");
     if (B == 0) return CGIC_OK;
     PackArgs a{};
@@ -290,16 +362,18 @@ extern "C" int cgic_pack(const int64_t *idx, const int32_t *m_c, const int32_t *
         a.slot_cap[s] = L.cap[s];
     }
     a.sizes = sizes_out;
-    const size_t smem = stage_bytes(a.T.max_len);
+    const int items = a.T.enc ? 8 : 1;
+    const size_t smem = pack_smem_bytes(a.T, items);
     CGIC_REQUIRE(smem <= 200 * 1024, CGIC_EINVAL, "cgic_pack: code length %d needs %zu bytes of staging", a.T.max_len, smem);
-    rc = ensure_smem((const void *)pack_kernel, smem);
+    rc = ensure_smem(items == 8 ? (const void *)pack_kernel<8> : (const void *)pack_kernel<1>, smem);
     if (rc) return rc;
     // the coarse-mask payload must stay int4-loadable per image: (h/4)*(w/4) ints per image
     CGIC_REQUIRE(((int64_t)(h / 4) * (w / 4)) % 4 == 0 || B == 1, CGIC_EINVAL,
                  "cgic_pack: (h/4)*(w/4) must be a multiple of 4 for batched masks");
     {
         CGIC_PROF("pack_kernel", as_stream(stream));
-        pack_kernel<<<dim3(5, B), PK_THREADS, smem, as_stream(stream)>>>(a);
+        if (items == 8) pack_kernel<8><<<dim3(5, B), PK_THREADS, smem, as_stream(stream)>>>(a);
+        else pack_kernel<1><<<dim3(5, B), PK_THREADS, smem, as_stream(stream)>>>(a);
     }
     CGIC_LAUNCH_CHECK();
     return CGIC_OK;
@@ -318,11 +392,13 @@ extern "C" int cgic_huff_encode(const int64_t *symbols, int64_t n, const cgic_ta
     a.out = out;
     a.slot_cap[0] = cap;
     a.sizes = size_out;
-    const size_t smem = stage_bytes(a.T.max_len);
+    const int items = a.T.enc ? 8 : 1;
+    const size_t smem = pack_smem_bytes(a.T, items);
     CGIC_REQUIRE(smem <= 200 * 1024, CGIC_EINVAL, "cgic_huff_encode: code length %d too long", a.T.max_len);
-    rc = ensure_smem((const void *)pack_single_kernel, smem);
+    rc = ensure_smem(items == 8 ? (const void *)pack_single_kernel<8> : (const void *)pack_single_kernel<1>, smem);
     if (rc) return rc;
-    pack_single_kernel<<<1, PK_THREADS, smem, as_stream(stream)>>>(a);
+    if (items == 8) pack_single_kernel<8><<<1, PK_THREADS, smem, as_stream(stream)>>>(a);
+    else pack_single_kernel<1><<<1, PK_THREADS, smem, as_stream(stream)>>>(a);
     CGIC_LAUNCH_CHECK();
     return CGIC_OK;
 }
