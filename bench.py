@@ -252,7 +252,7 @@ def run_b200(args):
         packed, sizes = cg.ops.pack(idx, mc, mm, mf, mode, table, h, w)
         dmc, dmm, dmf, ind, quant, status = cg.ops.unpack(packed, sizes, mode, table, cb, h, w)
         return idx, sq, sizes, ind, quant, status
-    kernels_per_step = 6    # vq_classify, vq_search, vq_finalize, pack, unpack_decode, unpack_assemble
+    kernels_per_step = 4    # vq_fused, pack, unpack_decode, unpack_assemble
 
     # correctness gate of the run itself (round trip + status), before any timing
     idx, sq, sizes, ind, quant, status = step()
@@ -411,9 +411,7 @@ def algorithmic_bytes(B, h, w, stream_bytes):
     masks64 = masks32            # SURVEY 8d counts the decoded masks at 5.25 B/token (we write them as int64 like the reference)
     consts = 1024 * 16
     out = {
-        "vq_classify_kernel": n4 * 16,                       # reads z
-        "vq_search_kernel": n4 * 16 + consts,                # reads (at most) z + codebook
-        "vq_finalize_kernel": n4 * (16 + 16 + 8) + consts,   # reads z, writes z_q + idx
+        "vq_fused_kernel": n4 * (16 + 16 + 8) + consts,      # reads z once, writes z_q + idx once
         "pack_kernel": n4 * 8 + masks32 + stream_bytes,
         "unpack_decode_kernel": stream_bytes,
         "unpack_assemble_kernel": masks64 + n4 * (8 + 16) + consts,

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcgic_b200.so")
+LIB_PATH = os.environ.get("CGIC_B200_LIB") or os.path.join(_HERE, "libcgic_b200.so")   # env override: kernel-tuning experiments only
 
 OK, EINVAL, ENOMEM, ESPACE, ECUDA, EFORMAT = 0, -1, -2, -3, -4, -5
 

@@ -9,6 +9,8 @@ SRCS=(table.cu vq_assign.cu pack.cu unpack.cu router.cu entropy.cu session.cu)
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --ftz=false --prec-div=true --prec-sqrt=true
        --fmad=false -Xcompiler -fPIC,-O2,-fvisibility=hidden -shared -cudart shared)
 if [[ "${CGIC_PTXAS_V:-0}" == "1" ]]; then FLAGS+=(-Xptxas -v); fi
+if [[ -n "${CGIC_EXTRA_FLAGS:-}" ]]; then FLAGS+=(${CGIC_EXTRA_FLAGS}); fi
+OUT="${CGIC_OUT:-${OUT}}"
 cd "${HERE}"
 "${NVCC}" "${FLAGS[@]}" -o "${OUT}" "${SRCS[@]}"
 echo "built ${OUT}"

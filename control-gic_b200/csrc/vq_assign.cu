@@ -1,17 +1,22 @@
-// a1  VectorQuantize2.forward  (CGIC/modules/vqvae/quantize.py:69-98) as three sm_100a kernels.
+// a1  VectorQuantize2.forward  (CGIC/modules/vqvae/quantize.py:69-98) as ONE persistent sm_100a kernel.
 //
-//   vq_classify : one thread per token.  A token whose 4 latent channels are bit-identical to the
-//                 top-left token of its 4x4 (else 2x2) block is a FOLLOWER of that token; all other
-//                 tokens are LEADERS and are appended to a compact work list.  The encoder's
-//                 mask-mix (vqvae_blocks.py:364-366) makes coarse / medium regions constant over
-//                 4x4 / 2x2 blocks, so only n_c + n_m + n_f of the h*w tokens need a search; the test
-//                 is on the data itself, so the result is exact for ANY input.
-//   vq_search   : persistent grid, exhaustive search of the leaders over the K codes with the
-//                 reference's rounding sequence (see below), packed two codes per instruction
-//                 (FMUL2/FFMA2/FADD2) with the codebook staged in shared memory by one TMA bulk
-//                 copy.  Work = (32*T-token block) x (8-code chunk) units dealt evenly to warps.
-//   vq_finalize : one thread per token: index of its leader -> idx (int64), z_q = fl(z + fl(e - z))
-//                 in NCHW, and a deterministic two-stage reduction of sum((e-z)^2).
+// Each CTA stages the codebook once (TMA bulk copy -> shared memory, re-laid out as packed code
+// pairs), then loops over tiles of the token grid (R rows x C columns of one image, multiples
+// of 4, at most 1024 tokens).  Per tile:
+//   load     z of the tile, NCHW global -> one float4 per token in shared memory (coalesced);
+//   classify a token whose 4 latent channels are bit-identical to the top-left token of its 4x4
+//            (else 2x2) block is a FOLLOWER of that token; the others are LEADERS, compacted into
+//            a list.  The encoder's mask-mix (vqvae_blocks.py:364-366) makes coarse / medium
+//            regions constant over 4x4 / 2x2 blocks, so only n_c + n_m + n_f of the tokens need a
+//            search; the test is on the data itself, hence exact for ANY input;
+//   search   exhaustive over the K codes with the reference's rounding sequence (below), two codes
+//            per instruction (FMUL2 / FFMA2 / FADD2).  Work units = (64 leaders) x (a range of
+//            8-code chunks), dealt round-robin to the warps; partial results meet in a 64-bit
+//            shared-memory atomicMin on (ordered distance bits, code index);
+//   finalize every token takes its leader's index: idx (int64), z_q = fl(z + fl(e - z)) in NCHW,
+//            and sum((e-z)^2) accumulated per CTA; the last CTA adds the per-CTA partials in a
+//            fixed order (deterministic).
+// z is read once and idx / z_q written once: no intermediate ever goes to global memory.
 //
 // Rounding contract (bit-exact against torch CPU, see oracle/cgic_oracle.c and SURVEY.md 7.1):
 //     z2  = ((z0*z0 + z1*z1) + z2*z2) + z3*z3      every product and sum rounded to fp32
@@ -24,11 +29,23 @@
 namespace cgic {
 namespace {
 
-constexpr int VQ_T = 4;        // tokens per lane in the search
+#ifndef CGIC_VQ_T
+#define CGIC_VQ_T 2
+#endif
+#ifndef CGIC_VQ_TILE
+#define CGIC_VQ_TILE 2048
+#endif
+#ifndef CGIC_VQ_THREADS
+#define CGIC_VQ_THREADS 512
+#endif
+constexpr int VQ_T = CGIC_VQ_T;  // tokens per lane in the search
 constexpr int VQ_CHUNK = 8;    // codes per chunk = 4 code pairs
-constexpr int VQ_THREADS = 256;
+constexpr int VQ_THREADS = CGIC_VQ_THREADS;
+constexpr int VQ_WARPS = VQ_THREADS / 32;
 constexpr int VQ_ROWS = 5;     // e0 e1 e2 e3 e^2
 constexpr int VQ_MAX_K = 4096;
+constexpr int VQ_TILE = CGIC_VQ_TILE;  // tokens per batch of strips (shared-memory capacity)
+constexpr int VQ_MAX_STRIPS = VQ_TILE / 16;  // a strip has at least 4 x 4 tokens
 
 typedef unsigned long long u64;
 
@@ -67,8 +84,6 @@ __device__ __forceinline__ float min3(float a, float b, float c)
     return r;
 }
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
 __device__ __forceinline__ float sumsq4(float a, float b, float c, float d)
 {
     float s = __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b));
@@ -83,281 +98,338 @@ __device__ __forceinline__ uint32_t order_key(float d)
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(VQ_THREADS)
-vq_classify_kernel(const float *__restrict__ z, int64_t n_tokens, int h, int w, int32_t *__restrict__ leader_of,
-                   int32_t *__restrict__ list, u64 *__restrict__ best, int32_t *__restrict__ counters)
+#ifdef CGIC_VQ_TRACE
+#define VQ_STAMP(k)                                                                                  \
+    do {                                                                                             \
+        if (threadIdx.x == 0 && blockIdx.x < 300) {                                                  \
+            unsigned long long t__;                                                                  \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                                  \
+            reinterpret_cast<unsigned long long *>(partials)[512 + blockIdx.x * 8 + (k)] = t__;      \
+            if ((k) == 0) {                                                                          \
+                unsigned sm__;                                                                       \
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(sm__));                                    \
+                reinterpret_cast<unsigned long long *>(partials)[512 + blockIdx.x * 8 + 7] = sm__;   \
+            }                                                                                        \
+        }                                                                                            \
+    } while (0)
+#else
+#define VQ_STAMP(k)
+#endif
+
+// Work decomposition: a STRIP is 4 rows x C columns of one image (C a multiple of 4, <= 256), so
+// every 4x4 / 2x2 block lies inside one strip.  The strips of the whole batch are numbered
+// image-major and dealt to the CTAs as contiguous, equally long ranges (one CTA per SM: the
+// per-SM load differs by at most one strip); a CTA processes its range in batches of NB strips.
+struct VqTiles {
+    int C;                 // columns per strip
+    int SC;                // tokens per strip = 4 * C
+    int tiles_x, tiles_y;  // strips per image row / strip rows per image
+    int NB;                // strips per batch (NB * SC <= VQ_TILE)
+    int64_t n_strips;      // B * tiles_y * tiles_x
+};
+
+__host__ __device__ inline VqTiles make_tiles(int B, int h, int w)
 {
-    __shared__ int s_warp[VQ_THREADS / 32];
-    __shared__ int s_base;
-    const int64_t t = (int64_t)blockIdx.x * VQ_THREADS + threadIdx.x;
-    const int plane = h * w;
-    bool leader = false;
-    if (t < n_tokens) {
-        const int b = (int)(t / plane);
-        const int p = (int)(t - (int64_t)b * plane);
-        const int y = p / w, x = p - y * w;
-        const float *zb = z + (int64_t)b * 4 * plane;
-        const uint32_t v0 = __float_as_uint(zb[p]), v1 = __float_as_uint(zb[plane + p]),
-                       v2 = __float_as_uint(zb[2 * plane + p]), v3 = __float_as_uint(zb[3 * plane + p]);
-        int lead = p;
-        const int p4 = (y & ~3) * w + (x & ~3);
-        if (p4 != p && __float_as_uint(zb[p4]) == v0 && __float_as_uint(zb[plane + p4]) == v1 &&
-            __float_as_uint(zb[2 * plane + p4]) == v2 && __float_as_uint(zb[3 * plane + p4]) == v3)
-            lead = p4;
-        if (lead == p) {
-            const int p2 = (y & ~1) * w + (x & ~1);
-            if (p2 != p && __float_as_uint(zb[p2]) == v0 && __float_as_uint(zb[plane + p2]) == v1 &&
-                __float_as_uint(zb[2 * plane + p2]) == v2 && __float_as_uint(zb[3 * plane + p2]) == v3)
-                lead = p2;
-        }
-        leader = (lead == p);
-        leader_of[t] = (int32_t)((int64_t)b * plane + lead);
-        if (leader) best[t] = ~0ull;
-    }
-    // block-aggregated append to the work list (order is irrelevant to the result)
-    const unsigned m = __ballot_sync(0xffffffffu, leader);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) s_warp[wid] = __popc(m);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int tot = 0;
-        for (int i = 0; i < VQ_THREADS / 32; ++i) {
-            const int c = s_warp[i];
-            s_warp[i] = tot;
-            tot += c;
-        }
-        s_base = tot ? atomicAdd(&counters[0], tot) : 0;
-    }
-    __syncthreads();
-    if (leader) list[s_base + s_warp[wid] + __popc(m & ((1u << lane) - 1u))] = (int32_t)t;
+    VqTiles t;
+    const int w4 = (w + 3) & ~3;
+    t.C = w4 < 256 ? w4 : 256;
+    t.SC = 4 * t.C;
+    t.tiles_x = (w + t.C - 1) / t.C;
+    t.tiles_y = (h + 3) / 4;
+    t.NB = VQ_TILE / t.SC;
+    t.n_strips = (int64_t)B * t.tiles_x * t.tiles_y;
+    return t;
 }
 
-// ---------------------------------------------------------------------------------------------
-// shared memory: [raw codebook Kpad*4 floats][chunk table (Kpad/8) * 5 rows * 4 pairs * float2]
-__global__ void __launch_bounds__(VQ_THREADS, 2)
-vq_search_kernel(const float *__restrict__ z, int h, int w, const float *__restrict__ codebook, int K, int Kpad,
-                 const int32_t *__restrict__ list, const int32_t *__restrict__ counters, u64 *__restrict__ best)
+// shared memory: [raw codebook Kpad*16][pair table (Kpad/8)*5*4 float2][z float4 x TILE][best u64 x TILE]
+//                [lead u16 x TILE][list u16 x TILE]
+__global__ void __launch_bounds__(VQ_THREADS, 1)
+vq_fused_kernel(const float *__restrict__ z, int B, int h, int w, const VqTiles tl, const float *__restrict__ codebook, int K,
+                int Kpad, int64_t *__restrict__ idx_out, float *__restrict__ zq_out, double *__restrict__ partials,
+                int32_t *__restrict__ counters, double *__restrict__ sqerr_out)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) u64 mbar;
+    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ int s_count;
+    __shared__ double s_red[VQ_WARPS];
+    __shared__ bool s_last;
+    __shared__ int s_sb[VQ_MAX_STRIPS], s_sy[VQ_MAX_STRIPS], s_sx[VQ_MAX_STRIPS];  // image, first row, first column of a strip
     float *raw = reinterpret_cast<float *>(smem);
     float2 *tab = reinterpret_cast<float2 *>(smem + (size_t)Kpad * 16);
+    float4 *zs = reinterpret_cast<float4 *>(smem + (size_t)Kpad * 36);
+    u64 *best = reinterpret_cast<u64 *>(zs + VQ_TILE);
+    uint16_t *lead = reinterpret_cast<uint16_t *>(best + VQ_TILE);
+    uint16_t *list = lead + VQ_TILE;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+    VQ_STAMP(0);
     // --- stage the codebook with one TMA bulk copy (cp.async.bulk -> UBLKCP), mbarrier completion
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+    if (tid == 0) mbar_init(&mbar);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t bytes = (uint32_t)K * 16u;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         smem_u32(raw)),
-                     "l"(codebook), "r"(bytes), "r"(smem_u32(&mbar))
-                     : "memory");
-    }
-    {
-        uint32_t done = 0;
-        while (!done)
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done)
-                         : "r"(smem_u32(&mbar)), "r"(0u)
-                         : "memory");
-    }
-    // --- chunk table: row r of chunk c holds (v[8c+0],v[8c+1]) (v[8c+2],v[8c+3]) ... for v = e_r or e^2
-    const int npairs = Kpad / 2;
-    for (int pr = threadIdx.x; pr < npairs; pr += VQ_THREADS) {
-        const int k0 = 2 * pr, k1 = k0 + 1;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-        float sa = __int_as_float(0x7f800000), sb = sa;  // padding codes: d = +inf, never selected
-        if (k0 < K) {
-            a = reinterpret_cast<const float4 *>(raw)[k0];
-            sa = sumsq4(a.x, a.y, a.z, a.w);
-        }
-        if (k1 < K) {
-            b = reinterpret_cast<const float4 *>(raw)[k1];
-            sb = sumsq4(b.x, b.y, b.z, b.w);
-        }
-        float2 *dst = tab + (size_t)(pr >> 2) * (VQ_ROWS * 4) + (pr & 3);
-        dst[0] = make_float2(a.x, b.x);
-        dst[4] = make_float2(a.y, b.y);
-        dst[8] = make_float2(a.z, b.z);
-        dst[12] = make_float2(a.w, b.w);
-        dst[16] = make_float2(sa, sb);
-    }
-    __syncthreads();
+    if (tid == 0) tma_load_1d(raw, codebook, (uint32_t)K * 16u, &mbar);
+    bool table_ready = false;  // the pair table is built after the first batch's loads are in flight
 
-    const int L = counters[0];
-    const int plane = h * w;
+    const int64_t plane = (int64_t)h * w;
     const int nchunks = Kpad / VQ_CHUNK;
-    const int lane = threadIdx.x & 31;
-    const int64_t n_blocks = ((int64_t)L + 32 * VQ_T - 1) / (32 * VQ_T);
-    const int64_t total = n_blocks * nchunks;
-    const int64_t n_warps = (int64_t)gridDim.x * (VQ_THREADS / 32);
-    const int64_t per_warp = (total + n_warps - 1) / n_warps;
-    const int64_t gw = (int64_t)blockIdx.x * (VQ_THREADS / 32) + (threadIdx.x >> 5);
-    int64_t u = gw * per_warp;
-    const int64_t u_end = min(total, u + per_warp);
     const u64 minus2 = pack2(-2.f, -2.f);
     const ulonglong2 *ctab = reinterpret_cast<const ulonglong2 *>(tab);
     const float *ftab = reinterpret_cast<const float *>(tab);
-
-    while (u < u_end) {
-        const int64_t blk = u / nchunks;
-        const int c_begin = (int)(u - blk * nchunks);
-        const int c_end = (int)min((int64_t)nchunks, c_begin + (u_end - u));
-        // --- load this lane's T tokens
-        int tok[VQ_T];
-        float zf[VQ_T][4], z2[VQ_T];
-        u64 zd[VQ_T][4], zs[VQ_T];
-        float bestd[VQ_T];
-        int bestc[VQ_T];
-#pragma unroll
-        for (int t = 0; t < VQ_T; ++t) {
-            const int64_t li = blk * (32 * VQ_T) + t * 32 + lane;
-            tok[t] = li < L ? list[li] : -1;
-            if (tok[t] >= 0) {
-                const int b = tok[t] / plane;
-                const int p = tok[t] - b * plane;
-                const float *zb = z + (int64_t)b * 4 * plane + p;
-                zf[t][0] = zb[0];
-                zf[t][1] = zb[plane];
-                zf[t][2] = zb[2 * (int64_t)plane];
-                zf[t][3] = zb[3 * (int64_t)plane];
-            } else {
-                zf[t][0] = zf[t][1] = zf[t][2] = zf[t][3] = 0.f;
-            }
-            z2[t] = sumsq4(zf[t][0], zf[t][1], zf[t][2], zf[t][3]);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) zd[t][c] = pack2(zf[t][c], zf[t][c]);
-            zs[t] = pack2(z2[t], z2[t]);
-            bestd[t] = __int_as_float(0x7f800000);
-            bestc[t] = c_begin;
-        }
-        // --- scan chunks [c_begin, c_end): per token the minimum distance of each chunk
-        for (int c = c_begin; c < c_end; ++c) {
-            float cm[VQ_T];
-#pragma unroll
-            for (int t = 0; t < VQ_T; ++t) cm[t] = __int_as_float(0x7f800000);
-            const ulonglong2 *row = ctab + (size_t)c * (VQ_ROWS * 2);
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const ulonglong2 e0 = row[0 + half], e1 = row[2 + half], e2 = row[4 + half], e3 = row[6 + half],
-                                 es = row[8 + half];
-#pragma unroll
-                for (int t = 0; t < VQ_T; ++t) {
-                    u64 a = mul2(zd[t][0], e0.x);
-                    u64 b = mul2(zd[t][0], e0.y);
-                    a = fma2(zd[t][1], e1.x, a);
-                    b = fma2(zd[t][1], e1.y, b);
-                    a = fma2(zd[t][2], e2.x, a);
-                    b = fma2(zd[t][2], e2.y, b);
-                    a = fma2(zd[t][3], e3.x, a);
-                    b = fma2(zd[t][3], e3.y, b);
-                    const u64 sa = add2(zs[t], es.x);
-                    const u64 sb = add2(zs[t], es.y);
-                    a = fma2(a, minus2, sa);
-                    b = fma2(b, minus2, sb);
-                    float a0, a1, b0, b1;
-                    unpack2(a, a0, a1);
-                    unpack2(b, b0, b1);
-                    cm[t] = min3(cm[t], a0, a1);
-                    cm[t] = min3(cm[t], b0, b1);
-                }
-            }
-#pragma unroll
-            for (int t = 0; t < VQ_T; ++t)
-                if (cm[t] < bestd[t]) {
-                    bestd[t] = cm[t];
-                    bestc[t] = c;
-                }
-        }
-        // --- resolve the first code of the winning chunk that attains the minimum, publish
-#pragma unroll
-        for (int t = 0; t < VQ_T; ++t) {
-            if (tok[t] < 0 || !(bestd[t] < __int_as_float(0x7f800000))) continue;
-            const float *rowf = ftab + (size_t)bestc[t] * (VQ_ROWS * 8);
-            int k = 0;
-#pragma unroll
-            for (int j = VQ_CHUNK - 1; j >= 0; --j) {
-                float dot = __fmul_rn(zf[t][0], rowf[j]);
-                dot = __fmaf_rn(zf[t][1], rowf[8 + j], dot);
-                dot = __fmaf_rn(zf[t][2], rowf[16 + j], dot);
-                dot = __fmaf_rn(zf[t][3], rowf[24 + j], dot);
-                const float d = __fmaf_rn(dot, -2.f, __fadd_rn(z2[t], rowf[32 + j]));
-                if (d == bestd[t]) k = j;
-            }
-            const u64 key = ((u64)order_key(bestd[t]) << 32) | (uint32_t)(bestc[t] * VQ_CHUNK + k);
-            atomicMin(&best[tok[t]], key);
-        }
-        u += (c_end - c_begin);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(VQ_THREADS)
-vq_finalize_kernel(const float *__restrict__ z, int64_t n_tokens, int h, int w, const float *__restrict__ codebook,
-                   const int32_t *__restrict__ leader_of, const u64 *__restrict__ best, int64_t *__restrict__ idx_out,
-                   float *__restrict__ zq_out, double *__restrict__ partials, int32_t *__restrict__ counters,
-                   double *__restrict__ sqerr_out)
-{
-    __shared__ double s_red[VQ_THREADS / 32];
-    __shared__ bool s_last;
-    const int64_t t = (int64_t)blockIdx.x * VQ_THREADS + threadIdx.x;
-    const int plane = h * w;
+    const int C = tl.C, SC = tl.SC;
     double sq = 0.0;
-    if (t < n_tokens) {
-        const u64 key = best[leader_of[t]];
-        const int k = key == ~0ull ? 0 : (int)(uint32_t)key;
-        idx_out[t] = k;
-        if (zq_out || sqerr_out) {
-            const float4 e = reinterpret_cast<const float4 *>(codebook)[k];
-            const int b = (int)(t / plane);
-            const int p = (int)(t - (int64_t)b * plane);
-            const int64_t o = (int64_t)b * 4 * plane + p;
-            const float ev[4] = {e.x, e.y, e.z, e.w};
-            float acc = 0.f;
+    const int64_t s_begin = tl.n_strips * blockIdx.x / gridDim.x, s_end = tl.n_strips * (blockIdx.x + 1) / gridDim.x;
+
+    for (int64_t s0 = s_begin; s0 < s_end; s0 += tl.NB) {
+        const int ns = (int)min((int64_t)tl.NB, s_end - s0);
+        const int ntok = ns * SC;
+        __syncthreads();  // previous batch fully consumed (and the pair table complete on the first pass)
+        VQ_STAMP(1);
+        if (tid == 0) s_count = 0;
+        if (tid < ns) {
+            const int64_t id = s0 + tid;
+            const int spi = tl.tiles_x * tl.tiles_y;
+            const int b = (int)(id / spi), r = (int)(id - (int64_t)b * spi);
+            s_sb[tid] = b;
+            s_sy[tid] = (r / tl.tiles_x) * 4;
+            s_sx[tid] = (r % tl.tiles_x) * C;
+        }
+        __syncthreads();
+        // ---- load (4 tokens per thread and pass: 16 independent loads in flight)
+        for (int t0 = tid; t0 < ntok; t0 += 4 * VQ_THREADS) {
+            float4 v[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const float zc = z[o + (int64_t)c * plane];
-                const float diff = __fsub_rn(ev[c], zc);
-                if (zq_out) zq_out[o + (int64_t)c * plane] = __fadd_rn(zc, diff);
-                acc = __fmaf_rn(diff, diff, acc);
+            for (int i = 0; i < 4; ++i) {
+                const int t = t0 + i * VQ_THREADS;
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t < ntok) {
+                    const int sl = t / SC, r = t - sl * SC;
+                    const int ly = r / C, lx = r - ly * C;
+                    const int gy = s_sy[sl] + ly, gx = s_sx[sl] + lx;
+                    if (gy < h && gx < w) {
+                        const float *zb = z + (int64_t)s_sb[sl] * 4 * plane;
+                        const int64_t p = (int64_t)gy * w + gx;
+                        v[i] = make_float4(__ldg(zb + p), __ldg(zb + plane + p), __ldg(zb + 2 * plane + p), __ldg(zb + 3 * plane + p));
+                    }
+                }
             }
-            sq = (double)acc;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (t0 + i * VQ_THREADS < ntok) zs[t0 + i * VQ_THREADS] = v[i];
+        }
+        if (!table_ready) {
+            table_ready = true;
+            mbar_wait(&mbar, 0);
+        // --- pair table: row r of chunk c holds (v[8c+0],v[8c+1]) (v[8c+2],v[8c+3]) ... for v = e_r or e^2
+        for (int pr = tid; pr < Kpad / 2; pr += VQ_THREADS) {
+            const int k0 = 2 * pr, k1 = k0 + 1;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+            float sa = __int_as_float(0x7f800000), sb = sa;  // padding codes: d = +inf, never selected
+            if (k0 < K) {
+                a = reinterpret_cast<const float4 *>(raw)[k0];
+                sa = sumsq4(a.x, a.y, a.z, a.w);
+            }
+            if (k1 < K) {
+                b = reinterpret_cast<const float4 *>(raw)[k1];
+                sb = sumsq4(b.x, b.y, b.z, b.w);
+            }
+            float2 *dst = tab + (size_t)(pr >> 2) * (VQ_ROWS * 4) + (pr & 3);
+            dst[0] = make_float2(a.x, b.x);
+            dst[4] = make_float2(a.y, b.y);
+            dst[8] = make_float2(a.z, b.z);
+            dst[12] = make_float2(a.w, b.w);
+            dst[16] = make_float2(sa, sb);
+        }
+        }
+        __syncthreads();
+        VQ_STAMP(2);
+        // ---- classify + compact
+        for (int t0 = 0; t0 < ntok; t0 += VQ_THREADS) {
+            const int t = t0 + tid;
+            bool leader = false;
+            if (t < ntok) {
+                const int sl = t / SC, r = t - sl * SC;
+                const int ly = r / C, lx = r - ly * C;
+                if (s_sy[sl] + ly < h && s_sx[sl] + lx < w) {
+                    const uint4 v = reinterpret_cast<const uint4 *>(zs)[t];
+                    int ld = t;
+                    const int t4 = sl * SC + (lx & ~3);  // a strip is one row of 4x4 blocks
+                    if (t4 != t) {
+                        const uint4 u = reinterpret_cast<const uint4 *>(zs)[t4];
+                        if (u.x == v.x && u.y == v.y && u.z == v.z && u.w == v.w) ld = t4;
+                    }
+                    if (ld == t) {
+                        const int t2 = sl * SC + (ly & ~1) * C + (lx & ~1);
+                        if (t2 != t) {
+                            const uint4 u = reinterpret_cast<const uint4 *>(zs)[t2];
+                            if (u.x == v.x && u.y == v.y && u.z == v.z && u.w == v.w) ld = t2;
+                        }
+                    }
+                    leader = ld == t;
+                    lead[t] = (uint16_t)ld;
+                    if (leader) best[t] = ~0ull;
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, leader);
+            int base = 0;
+            if (lane == 0 && m) base = atomicAdd(&s_count, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (leader) list[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)t;  // order is irrelevant to the result
+        }
+        __syncthreads();
+        VQ_STAMP(3);
+        // ---- search: units = (64 leaders) x (chunk range), round-robin over the warps
+        const int L = s_count;
+        const int groups = (L + 32 * VQ_T - 1) / (32 * VQ_T);
+        // (group, chunk) items are dealt to the warps as contiguous, equally long ranges: a warp
+        // works on at most two groups and every warp gets the same number of chunks
+        const int total_items = groups * nchunks;
+        const int per_warp = (total_items + VQ_WARPS - 1) / VQ_WARPS;
+        int u = warp * per_warp;
+        const int u_end = min(total_items, u + per_warp);
+        while (u < u_end) {
+            const int g = u / nchunks;
+            const int c_begin = u - g * nchunks;
+            const int c_end = min(nchunks, c_begin + (u_end - u));
+            u += c_end - c_begin;
+            int tok[VQ_T];
+            float zf[VQ_T][4], z2[VQ_T];
+            u64 zd[VQ_T][4], zsum[VQ_T];
+            float bestd[VQ_T];
+            int bestc[VQ_T];
+#pragma unroll
+            for (int t = 0; t < VQ_T; ++t) {
+                const int li = g * (32 * VQ_T) + t * 32 + lane;
+                tok[t] = li < L ? (int)list[li] : -1;
+                const float4 v = tok[t] >= 0 ? zs[tok[t]] : make_float4(0.f, 0.f, 0.f, 0.f);
+                zf[t][0] = v.x;
+                zf[t][1] = v.y;
+                zf[t][2] = v.z;
+                zf[t][3] = v.w;
+                z2[t] = sumsq4(v.x, v.y, v.z, v.w);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) zd[t][c] = pack2(zf[t][c], zf[t][c]);
+                zsum[t] = pack2(z2[t], z2[t]);
+                bestd[t] = __int_as_float(0x7f800000);
+                bestc[t] = c_begin;
+            }
+            // per token the minimum distance of each chunk
+            for (int c = c_begin; c < c_end; ++c) {
+                float cm[VQ_T];
+#pragma unroll
+                for (int t = 0; t < VQ_T; ++t) cm[t] = __int_as_float(0x7f800000);
+                const ulonglong2 *row = ctab + (size_t)c * (VQ_ROWS * 2);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const ulonglong2 e0 = row[0 + half], e1 = row[2 + half], e2 = row[4 + half], e3 = row[6 + half],
+                                     es = row[8 + half];
+#pragma unroll
+                    for (int t = 0; t < VQ_T; ++t) {
+                        u64 a = mul2(zd[t][0], e0.x);
+                        u64 b2 = mul2(zd[t][0], e0.y);
+                        a = fma2(zd[t][1], e1.x, a);
+                        b2 = fma2(zd[t][1], e1.y, b2);
+                        a = fma2(zd[t][2], e2.x, a);
+                        b2 = fma2(zd[t][2], e2.y, b2);
+                        a = fma2(zd[t][3], e3.x, a);
+                        b2 = fma2(zd[t][3], e3.y, b2);
+                        const u64 sa = add2(zsum[t], es.x);
+                        const u64 sb = add2(zsum[t], es.y);
+                        a = fma2(a, minus2, sa);
+                        b2 = fma2(b2, minus2, sb);
+                        float a0, a1, b0, b1;
+                        unpack2(a, a0, a1);
+                        unpack2(b2, b0, b1);
+                        cm[t] = min3(cm[t], a0, a1);
+                        cm[t] = min3(cm[t], b0, b1);
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < VQ_T; ++t)
+                    if (cm[t] < bestd[t]) {
+                        bestd[t] = cm[t];
+                        bestc[t] = c;
+                    }
+            }
+            // the first code of the winning chunk that attains the minimum; publish
+#pragma unroll
+            for (int t = 0; t < VQ_T; ++t) {
+                if (tok[t] < 0 || !(bestd[t] < __int_as_float(0x7f800000))) continue;
+                const float *rowf = ftab + (size_t)bestc[t] * (VQ_ROWS * 8);
+                int k = 0;
+#pragma unroll
+                for (int j = VQ_CHUNK - 1; j >= 0; --j) {
+                    float dot = __fmul_rn(zf[t][0], rowf[j]);
+                    dot = __fmaf_rn(zf[t][1], rowf[8 + j], dot);
+                    dot = __fmaf_rn(zf[t][2], rowf[16 + j], dot);
+                    dot = __fmaf_rn(zf[t][3], rowf[24 + j], dot);
+                    const float d = __fmaf_rn(dot, -2.f, __fadd_rn(z2[t], rowf[32 + j]));
+                    if (d == bestd[t]) k = j;
+                }
+                const u64 key = ((u64)order_key(bestd[t]) << 32) | (uint32_t)(bestc[t] * VQ_CHUNK + k);
+                atomicMin(&best[tok[t]], key);
+            }
+        }
+        __syncthreads();
+        VQ_STAMP(4);
+        // ---- finalize
+        for (int t = tid; t < ntok; t += VQ_THREADS) {
+            const int sl = t / SC, r = t - sl * SC;
+            const int ly = r / C, lx = r - ly * C;
+            const int gy = s_sy[sl] + ly, gx = s_sx[sl] + lx, b = s_sb[sl];
+            if (gy >= h || gx >= w) continue;
+            const u64 key = best[lead[t]];
+            const int k = key == ~0ull ? 0 : (int)(uint32_t)key;  // every distance NaN / inf: torch.argmin gives 0 only
+                                                                  // if all are equal; see tests (inputs are finite)
+            const int64_t p = (int64_t)gy * w + gx;
+            idx_out[(int64_t)b * plane + p] = k;
+            if (zq_out || sqerr_out) {
+                const float4 e = reinterpret_cast<const float4 *>(raw)[k];
+                const float4 zv = zs[t];
+                const float d0 = __fsub_rn(e.x, zv.x), d1 = __fsub_rn(e.y, zv.y), d2 = __fsub_rn(e.z, zv.z), d3 = __fsub_rn(e.w, zv.w);
+                if (zq_out) {
+                    float *q = zq_out + (int64_t)b * 4 * plane + p;
+                    q[0] = __fadd_rn(zv.x, d0);
+                    q[plane] = __fadd_rn(zv.y, d1);
+                    q[2 * plane] = __fadd_rn(zv.z, d2);
+                    q[3 * plane] = __fadd_rn(zv.w, d3);
+                }
+                float acc = __fmul_rn(d0, d0);
+                acc = __fmaf_rn(d1, d1, acc);
+                acc = __fmaf_rn(d2, d2, acc);
+                acc = __fmaf_rn(d3, d3, acc);
+                sq += (double)acc;
+            }
         }
     }
+    VQ_STAMP(5);
     if (!sqerr_out) return;
-    // deterministic reduction: warp shuffle -> block -> per-block partial -> last block sums in order
+    // deterministic reduction: warp shuffle -> CTA -> per-CTA partial -> the last CTA sums them in order
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = sq;
+    if (lane == 0) s_red[warp] = sq;
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         double tot = 0.0;
-        for (int i = 0; i < VQ_THREADS / 32; ++i) tot += s_red[i];
+        for (int i = 0; i < VQ_WARPS; ++i) tot += s_red[i];
         partials[blockIdx.x] = tot;
         __threadfence();
-        s_last = (atomicAdd(&counters[1], 1) == (int)gridDim.x - 1);
+        s_last = (atomicAdd(&counters[0], 1) == (int)gridDim.x - 1);
     }
     __syncthreads();
     if (s_last) {
         __threadfence();
         double tot = 0.0;
-        for (int i = threadIdx.x; i < (int)gridDim.x; i += VQ_THREADS) tot += __ldcg(&partials[i]);
-        // fixed tree: thread-strided partial sums, then the same shuffle/serial order as above
+        for (int i = tid; i < (int)gridDim.x; i += VQ_THREADS) tot += __ldcg(&partials[i]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = tot;
+        if (lane == 0) s_red[warp] = tot;
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (tid == 0) {
             double all = 0.0;
-            for (int i = 0; i < VQ_THREADS / 32; ++i) all += s_red[i];
+            for (int i = 0; i < VQ_WARPS; ++i) all += s_red[i];
             *sqerr_out = all;
         }
     }
+    VQ_STAMP(6);
 }
 
 __global__ void vq_count_kernel(const int64_t *__restrict__ idx, int64_t n, float *__restrict__ counters, int K)
@@ -369,45 +441,13 @@ __global__ void vq_count_kernel(const int64_t *__restrict__ idx, int64_t n, floa
     if (k >= 0 && k < K) atomicAdd(&counters[k], 1.0f);
 }
 
-struct VqCarve {
-    int32_t *counters;  // [0] leader count, [1] finalize ticket   (64 bytes reserved)
-    int32_t *leader_of;
-    int32_t *list;
-    u64 *best;
-    double *partials;
-    size_t bytes;
-};
-
-VqCarve carve(void *ws, int64_t n)
-{
-    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
-    VqCarve c{};
-    unsigned char *p = static_cast<unsigned char *>(ws);
-    size_t o = 0;
-    c.counters = reinterpret_cast<int32_t *>(p + o);
-    o += 256;
-    c.leader_of = reinterpret_cast<int32_t *>(p + o);
-    o += up((size_t)n * 4);
-    c.list = reinterpret_cast<int32_t *>(p + o);
-    o += up((size_t)n * 4);
-    c.best = reinterpret_cast<u64 *>(p + o);
-    o += up((size_t)n * 8);
-    c.partials = reinterpret_cast<double *>(p + o);
-    o += up((size_t)((n + VQ_THREADS - 1) / VQ_THREADS) * 8);
-    c.bytes = o;
-    return c;
-}
-
 }  // namespace
 }  // namespace cgic
 
 using namespace cgic;
 
-extern "C" size_t cgic_vq_workspace_bytes(int64_t n_tokens)
-{
-    if (n_tokens <= 0) return 256;
-    return carve(nullptr, n_tokens).bytes;
-}
+// workspace: [64 bytes of counters][one double per CTA]; sized for any grid this library launches
+extern "C" size_t cgic_vq_workspace_bytes(int64_t) { return 256 + 8 * 4096; }
 
 extern "C" int cgic_vq_assign(const float *z, int B, int h, int w, const float *codebook, int K, int64_t *idx_out,
                               float *zq_out, double *sqerr_out, void *workspace, size_t workspace_bytes,
@@ -419,44 +459,35 @@ extern "C" int cgic_vq_assign(const float *z, int B, int h, int w, const float *
     CGIC_REQUIRE((reinterpret_cast<uintptr_t>(codebook) & 15) == 0, CGIC_EINVAL, "cgic_vq_assign: codebook must be 16-byte aligned");
     const int64_t n = (int64_t)B * h * w;
     CGIC_REQUIRE(n < (int64_t)1 << 31, CGIC_EINVAL, "cgic_vq_assign: %lld tokens exceed 2^31", (long long)n);
+    cudaStream_t stream = as_stream(stream_);
     if (n == 0) {
-        if (sqerr_out) CGIC_CUDA_CHECK(cudaMemsetAsync(sqerr_out, 0, sizeof(double), as_stream(stream_)));
+        if (sqerr_out) CGIC_CUDA_CHECK(cudaMemsetAsync(sqerr_out, 0, sizeof(double), stream));
         return CGIC_OK;
     }
-    const VqCarve c = carve(workspace, n);
-    CGIC_REQUIRE(workspace_bytes >= c.bytes, CGIC_ESPACE, "cgic_vq_assign: workspace %zu < %zu bytes", workspace_bytes, c.bytes);
-    cudaStream_t stream = as_stream(stream_);
+    CGIC_REQUIRE(workspace_bytes >= cgic_vq_workspace_bytes(n), CGIC_ESPACE, "cgic_vq_assign: workspace %zu < %zu bytes",
+                 workspace_bytes, cgic_vq_workspace_bytes(n));
+    int32_t *counters = static_cast<int32_t *>(workspace);
+    double *partials = reinterpret_cast<double *>(static_cast<unsigned char *>(workspace) + 256);
 
     static int n_sm = 0;
     if (!n_sm) {
-        int dev = 0;
+        int dev = 0, sm = 0;
         CGIC_CUDA_CHECK(cudaGetDevice(&dev));
-        CGIC_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        CGIC_CUDA_CHECK(cudaFuncSetAttribute(vq_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VQ_MAX_K * 36));
+        CGIC_CUDA_CHECK(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
+        CGIC_CUDA_CHECK(cudaFuncSetAttribute(vq_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             VQ_MAX_K * 36 + VQ_TILE * (16 + 8 + 2 + 2)));
+        n_sm = sm;
     }
     const int Kpad = (K + VQ_CHUNK - 1) / VQ_CHUNK * VQ_CHUNK;
-    const size_t smem = (size_t)Kpad * 16 + (size_t)(Kpad / VQ_CHUNK) * VQ_ROWS * 4 * sizeof(float2);
-    const int blocks = (int)((n + VQ_THREADS - 1) / VQ_THREADS);
-
-    CGIC_CUDA_CHECK(cudaMemsetAsync(c.counters, 0, 64, stream));
+    const size_t smem = (size_t)Kpad * 36 + (size_t)VQ_TILE * (16 + 8 + 2 + 2);
+    const VqTiles tl = make_tiles(B, h, w);
+    // persistent grid: one CTA per SM, never more CTAs than strips
+    const int grid = (int)(tl.n_strips < (int64_t)n_sm ? tl.n_strips : (int64_t)n_sm);
+    if (sqerr_out) CGIC_CUDA_CHECK(cudaMemsetAsync(counters, 0, 64, stream));
     {
-        CGIC_PROF("vq_classify_kernel", stream);
-        vq_classify_kernel<<<blocks, VQ_THREADS, 0, stream>>>(z, n, h, w, c.leader_of, c.list, c.best, c.counters);
-    }
-    CGIC_LAUNCH_CHECK();
-    // persistent grid: 2 CTAs per SM, never more CTAs than there is work for in the worst case
-    const int64_t max_units = ((n + 32 * VQ_T - 1) / (32 * VQ_T)) * (Kpad / VQ_CHUNK);
-    const int64_t want = (max_units + VQ_THREADS / 32 - 1) / (VQ_THREADS / 32);
-    const int grid = (int)(want < 2 * (int64_t)n_sm ? (want < 1 ? 1 : want) : 2 * (int64_t)n_sm);
-    {
-        CGIC_PROF("vq_search_kernel", stream);
-        vq_search_kernel<<<grid, VQ_THREADS, smem, stream>>>(z, h, w, codebook, K, Kpad, c.list, c.counters, c.best);
-    }
-    CGIC_LAUNCH_CHECK();
-    {
-        CGIC_PROF("vq_finalize_kernel", stream);
-        vq_finalize_kernel<<<blocks, VQ_THREADS, 0, stream>>>(z, n, h, w, codebook, c.leader_of, c.best, idx_out, zq_out,
-                                                              c.partials, c.counters, sqerr_out);
+        CGIC_PROF("vq_fused_kernel", stream);
+        vq_fused_kernel<<<grid, VQ_THREADS, smem, stream>>>(z, B, h, w, tl, codebook, K, Kpad, idx_out, zq_out, partials, counters,
+                                                            sqerr_out);
     }
     CGIC_LAUNCH_CHECK();
     return CGIC_OK;
