@@ -14,8 +14,9 @@ over ranks with no data-path collective, one all-reduce of {bytes, pixels, sqerr
 
     value     device-resident: inputs already in HBM, each step timed by a CUDA-event pair on the
               launching stream, L2 flushed (256 MiB memset) between steps outside the pairs.
-    e2e       the host-buffer C-ABI call (cgic_session_compress_host + _decompress_host): pinned
-              host inputs -> H2D -> kernels -> D2H of every result, wall clock, per step.
+    e2e       the host-buffer C-ABI call cgic_session_roundtrip_host (= CGIC.compress, model.py:206-401:
+              encode + pack + unpack + re-assembly): pinned host inputs -> H2D -> kernels -> D2H of
+              every result (streams, sizes, decoded indices / masks / latents), wall clock, per step.
     roofline  dominant kernel, its duration measured live with the library's per-launch CUDA
               events (cgic_prof_*), against the algorithmic bytes of DESIGN.md and the measured
               HBM peak of MEASURED_PEAKS.json.
@@ -116,6 +117,7 @@ def parse_args():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-parts", type=int, default=0, help="pipeline depth of the host-buffer session (0 = library default)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -312,19 +314,23 @@ def run_b200(args):
 
     # ---- e2e: host buffers through the C-ABI session (H2D + kernels + D2H inside the timed region)
     sess = cg.ops.Session(B, h, w, mode, table, cbk)
+    if args.e2e_parts:
+        sess.set_pipeline(args.e2e_parts)
     zh = z.cpu().pin_memory()
     mh = [t_.cpu().pin_memory() for t_ in (mc, mm, mf)]
     for _ in range(3):
         by, sz = sess.compress(zh, *mh)
         out = sess.decompress(by, sz)
     assert torch.equal(sz, sizes_first) and torch.equal(out[3].view(-1), idx.cpu()) and int(out[5].abs().sum()) == 0
+    for _ in range(3):
+        rt = sess.roundtrip(zh, *mh)
+    assert torch.equal(rt[1], sizes_first) and torch.equal(rt[5].view(-1), idx.cpu()) and int(rt[7].abs().sum()) == 0
     n_e2e = max(10, min(args.steps, 100))
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for _ in range(n_e2e):
-        by, sz = sess.compress(zh, *mh)
-        sess.decompress(by, sz)
+        sess.roundtrip(zh, *mh)           # = CGIC.compress: encode + pack + unpack + re-assembly, host in / host out
     e2e_s = time.perf_counter() - t0
     t_end = time.time()
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -333,7 +339,7 @@ def run_b200(args):
     e2e_s = float(t.item())
     n4, n8, n16 = B * h * w, B * h * w // 4, B * h * w // 16
     blob = B * sess.image_stride
-    h2d = n4 * 16 + (n4 + n8 + n16) * 4 + blob + B * 20
+    h2d = n4 * 16 + (n4 + n8 + n16) * 4
     d2h = blob + B * 20 + n4 * 8 + n4 * 16 + (n4 + n8 + n16) * 8 + B * 4
     sess.close()
     clocks = sampler.stop(t_begin, t_end) if sampler else None

@@ -53,8 +53,10 @@ _SIGNATURES = {
     "cgic_session_create": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, C.POINTER(c_void_p)]),
     "cgic_session_destroy": (None, [c_void_p]),
     "cgic_session_image_stride": (c_int64, [c_void_p]),
+    "cgic_session_set_pipeline": (c_int, [c_void_p, c_int]),
     "cgic_session_compress_host": (c_int, [c_void_p] * 10),
     "cgic_session_decompress_host": (c_int, [c_void_p] * 9),
+    "cgic_session_roundtrip_host": (c_int, [c_void_p] * 16),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -1,7 +1,9 @@
 // Host-buffer session: what a reference-side plugin calls per batch when its tensors live in
-// host memory.  Device buffers, workspaces, the stream and the uploaded codebook are created
-// once; compress / decompress only enqueue H2D copies, the kernels and D2H copies, then
-// synchronise.  Mirrors CGIC.compress (CGIC/models/model.py:206-401) minus the CNNs:
+// host memory.  Device buffers, workspaces, streams and the uploaded codebook are created once;
+// compress / decompress only enqueue H2D copies, the kernels and D2H copies, then synchronise.
+// The batch is cut into `parts` contiguous image ranges, each on its own stream, so that the
+// H2D copy of one part, the kernels of the previous one and the D2H copy of the one before
+// overlap (PCIe is full duplex and the copy engines run beside the SMs).  Mirrors CGIC.compress (CGIC/models/model.py:206-401) minus the CNNs:
 //   compress   = VectorQuantize2.forward (a1) + selection (a7) + 5-stream pack (a9/a11/a12)
 //   decompress = decompress_string x5 (a10/a11) + re-assembly (a13) + codebook gather (a14)
 #include <new>
@@ -12,15 +14,19 @@ struct cgic_session {
     int B = 0, h = 0, w = 0, mode = 0, K = 0;
     const cgic_table *table = nullptr;
     cgic::PackLayout L{};
-    cudaStream_t stream = nullptr;
+    static constexpr int MAX_PARTS = 8;
+    int parts = 1;
+    cudaStream_t streams[MAX_PARTS] = {};
+    cudaEvent_t packed = nullptr;  // roundtrip: pack finished, the decode stream may start
     unsigned char *arena = nullptr;
     // carved device buffers
     float *codebook = nullptr, *z = nullptr, *zq = nullptr, *quant = nullptr;
     int32_t *mc = nullptr, *mm = nullptr, *mf = nullptr, *sizes = nullptr, *status = nullptr;
     int64_t *idx = nullptr, *dmc = nullptr, *dmm = nullptr, *dmf = nullptr, *ind = nullptr;
     uint8_t *bytes = nullptr;
-    double *sqerr = nullptr;
-    void *ws_vq = nullptr, *ws_un = nullptr;
+    double *sqerr = nullptr;  // [MAX_PARTS]
+    double *sqerr_host = nullptr;  // pinned, [MAX_PARTS]
+    unsigned char *ws_vq = nullptr, *ws_un = nullptr;  // MAX_PARTS slices each
     size_t ws_vq_bytes = 0, ws_un_bytes = 0;
 };
 
@@ -55,10 +61,12 @@ extern "C" int cgic_session_create(int B, int h, int w, int mode, const cgic_tab
     const size_t o_cb = take((size_t)K * 16), o_z = take(n4 * 16), o_zq = take(n4 * 16), o_quant = take(n4 * 16),
                  o_mc = take(n16 * 4), o_mm = take(n8 * 4), o_mf = take(n4 * 4), o_sizes = take((size_t)B * 5 * 4),
                  o_status = take((size_t)B * 4), o_idx = take(n4 * 8), o_dmc = take(n16 * 8), o_dmm = take(n8 * 8),
-                 o_dmf = take(n4 * 8), o_ind = take(n4 * 8), o_bytes = take((size_t)B * s->L.stride), o_sq = take(8),
-                 o_wv = take(s->ws_vq_bytes), o_wu = take(s->ws_un_bytes);
+                 o_dmf = take(n4 * 8), o_ind = take(n4 * 8), o_bytes = take((size_t)B * s->L.stride), o_sq = take(8 * cgic_session::MAX_PARTS),
+                 o_wv = take(s->ws_vq_bytes * cgic_session::MAX_PARTS), o_wu = take(s->ws_un_bytes * cgic_session::MAX_PARTS);
     cudaError_t e = cudaMalloc(&s->arena, o);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < cgic_session::MAX_PARTS && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&s->streams[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->packed, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMallocHost(&s->sqerr_host, 8 * cgic_session::MAX_PARTS);
     if (e == cudaSuccess) e = cudaMemcpy(s->arena + o_cb, codebook_host, (size_t)K * 16, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         cgic::set_error("cgic_session_create: %s", cudaGetErrorString(e));
@@ -84,6 +92,9 @@ extern "C" int cgic_session_create(int B, int h, int w, int mode, const cgic_tab
     s->sqerr = reinterpret_cast<double *>(a + o_sq);
     s->ws_vq = a + o_wv;
     s->ws_un = a + o_wu;
+    s->ws_vq_bytes = (s->ws_vq_bytes + 255) / 256 * 256;
+    s->ws_un_bytes = (s->ws_un_bytes + 255) / 256 * 256;
+    s->parts = 1;  // measured on B200 + PCIe gen5: per-copy latency (5-8 us) outweighs the overlap for batches of a few MB
     *out = s;
     return CGIC_OK;
 }
@@ -91,35 +102,58 @@ extern "C" int cgic_session_create(int B, int h, int w, int mode, const cgic_tab
 extern "C" void cgic_session_destroy(cgic_session *s)
 {
     if (!s) return;
-    if (s->stream) cudaStreamDestroy(s->stream);
+    for (cudaStream_t st : s->streams)
+        if (st) cudaStreamDestroy(st);
+    if (s->packed) cudaEventDestroy(s->packed);
     if (s->arena) cudaFree(s->arena);
+    if (s->sqerr_host) cudaFreeHost(s->sqerr_host);
     delete s;
 }
 
 extern "C" int64_t cgic_session_image_stride(const cgic_session *s) { return s ? s->L.stride : CGIC_EINVAL; }
+
+extern "C" int cgic_session_set_pipeline(cgic_session *s, int parts)
+{
+    CGIC_REQUIRE(s && parts >= 1 && parts <= cgic_session::MAX_PARTS, CGIC_EINVAL, "cgic_session_set_pipeline: parts must be in [1, %d]",
+                 cgic_session::MAX_PARTS);
+    s->parts = parts < s->B ? parts : s->B;
+    return CGIC_OK;
+}
 
 extern "C" int cgic_session_compress_host(cgic_session *s, const float *z, const int32_t *m_c, const int32_t *m_m,
                                           const int32_t *m_f, uint8_t *bytes_out, int32_t *sizes_out, int64_t *idx_out,
                                           float *zq_out, double *sqerr_out)
 {
     CGIC_REQUIRE(s && z && m_c && m_m && m_f && bytes_out && sizes_out, CGIC_EINVAL, "cgic_session_compress_host: null argument");
-    const size_t n4 = (size_t)s->B * s->h * s->w, n8 = n4 / 4, n16 = n4 / 16;
-    cudaStream_t st = s->stream;
-    CGIC_CUDA_CHECK(cudaMemcpyAsync(s->z, z, n4 * 16, cudaMemcpyHostToDevice, st));
-    CGIC_CUDA_CHECK(cudaMemcpyAsync(s->mc, m_c, n16 * 4, cudaMemcpyHostToDevice, st));
-    CGIC_CUDA_CHECK(cudaMemcpyAsync(s->mm, m_m, n8 * 4, cudaMemcpyHostToDevice, st));
-    CGIC_CUDA_CHECK(cudaMemcpyAsync(s->mf, m_f, n4 * 4, cudaMemcpyHostToDevice, st));
-    int rc = cgic_vq_assign(s->z, s->B, s->h, s->w, s->codebook, s->K, s->idx, zq_out ? s->zq : nullptr,
-                            sqerr_out ? s->sqerr : nullptr, s->ws_vq, s->ws_vq_bytes, st);
-    if (rc) return rc;
-    rc = cgic_pack(s->idx, s->mc, s->mm, s->mf, s->B, s->h, s->w, s->mode, s->table, s->bytes, s->sizes, st);
-    if (rc) return rc;
-    CGIC_CUDA_CHECK(cudaMemcpyAsync(bytes_out, s->bytes, (size_t)s->B * s->L.stride, cudaMemcpyDeviceToHost, st));
-    CGIC_CUDA_CHECK(cudaMemcpyAsync(sizes_out, s->sizes, (size_t)s->B * 5 * 4, cudaMemcpyDeviceToHost, st));
-    if (idx_out) CGIC_CUDA_CHECK(cudaMemcpyAsync(idx_out, s->idx, n4 * 8, cudaMemcpyDeviceToHost, st));
-    if (zq_out) CGIC_CUDA_CHECK(cudaMemcpyAsync(zq_out, s->zq, n4 * 16, cudaMemcpyDeviceToHost, st));
-    if (sqerr_out) CGIC_CUDA_CHECK(cudaMemcpyAsync(sqerr_out, s->sqerr, 8, cudaMemcpyDeviceToHost, st));
-    CGIC_CUDA_CHECK(cudaStreamSynchronize(st));
+    const size_t i4 = (size_t)s->h * s->w, i8 = i4 / 4, i16 = i4 / 16;  // cells per image and level
+    const int P = s->parts;
+    for (int p = 0; p < P; ++p) {
+        const int b0 = (int)((int64_t)s->B * p / P), nb = (int)((int64_t)s->B * (p + 1) / P) - b0;
+        if (nb == 0) continue;
+        cudaStream_t st = s->streams[p];
+        CGIC_CUDA_CHECK(cudaMemcpyAsync(s->z + b0 * i4 * 4, z + b0 * i4 * 4, nb * i4 * 16, cudaMemcpyHostToDevice, st));
+        CGIC_CUDA_CHECK(cudaMemcpyAsync(s->mc + b0 * i16, m_c + b0 * i16, nb * i16 * 4, cudaMemcpyHostToDevice, st));
+        CGIC_CUDA_CHECK(cudaMemcpyAsync(s->mm + b0 * i8, m_m + b0 * i8, nb * i8 * 4, cudaMemcpyHostToDevice, st));
+        CGIC_CUDA_CHECK(cudaMemcpyAsync(s->mf + b0 * i4, m_f + b0 * i4, nb * i4 * 4, cudaMemcpyHostToDevice, st));
+        int rc = cgic_vq_assign(s->z + b0 * i4 * 4, nb, s->h, s->w, s->codebook, s->K, s->idx + b0 * i4, zq_out ? s->zq + b0 * i4 * 4 : nullptr,
+                                sqerr_out ? s->sqerr + p : nullptr, s->ws_vq + p * s->ws_vq_bytes, s->ws_vq_bytes, st);
+        if (rc) return rc;
+        rc = cgic_pack(s->idx + b0 * i4, s->mc + b0 * i16, s->mm + b0 * i8, s->mf + b0 * i4, nb, s->h, s->w, s->mode, s->table,
+                       s->bytes + (size_t)b0 * s->L.stride, s->sizes + b0 * 5, st);
+        if (rc) return rc;
+        CGIC_CUDA_CHECK(cudaMemcpyAsync(bytes_out + (size_t)b0 * s->L.stride, s->bytes + (size_t)b0 * s->L.stride, (size_t)nb * s->L.stride,
+                                        cudaMemcpyDeviceToHost, st));
+        CGIC_CUDA_CHECK(cudaMemcpyAsync(sizes_out + b0 * 5, s->sizes + b0 * 5, (size_t)nb * 5 * 4, cudaMemcpyDeviceToHost, st));
+        if (idx_out) CGIC_CUDA_CHECK(cudaMemcpyAsync(idx_out + b0 * i4, s->idx + b0 * i4, nb * i4 * 8, cudaMemcpyDeviceToHost, st));
+        if (zq_out) CGIC_CUDA_CHECK(cudaMemcpyAsync(zq_out + b0 * i4 * 4, s->zq + b0 * i4 * 4, nb * i4 * 16, cudaMemcpyDeviceToHost, st));
+        if (sqerr_out) CGIC_CUDA_CHECK(cudaMemcpyAsync(s->sqerr_host + p, s->sqerr + p, 8, cudaMemcpyDeviceToHost, st));
+    }
+    for (int p = 0; p < P; ++p) CGIC_CUDA_CHECK(cudaStreamSynchronize(s->streams[p]));
+    if (sqerr_out) {
+        double tot = 0.0;
+        for (int p = 0; p < P; ++p) tot += s->sqerr_host[p];  // fixed order: deterministic
+        *sqerr_out = tot;
+    }
     return CGIC_OK;
 }
 
@@ -128,19 +162,71 @@ extern "C" int cgic_session_decompress_host(cgic_session *s, const uint8_t *byte
                                             int32_t *status_out)
 {
     CGIC_REQUIRE(s && bytes && sizes && ind_out && status_out, CGIC_EINVAL, "cgic_session_decompress_host: null argument");
+    const size_t i4 = (size_t)s->h * s->w, i8 = i4 / 4, i16 = i4 / 16;
+    const int P = s->parts;
+    for (int p = 0; p < P; ++p) {
+        const int b0 = (int)((int64_t)s->B * p / P), nb = (int)((int64_t)s->B * (p + 1) / P) - b0;
+        if (nb == 0) continue;
+        cudaStream_t st = s->streams[p];
+        CGIC_CUDA_CHECK(cudaMemcpyAsync(s->bytes + (size_t)b0 * s->L.stride, bytes + (size_t)b0 * s->L.stride, (size_t)nb * s->L.stride,
+                                        cudaMemcpyHostToDevice, st));
+        CGIC_CUDA_CHECK(cudaMemcpyAsync(s->sizes + b0 * 5, sizes + b0 * 5, (size_t)nb * 5 * 4, cudaMemcpyHostToDevice, st));
+        int rc = cgic_unpack(s->bytes + (size_t)b0 * s->L.stride, s->sizes + b0 * 5, nb, s->h, s->w, s->mode, s->table, s->codebook,
+                             s->dmc + b0 * i16, s->dmm + b0 * i8, s->dmf + b0 * i4, s->ind + b0 * i4,
+                             quant_out ? s->quant + b0 * i4 * 4 : nullptr, s->status + b0, s->ws_un + p * s->ws_un_bytes, s->ws_un_bytes, st);
+        if (rc) return rc;
+        CGIC_CUDA_CHECK(cudaMemcpyAsync(ind_out + b0 * i4, s->ind + b0 * i4, nb * i4 * 8, cudaMemcpyDeviceToHost, st));
+        if (quant_out) CGIC_CUDA_CHECK(cudaMemcpyAsync(quant_out + b0 * i4 * 4, s->quant + b0 * i4 * 4, nb * i4 * 16, cudaMemcpyDeviceToHost, st));
+        if (mc_out) CGIC_CUDA_CHECK(cudaMemcpyAsync(mc_out + b0 * i16, s->dmc + b0 * i16, nb * i16 * 8, cudaMemcpyDeviceToHost, st));
+        if (mm_out) CGIC_CUDA_CHECK(cudaMemcpyAsync(mm_out + b0 * i8, s->dmm + b0 * i8, nb * i8 * 8, cudaMemcpyDeviceToHost, st));
+        if (mf_out) CGIC_CUDA_CHECK(cudaMemcpyAsync(mf_out + b0 * i4, s->dmf + b0 * i4, nb * i4 * 8, cudaMemcpyDeviceToHost, st));
+        CGIC_CUDA_CHECK(cudaMemcpyAsync(status_out + b0, s->status + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+    }
+    for (int p = 0; p < P; ++p) CGIC_CUDA_CHECK(cudaStreamSynchronize(s->streams[p]));
+    return CGIC_OK;
+}
+
+// CGIC.compress (model.py:206-401) in one call: encode + pack, then unpack + re-assembly + gather
+// from the device-resident streams.  Stream 0 carries H2D -> VQ -> pack -> D2H of the streams,
+// stream 1 waits for pack and carries unpack -> D2H of the decoded tensors, so the two D2H
+// groups and the decode kernels overlap.
+extern "C" int cgic_session_roundtrip_host(cgic_session *s, const float *z, const int32_t *m_c, const int32_t *m_m,
+                                           const int32_t *m_f, uint8_t *bytes_out, int32_t *sizes_out, int64_t *idx_out,
+                                           float *zq_out, double *sqerr_out, int64_t *mc_out, int64_t *mm_out, int64_t *mf_out,
+                                           int64_t *ind_out, float *quant_out, int32_t *status_out)
+{
+    CGIC_REQUIRE(s && z && m_c && m_m && m_f && bytes_out && sizes_out && ind_out && status_out, CGIC_EINVAL,
+                 "cgic_session_roundtrip_host: null argument");
     const size_t n4 = (size_t)s->B * s->h * s->w, n8 = n4 / 4, n16 = n4 / 16;
-    cudaStream_t st = s->stream;
-    CGIC_CUDA_CHECK(cudaMemcpyAsync(s->bytes, bytes, (size_t)s->B * s->L.stride, cudaMemcpyHostToDevice, st));
-    CGIC_CUDA_CHECK(cudaMemcpyAsync(s->sizes, sizes, (size_t)s->B * 5 * 4, cudaMemcpyHostToDevice, st));
-    int rc = cgic_unpack(s->bytes, s->sizes, s->B, s->h, s->w, s->mode, s->table, s->codebook, s->dmc, s->dmm, s->dmf, s->ind,
-                         quant_out ? s->quant : nullptr, s->status, s->ws_un, s->ws_un_bytes, st);
+    cudaStream_t enc = s->streams[0], dec = s->streams[1];
+    CGIC_CUDA_CHECK(cudaMemcpyAsync(s->z, z, n4 * 16, cudaMemcpyHostToDevice, enc));
+    CGIC_CUDA_CHECK(cudaMemcpyAsync(s->mc, m_c, n16 * 4, cudaMemcpyHostToDevice, enc));
+    CGIC_CUDA_CHECK(cudaMemcpyAsync(s->mm, m_m, n8 * 4, cudaMemcpyHostToDevice, enc));
+    CGIC_CUDA_CHECK(cudaMemcpyAsync(s->mf, m_f, n4 * 4, cudaMemcpyHostToDevice, enc));
+    int rc = cgic_vq_assign(s->z, s->B, s->h, s->w, s->codebook, s->K, s->idx, zq_out ? s->zq : nullptr,
+                            sqerr_out ? s->sqerr : nullptr, s->ws_vq, s->ws_vq_bytes, enc);
     if (rc) return rc;
-    CGIC_CUDA_CHECK(cudaMemcpyAsync(ind_out, s->ind, n4 * 8, cudaMemcpyDeviceToHost, st));
-    if (quant_out) CGIC_CUDA_CHECK(cudaMemcpyAsync(quant_out, s->quant, n4 * 16, cudaMemcpyDeviceToHost, st));
-    if (mc_out) CGIC_CUDA_CHECK(cudaMemcpyAsync(mc_out, s->dmc, n16 * 8, cudaMemcpyDeviceToHost, st));
-    if (mm_out) CGIC_CUDA_CHECK(cudaMemcpyAsync(mm_out, s->dmm, n8 * 8, cudaMemcpyDeviceToHost, st));
-    if (mf_out) CGIC_CUDA_CHECK(cudaMemcpyAsync(mf_out, s->dmf, n4 * 8, cudaMemcpyDeviceToHost, st));
-    CGIC_CUDA_CHECK(cudaMemcpyAsync(status_out, s->status, (size_t)s->B * 4, cudaMemcpyDeviceToHost, st));
-    CGIC_CUDA_CHECK(cudaStreamSynchronize(st));
+    rc = cgic_pack(s->idx, s->mc, s->mm, s->mf, s->B, s->h, s->w, s->mode, s->table, s->bytes, s->sizes, enc);
+    if (rc) return rc;
+    CGIC_CUDA_CHECK(cudaEventRecord(s->packed, enc));
+    CGIC_CUDA_CHECK(cudaStreamWaitEvent(dec, s->packed, 0));
+    rc = cgic_unpack(s->bytes, s->sizes, s->B, s->h, s->w, s->mode, s->table, s->codebook, s->dmc, s->dmm, s->dmf, s->ind,
+                     quant_out ? s->quant : nullptr, s->status, s->ws_un, s->ws_un_bytes, dec);
+    if (rc) return rc;
+    // largest transfers first on the decode stream; the encode stream's D2H group runs beside the decode kernels
+    if (quant_out) CGIC_CUDA_CHECK(cudaMemcpyAsync(quant_out, s->quant, n4 * 16, cudaMemcpyDeviceToHost, dec));
+    CGIC_CUDA_CHECK(cudaMemcpyAsync(ind_out, s->ind, n4 * 8, cudaMemcpyDeviceToHost, dec));
+    if (mf_out) CGIC_CUDA_CHECK(cudaMemcpyAsync(mf_out, s->dmf, n4 * 8, cudaMemcpyDeviceToHost, dec));
+    if (mm_out) CGIC_CUDA_CHECK(cudaMemcpyAsync(mm_out, s->dmm, n8 * 8, cudaMemcpyDeviceToHost, dec));
+    if (mc_out) CGIC_CUDA_CHECK(cudaMemcpyAsync(mc_out, s->dmc, n16 * 8, cudaMemcpyDeviceToHost, dec));
+    CGIC_CUDA_CHECK(cudaMemcpyAsync(status_out, s->status, (size_t)s->B * 4, cudaMemcpyDeviceToHost, dec));
+    CGIC_CUDA_CHECK(cudaMemcpyAsync(bytes_out, s->bytes, (size_t)s->B * s->L.stride, cudaMemcpyDeviceToHost, enc));
+    CGIC_CUDA_CHECK(cudaMemcpyAsync(sizes_out, s->sizes, (size_t)s->B * 5 * 4, cudaMemcpyDeviceToHost, enc));
+    if (idx_out) CGIC_CUDA_CHECK(cudaMemcpyAsync(idx_out, s->idx, n4 * 8, cudaMemcpyDeviceToHost, enc));
+    if (zq_out) CGIC_CUDA_CHECK(cudaMemcpyAsync(zq_out, s->zq, n4 * 16, cudaMemcpyDeviceToHost, enc));
+    if (sqerr_out) CGIC_CUDA_CHECK(cudaMemcpyAsync(s->sqerr_host, s->sqerr, 8, cudaMemcpyDeviceToHost, enc));
+    CGIC_CUDA_CHECK(cudaStreamSynchronize(enc));
+    CGIC_CUDA_CHECK(cudaStreamSynchronize(dec));
+    if (sqerr_out) *sqerr_out = s->sqerr_host[0];
     return CGIC_OK;
 }

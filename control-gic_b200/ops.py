@@ -364,6 +364,11 @@ class Session:
         self.quant = torch.empty(B, 4, h, w, dtype=torch.float32, **pin)
         self.status = torch.empty(B, dtype=torch.int32, **pin)
 
+    def set_pipeline(self, parts: int) -> "Session":
+        """Number of image ranges (streams) the batch is pipelined in; default min(B, 4)."""
+        check(lib().cgic_session_set_pipeline(self._s, int(parts)), "cgic_session_set_pipeline")
+        return self
+
     def close(self):
         s, self._s = getattr(self, "_s", None), None
         if s:
@@ -393,3 +398,14 @@ class Session:
                                                  self.mf.data_ptr(), self.ind.data_ptr(), self.quant.data_ptr(),
                                                  self.status.data_ptr()), "cgic_session_decompress_host")
         return self.mc, self.mm, self.mf, self.ind, self.quant, self.status
+
+    def roundtrip(self, z, m_c, m_m, m_f, want_idx: bool = False):
+        """CGIC.compress in one call: host z + masks -> (bytes, sizes, mc, mm, mf, ind, quant, status[, idx]) (pinned host)."""
+        check(lib().cgic_session_roundtrip_host(self._s, self._host(z, torch.float32, "z"), self._host(m_c, torch.int32, "m_c"),
+                                                self._host(m_m, torch.int32, "m_m"), self._host(m_f, torch.int32, "m_f"),
+                                                self.bytes.data_ptr(), self.sizes.data_ptr(),
+                                                self.idx.data_ptr() if want_idx else None, None, None,
+                                                self.mc.data_ptr(), self.mm.data_ptr(), self.mf.data_ptr(), self.ind.data_ptr(),
+                                                self.quant.data_ptr(), self.status.data_ptr()), "cgic_session_roundtrip_host")
+        out = (self.bytes, self.sizes, self.mc, self.mm, self.mf, self.ind, self.quant, self.status)
+        return out + (self.idx,) if want_idx else out

@@ -177,18 +177,28 @@ CGIC_API int cgic_bits_decode(const uint8_t *bytes, int64_t nbytes, int32_t *val
  * in host memory (pinned for full PCIe speed).  Owns its device buffers, workspace and stream
  * (allocated at create time, never on the hot path).  compress = a1 + a7 + a12 for B
  * independent images; decompress = a13 + a14.  Both copy host->device, run, copy device->host
- * and synchronise before returning.
+ * and synchronise before returning; the batch is processed in `parts` image ranges on separate
+ * streams so that copies in both directions overlap the kernels.
  * ------------------------------------------------------------------------------------------ */
 CGIC_API int cgic_session_create(int B, int h, int w, int mode, const cgic_table *t, const float *codebook_host, int K,
                         cgic_session **out);
 CGIC_API void cgic_session_destroy(cgic_session *s);
 CGIC_API int64_t cgic_session_image_stride(const cgic_session *s);
+/* number of contiguous image ranges the batch is pipelined in (own stream each; default min(B, 4)) */
+CGIC_API int cgic_session_set_pipeline(cgic_session *s, int parts);
 CGIC_API int cgic_session_compress_host(cgic_session *s, const float *z, const int32_t *m_c, const int32_t *m_m,
                                const int32_t *m_f, uint8_t *bytes_out, int32_t *sizes_out, int64_t *idx_out,
                                float *zq_out, double *sqerr_out);
 CGIC_API int cgic_session_decompress_host(cgic_session *s, const uint8_t *bytes, const int32_t *sizes, int64_t *mc_out,
                                  int64_t *mm_out, int64_t *mf_out, int64_t *ind_out, float *quant_out,
                                  int32_t *status_out);
+
+/* CGIC.compress (CGIC/models/model.py:206-401) in one call: compress_host followed by the decode
+ * of the device-resident streams (no H2D of the streams; the two D2H groups overlap). */
+CGIC_API int cgic_session_roundtrip_host(cgic_session *s, const float *z, const int32_t *m_c, const int32_t *m_m,
+                                const int32_t *m_f, uint8_t *bytes_out, int32_t *sizes_out, int64_t *idx_out,
+                                float *zq_out, double *sqerr_out, int64_t *mc_out, int64_t *mm_out, int64_t *mf_out,
+                                int64_t *ind_out, float *quant_out, int32_t *status_out);
 
 #ifdef __cplusplus
 }

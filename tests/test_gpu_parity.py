@@ -418,6 +418,20 @@ def test_session_host_roundtrip(cg, orc):
     mc, mm, mf, ind, quant, status = sess.decompress(by, sz)
     assert int(status.abs().sum()) == 0 and torch.equal(ind.view(-1), idx)
     assert torch.equal(quant, cb.cpu()[idx].view(B, h, w, 4).permute(0, 3, 1, 2))
+    # CGIC.compress in one call (encode + pack + unpack + re-assembly), and with the batch pipelined in 3 parts
+    for parts in (1, 3):
+        sess.set_pipeline(parts)
+        by2, sz2 = (t.clone() for t in sess.compress(zh, *mh))
+        assert torch.equal(sz2, sizes.cpu())
+        rt = sess.roundtrip(zh, *mh, want_idx=True)
+        assert torch.equal(rt[1], sizes.cpu()) and torch.equal(rt[8], idx_d.cpu()) and int(rt[7].abs().sum()) == 0
+        assert torch.equal(rt[5].view(-1), idx_d.cpu()) and torch.equal(rt[6], quant)
+        for got, want in zip(rt[2:5], masks):
+            assert torch.equal(got, want[:, 0].long().cpu())
+        for b in range(B):
+            for s in range(5):
+                assert torch.equal(rt[0][b, offs[s]: offs[s] + sz[b, s]], packed[b, offs[s]: offs[s] + sz[b, s]].cpu())
+                assert torch.equal(by2[b, offs[s]: offs[s] + sz[b, s]], packed[b, offs[s]: offs[s] + sz[b, s]].cpu())
     sess.close()
 
 
