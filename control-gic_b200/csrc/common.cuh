@@ -59,6 +59,31 @@ __host__ __device__ inline bool stream_present(int mode, int s)
 }
 
 #ifdef __CUDACC__
+// ---- programmatic dependent launch (PDL): the hot kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so a kernel may start while its predecessor
+// in the stream is still running.  Contract inside every such kernel: before pdl_wait() it may only
+// touch its parameters, shared memory and IMMUTABLE global tables (the uploaded Huffman table);
+// every read of data a predecessor may have produced and EVERY global write come after pdl_wait(),
+// which returns once the predecessor grid has completed and its memory is visible.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) global -> shared with mbarrier completion ----
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -93,6 +118,31 @@ struct PackLayout {
     int64_t stride;
 };
 PackLayout make_pack_layout(int max_len, int h, int w);
+
+// Phase tracing (debug builds only, -DCGIC_TRACE): thread 0 of a CTA stamps %globaltimer into a
+// per-translation-unit device array; cgic_trace_<unit>() copies it out (profiles/trace_*.py).
+#ifdef CGIC_TRACE
+#define CGIC_TRACE_SLOTS 8
+#define CGIC_TRACE_CTAS 1024
+#define CGIC_TRACE_DECL(unit)                                                                        \
+    static __device__ unsigned long long g_trace_##unit[CGIC_TRACE_CTAS * CGIC_TRACE_SLOTS];         \
+    extern "C" __attribute__((visibility("default"))) int cgic_trace_##unit(unsigned long long *host)  \
+    {                                                                                                \
+        return (int)cudaMemcpyFromSymbol(host, g_trace_##unit, sizeof(g_trace_##unit));              \
+    }
+#define CGIC_STAMP(unit, k)                                                                          \
+    do {                                                                                             \
+        const unsigned cta__ = blockIdx.y * gridDim.x + blockIdx.x;                                  \
+        if (threadIdx.x == 0 && cta__ < CGIC_TRACE_CTAS) {                                           \
+            unsigned long long t__;                                                                  \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                                  \
+            g_trace_##unit[cta__ * CGIC_TRACE_SLOTS + (k)] = t__;                                    \
+        }                                                                                            \
+    } while (0)
+#else
+#define CGIC_TRACE_DECL(unit)
+#define CGIC_STAMP(unit, k)
+#endif
 
 static inline cudaStream_t as_stream(cgic_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

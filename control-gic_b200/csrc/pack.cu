@@ -268,6 +268,7 @@ __device__ __forceinline__ void pack_stream_entry(const PackArgs &a, int s, int 
         s_enc = reinterpret_cast<const uint2 *>(dyn);
         stage = reinterpret_cast<uint32_t *>(dyn + bytes);
     }
+    pdl_wait();  // the code table above is immutable; indices and masks come from the predecessor
     pack_index_stream<ITEMS>(a, s, b, stage, s_enc);
 }
 
@@ -277,13 +278,16 @@ __global__ void __launch_bounds__(PK_THREADS) pack_kernel(const PackArgs a)
     extern __shared__ __align__(128) unsigned char dyn[];
     __shared__ __align__(8) unsigned long long mbar;
     const int s = blockIdx.x, b = blockIdx.y;
+    pdl_launch_dependents();
     if (!stream_present(a.mode, s)) {
+        pdl_wait();
         if (threadIdx.x == 0) a.sizes[b * 5 + s] = 0;
         return;
     }
     if (s < 3) {
         pack_stream_entry<ITEMS>(a, s, b, dyn, &mbar);
     } else {
+        pdl_wait();
         const int lvl = s - 3;  // 0 coarse, 1 medium
         const int div = lvl == 0 ? 4 : 2;
         const int64_t n = (int64_t)(a.h / div) * (a.w / div);
@@ -372,8 +376,8 @@ extern "C" int cgic_pack(const int64_t *idx, const int32_t *m_c, const int32_t *
                  "cgic_pack: (h/4)*(w/4) must be a multiple of 4 for batched masks");
     {
         CGIC_PROF("pack_kernel", as_stream(stream));
-        if (items == 8) pack_kernel<8><<<dim3(5, B), PK_THREADS, smem, as_stream(stream)>>>(a);
-        else pack_kernel<1><<<dim3(5, B), PK_THREADS, smem, as_stream(stream)>>>(a);
+        if (items == 8) CGIC_CUDA_CHECK(launch_pdl(pack_kernel<8>, dim3(5, B), dim3(PK_THREADS), smem, as_stream(stream), a));
+        else CGIC_CUDA_CHECK(launch_pdl(pack_kernel<1>, dim3(5, B), dim3(PK_THREADS), smem, as_stream(stream), a));
     }
     CGIC_LAUNCH_CHECK();
     return CGIC_OK;

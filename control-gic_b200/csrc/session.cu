@@ -67,6 +67,7 @@ extern "C" int cgic_session_create(int B, int h, int w, int mode, const cgic_tab
     for (int i = 0; i < cgic_session::MAX_PARTS && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&s->streams[i], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->packed, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMallocHost(&s->sqerr_host, 8 * cgic_session::MAX_PARTS);
+    if (e == cudaSuccess) e = cudaMemset(s->arena, 0, o);  // workspaces start zeroed (cgic_vq_assign's contract)
     if (e == cudaSuccess) e = cudaMemcpy(s->arena + o_cb, codebook_host, (size_t)K * 16, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         cgic::set_error("cgic_session_create: %s", cudaGetErrorString(e));

@@ -20,6 +20,8 @@
 
 #include "common.cuh"
 
+CGIC_TRACE_DECL(unpack)
+
 namespace cgic {
 namespace {
 
@@ -29,6 +31,7 @@ struct UnpackWs {
     uint16_t *sym;     // [B][n16 + n8 + n4]
     int32_t *count;    // [B][3]  decoded symbols per index stream (-1: empty stream)
     int32_t *pop;      // [B][3]  population of each mask level
+    int32_t *flag;     // [B][5]  per decode CTA: 0 or CGIC_EFORMAT (no zeroing needed: every CTA writes its slot)
     uint32_t *bits;    // [B][nw16 + nw8 + nw4] bitmaps
     uint32_t *prefix;  // same shape: exclusive popcount prefix
     size_t bytes;
@@ -68,6 +71,8 @@ UnpackWs carve_unpack(void *ws, int B, const Geo &g)
     o += up((size_t)B * 3 * 4);
     c.pop = reinterpret_cast<int32_t *>(p + o);
     o += up((size_t)B * 3 * 4);
+    c.flag = reinterpret_cast<int32_t *>(p + o);
+    o += up((size_t)B * 5 * 4);
     c.sym = reinterpret_cast<uint16_t *>(p + o);
     o += up((size_t)B * (g.n16 + g.n8 + g.n4) * 2);
     c.bits = reinterpret_cast<uint32_t *>(p + o);
@@ -280,59 +285,61 @@ constexpr int DEC_MAX_D = 128;       // candidate path handles max_len <= 128 (=
 constexpr int DEC_MAX_CH = 1024;     // subsequences per chunk
 constexpr int DEC_LOOKAHEAD_WORDS = 16;  // staged words past the chunk: straddling codeword + a 64-bit window
 constexpr uint32_t DEC_OFF_STOP = 0xFF;
-constexpr uint32_t DEC_QSTOP = 0x7FFFFFFFu;
 
-// Decode loop over a chunk staged in shared memory as native-endian words (bit 31 of word 0 is
-// stream bit 0 of the chunk; words past the stream are zero).  32-bit positions local to the chunk.
+// Decoding from a chunk staged in shared memory as native-endian words (bit 31 of word 0 is stream
+// bit 0 of the chunk; words past the stream are zero), 32-bit positions local to the chunk.
+// One codeword at bit q: returns (sym << 8) | len.  Branch-free for one- and two-level codes (the
+// second lookup is always issued, on entry 0 when unused); only codes deeper than the second
+// level walk the tree.  LUT2S: the second-level tables are in shared memory too.
+template <bool LUT2S>
+__device__ __forceinline__ uint32_t decode_one(const uint32_t *s_words, uint32_t q, const uint32_t *s_lut, const uint32_t *lut2,
+                                               const DevTable &T, int L)
+{
+    const uint32_t i = q >> 5;
+    const uint32_t win = __funnelshift_l(s_words[i + 1], s_words[i], q & 31);
+    const uint32_t e = s_lut[win >> (32 - L)];
+    const uint32_t f = e & 0xFFu;
+    if (f == 0xFFu) {  // long code (<= DEC_MAX_D bits): walk the tree; bits past the payload read as 0
+        int node = (int)(e >> 8);
+        uint32_t qq = q + L;
+        while (node >= T.K) {
+            const uint32_t bit = (s_words[qq >> 5] >> (31 - (qq & 31))) & 1u;
+            node = __ldg(&T.child[2 * node + (int)bit]);
+            ++qq;
+        }
+        return ((uint32_t)node << 8) | (qq - q);
+    }
+    const bool two = (f & 0x80u) != 0;
+    const uint32_t hgt = two ? (f & 0x7Fu) : 1u;
+    const uint32_t i2 = two ? (e >> 8) + ((win << L) >> (32 - hgt)) : 0u;
+    const uint32_t e2 = LUT2S ? lut2[i2] : __ldg(&lut2[i2]);
+    return two ? e2 + (uint32_t)L : e;  // second-level entries hold the bits used beyond L
+}
+
 // Codewords starting in [q, q_sub_end); returns their number, *q_next = start of the next
-// codeword or DEC_QSTOP once the payload end q_end is reached.
-template <bool WRITE, typename Out>
-__device__ __forceinline__ int decode_range_smem(const uint32_t *s_words, uint32_t q, uint32_t q_sub_end, uint32_t q_end,
-                                                 const uint32_t *s_lut, const uint32_t *lut2, const DevTable &T, Out *out,
-                                                 uint32_t *q_next)
+// codeword or DEC_QSTOP once the payload end q_end is reached (a trailing incomplete code, or one
+// completed only by bits past the payload, is dropped like in the reference).
+template <bool LUT2S, typename Out>
+__device__ __forceinline__ int decode_write_smem(const uint32_t *s_words, uint32_t q, uint32_t q_sub_end, uint32_t q_end,
+                                                 const uint32_t *s_lut, const uint32_t *lut2, const DevTable &T, Out *out)
 {
     int cnt = 0;
     const int L = T.lut_bits;
     while (q < q_sub_end) {
-        const uint32_t i = q >> 5;
-        const uint32_t win = __funnelshift_l(s_words[i + 1], s_words[i], q & 31);
-        const uint32_t e = s_lut[win >> (32 - L)];
-        uint32_t len = e & 0xFFu;
-        uint32_t sym = e >> 8;
-        if (len & 0x80u) {
-            if (len != 0xFFu) {  // second-level table on the next `hgt` bits
-                const uint32_t hgt = len & 0x7Fu;
-                const uint32_t e2 = lut2[sym + ((win << L) >> (32 - hgt))];
-                sym = e2 >> 8;
-                len = L + (e2 & 0xFFu);
-            } else {             // long code (<= DEC_MAX_D bits): walk the tree; bits past the payload read as 0
-                int node = (int)sym;
-                uint32_t qq = q + L;
-                while (node >= T.K) {
-                    const uint32_t bit = (s_words[qq >> 5] >> (31 - (qq & 31))) & 1u;
-                    node = __ldg(&T.child[2 * node + (int)bit]);
-                    ++qq;
-                }
-                sym = (uint32_t)node;
-                len = qq - q;
-            }
-        }
-        if (q + len > q_end) {  // incomplete, or completed only by bits past the payload: dropped, decoding ends
-            q = DEC_QSTOP;
-            break;
-        }
-        if (WRITE) out[cnt] = (Out)sym;
-        ++cnt;
+        const uint32_t r = decode_one<LUT2S>(s_words, q, s_lut, lut2, T, L);
+        const uint32_t len = r & 0xFFu;
+        if (q + len > q_end) break;
+        out[cnt++] = (Out)(r >> 8);
         q += len;
     }
-    *q_next = q;
     return cnt;
 }
 
-// dynamic shared memory behind the staged tables: f[ch * D] (uint16) then the chunk's words
-template <typename Out>
+// dynamic shared memory behind the staged tables: the chunk's words, len8[] (code length at every
+// bit position of the chunk, 0 = no complete codeword before the payload end), f[ch * D] (uint16)
+template <bool LUT2S, typename Out>
 __device__ int decode_stream_cta_cand(const uint8_t *in, int64_t nbytes, const DevTable &T, const uint32_t *s_lut, const uint32_t *lut2,
-                                      uint16_t *s_fn, uint32_t *s_words, int ch, Out *out, int64_t cap)
+                                      uint32_t *s_words, uint8_t *s_len, uint16_t *s_fn, int ch, Out *out, int64_t cap)
 {
     __shared__ uint8_t s_blockfn[32 * DEC_MAX_D];
     __shared__ uint8_t s_blkstart[32];
@@ -345,14 +352,15 @@ __device__ int decode_stream_cta_cand(const uint8_t *in, int64_t nbytes, const D
     int64_t nbits = (nbytes - 1) * 8 - pad;
     if (pad == 0 || nbits < 0) nbits = 0;
     const int64_t q_end_abs = 8 + nbits;  // stream bit coordinates (header byte = bits 0..7)
-    const int D = T.max_len;
+    const int D = T.max_len, L = T.lut_bits;
     const int64_t nsub_total = (nbits + DEC_SUB_BITS - 1) / DEC_SUB_BITS;
-    const int nwords_stage = ch * (DEC_SUB_BITS / 32) + DEC_LOOKAHEAD_WORDS;
     uint32_t start_off = 0;
     int64_t total = 0;
     for (int64_t c0 = 0; c0 < nsub_total && start_off != DEC_OFF_STOP; c0 += ch) {
         const int nsub = (int)min((int64_t)ch, nsub_total - c0);
+        CGIC_STAMP(unpack, 2);
         // ---- stage the chunk: bytes [c0 * 16, ...) of the stream as big-endian words, zero past the end
+        const int npos_words = nsub * (DEC_SUB_BITS / 32) + (DEC_MAX_D + 8 + 31) / 32;  // positions a chain can visit
         {
             const int64_t byte0 = c0 * (DEC_SUB_BITS / 8);
             const int nw = nsub * (DEC_SUB_BITS / 32) + DEC_LOOKAHEAD_WORDS;
@@ -368,21 +376,101 @@ __device__ int decode_stream_cta_cand(const uint8_t *in, int64_t nbytes, const D
                 }
                 s_words[wi] = v;
             }
-            (void)nwords_stage;
         }
         __syncthreads();
         const int64_t rel_end = q_end_abs - c0 * DEC_SUB_BITS;  // payload end, local to the chunk
         const uint32_t q_end = (uint32_t)min(rel_end, (int64_t)(nsub * DEC_SUB_BITS + 8 + DEC_MAX_D + 64));
-        // ---- A: every (subsequence, candidate) pair
-        for (int pair = tid; pair < nsub * D; pair += DEC_THREADS) {
-            const int i = pair / D, c = pair - i * D;
-            const uint32_t sub0 = 8u + (uint32_t)i * DEC_SUB_BITS;
-            uint32_t qn;
-            const int n = decode_range_smem<false, Out>(s_words, sub0 + c, sub0 + DEC_SUB_BITS, q_end, s_lut, lut2, T, nullptr, &qn);
-            const uint32_t e = qn == DEC_QSTOP ? DEC_OFF_STOP : qn - (sub0 + DEC_SUB_BITS);
-            s_fn[pair] = (uint16_t)((e << 8) | (uint32_t)n);
+        CGIC_STAMP(unpack, 3);
+        // ---- A0: code length at EVERY bit position (independent, branch-free lookups: 32 positions per
+        //      thread and pass sharing one word pair); 0 where the codeword would run past the payload.
+        //      Codes deeper than both LUT levels (rare) are marked 0xFF and walked in a second sweep.
+        bool any_walk = false;
+        for (int wi = tid; wi < npos_words; wi += DEC_THREADS) {
+            const uint32_t w0 = s_words[wi], w1 = s_words[wi + 1];
+            uint32_t *dst = reinterpret_cast<uint32_t *>(s_len) + wi * 8;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+                uint32_t e[4], win[4], e2[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    win[k] = __funnelshift_l(w1, w0, j4 * 4 + k);
+                    e[k] = s_lut[win[k] >> (32 - L)];
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t f = e[k] & 0xFFu;
+                    const bool two = (f & 0x80u) != 0 && f != 0xFFu;
+                    const uint32_t hgt = two ? (f & 0x7Fu) : 1u;
+                    const uint32_t i2 = two ? (e[k] >> 8) + ((win[k] << L) >> (32 - hgt)) : 0u;  // win holds 32 bits from q on
+                    e2[k] = LUT2S ? lut2[i2] : __ldg(&lut2[i2]);
+                }
+                uint32_t packed = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t f = e[k] & 0xFFu;
+                    const uint32_t q = (uint32_t)wi * 32u + (uint32_t)(j4 * 4 + k);
+                    uint32_t len = (f & 0x80u) ? (e2[k] & 0xFFu) + (uint32_t)L : f;
+                    if (f == 0xFFu) {
+                        len = 0xFFu;
+                        any_walk = true;
+                    } else if (q + len > q_end) {
+                        len = 0;
+                    }
+                    packed |= len << (8 * k);
+                }
+                dst[j4] = packed;
+            }
+        }
+        if (__syncthreads_or(any_walk)) {
+            for (int q = tid; q < npos_words * 32; q += DEC_THREADS) {
+                if (s_len[q] != 0xFFu) continue;
+                uint32_t len = decode_one<LUT2S>(s_words, (uint32_t)q, s_lut, lut2, T, L) & 0xFFu;
+                if ((uint32_t)q + len > q_end || len == 0xFFu) len = 0;  // (DEC_MAX_D = 128 < 0xFF)
+                s_len[q] = (uint8_t)len;
+            }
+            __syncthreads();
+        }
+        CGIC_STAMP(unpack, 7);
+        // ---- A: every (subsequence, candidate offset) pair follows its chain through len8[];
+        //      four chains per thread in lock step (each step is one dependent shared-memory load)
+        for (int pair0 = tid; pair0 < nsub * D; pair0 += 4 * DEC_THREADS) {
+            uint32_t q[4], se[4], n[4];
+            bool live[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int pair = pair0 + k * DEC_THREADS;
+                const bool ok = pair < nsub * D;
+                const int i = ok ? pair / D : 0, c = ok ? pair - i * D : 0;
+                se[k] = 8u + (uint32_t)(i + 1) * DEC_SUB_BITS;
+                q[k] = se[k] - DEC_SUB_BITS + (uint32_t)c;
+                n[k] = 0;
+                live[k] = ok;
+            }
+            while (live[0] || live[1] || live[2] || live[3]) {
+                uint32_t len[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) len[k] = s_len[live[k] ? q[k] : 0u];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (!live[k]) continue;
+                    if (len[k] == 0) {        // decoding ends inside this subsequence
+                        q[k] = 0xFFFFFFFFu;
+                        live[k] = false;
+                    } else {
+                        q[k] += len[k];
+                        ++n[k];
+                        live[k] = q[k] < se[k];
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int pair = pair0 + k * DEC_THREADS;
+                if (pair < nsub * D) s_fn[pair] = (uint16_t)(((q[k] == 0xFFFFFFFFu ? DEC_OFF_STOP : q[k] - se[k]) << 8) | n[k]);
+            }
         }
         __syncthreads();
+        CGIC_STAMP(unpack, 4);
         // ---- B: true start offset of every subsequence
         const int bs = nsub <= 128 ? 8 : 32;  // subsequences per block; at most 32 blocks either way
         const int nblk = (nsub + bs - 1) / bs;
@@ -412,6 +500,7 @@ __device__ int decode_stream_cta_cand(const uint8_t *in, int64_t nbytes, const D
             }
         }
         __syncthreads();
+        CGIC_STAMP(unpack, 5);
         // ---- C: counts -> offsets -> symbols
         for (int base = 0; base < nsub; base += DEC_THREADS) {
             const int i = base + tid;
@@ -440,8 +529,7 @@ __device__ int decode_stream_cta_cand(const uint8_t *in, int64_t nbytes, const D
             if (total + ctot > cap) return -2;
             if (cnt) {
                 const uint32_t sub0 = 8u + (uint32_t)i * DEC_SUB_BITS;
-                uint32_t dummy;
-                decode_range_smem<true, Out>(s_words, sub0 + st, sub0 + DEC_SUB_BITS, q_end, s_lut, lut2, T, out + total + woff + inc - cnt, &dummy);
+                decode_write_smem<LUT2S, Out>(s_words, sub0 + st, sub0 + DEC_SUB_BITS, q_end, s_lut, lut2, T, out + total + woff + inc - cnt);
             }
             total += ctot;
             __syncthreads();
@@ -451,12 +539,14 @@ __device__ int decode_stream_cta_cand(const uint8_t *in, int64_t nbytes, const D
     return (int)total;
 }
 
-// subsequences per chunk for a table: f[] takes ch * D * 2 bytes of shared memory (<= 40 KB)
+// subsequences per chunk for a table: words 16 B + len8[] 128 B + f[] 2 D bytes per subsequence, <= 48 KB
 __host__ __device__ inline int cand_chunk_subs(int max_len)
 {
-    int ch = (40 * 1024 / (max_len * 2)) & ~31;
+    int ch = (48 * 1024 / (16 + DEC_SUB_BITS + max_len * 2)) & ~31;
     return ch > DEC_MAX_CH ? DEC_MAX_CH : ch;
 }
+__host__ __device__ inline int cand_words(int ch) { return ch * (DEC_SUB_BITS / 32) + DEC_LOOKAHEAD_WORDS; }
+__host__ __device__ inline int cand_len_bytes(int ch) { return (ch * (DEC_SUB_BITS / 32) + (DEC_MAX_D + 8 + 31) / 32 + 1) * 32; }
 
 template <typename Out>
 __device__ __forceinline__ int decode_stream_any(const uint8_t *in, int64_t nbytes, const DevTable &T, const uint32_t *s_dec,
@@ -466,8 +556,11 @@ __device__ __forceinline__ int decode_stream_any(const uint8_t *in, int64_t nbyt
         // f[] lives right behind the staged tables in dynamic shared memory
         const int ch = cand_chunk_subs(T.max_len);
         uint32_t *s_words = const_cast<uint32_t *>(s_dec) + T.dec_stage_words;
-        uint16_t *s_fn = reinterpret_cast<uint16_t *>(s_words + ch * (DEC_SUB_BITS / 32) + DEC_LOOKAHEAD_WORDS);
-        return decode_stream_cta_cand<Out>(in, nbytes, T, s_dec, lut2, s_fn, s_words, ch, out, cap);
+        uint8_t *s_len = reinterpret_cast<uint8_t *>(s_words + cand_words(ch));
+        uint16_t *s_fn = reinterpret_cast<uint16_t *>(s_len + cand_len_bytes(ch));
+        if (T.dec_stage_words > T.lut_pad)
+            return decode_stream_cta_cand<true, Out>(in, nbytes, T, s_dec, lut2, s_words, s_len, s_fn, ch, out, cap);
+        return decode_stream_cta_cand<false, Out>(in, nbytes, T, s_dec, lut2, s_words, s_len, s_fn, ch, out, cap);
     }
     return decode_stream_cta<Out>(in, nbytes, T, s_dec, lut2, out, cap);
 }
@@ -600,6 +693,8 @@ __global__ void __launch_bounds__(UP_THREADS) unpack_decode_kernel(const UnpackA
     __shared__ __align__(8) unsigned long long mbar;
     const int s = blockIdx.x, b = blockIdx.y;
     const Geo &g = a.g;
+    CGIC_STAMP(unpack, 0);
+    pdl_launch_dependents();
     const uint8_t *img = a.bytes + (int64_t)b * a.image_stride;
     const int32_t *sz = a.sizes + b * 5;
     const int nwt = g.nw16 + g.nw8 + g.nw4;
@@ -607,19 +702,24 @@ __global__ void __launch_bounds__(UP_THREADS) unpack_decode_kernel(const UnpackA
         const int64_t soff = s == 0 ? 0 : (s == 1 ? g.n16 : g.n16 + g.n8);
         const int64_t cap = s == 0 ? g.n16 : (s == 1 ? g.n8 : g.n4);
         int cnt = -1;
+        // the (immutable) decode tables are staged while the predecessor kernel may still be running
+        uint32_t *s_dec = reinterpret_cast<uint32_t *>(dyn);
+        const uint32_t *lut2 = nullptr;
+        if (stream_present(a.mode, s)) lut2 = stage_decode_tables(a.T, s_dec, &mbar);
+        pdl_wait();
         const int nbytes = stream_present(a.mode, s) ? sz[s] : 0;
-        if (nbytes > 0) {
-            uint32_t *s_dec = reinterpret_cast<uint32_t *>(dyn);
-            const uint32_t *lut2 = stage_decode_tables(a.T, s_dec, &mbar);
+        CGIC_STAMP(unpack, 1);
+        if (nbytes > 0)
             cnt = decode_stream_any<uint16_t>(img + a.slot_off[s], nbytes, a.T, s_dec, lut2,
                                               a.ws.sym + (int64_t)b * (g.n16 + g.n8 + g.n4) + soff, cap);
-        }
+        CGIC_STAMP(unpack, 6);
         if (threadIdx.x == 0) {
             a.ws.count[b * 3 + s] = cnt;
-            if (cnt == -2) atomicExch(&a.status[b], CGIC_EFORMAT);
+            a.ws.flag[b * 5 + s] = cnt == -2 ? CGIC_EFORMAT : 0;
         }
         return;
     }
+    pdl_wait();
     const bool need_c = a.mode == 0 || a.mode == 2 || a.mode == 3;
     const bool need_m = a.mode == 0 || a.mode == 1;
     const int cap_c = (int)(g.n16 / 8 + 2), cap_m = (int)(g.n8 / 8 + 2);
@@ -627,7 +727,10 @@ __global__ void __launch_bounds__(UP_THREADS) unpack_decode_kernel(const UnpackA
     bool ok_c = true, ok_m = true;
     if (need_c) ok_c = sz[3] == cap_c && img[a.slot_off[3]] == 8 - (int)(g.n16 & 7);
     if (need_m && s == 4) ok_m = sz[4] == cap_m && img[a.slot_off[4]] == 8 - (int)(g.n8 & 7);
-    if (threadIdx.x == 0 && ((s == 3 && !ok_c) || (s == 4 && !ok_m))) atomicExch(&a.status[b], CGIC_EFORMAT);
+    if (threadIdx.x == 0) {
+        a.ws.flag[b * 5 + s] = ((s == 3 && !ok_c) || (s == 4 && !ok_m)) ? CGIC_EFORMAT : 0;
+        if (s == 3) a.status[b] = 0;  // the assemble kernel (which runs after this grid) raises it atomically
+    }
     // mask bytes: shared copies when they fit (a.mask_stage), else straight from global
     const uint8_t *mc = img + a.slot_off[3];
     const uint8_t *mm = img + a.slot_off[4];
@@ -693,15 +796,20 @@ __global__ void __launch_bounds__(256) unpack_assemble_kernel(const UnpackArgs a
     const uint32_t *bits = a.ws.bits + (int64_t)b * nwt;
     const uint32_t *prefix = a.ws.prefix + (int64_t)b * nwt;
     const int32_t *cntp = a.ws.count + b * 3;
+    pdl_launch_dependents();
+    pdl_wait();
     if (quad == 0) {
         // the reference's masked assignment raises unless #symbols == #set cells (an empty
         // coarse / medium stream stands for zeros, model.py:284-290)
         const int32_t *pop = a.ws.pop + b * 3;
+        bool bad = false;
+        for (int s = 0; s < 5; ++s) bad |= a.ws.flag[b * 5 + s] != 0;
         for (int s = 0; s < 3; ++s) {
             if (!stream_present(a.mode, s)) continue;
             const bool empty_ok = cntp[s] == -1 && (s < 2 || pop[s] == 0);
-            if (!empty_ok && cntp[s] != pop[s]) atomicExch(&a.status[b], CGIC_EFORMAT);
+            if (!empty_ok && cntp[s] != pop[s]) bad = true;
         }
+        if (bad) atomicExch(&a.status[b], CGIC_EFORMAT);
     }
     const int64_t p = quad * 4;
     if (p >= g.n4) return;
@@ -805,8 +913,8 @@ size_t decode_smem_bytes(const DevTable &T)
 {
     size_t b = (size_t)T.dec_stage_words * 4;
     if (T.max_len <= DEC_MAX_D) {
-        const size_t ch = (size_t)cand_chunk_subs(T.max_len);
-        b += ch * T.max_len * 2 + (ch * (DEC_SUB_BITS / 32) + DEC_LOOKAHEAD_WORDS) * 4;
+        const int ch = cand_chunk_subs(T.max_len);
+        b += (size_t)ch * T.max_len * 2 + (size_t)cand_words(ch) * 4 + (size_t)cand_len_bytes(ch);
     }
     return b;
 }
@@ -862,20 +970,19 @@ extern "C" int cgic_unpack(const uint8_t *bytes, const int32_t *sizes, int B, in
     const size_t mask_bytes = (size_t)(((a.g.n16 / 8 + 2 + 15) & ~15) + ((a.g.n8 / 8 + 2 + 15) & ~15));
     a.mask_stage = mask_bytes <= 96 * 1024;
     const size_t smem = std::max(dec_bytes, a.mask_stage ? mask_bytes : (size_t)0);
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        CGIC_CUDA_CHECK(cudaFuncSetAttribute(unpack_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+    static bool smem_opt_in = false;  // static + dynamic shared memory may exceed the 48 KB default
+    if (!smem_opt_in) {
+        CGIC_CUDA_CHECK(cudaFuncSetAttribute(unpack_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        smem_opt_in = true;
     }
-    CGIC_CUDA_CHECK(cudaMemsetAsync(status_out, 0, (size_t)B * 4, stream));
     {
         CGIC_PROF("unpack_decode_kernel", stream);
-        unpack_decode_kernel<<<dim3(5, B), UP_THREADS, smem, stream>>>(a);
+        CGIC_CUDA_CHECK(launch_pdl(unpack_decode_kernel, dim3(5, B), dim3(UP_THREADS), smem, stream, a));
     }
     CGIC_LAUNCH_CHECK();
     {
         CGIC_PROF("unpack_assemble_kernel", stream);
-        unpack_assemble_kernel<<<dim3((unsigned)((a.g.n4 / 4 + 255) / 256), B), 256, 0, stream>>>(a);
+        CGIC_CUDA_CHECK(launch_pdl(unpack_assemble_kernel, dim3((unsigned)((a.g.n4 / 4 + 255) / 256), B), dim3(256), 0, stream, a));
     }
     CGIC_LAUNCH_CHECK();
     return CGIC_OK;
@@ -891,10 +998,10 @@ extern "C" int cgic_huff_decode(const uint8_t *bytes, int64_t nbytes, const cgic
     int rc = table_device_view(t, &T);
     if (rc) return rc;
     const size_t smem = decode_smem_bytes(T);
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        CGIC_CUDA_CHECK(cudaFuncSetAttribute(huff_decode_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+    static bool smem_opt_in = false;
+    if (!smem_opt_in) {
+        CGIC_CUDA_CHECK(cudaFuncSetAttribute(huff_decode_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        smem_opt_in = true;
     }
     huff_decode_single_kernel<<<1, DEC_THREADS, smem, as_stream(stream)>>>(bytes, nbytes, T, symbols_out, cap, count_out);
     CGIC_LAUNCH_CHECK();

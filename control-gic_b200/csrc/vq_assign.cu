@@ -163,6 +163,8 @@ vq_fused_kernel(const float *__restrict__ z, int B, int h, int w, const VqTiles 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     VQ_STAMP(0);
+    pdl_launch_dependents();
+    pdl_wait();  // the codebook and z may come straight from a preceding kernel
     // --- stage the codebook with one TMA bulk copy (cp.async.bulk -> UBLKCP), mbarrier completion
     if (tid == 0) mbar_init(&mbar);
     __syncthreads();
@@ -427,6 +429,7 @@ vq_fused_kernel(const float *__restrict__ z, int B, int h, int w, const VqTiles 
             double all = 0.0;
             for (int i = 0; i < VQ_WARPS; ++i) all += s_red[i];
             *sqerr_out = all;
+            counters[0] = 0;  // leave the ticket zeroed for the next launch (workspace contract)
         }
     }
     VQ_STAMP(6);
@@ -446,7 +449,8 @@ __global__ void vq_count_kernel(const int64_t *__restrict__ idx, int64_t n, floa
 
 using namespace cgic;
 
-// workspace: [64 bytes of counters][one double per CTA]; sized for any grid this library launches
+// workspace: [64 bytes of counters][one double per CTA]; sized for any grid this library launches.
+// Contract: the first 64 bytes must be ZERO before the first use; the kernel leaves them zero.
 extern "C" size_t cgic_vq_workspace_bytes(int64_t) { return 256 + 8 * 4096; }
 
 extern "C" int cgic_vq_assign(const float *z, int B, int h, int w, const float *codebook, int K, int64_t *idx_out,
@@ -483,11 +487,10 @@ extern "C" int cgic_vq_assign(const float *z, int B, int h, int w, const float *
     const VqTiles tl = make_tiles(B, h, w);
     // persistent grid: one CTA per SM, never more CTAs than strips
     const int grid = (int)(tl.n_strips < (int64_t)n_sm ? tl.n_strips : (int64_t)n_sm);
-    if (sqerr_out) CGIC_CUDA_CHECK(cudaMemsetAsync(counters, 0, 64, stream));
     {
         CGIC_PROF("vq_fused_kernel", stream);
-        vq_fused_kernel<<<grid, VQ_THREADS, smem, stream>>>(z, B, h, w, tl, codebook, K, Kpad, idx_out, zq_out, partials, counters,
-                                                            sqerr_out);
+        CGIC_CUDA_CHECK(launch_pdl(vq_fused_kernel, dim3(grid), dim3(VQ_THREADS), smem, stream, z, B, h, w, tl, codebook, K, Kpad, idx_out,
+                                   zq_out, partials, counters, sqerr_out));
     }
     CGIC_LAUNCH_CHECK();
     return CGIC_OK;

@@ -116,7 +116,7 @@ def _workspace(tag: str, nbytes: int, device: torch.device) -> torch.Tensor:
     key = (tag, device.index, _stream())
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        buf = torch.zeros(max(nbytes, 256), dtype=torch.uint8, device=device)   # cgic_vq_assign wants its ticket zeroed once
         _ws_cache[key] = buf
     return buf
 

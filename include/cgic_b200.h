@@ -86,6 +86,8 @@ CGIC_API int cgic_huff_upload(cgic_table *t);
  *     zq_out   fp32 [B,4,h,w]  fl(z + fl(e - z))            (nullable)
  *     sqerr_out double[1]      sum over all elements of (e - z)^2; loss = (1+beta)*sqerr/numel
  *                              (nullable)
+ *     workspace: cgic_vq_workspace_bytes() bytes whose first 64 bytes are ZERO before the first call
+ *     (the kernel leaves them zero); one workspace per concurrently running call.
  *     Tokens whose latent is bit-identical to the top-left token of their 4x4 / 2x2 block (the
  *     structure the mask-mix of vqvae_blocks.py:364-366 creates) share that token's search.
  * ------------------------------------------------------------------------------------------ */
