@@ -32,6 +32,12 @@ _SIGNATURES = {
     "cgic_vq_workspace_bytes": (c_size_t, [c_int64]),
     "cgic_vq_assign": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_size_t, c_void_p]),
+    "cgic_codebook_create": (c_int, [c_int, C.POINTER(c_void_p)]),
+    "cgic_codebook_free": (None, [c_void_p]),
+    "cgic_codebook_update": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "cgic_codebook_stats_host": (c_int, [c_void_p, c_void_p]),
+    "cgic_vq_assign_indexed": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_size_t, c_void_p]),
     "cgic_vq_count": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     "cgic_entropy_maps": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cgic_router_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

@@ -17,6 +17,7 @@ struct cgic_session {
     static constexpr int MAX_PARTS = 8;
     int parts = 1;
     cudaStream_t streams[MAX_PARTS] = {};
+    cgic_codebook *index = nullptr;  // prepared codebook (cell index) built once at create time
     cudaEvent_t packed = nullptr;  // roundtrip: pack finished, the decode stream may start
     unsigned char *arena = nullptr;
     // carved device buffers
@@ -95,6 +96,16 @@ extern "C" int cgic_session_create(int B, int h, int w, int mode, const cgic_tab
     s->ws_un = a + o_wu;
     s->ws_vq_bytes = (s->ws_vq_bytes + 255) / 256 * 256;
     s->ws_un_bytes = (s->ws_un_bytes + 255) / 256 * 256;
+    rc = cgic_codebook_create(K, &s->index);
+    if (rc == CGIC_OK) rc = cgic_codebook_update(s->index, s->codebook, s->streams[0]);
+    if (rc == CGIC_OK && cudaStreamSynchronize(s->streams[0]) != cudaSuccess) {
+        cgic::set_error("cgic_session_create: building the codebook index failed");
+        rc = CGIC_ECUDA;
+    }
+    if (rc != CGIC_OK) {
+        cgic_session_destroy(s);
+        return rc;
+    }
     s->parts = 1;  // measured on B200 + PCIe gen5: per-copy latency (5-8 us) outweighs the overlap for batches of a few MB
     *out = s;
     return CGIC_OK;
@@ -105,6 +116,7 @@ extern "C" void cgic_session_destroy(cgic_session *s)
     if (!s) return;
     for (cudaStream_t st : s->streams)
         if (st) cudaStreamDestroy(st);
+    if (s->index) cgic_codebook_free(s->index);
     if (s->packed) cudaEventDestroy(s->packed);
     if (s->arena) cudaFree(s->arena);
     if (s->sqerr_host) cudaFreeHost(s->sqerr_host);
@@ -136,7 +148,7 @@ extern "C" int cgic_session_compress_host(cgic_session *s, const float *z, const
         CGIC_CUDA_CHECK(cudaMemcpyAsync(s->mc + b0 * i16, m_c + b0 * i16, nb * i16 * 4, cudaMemcpyHostToDevice, st));
         CGIC_CUDA_CHECK(cudaMemcpyAsync(s->mm + b0 * i8, m_m + b0 * i8, nb * i8 * 4, cudaMemcpyHostToDevice, st));
         CGIC_CUDA_CHECK(cudaMemcpyAsync(s->mf + b0 * i4, m_f + b0 * i4, nb * i4 * 4, cudaMemcpyHostToDevice, st));
-        int rc = cgic_vq_assign(s->z + b0 * i4 * 4, nb, s->h, s->w, s->codebook, s->K, s->idx + b0 * i4, zq_out ? s->zq + b0 * i4 * 4 : nullptr,
+        int rc = cgic_vq_assign_indexed(s->z + b0 * i4 * 4, nb, s->h, s->w, s->index, s->idx + b0 * i4, zq_out ? s->zq + b0 * i4 * 4 : nullptr,
                                 sqerr_out ? s->sqerr + p : nullptr, s->ws_vq + p * s->ws_vq_bytes, s->ws_vq_bytes, st);
         if (rc) return rc;
         rc = cgic_pack(s->idx + b0 * i4, s->mc + b0 * i16, s->mm + b0 * i8, s->mf + b0 * i4, nb, s->h, s->w, s->mode, s->table,
@@ -204,7 +216,7 @@ extern "C" int cgic_session_roundtrip_host(cgic_session *s, const float *z, cons
     CGIC_CUDA_CHECK(cudaMemcpyAsync(s->mc, m_c, n16 * 4, cudaMemcpyHostToDevice, enc));
     CGIC_CUDA_CHECK(cudaMemcpyAsync(s->mm, m_m, n8 * 4, cudaMemcpyHostToDevice, enc));
     CGIC_CUDA_CHECK(cudaMemcpyAsync(s->mf, m_f, n4 * 4, cudaMemcpyHostToDevice, enc));
-    int rc = cgic_vq_assign(s->z, s->B, s->h, s->w, s->codebook, s->K, s->idx, zq_out ? s->zq : nullptr,
+    int rc = cgic_vq_assign_indexed(s->z, s->B, s->h, s->w, s->index, s->idx, zq_out ? s->zq : nullptr,
                             sqerr_out ? s->sqerr : nullptr, s->ws_vq, s->ws_vq_bytes, enc);
     if (rc) return rc;
     rc = cgic_pack(s->idx, s->mc, s->mm, s->mf, s->B, s->h, s->w, s->mode, s->table, s->bytes, s->sizes, enc);

@@ -121,12 +121,55 @@ def _workspace(tag: str, nbytes: int, device: torch.device) -> torch.Tensor:
     return buf
 
 
-def vq_assign(z: torch.Tensor, codebook: torch.Tensor, want_zq: bool = True, want_sqerr: bool = True):
-    """quantize.py:69-98 -> (idx int64 [B*h*w], z_q fp32 NCHW or None, sqerr float64[1] or None)."""
+class Codebook:
+    """Owns a `cgic_codebook*`: the device copy of `embedding.weight` (quantize.py:25-26) plus the cell
+    index cgic_vq_assign_indexed searches.  update() rebuilds it on the current stream (no sync)."""
+
+    def __init__(self, weight: torch.Tensor):
+        w = _cuda(weight.detach(), torch.float32, "codebook")
+        if w.dim() != 2 or w.shape[1] != 4:
+            raise ValueError(f"Codebook supports e_dim == 4 (got {tuple(w.shape)})")
+        handle = C.c_void_p()
+        with torch.cuda.device(w.device):
+            check(lib().cgic_codebook_create(int(w.shape[0]), C.byref(handle)), "cgic_codebook_create")
+        self._h = handle
+        self._free = lib().cgic_codebook_free
+        self.K = int(w.shape[0])
+        self.device = w.device
+        self.update(w)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._free(h)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def update(self, weight: torch.Tensor) -> "Codebook":
+        w = _cuda(weight.detach(), torch.float32, "codebook")
+        if tuple(w.shape) != (self.K, 4) or w.device != self.device:
+            raise ValueError(f"codebook {tuple(w.shape)} on {w.device} does not match the prepared [{self.K}, 4] on {self.device}")
+        check(lib().cgic_codebook_update(self._h, w.data_ptr(), _stream()), "cgic_codebook_update")
+        return self
+
+    def stats(self) -> dict:
+        """{valid, cells, max_list, overflow_cells} (synchronises)."""
+        out = np.zeros(4, np.int32)
+        check(lib().cgic_codebook_stats_host(self._h, out.ctypes.data), "cgic_codebook_stats_host")
+        return dict(valid=int(out[0]), cells=int(out[1]), max_list=int(out[2]), overflow_cells=int(out[3]))
+
+
+def vq_assign(z: torch.Tensor, codebook, want_zq: bool = True, want_sqerr: bool = True):
+    """quantize.py:69-98 -> (idx int64 [B*h*w], z_q fp32 NCHW or None, sqerr float64[1] or None).
+    `codebook`: a [K,4] fp32 CUDA tensor (exhaustive search) or a prepared `Codebook` (indexed search,
+    identical results)."""
     z = _cuda(z, torch.float32, "z")
-    cb = _cuda(codebook, torch.float32, "codebook")
-    if z.dim() != 4 or z.shape[1] != 4 or cb.dim() != 2 or cb.shape[1] != 4:
-        raise ValueError(f"vq_assign supports e_dim == 4 (z {tuple(z.shape)}, codebook {tuple(cb.shape)})")
+    indexed = isinstance(codebook, Codebook)
+    cb = None if indexed else _cuda(codebook, torch.float32, "codebook")
+    if z.dim() != 4 or z.shape[1] != 4 or (cb is not None and (cb.dim() != 2 or cb.shape[1] != 4)):
+        raise ValueError(f"vq_assign supports e_dim == 4 (z {tuple(z.shape)})")
     B, _, h, w = z.shape
     n = B * h * w
     idx = torch.empty(n, dtype=torch.int64, device=z.device)
@@ -134,8 +177,12 @@ def vq_assign(z: torch.Tensor, codebook: torch.Tensor, want_zq: bool = True, wan
     sq = torch.empty(1, dtype=torch.float64, device=z.device) if want_sqerr else None
     nbytes = lib().cgic_vq_workspace_bytes(n)
     ws = _workspace("vq", nbytes, z.device)
-    check(lib().cgic_vq_assign(z.data_ptr(), B, h, w, cb.data_ptr(), cb.shape[0], idx.data_ptr(), _p(zq), _p(sq),
-                               ws.data_ptr(), ws.numel(), _stream()), "cgic_vq_assign")
+    if indexed:
+        check(lib().cgic_vq_assign_indexed(z.data_ptr(), B, h, w, codebook.handle, idx.data_ptr(), _p(zq), _p(sq),
+                                           ws.data_ptr(), ws.numel(), _stream()), "cgic_vq_assign_indexed")
+    else:
+        check(lib().cgic_vq_assign(z.data_ptr(), B, h, w, cb.data_ptr(), cb.shape[0], idx.data_ptr(), _p(zq), _p(sq),
+                                   ws.data_ptr(), ws.numel(), _stream()), "cgic_vq_assign")
     return idx, zq, sq
 
 

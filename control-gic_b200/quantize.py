@@ -1,4 +1,5 @@
-"""VectorQuantize2 -- drop-in for CGIC/modules/vqvae/quantize.py:9-98 backed by cgic_vq_assign.
+"""VectorQuantize2 -- drop-in for CGIC/modules/vqvae/quantize.py:9-98 backed by cgic_vq_assign_indexed
+(prepared codebook, csrc/codebook.cu; cgic_vq_assign is the exhaustive search with identical results).
 
 Same constructor, attributes (`embedding`, `embedding_counter`, n_e, e_dim, beta, legacy) and
 state-dict keys (`embedding.weight`, `embedding_counter.<i>` with shape [1]); forward returns
@@ -20,8 +21,8 @@ class _VQFunction(torch.autograd.Function):
     analytic gradient of the commitment loss (quantize.py:85-90)."""
 
     @staticmethod
-    def forward(ctx, z, weight, beta, legacy):
-        idx, zq, sq = ops.vq_assign(z.detach(), weight.detach())
+    def forward(ctx, z, weight, beta, legacy, prepared=None):
+        idx, zq, sq = ops.vq_assign(z.detach(), prepared if prepared is not None else weight.detach())
         mean = (sq / z.numel()).to(torch.float32)[0]
         loss = mean + beta * mean if legacy else beta * mean + mean
         ctx.save_for_backward(z, weight, idx)
@@ -41,7 +42,7 @@ class _VQFunction(torch.autograd.Function):
             g_z = g_zq + g_loss * wz * diff
         if ctx.needs_input_grad[1]:
             g_w = torch.zeros_like(weight).index_add_(0, idx, (-g_loss * we * diff).permute(0, 2, 3, 1).reshape(-1, C))
-        return g_z, g_w, None, None
+        return g_z, g_w, None, None, None
 
 
 class VectorQuantize2(nn.Module):
@@ -82,12 +83,27 @@ class VectorQuantize2(nn.Module):
         for k, p in self.embedding_counter.items():
             p.copy_(flat[int(k): int(k) + 1])
 
+    def prepared_codebook(self) -> "ops.Codebook":
+        """The search index of `embedding.weight` (ops.Codebook), rebuilt on the current stream whenever the
+        weight tensor was replaced or written in place (its `_version` moved)."""
+        w = self.embedding.weight
+        key = (w.data_ptr(), w._version, w.device)
+        if getattr(self, "_prepared_key", None) != key:
+            cb = getattr(self, "_prepared", None)
+            if cb is None or cb.device != w.device or cb.K != w.shape[0]:
+                self._prepared = ops.Codebook(w)
+            else:
+                cb.update(w)
+            self._prepared_key = key
+        return self._prepared
+
     def forward(self, z):
         w = self.embedding.weight
+        prepared = self.prepared_codebook()
         if torch.is_grad_enabled() and (z.requires_grad or w.requires_grad):
-            z_q, loss, idx = _VQFunction.apply(z, w, self.beta, self.legacy)
+            z_q, loss, idx = _VQFunction.apply(z, w, self.beta, self.legacy, prepared)
         else:
-            idx, z_q, sq = ops.vq_assign(z, w)
+            idx, z_q, sq = ops.vq_assign(z, prepared)
             mean = (sq / z.numel()).to(torch.float32)[0]
             loss = mean + self.beta * mean if self.legacy else self.beta * mean + mean
         if self.training:

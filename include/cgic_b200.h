@@ -49,6 +49,7 @@ extern "C" {
 typedef void *cgic_stream_t;          /* cudaStream_t */
 typedef struct cgic_table cgic_table; /* static Huffman code table (host + device copy) */
 typedef struct cgic_session cgic_session;
+typedef struct cgic_codebook cgic_codebook; /* prepared codebook: device copy + e^2 + cell index */
 
 CGIC_API int cgic_abi_version(void);
 CGIC_API const char *cgic_last_error(void);
@@ -95,6 +96,27 @@ CGIC_API size_t cgic_vq_workspace_bytes(int64_t n_tokens);
 CGIC_API int cgic_vq_assign(const float *z, int B, int h, int w, const float *codebook, int K, int64_t *idx_out,
                    float *zq_out, double *sqerr_out, void *workspace, size_t workspace_bytes,
                    cgic_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a1/a2  prepared codebook + indexed search.   State of VectorQuantize2 (`embedding.weight`,
+ *     quantize.py:25-26) turned into a search index: a 4-D grid over the codebook's bounding box
+ *     whose cells list every code that can be the reference's fp32 argmin for some latent in the
+ *     cell (all codes not dominated by more than the rounding slack of quantize.py:73-75, see
+ *     csrc/codebook.cu).  cgic_vq_assign_indexed evaluates the reference's rounding sequence on the
+ *     cell's list only; latents outside the grid or in an overflowing cell are searched
+ *     exhaustively in the same kernel, so results are bit-identical to cgic_vq_assign for ANY
+ *     input.  create allocates (init time); update (re)builds the index from a DEVICE codebook
+ *     [K,4] on `stream` (call it again whenever the weights change; no allocation, no sync);
+ *     stats_host synchronises and returns {valid, cells, longest list, overflowing cells}.
+ *     Arguments of cgic_vq_assign_indexed are those of cgic_vq_assign.
+ * ------------------------------------------------------------------------------------------ */
+CGIC_API int cgic_codebook_create(int K, cgic_codebook **out);
+CGIC_API void cgic_codebook_free(cgic_codebook *cb);
+CGIC_API int cgic_codebook_update(cgic_codebook *cb, const float *codebook, cgic_stream_t stream);
+CGIC_API int cgic_codebook_stats_host(const cgic_codebook *cb, int32_t out[4]);
+CGIC_API int cgic_vq_assign_indexed(const float *z, int B, int h, int w, const cgic_codebook *cb, int64_t *idx_out,
+                           float *zq_out, double *sqerr_out, void *workspace, size_t workspace_bytes,
+                           cgic_stream_t stream);
 
 /* a3  training-mode counter update, quantize.py:79-81: counters[idx[i]] += 1 (fp32 counters). */
 CGIC_API int cgic_vq_count(const int64_t *idx, int64_t n, float *counters, int K, cgic_stream_t stream);

@@ -15,6 +15,7 @@ dev = torch.device("cuda", 0)
 cbk, counts = workload.codebook_and_counts()
 table = cg.ops.HuffTable(counts.numpy(), workload.lexicographic_order()).upload()
 cb = cbk.to(dev)
+prepared = cg.ops.Codebook(cb)
 e16, e8 = workload.entropy_maps(B, H, W, 1000)
 mc, mm, mf, _, mode = cg.ops.router(e16.to(dev), e8.to(dev), c, m, per_image=True)
 hc, hm, hf = (t.to(dev) for t in workload.heads(B, H, W, cbk, 1000))
@@ -26,7 +27,7 @@ for it in range(iters + 5):
     flush.zero_()
     e = [ev() for _ in range(4)]
     e[0].record()
-    idx, zq, sq = cg.ops.vq_assign(z, cb)
+    idx, zq, sq = cg.ops.vq_assign(z, prepared)
     e[1].record()
     packed, sizes = cg.ops.pack(idx, mc, mm, mf, mode, table, h, w)
     e[2].record()

@@ -14,13 +14,14 @@ dev = torch.device("cuda", 0)
 cbk, counts = workload.codebook_and_counts()
 table = cg.ops.HuffTable(counts.numpy(), workload.lexicographic_order()).upload()
 cb = cbk.to(dev)
+prepared = cg.ops.Codebook(cb)
 e16, e8 = workload.entropy_maps(B, H, W, 1000)
 mc, mm, mf, _, mode = cg.ops.router(e16.to(dev), e8.to(dev), c, m, per_image=True)
 hc, hm, hf = (t.to(dev) for t in workload.heads(B, H, W, cbk, 1000))
 z = cg.ops.mask_mix(hc, hm, hf, mc, mm, mf)
 flush = torch.empty(1 << 28, dtype=torch.uint8, device=dev)
 for _ in range(3):
-    idx, zq, sq = cg.ops.vq_assign(z, cb)
+    idx, zq, sq = cg.ops.vq_assign(z, prepared)
     packed, sizes = cg.ops.pack(idx, mc, mm, mf, mode, table, h, w)
     flush.zero_()
     out = cg.ops.unpack(packed, sizes, mode, table, cb, h, w)
