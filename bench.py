@@ -420,7 +420,7 @@ def algorithmic_bytes(B, h, w, stream_bytes):
     consts = 1024 * 16
     out = {
         "vq_fused_kernel": n4 * (16 + 16 + 8) + consts,      # reads z once, writes z_q + idx once
-        "vq_indexed_kernel": n4 * (16 + 16 + 8) + consts,    # same bytes; the cell records it reads are not algorithmic
+        "vq_warp_kernel": n4 * (16 + 16 + 8) + consts,    # same bytes; the cell records it reads are not algorithmic
         "pack_kernel": n4 * 8 + masks32 + stream_bytes,
         "unpack_decode_kernel": stream_bytes,
         "unpack_assemble_kernel": masks64 + n4 * (8 + 16) + consts,

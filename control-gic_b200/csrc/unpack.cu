@@ -97,6 +97,7 @@ struct UnpackArgs {
     float *quant_out;
     int32_t *status;
     int mask_stage;  // 1: mask CTAs copy the mask streams to shared memory first
+    int ch;          // subsequences per chunk of the candidate decoder (shared-memory budget)
 };
 
 // ---- parallel prefix decoder (whole CTA, one stream) ------------------------------------------
@@ -381,92 +382,70 @@ __device__ int decode_stream_cta_cand(const uint8_t *in, int64_t nbytes, const D
         const int64_t rel_end = q_end_abs - c0 * DEC_SUB_BITS;  // payload end, local to the chunk
         const uint32_t q_end = (uint32_t)min(rel_end, (int64_t)(nsub * DEC_SUB_BITS + 8 + DEC_MAX_D + 64));
         CGIC_STAMP(unpack, 3);
-        // ---- A0: code length at EVERY bit position (independent, branch-free lookups: 32 positions per
-        //      thread and pass sharing one word pair); 0 where the codeword would run past the payload.
-        //      Codes deeper than both LUT levels (rare) are marked 0xFF and walked in a second sweep.
-        bool any_walk = false;
-        for (int wi = tid; wi < npos_words; wi += DEC_THREADS) {
+        // ---- A0: code length at EVERY bit position (independent lookups: 32 positions per thread and
+        //      pass sharing one word pair); 0 where the codeword would run past the payload.  Fast path:
+        //      the first-level entry's low byte IS the length; positions whose entry carries the
+        //      second-level / tree-walk flag (bit 7), and the few words near the payload end, are
+        //      resolved by a second sweep with the full decode.
+        for (int it = tid; it < npos_words * 4; it += DEC_THREADS) {  // work item: 8 positions of one word
+            const int wi = it >> 2, qtr = it & 3;
             const uint32_t w0 = s_words[wi], w1 = s_words[wi + 1];
-            uint32_t *dst = reinterpret_cast<uint32_t *>(s_len) + wi * 8;
+            uint32_t *dst = reinterpret_cast<uint32_t *>(s_len) + wi * 8 + qtr * 2;
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-                uint32_t e[4], win[4], e2[4];
+            for (int j = 0; j < 2; ++j) {
+                const int p0 = qtr * 8 + j * 4;
+                uint32_t f[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    win[k] = __funnelshift_l(w1, w0, j4 * 4 + k);
-                    e[k] = s_lut[win[k] >> (32 - L)];
+                for (int k = 0; k < 4; ++k) f[k] = s_lut[__funnelshift_l(w1, w0, p0 + k) >> (32 - L)] & 0xFFu;
+                if ((f[0] | f[1] | f[2] | f[3]) & 0x80u) {  // rare: second-level table or tree walk
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (f[k] & 0x80u) {
+                            f[k] = decode_one<LUT2S>(s_words, (uint32_t)wi * 32u + (uint32_t)(p0 + k), s_lut, lut2, T, L) & 0xFFu;
+                            if (f[k] == 0xFFu) f[k] = 0;  // (DEC_MAX_D = 128 < 0xFF)
+                        }
                 }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t f = e[k] & 0xFFu;
-                    const bool two = (f & 0x80u) != 0 && f != 0xFFu;
-                    const uint32_t hgt = two ? (f & 0x7Fu) : 1u;
-                    const uint32_t i2 = two ? (e[k] >> 8) + ((win[k] << L) >> (32 - hgt)) : 0u;  // win holds 32 bits from q on
-                    e2[k] = LUT2S ? lut2[i2] : __ldg(&lut2[i2]);
-                }
-                uint32_t packed = 0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t f = e[k] & 0xFFu;
-                    const uint32_t q = (uint32_t)wi * 32u + (uint32_t)(j4 * 4 + k);
-                    uint32_t len = (f & 0x80u) ? (e2[k] & 0xFFu) + (uint32_t)L : f;
-                    if (f == 0xFFu) {
-                        len = 0xFFu;
-                        any_walk = true;
-                    } else if (q + len > q_end) {
-                        len = 0;
-                    }
-                    packed |= len << (8 * k);
-                }
-                dst[j4] = packed;
+                dst[j] = f[0] | (f[1] << 8) | (f[2] << 16) | (f[3] << 24);
             }
         }
-        if (__syncthreads_or(any_walk)) {
-            for (int q = tid; q < npos_words * 32; q += DEC_THREADS) {
-                if (s_len[q] != 0xFFu) continue;
-                uint32_t len = decode_one<LUT2S>(s_words, (uint32_t)q, s_lut, lut2, T, L) & 0xFFu;
-                if ((uint32_t)q + len > q_end || len == 0xFFu) len = 0;  // (DEC_MAX_D = 128 < 0xFF)
-                s_len[q] = (uint8_t)len;
-            }
-            __syncthreads();
-        }
+        __syncthreads();
+        // no codeword may run past the payload: only positions within D bits of its end can
+        for (uint32_t q = (q_end > (uint32_t)D ? q_end - (uint32_t)D : 0u) + (uint32_t)tid; q < (uint32_t)npos_words * 32u; q += DEC_THREADS)
+            if (q + s_len[q] > q_end) s_len[q] = 0;
+        __syncthreads();
         CGIC_STAMP(unpack, 7);
         // ---- A: every (subsequence, candidate offset) pair follows its chain through len8[];
-        //      four chains per thread in lock step (each step is one dependent shared-memory load)
+        //      four chains per thread in lock step (each step is one dependent shared-memory load, no branches)
         for (int pair0 = tid; pair0 < nsub * D; pair0 += 4 * DEC_THREADS) {
             uint32_t q[4], se[4], n[4];
-            bool live[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int pair = pair0 + k * DEC_THREADS;
                 const bool ok = pair < nsub * D;
                 const int i = ok ? pair / D : 0, c = ok ? pair - i * D : 0;
-                se[k] = 8u + (uint32_t)(i + 1) * DEC_SUB_BITS;
-                q[k] = se[k] - DEC_SUB_BITS + (uint32_t)c;
+                se[k] = ok ? 8u + (uint32_t)(i + 1) * DEC_SUB_BITS : 0u;  // dead slot: q >= se from the start
+                q[k] = 8u + (uint32_t)i * DEC_SUB_BITS + (uint32_t)c;
                 n[k] = 0;
-                live[k] = ok;
             }
-            while (live[0] || live[1] || live[2] || live[3]) {
+            for (;;) {
                 uint32_t len[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) len[k] = s_len[live[k] ? q[k] : 0u];
+                for (int k = 0; k < 4; ++k) len[k] = s_len[q[k]];
+                uint32_t moved = 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (!live[k]) continue;
-                    if (len[k] == 0) {        // decoding ends inside this subsequence
-                        q[k] = 0xFFFFFFFFu;
-                        live[k] = false;
-                    } else {
-                        q[k] += len[k];
-                        ++n[k];
-                        live[k] = q[k] < se[k];
-                    }
+                    const uint32_t adv = q[k] < se[k] ? len[k] : 0u;  // 0 also where decoding ends inside the subsequence
+                    q[k] += adv;
+                    n[k] += adv != 0u;
+                    moved |= adv;
                 }
+                if (!moved) break;
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int pair = pair0 + k * DEC_THREADS;
-                if (pair < nsub * D) s_fn[pair] = (uint16_t)(((q[k] == 0xFFFFFFFFu ? DEC_OFF_STOP : q[k] - se[k]) << 8) | n[k]);
+                // a chain that stopped before the subsequence end met a position without a complete codeword: decoding is over
+                if (pair < nsub * D) s_fn[pair] = (uint16_t)(((q[k] < se[k] ? DEC_OFF_STOP : q[k] - se[k]) << 8) | n[k]);
             }
         }
         __syncthreads();
@@ -540,21 +519,24 @@ __device__ int decode_stream_cta_cand(const uint8_t *in, int64_t nbytes, const D
 }
 
 // subsequences per chunk for a table: words 16 B + len8[] 128 B + f[] 2 D bytes per subsequence, <= 48 KB
-__host__ __device__ inline int cand_chunk_subs(int max_len)
+// Small token grids (<= 4096 fine tokens: the typical stream fits 128 subsequences) take half the budget so
+// that three decode CTAs fit one SM and the whole (5, B) grid of a 64-image batch is resident at once.
+__host__ __device__ inline int cand_chunk_subs(int max_len, int64_t n4 = (int64_t)1 << 40)
 {
     int ch = (48 * 1024 / (16 + DEC_SUB_BITS + max_len * 2)) & ~31;
-    return ch > DEC_MAX_CH ? DEC_MAX_CH : ch;
+    ch = ch > DEC_MAX_CH ? DEC_MAX_CH : ch;
+    if (n4 <= 4096 && ch > 128) ch = 128;
+    return ch;
 }
 __host__ __device__ inline int cand_words(int ch) { return ch * (DEC_SUB_BITS / 32) + DEC_LOOKAHEAD_WORDS; }
 __host__ __device__ inline int cand_len_bytes(int ch) { return (ch * (DEC_SUB_BITS / 32) + (DEC_MAX_D + 8 + 31) / 32 + 1) * 32; }
 
 template <typename Out>
 __device__ __forceinline__ int decode_stream_any(const uint8_t *in, int64_t nbytes, const DevTable &T, const uint32_t *s_dec,
-                                                 const uint32_t *lut2, Out *out, int64_t cap)
+                                                 const uint32_t *lut2, Out *out, int64_t cap, int ch)
 {
     if (T.max_len <= DEC_MAX_D) {
         // f[] lives right behind the staged tables in dynamic shared memory
-        const int ch = cand_chunk_subs(T.max_len);
         uint32_t *s_words = const_cast<uint32_t *>(s_dec) + T.dec_stage_words;
         uint8_t *s_len = reinterpret_cast<uint8_t *>(s_words + cand_words(ch));
         uint16_t *s_fn = reinterpret_cast<uint16_t *>(s_len + cand_len_bytes(ch));
@@ -711,7 +693,7 @@ __global__ void __launch_bounds__(UP_THREADS) unpack_decode_kernel(const UnpackA
         CGIC_STAMP(unpack, 1);
         if (nbytes > 0)
             cnt = decode_stream_any<uint16_t>(img + a.slot_off[s], nbytes, a.T, s_dec, lut2,
-                                              a.ws.sym + (int64_t)b * (g.n16 + g.n8 + g.n4) + soff, cap);
+                                              a.ws.sym + (int64_t)b * (g.n16 + g.n8 + g.n4) + soff, cap, a.ch);
         CGIC_STAMP(unpack, 6);
         if (threadIdx.x == 0) {
             a.ws.count[b * 3 + s] = cnt;
@@ -881,13 +863,13 @@ __global__ void __launch_bounds__(256) unpack_assemble_kernel(const UnpackArgs a
 }
 
 __global__ void __launch_bounds__(DEC_THREADS)
-huff_decode_single_kernel(const uint8_t *bytes, int64_t nbytes, DevTable T, int32_t *out, int64_t cap, int32_t *count_out)
+huff_decode_single_kernel(const uint8_t *bytes, int64_t nbytes, DevTable T, int32_t *out, int64_t cap, int32_t *count_out, int ch)
 {
     extern __shared__ __align__(128) unsigned char dyn[];
     __shared__ __align__(8) unsigned long long mbar;
     uint32_t *s_dec = reinterpret_cast<uint32_t *>(dyn);
     const uint32_t *lut2 = stage_decode_tables(T, s_dec, &mbar);
-    const int cnt = decode_stream_any<int32_t>(bytes, nbytes, T, s_dec, lut2, out, cap);
+    const int cnt = decode_stream_any<int32_t>(bytes, nbytes, T, s_dec, lut2, out, cap, ch);
     if (threadIdx.x == 0) *count_out = cnt;
 }
 
@@ -909,11 +891,10 @@ __global__ void bits_decode_single_kernel(const uint8_t *bytes, int64_t nbytes, 
     if (threadIdx.x == 0 && blockIdx.x == 0) *count_out = (int32_t)nbits;
 }
 
-size_t decode_smem_bytes(const DevTable &T)
+size_t decode_smem_bytes(const DevTable &T, int ch)
 {
     size_t b = (size_t)T.dec_stage_words * 4;
     if (T.max_len <= DEC_MAX_D) {
-        const int ch = cand_chunk_subs(T.max_len);
         b += (size_t)ch * T.max_len * 2 + (size_t)cand_words(ch) * 4 + (size_t)cand_len_bytes(ch);
     }
     return b;
@@ -966,7 +947,8 @@ extern "C" int cgic_unpack(const uint8_t *bytes, const int32_t *sizes, int B, in
     for (const void *ptr : {(const void *)mm_out, (const void *)mf_out, (const void *)ind_out, (const void *)quant_out, (const void *)bytes})
         CGIC_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, CGIC_EINVAL, "cgic_unpack: buffers must be 16-byte aligned");
     // dynamic shared memory: decode tables for the stream CTAs, mask stream bytes for the mask CTAs
-    const size_t dec_bytes = decode_smem_bytes(a.T);
+    a.ch = cand_chunk_subs(a.T.max_len, a.g.n4);
+    const size_t dec_bytes = decode_smem_bytes(a.T, a.ch);
     const size_t mask_bytes = (size_t)(((a.g.n16 / 8 + 2 + 15) & ~15) + ((a.g.n8 / 8 + 2 + 15) & ~15));
     a.mask_stage = mask_bytes <= 96 * 1024;
     const size_t smem = std::max(dec_bytes, a.mask_stage ? mask_bytes : (size_t)0);
@@ -997,13 +979,14 @@ extern "C" int cgic_huff_decode(const uint8_t *bytes, int64_t nbytes, const cgic
     DevTable T;
     int rc = table_device_view(t, &T);
     if (rc) return rc;
-    const size_t smem = decode_smem_bytes(T);
+    const int ch = cand_chunk_subs(T.max_len);
+    const size_t smem = decode_smem_bytes(T, ch);
     static bool smem_opt_in = false;
     if (!smem_opt_in) {
         CGIC_CUDA_CHECK(cudaFuncSetAttribute(huff_decode_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         smem_opt_in = true;
     }
-    huff_decode_single_kernel<<<1, DEC_THREADS, smem, as_stream(stream)>>>(bytes, nbytes, T, symbols_out, cap, count_out);
+    huff_decode_single_kernel<<<1, DEC_THREADS, smem, as_stream(stream)>>>(bytes, nbytes, T, symbols_out, cap, count_out, ch);
     CGIC_LAUNCH_CHECK();
     return CGIC_OK;
 }

@@ -11,12 +11,14 @@
 //            search; the test is on the data itself, hence exact for ANY input;
 //   search   exhaustive over the K codes with the reference's rounding sequence (below), two codes
 //            per instruction (FMUL2 / FFMA2 / FADD2).  Work units = (64 leaders) x (a range of
-//            8-code chunks), dealt round-robin to the warps; partial results meet in a 64-bit
+//            8-code chunks), dealt evenly to the warps; partial results meet in a 64-bit
 //            shared-memory atomicMin on (ordered distance bits, code index);
 //   finalize every token takes its leader's index: idx (int64), z_q = fl(z + fl(e - z)) in NCHW,
 //            and sum((e-z)^2) accumulated per CTA; the last CTA adds the per-CTA partials in a
 //            fixed order (deterministic).
 // z is read once and idx / z_q written once: no intermediate ever goes to global memory.
+// This kernel serves cgic_vq_assign (raw codebook).  cgic_vq_assign_indexed (prepared codebook, codebook.cu)
+// runs vq_warp_kernel further down: same results from a handful of candidate codes per token.
 //
 // Rounding contract (bit-exact against torch CPU, see oracle/cgic_oracle.c and SURVEY.md 7.1):
 //     z2  = ((z0*z0 + z1*z1) + z2*z2) + z3*z3      every product and sum rounded to fp32
@@ -24,19 +26,26 @@
 //     dot = fma(z3,e3, fma(z2,e2, fma(z1,e1, fl(z0*e0))))
 //     d   = fl(fl(z2 + e2) - 2*dot) = fma(-2, dot, fl(z2 + e2))
 //     argmin with the LOWEST index among equal minima (torch.argmin).
-#include "common.cuh"
+#include "codebook.cuh"
 
 namespace cgic {
+
+const unsigned char *codebook_blob(const cgic_codebook *cb);  // codebook.cu
+int codebook_size(const cgic_codebook *cb);
+
 namespace {
 
 #ifndef CGIC_VQ_T
 #define CGIC_VQ_T 2
 #endif
 #ifndef CGIC_VQ_TILE
-#define CGIC_VQ_TILE 2048
+#define CGIC_VQ_TILE 1024
 #endif
 #ifndef CGIC_VQ_THREADS
-#define CGIC_VQ_THREADS 512
+#define CGIC_VQ_THREADS 256
+#endif
+#ifndef CGIC_VQ_CTAS
+#define CGIC_VQ_CTAS 2
 #endif
 constexpr int VQ_T = CGIC_VQ_T;  // tokens per lane in the search
 constexpr int VQ_CHUNK = 8;    // codes per chunk = 4 code pairs
@@ -46,6 +55,13 @@ constexpr int VQ_ROWS = 5;     // e0 e1 e2 e3 e^2
 constexpr int VQ_MAX_K = 4096;
 constexpr int VQ_TILE = CGIC_VQ_TILE;  // tokens per batch of strips (shared-memory capacity)
 constexpr int VQ_MAX_STRIPS = VQ_TILE / 16;  // a strip has at least 4 x 4 tokens
+constexpr int VQ_CTAS = CGIC_VQ_CTAS;        // resident CTAs per SM (persistent grid = VQ_CTAS x #SM)
+
+// dynamic shared memory of vq_fused_kernel: [raw codebook Kpad * 16][pair table Kpad * 20]
+//                                           [z float4 x TILE][best u64 x TILE][lead u16 x TILE][list u16 x TILE]
+__host__ __device__ inline size_t vq_smem_bytes(int Kpad) { return (size_t)Kpad * 36 + (size_t)VQ_TILE * (16 + 8 + 2 + 2); }
+// staged head of a prepared codebook (header | bin -> cell table | codebook | e^2), vq_warp_kernel
+__host__ __device__ inline size_t vq_stage_bytes(int K) { return (cb_layout(K).stage + 127) & ~(size_t)127; }
 
 typedef unsigned long long u64;
 
@@ -84,11 +100,34 @@ __device__ __forceinline__ float min3(float a, float b, float c)
     return r;
 }
 
-__device__ __forceinline__ float sumsq4(float a, float b, float c, float d)
+__device__ __forceinline__ float sumsq4(float a, float b, float c, float d) { return sumsq4f(a, b, c, d); }
+
+// exact reference distance of one code (rounding sequence of quantize.py:73-75, see the header)
+__device__ __forceinline__ void eval_cand(unsigned k, const float4 &zv, float z2, const float4 *__restrict__ cbs,
+                                          const float *__restrict__ e2s, float &best, int &bk)
 {
-    float s = __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b));
-    s = __fadd_rn(s, __fmul_rn(c, c));
-    return __fadd_rn(s, __fmul_rn(d, d));
+    const float4 e = cbs[k];
+    float dot = __fmul_rn(zv.x, e.x);
+    dot = __fmaf_rn(zv.y, e.y, dot);
+    dot = __fmaf_rn(zv.z, e.z, dot);
+    dot = __fmaf_rn(zv.w, e.w, dot);
+    const float d = __fmaf_rn(dot, -2.f, __fadd_rn(z2, e2s[k]));
+    if (d < best) {  // candidate lists ascend, so the lowest index wins ties (torch.argmin)
+        best = d;
+        bk = (int)k;
+    }
+}
+__device__ __forceinline__ void eval_word(unsigned wd, const float4 &zv, float z2, const float4 *cbs, const float *e2s, float &best, int &bk)
+{
+    eval_cand(wd & 0xffffu, zv, z2, cbs, e2s, best, bk);
+    eval_cand(wd >> 16, zv, z2, cbs, e2s, best, bk);
+}
+__device__ __forceinline__ void eval_piece(const uint4 &q, const float4 &zv, float z2, const float4 *cbs, const float *e2s, float &best, int &bk)
+{
+    eval_word(q.x, zv, z2, cbs, e2s, best, bk);
+    eval_word(q.y, zv, z2, cbs, e2s, best, bk);
+    eval_word(q.z, zv, z2, cbs, e2s, best, bk);
+    eval_word(q.w, zv, z2, cbs, e2s, best, bk);
 }
 
 // monotone map float -> uint32 (a < b  <=>  key(a) < key(b)); d is never -0 nor NaN here
@@ -125,6 +164,7 @@ struct VqTiles {
     int SC;                // tokens per strip = 4 * C
     int tiles_x, tiles_y;  // strips per image row / strip rows per image
     int NB;                // strips per batch (NB * SC <= VQ_TILE)
+    unsigned mSC, mC;      // ceil(2^32 / SC), ceil(2^32 / C): t / SC == __umulhi(t, mSC) for the small t used here
     int64_t n_strips;      // B * tiles_y * tiles_x
 };
 
@@ -137,15 +177,15 @@ __host__ __device__ inline VqTiles make_tiles(int B, int h, int w)
     t.tiles_x = (w + t.C - 1) / t.C;
     t.tiles_y = (h + 3) / 4;
     t.NB = VQ_TILE / t.SC;
+    t.mSC = (unsigned)((((unsigned long long)1 << 32) + t.SC - 1) / t.SC);
+    t.mC = (unsigned)((((unsigned long long)1 << 32) + t.C - 1) / t.C);
     t.n_strips = (int64_t)B * t.tiles_x * t.tiles_y;
     return t;
 }
 
-// shared memory: [raw codebook Kpad*16][pair table (Kpad/8)*5*4 float2][z float4 x TILE][best u64 x TILE]
-//                [lead u16 x TILE][list u16 x TILE]
-__global__ void __launch_bounds__(VQ_THREADS, 1)
-vq_fused_kernel(const float *__restrict__ z, int B, int h, int w, const VqTiles tl, const float *__restrict__ codebook, int K,
-                int Kpad, int64_t *__restrict__ idx_out, float *__restrict__ zq_out, double *__restrict__ partials,
+__global__ void __launch_bounds__(VQ_THREADS, VQ_CTAS)
+vq_fused_kernel(const float *__restrict__ z, int B, int h, int w, const VqTiles tl, const float *__restrict__ codebook, int K, int Kpad,
+                int64_t *__restrict__ idx_out, float *__restrict__ zq_out, double *__restrict__ partials,
                 int32_t *__restrict__ counters, double *__restrict__ sqerr_out)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -169,7 +209,8 @@ vq_fused_kernel(const float *__restrict__ z, int B, int h, int w, const VqTiles 
     if (tid == 0) mbar_init(&mbar);
     __syncthreads();
     if (tid == 0) tma_load_1d(raw, codebook, (uint32_t)K * 16u, &mbar);
-    bool table_ready = false;  // the pair table is built after the first batch's loads are in flight
+    bool staged = false;       // waited for the bulk copy (after the first batch's loads are in flight)
+    bool table_ready = false;  // the pair table of the exhaustive search is built when a batch first needs it
 
     const int64_t plane = (int64_t)h * w;
     const int nchunks = Kpad / VQ_CHUNK;
@@ -203,8 +244,8 @@ vq_fused_kernel(const float *__restrict__ z, int B, int h, int w, const VqTiles 
                 const int t = t0 + i * VQ_THREADS;
                 v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (t < ntok) {
-                    const int sl = t / SC, r = t - sl * SC;
-                    const int ly = r / C, lx = r - ly * C;
+                    const int sl = (int)__umulhi((unsigned)t, tl.mSC), r = t - sl * SC;
+                    const int ly = (int)__umulhi((unsigned)r, tl.mC), lx = r - ly * C;
                     const int gy = s_sy[sl] + ly, gx = s_sx[sl] + lx;
                     if (gy < h && gx < w) {
                         const float *zb = z + (int64_t)s_sb[sl] * 4 * plane;
@@ -217,29 +258,9 @@ vq_fused_kernel(const float *__restrict__ z, int B, int h, int w, const VqTiles 
             for (int i = 0; i < 4; ++i)
                 if (t0 + i * VQ_THREADS < ntok) zs[t0 + i * VQ_THREADS] = v[i];
         }
-        if (!table_ready) {
-            table_ready = true;
+        if (!staged) {
+            staged = true;
             mbar_wait(&mbar, 0);
-        // --- pair table: row r of chunk c holds (v[8c+0],v[8c+1]) (v[8c+2],v[8c+3]) ... for v = e_r or e^2
-        for (int pr = tid; pr < Kpad / 2; pr += VQ_THREADS) {
-            const int k0 = 2 * pr, k1 = k0 + 1;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-            float sa = __int_as_float(0x7f800000), sb = sa;  // padding codes: d = +inf, never selected
-            if (k0 < K) {
-                a = reinterpret_cast<const float4 *>(raw)[k0];
-                sa = sumsq4(a.x, a.y, a.z, a.w);
-            }
-            if (k1 < K) {
-                b = reinterpret_cast<const float4 *>(raw)[k1];
-                sb = sumsq4(b.x, b.y, b.z, b.w);
-            }
-            float2 *dst = tab + (size_t)(pr >> 2) * (VQ_ROWS * 4) + (pr & 3);
-            dst[0] = make_float2(a.x, b.x);
-            dst[4] = make_float2(a.y, b.y);
-            dst[8] = make_float2(a.z, b.z);
-            dst[12] = make_float2(a.w, b.w);
-            dst[16] = make_float2(sa, sb);
-        }
         }
         __syncthreads();
         VQ_STAMP(2);
@@ -248,8 +269,8 @@ vq_fused_kernel(const float *__restrict__ z, int B, int h, int w, const VqTiles 
             const int t = t0 + tid;
             bool leader = false;
             if (t < ntok) {
-                const int sl = t / SC, r = t - sl * SC;
-                const int ly = r / C, lx = r - ly * C;
+                const int sl = (int)__umulhi((unsigned)t, tl.mSC), r = t - sl * SC;
+                const int ly = (int)__umulhi((unsigned)r, tl.mC), lx = r - ly * C;
                 if (s_sy[sl] + ly < h && s_sx[sl] + lx < w) {
                     const uint4 v = reinterpret_cast<const uint4 *>(zs)[t];
                     int ld = t;
@@ -278,8 +299,33 @@ vq_fused_kernel(const float *__restrict__ z, int B, int h, int w, const VqTiles 
         }
         __syncthreads();
         VQ_STAMP(3);
-        // ---- search: units = (64 leaders) x (chunk range), round-robin over the warps
+        // ---- search: exhaustive, units = (64 leaders) x (chunk range) dealt evenly to the warps
         const int L = s_count;
+        if (L > 0 && !table_ready) {
+            table_ready = true;
+        // --- pair table: row r of chunk c holds (v[8c+0],v[8c+1]) (v[8c+2],v[8c+3]) ... for v = e_r or e^2
+        for (int pr = tid; pr < Kpad / 2; pr += VQ_THREADS) {
+            const int k0 = 2 * pr, k1 = k0 + 1;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+            float sa = __int_as_float(0x7f800000), sb = sa;  // padding codes: d = +inf, never selected
+            if (k0 < K) {
+                a = reinterpret_cast<const float4 *>(raw)[k0];
+                sa = sumsq4(a.x, a.y, a.z, a.w);
+            }
+            if (k1 < K) {
+                b = reinterpret_cast<const float4 *>(raw)[k1];
+                sb = sumsq4(b.x, b.y, b.z, b.w);
+            }
+            float2 *dst = tab + (size_t)(pr >> 2) * (VQ_ROWS * 4) + (pr & 3);
+            dst[0] = make_float2(a.x, b.x);
+            dst[4] = make_float2(a.y, b.y);
+            dst[8] = make_float2(a.z, b.z);
+            dst[12] = make_float2(a.w, b.w);
+            dst[16] = make_float2(sa, sb);
+        }
+
+            __syncthreads();
+        }
         const int groups = (L + 32 * VQ_T - 1) / (32 * VQ_T);
         // (group, chunk) items are dealt to the warps as contiguous, equally long ranges: a warp
         // works on at most two groups and every warp gets the same number of chunks
@@ -374,8 +420,8 @@ vq_fused_kernel(const float *__restrict__ z, int B, int h, int w, const VqTiles 
         VQ_STAMP(4);
         // ---- finalize
         for (int t = tid; t < ntok; t += VQ_THREADS) {
-            const int sl = t / SC, r = t - sl * SC;
-            const int ly = r / C, lx = r - ly * C;
+            const int sl = (int)__umulhi((unsigned)t, tl.mSC), r = t - sl * SC;
+            const int ly = (int)__umulhi((unsigned)r, tl.mC), lx = r - ly * C;
             const int gy = s_sy[sl] + ly, gx = s_sx[sl] + lx, b = s_sb[sl];
             if (gy >= h || gx >= w) continue;
             const u64 key = best[lead[t]];
@@ -403,6 +449,7 @@ vq_fused_kernel(const float *__restrict__ z, int B, int h, int w, const VqTiles 
         }
     }
     VQ_STAMP(5);
+    if (!staged) mbar_wait(&mbar, 0);  // never leave with the bulk copy in flight
     if (!sqerr_out) return;
     // deterministic reduction: warp shuffle -> CTA -> per-CTA partial -> the last CTA sums them in order
 #pragma unroll
@@ -435,6 +482,225 @@ vq_fused_kernel(const float *__restrict__ z, int B, int h, int w, const VqTiles 
     VQ_STAMP(6);
 }
 
+// ---- indexed search, warp-autonomous ---------------------------------------------------------
+// The prepared-codebook path needs so little arithmetic per token that CTA-wide phases (and their
+// barriers) dominate; here every WARP owns a tile of 4 rows x 32 columns of one image and runs
+// load -> classify -> search -> finalize on its own, synchronising with __syncwarp only, so the
+// warps of an SM sit in different phases and hide each other's memory latency.
+//   load      lane = column: 4 rows x 4 channels per lane, each warp load is one 128-byte row segment;
+//             the tile is also written to the warp's shared-memory slice as one float4 per token;
+//   classify  as in vq_fused_kernel (bit-identical to the top-left token of the 4x4 / 2x2 block =>
+//             follower); leaders are compacted with ballots, no atomics;
+//   search    one lane per leader: grid cell -> candidate record (4 x 16-byte loads) -> the reference's
+//             rounding sequence on the candidates; leaders the index cannot serve are searched
+//             exhaustively by their lane (rare; same result);
+//   finalize  idx / z_q row segments, sum((e - z)^2) per lane, reduced per CTA at the end.
+constexpr int VQW_THREADS = 256;
+constexpr int VQW_WARPS = VQW_THREADS / 32;
+constexpr int VQW_TILE = 128;  // tokens per warp tile
+__host__ __device__ inline size_t vqw_smem_bytes(int K) { return vq_stage_bytes(K) + (size_t)VQW_WARPS * VQW_TILE * (16 + 2 + 1 + 1); }
+
+__global__ void __launch_bounds__(VQW_THREADS, 3)
+vq_warp_kernel(const float *__restrict__ z, int h, int w, int tiles_x, int tiles_y, int64_t n_tiles, const unsigned char *__restrict__ blob,
+               int K, int64_t *__restrict__ idx_out, float *__restrict__ zq_out, double *__restrict__ partials,
+               int32_t *__restrict__ counters, double *__restrict__ sqerr_out)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ double s_red[VQW_WARPS];
+    __shared__ bool s_last;
+    const CbLayout CL = cb_layout(K);
+    const CbHeader *hdr = reinterpret_cast<const CbHeader *>(smem);
+    const unsigned char *lut = smem + CL.lut;
+    const float4 *cbs = reinterpret_cast<const float4 *>(smem + CL.cb);
+    const float *e2s = reinterpret_cast<const float *>(smem + CL.e2);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned char *wbase = smem + vq_stage_bytes(K) + (size_t)warp * VQW_TILE * (16 + 2 + 1 + 1);
+    float4 *zs = reinterpret_cast<float4 *>(wbase);                      // [128] the tile, row-major
+    uint16_t *res = reinterpret_cast<uint16_t *>(zs + VQW_TILE);         // [128] code of a leader token
+    uint8_t *list = reinterpret_cast<uint8_t *>(res + VQW_TILE);         // [128] leader tokens, compacted
+    uint8_t *lead = list + VQW_TILE;                                     // [128] leader of every token
+    const uint4 *recs = reinterpret_cast<const uint4 *>(blob + CL.rec);
+
+    pdl_launch_dependents();
+    pdl_wait();  // the prepared blob and z may come straight from a preceding kernel
+    if (tid == 0) mbar_init(&mbar);
+    __syncthreads();
+    if (tid == 0) tma_load_1d(smem, blob, (uint32_t)CL.stage, &mbar);
+    bool staged = false;
+
+    const int64_t plane = (int64_t)h * w;
+    const int tpi = tiles_x * tiles_y;
+    double sq = 0.0;
+    const int64_t wid = (int64_t)blockIdx.x * VQW_WARPS + warp, nwarps = (int64_t)gridDim.x * VQW_WARPS;
+    for (int64_t tile = wid; tile < n_tiles; tile += nwarps) {
+        const int b = (int)(tile / tpi), rt = (int)(tile - (int64_t)b * tpi);
+        const int ty = rt / tiles_x, tx = rt - ty * tiles_x;
+        const int gx = tx * 32 + lane, gy0 = ty * 4;
+        const bool col_ok = gx < w;
+        const float *zb = z + (int64_t)b * 4 * plane;
+        // ---- load
+        float zt[4][4];  // [row][channel]
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const bool ok = col_ok && gy0 + r < h;
+            const int64_t p = (int64_t)(gy0 + r) * w + gx;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) zt[r][c] = ok ? __ldg(zb + c * plane + p) : 0.f;
+        }
+        __syncwarp();  // the previous tile's slice is no longer read
+#pragma unroll
+        for (int r = 0; r < 4; ++r) zs[r * 32 + lane] = make_float4(zt[r][0], zt[r][1], zt[r][2], zt[r][3]);
+        if (!staged) {
+            staged = true;
+            mbar_wait(&mbar, 0);
+        }
+        __syncwarp();
+        // ---- classify + compact
+        int nlead = 0;
+        unsigned lmask[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int t = r * 32 + lane;
+            int ld = t;
+            const bool ok = col_ok && gy0 + r < h;
+            if (ok) {
+                const uint4 v = reinterpret_cast<const uint4 *>(zs)[t];
+                const int t4 = lane & ~3;  // row 0 of the tile is the top row of every 4x4 block
+                if (t4 != t) {
+                    const uint4 u = reinterpret_cast<const uint4 *>(zs)[t4];
+                    if (u.x == v.x && u.y == v.y && u.z == v.z && u.w == v.w) ld = t4;
+                }
+                if (ld == t) {
+                    const int t2 = (r & ~1) * 32 + (lane & ~1);
+                    if (t2 != t) {
+                        const uint4 u = reinterpret_cast<const uint4 *>(zs)[t2];
+                        if (u.x == v.x && u.y == v.y && u.z == v.z && u.w == v.w) ld = t2;
+                    }
+                }
+            }
+            lead[t] = (uint8_t)ld;
+            lmask[r] = __ballot_sync(0xffffffffu, ok && ld == t);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if ((lmask[r] >> lane) & 1u) list[nlead + __popc(lmask[r] & ((1u << lane) - 1u))] = (uint8_t)(r * 32 + lane);
+            nlead += __popc(lmask[r]);
+        }
+        __syncwarp();
+        // ---- search: one lane per leader
+        const bool usable = hdr->valid != 0;
+        for (int j = lane; j < nlead; j += 32) {
+            const int t = list[j];
+            const float4 v = zs[t];
+            int cell = -1;
+            if (usable) {
+                const int b0 = cb_bin(v.x, hdr->lo[0], hdr->inv[0]), b1 = cb_bin(v.y, hdr->lo[1], hdr->inv[1]),
+                          b2 = cb_bin(v.z, hdr->lo[2], hdr->inv[2]), b3 = cb_bin(v.w, hdr->lo[3], hdr->inv[3]);
+                if ((b0 | b1 | b2 | b3) >= 0)
+                    cell = (((int)lut[b0] * CB_G + (int)lut[CB_NB + b1]) * CB_G + (int)lut[2 * CB_NB + b2]) * CB_G + (int)lut[3 * CB_NB + b3];
+            }
+            unsigned count = 0xffffu;
+            uint4 q0, q1, q2, q3;
+            const uint4 *rp = recs + (size_t)max(cell, 0) * (CB_RW / 8);
+            if (cell >= 0) {
+                q0 = __ldg(rp);
+                q1 = __ldg(rp + 1);
+                q2 = __ldg(rp + 2);
+                q3 = __ldg(rp + 3);
+                count = q0.x & 0xffffu;
+            }
+            const float z2 = sumsq4(v.x, v.y, v.z, v.w);
+            float bd = __int_as_float(0x7f800000);
+            int bk = 0;
+            if (count != 0xffffu) {
+                // entries past `count` repeat the last candidate, so whole 16-byte pieces are evaluated
+                eval_cand(q0.x >> 16, v, z2, cbs, e2s, bd, bk);
+                eval_word(q0.y, v, z2, cbs, e2s, bd, bk);
+                eval_word(q0.z, v, z2, cbs, e2s, bd, bk);
+                eval_word(q0.w, v, z2, cbs, e2s, bd, bk);
+                if (count > 7) eval_piece(q1, v, z2, cbs, e2s, bd, bk);
+                if (count > 15) eval_piece(q2, v, z2, cbs, e2s, bd, bk);
+                if (count > 23) eval_piece(q3, v, z2, cbs, e2s, bd, bk);
+                for (unsigned pc = 4; pc * 8 < count + 1; ++pc) eval_piece(__ldg(rp + pc), v, z2, cbs, e2s, bd, bk);
+            } else {
+                // outside the grid / overflowing cell / no usable index: every code, ascending (lowest index wins ties;
+                // no finite distance at all leaves index 0, like vq_fused_kernel)
+                for (int k = 0; k < K; ++k) {
+                    const float4 e = cbs[k];
+                    float dot = __fmul_rn(v.x, e.x);
+                    dot = __fmaf_rn(v.y, e.y, dot);
+                    dot = __fmaf_rn(v.z, e.z, dot);
+                    dot = __fmaf_rn(v.w, e.w, dot);
+                    const float d = __fmaf_rn(dot, -2.f, __fadd_rn(z2, sumsq4(e.x, e.y, e.z, e.w)));
+                    if (d < bd) {
+                        bd = d;
+                        bk = k;
+                    }
+                }
+            }
+            res[t] = (uint16_t)bk;
+        }
+        __syncwarp();
+        // ---- finalize
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (!(col_ok && gy0 + r < h)) continue;
+            const int k = res[lead[r * 32 + lane]];
+            const int64_t p = (int64_t)(gy0 + r) * w + gx;
+            idx_out[(int64_t)b * plane + p] = k;
+            if (zq_out || sqerr_out) {
+                const float4 e = cbs[k];
+                const float d0 = __fsub_rn(e.x, zt[r][0]), d1 = __fsub_rn(e.y, zt[r][1]), d2 = __fsub_rn(e.z, zt[r][2]),
+                            d3 = __fsub_rn(e.w, zt[r][3]);
+                if (zq_out) {
+                    float *q = zq_out + (int64_t)b * 4 * plane + p;
+                    q[0] = __fadd_rn(zt[r][0], d0);
+                    q[plane] = __fadd_rn(zt[r][1], d1);
+                    q[2 * plane] = __fadd_rn(zt[r][2], d2);
+                    q[3 * plane] = __fadd_rn(zt[r][3], d3);
+                }
+                float acc = __fmul_rn(d0, d0);
+                acc = __fmaf_rn(d1, d1, acc);
+                acc = __fmaf_rn(d2, d2, acc);
+                acc = __fmaf_rn(d3, d3, acc);
+                sq += (double)acc;
+            }
+        }
+    }
+    if (!staged) mbar_wait(&mbar, 0);  // never leave with the bulk copy in flight
+    if (!sqerr_out) return;
+    // deterministic reduction: warp shuffle -> CTA -> per-CTA partial -> the last CTA sums them in order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if (lane == 0) s_red[warp] = sq;
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int i = 0; i < VQW_WARPS; ++i) tot += s_red[i];
+        partials[blockIdx.x] = tot;
+        __threadfence();
+        s_last = (atomicAdd(&counters[0], 1) == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double tot = 0.0;
+        for (int i = tid; i < (int)gridDim.x; i += VQW_THREADS) tot += __ldcg(&partials[i]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if (lane == 0) s_red[warp] = tot;
+        __syncthreads();
+        if (tid == 0) {
+            double all = 0.0;
+            for (int i = 0; i < VQW_WARPS; ++i) all += s_red[i];
+            *sqerr_out = all;
+            counters[0] = 0;  // leave the ticket zeroed for the next launch (workspace contract)
+        }
+    }
+}
+
+
 __global__ void vq_count_kernel(const int64_t *__restrict__ idx, int64_t n, float *__restrict__ counters, int K)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -453,23 +719,21 @@ using namespace cgic;
 // Contract: the first 64 bytes must be ZERO before the first use; the kernel leaves them zero.
 extern "C" size_t cgic_vq_workspace_bytes(int64_t) { return 256 + 8 * 4096; }
 
-extern "C" int cgic_vq_assign(const float *z, int B, int h, int w, const float *codebook, int K, int64_t *idx_out,
-                              float *zq_out, double *sqerr_out, void *workspace, size_t workspace_bytes,
-                              cgic_stream_t stream_)
+static int vq_launch(const char *who, const float *z, int B, int h, int w, const float *codebook, int K, int64_t *idx_out, float *zq_out,
+                     double *sqerr_out, void *workspace, size_t workspace_bytes, cgic_stream_t stream_)
 {
-    CGIC_REQUIRE(z && codebook && idx_out && workspace, CGIC_EINVAL, "cgic_vq_assign: null argument");
-    CGIC_REQUIRE(B >= 0 && h > 0 && w > 0, CGIC_EINVAL, "cgic_vq_assign: bad shape B=%d h=%d w=%d", B, h, w);
-    CGIC_REQUIRE(K >= 1 && K <= VQ_MAX_K, CGIC_EINVAL, "cgic_vq_assign: K=%d outside [1, %d]", K, VQ_MAX_K);
-    CGIC_REQUIRE((reinterpret_cast<uintptr_t>(codebook) & 15) == 0, CGIC_EINVAL, "cgic_vq_assign: codebook must be 16-byte aligned");
+    CGIC_REQUIRE(z && idx_out && workspace, CGIC_EINVAL, "%s: null argument", who);
+    CGIC_REQUIRE(B >= 0 && h > 0 && w > 0, CGIC_EINVAL, "%s: bad shape B=%d h=%d w=%d", who, B, h, w);
+    CGIC_REQUIRE(K >= 1 && K <= VQ_MAX_K, CGIC_EINVAL, "%s: K=%d outside [1, %d]", who, K, VQ_MAX_K);
     const int64_t n = (int64_t)B * h * w;
-    CGIC_REQUIRE(n < (int64_t)1 << 31, CGIC_EINVAL, "cgic_vq_assign: %lld tokens exceed 2^31", (long long)n);
+    CGIC_REQUIRE(n < (int64_t)1 << 31, CGIC_EINVAL, "%s: %lld tokens exceed 2^31", who, (long long)n);
     cudaStream_t stream = as_stream(stream_);
     if (n == 0) {
         if (sqerr_out) CGIC_CUDA_CHECK(cudaMemsetAsync(sqerr_out, 0, sizeof(double), stream));
         return CGIC_OK;
     }
-    CGIC_REQUIRE(workspace_bytes >= cgic_vq_workspace_bytes(n), CGIC_ESPACE, "cgic_vq_assign: workspace %zu < %zu bytes",
-                 workspace_bytes, cgic_vq_workspace_bytes(n));
+    CGIC_REQUIRE(workspace_bytes >= cgic_vq_workspace_bytes(n), CGIC_ESPACE, "%s: workspace %zu < %zu bytes", who, workspace_bytes,
+                 cgic_vq_workspace_bytes(n));
     int32_t *counters = static_cast<int32_t *>(workspace);
     double *partials = reinterpret_cast<double *>(static_cast<unsigned char *>(workspace) + 256);
 
@@ -478,19 +742,70 @@ extern "C" int cgic_vq_assign(const float *z, int B, int h, int w, const float *
         int dev = 0, sm = 0;
         CGIC_CUDA_CHECK(cudaGetDevice(&dev));
         CGIC_CUDA_CHECK(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
-        CGIC_CUDA_CHECK(cudaFuncSetAttribute(vq_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             VQ_MAX_K * 36 + VQ_TILE * (16 + 8 + 2 + 2)));
+        CGIC_CUDA_CHECK(cudaFuncSetAttribute(vq_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vq_smem_bytes(VQ_MAX_K)));
         n_sm = sm;
     }
     const int Kpad = (K + VQ_CHUNK - 1) / VQ_CHUNK * VQ_CHUNK;
-    const size_t smem = (size_t)Kpad * 36 + (size_t)VQ_TILE * (16 + 8 + 2 + 2);
+    const size_t smem = vq_smem_bytes(Kpad);
     const VqTiles tl = make_tiles(B, h, w);
-    // persistent grid: one CTA per SM, never more CTAs than strips
-    const int grid = (int)(tl.n_strips < (int64_t)n_sm ? tl.n_strips : (int64_t)n_sm);
+    // persistent grid: VQ_CTAS CTAs per SM (when the codebook leaves room), never more CTAs than strips
+    const int per_sm = smem * VQ_CTAS <= 220 * 1024 ? VQ_CTAS : 1;
+    const int64_t cap = (int64_t)n_sm * per_sm;
+    const int grid = (int)(tl.n_strips < cap ? tl.n_strips : cap);
     {
         CGIC_PROF("vq_fused_kernel", stream);
-        CGIC_CUDA_CHECK(launch_pdl(vq_fused_kernel, dim3(grid), dim3(VQ_THREADS), smem, stream, z, B, h, w, tl, codebook, K, Kpad, idx_out,
-                                   zq_out, partials, counters, sqerr_out));
+        CGIC_CUDA_CHECK(launch_pdl(vq_fused_kernel, dim3(grid), dim3(VQ_THREADS), smem, stream, z, B, h, w, tl, codebook, K, Kpad, idx_out, zq_out,
+                                   partials, counters, sqerr_out));
+    }
+    CGIC_LAUNCH_CHECK();
+    return CGIC_OK;
+}
+
+extern "C" int cgic_vq_assign(const float *z, int B, int h, int w, const float *codebook, int K, int64_t *idx_out,
+                              float *zq_out, double *sqerr_out, void *workspace, size_t workspace_bytes,
+                              cgic_stream_t stream)
+{
+    CGIC_REQUIRE(codebook, CGIC_EINVAL, "cgic_vq_assign: null argument");
+    CGIC_REQUIRE((reinterpret_cast<uintptr_t>(codebook) & 15) == 0, CGIC_EINVAL, "cgic_vq_assign: codebook must be 16-byte aligned");
+    return vq_launch("cgic_vq_assign", z, B, h, w, codebook, K, idx_out, zq_out, sqerr_out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int cgic_vq_assign_indexed(const float *z, int B, int h, int w, const cgic_codebook *cb, int64_t *idx_out, float *zq_out,
+                                      double *sqerr_out, void *workspace, size_t workspace_bytes, cgic_stream_t stream_)
+{
+    const unsigned char *blob = codebook_blob(cb);
+    CGIC_REQUIRE(blob, CGIC_EINVAL, "cgic_vq_assign_indexed: no prepared codebook (cgic_codebook_update has not been called)");
+    CGIC_REQUIRE(z && idx_out && workspace, CGIC_EINVAL, "cgic_vq_assign_indexed: null argument");
+    CGIC_REQUIRE(B >= 0 && h > 0 && w > 0, CGIC_EINVAL, "cgic_vq_assign_indexed: bad shape B=%d h=%d w=%d", B, h, w);
+    const int K = codebook_size(cb);
+    const int64_t n = (int64_t)B * h * w;
+    CGIC_REQUIRE(n < (int64_t)1 << 31, CGIC_EINVAL, "cgic_vq_assign_indexed: %lld tokens exceed 2^31", (long long)n);
+    cudaStream_t stream = as_stream(stream_);
+    if (n == 0) {
+        if (sqerr_out) CGIC_CUDA_CHECK(cudaMemsetAsync(sqerr_out, 0, sizeof(double), stream));
+        return CGIC_OK;
+    }
+    CGIC_REQUIRE(workspace_bytes >= cgic_vq_workspace_bytes(n), CGIC_ESPACE, "cgic_vq_assign_indexed: workspace %zu < %zu bytes",
+                 workspace_bytes, cgic_vq_workspace_bytes(n));
+    int32_t *counters = static_cast<int32_t *>(workspace);
+    double *partials = reinterpret_cast<double *>(static_cast<unsigned char *>(workspace) + 256);
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0, sm = 0;
+        CGIC_CUDA_CHECK(cudaGetDevice(&dev));
+        CGIC_CUDA_CHECK(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
+        CGIC_CUDA_CHECK(cudaFuncSetAttribute(vq_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vqw_smem_bytes(VQ_MAX_K)));
+        n_sm = sm;
+    }
+    const int tiles_x = (w + 31) / 32, tiles_y = (h + 3) / 4;
+    const int64_t n_tiles = (int64_t)B * tiles_x * tiles_y;
+    // one tile per warp while the grid fits the machine (3 CTAs of 8 warps per SM), persistent beyond that
+    const int64_t want = (n_tiles + VQW_WARPS - 1) / VQW_WARPS, cap = (int64_t)3 * n_sm;
+    const int grid = (int)(want < cap ? want : cap);
+    {
+        CGIC_PROF("vq_warp_kernel", stream);
+        CGIC_CUDA_CHECK(launch_pdl(vq_warp_kernel, dim3(grid), dim3(VQW_THREADS), vqw_smem_bytes(K), stream, z, h, w, tiles_x, tiles_y, n_tiles,
+                                   blob, K, idx_out, zq_out, partials, counters, sqerr_out));
     }
     CGIC_LAUNCH_CHECK();
     return CGIC_OK;

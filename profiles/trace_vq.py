@@ -14,12 +14,13 @@ mc, mm, mf, _, mode = cg.ops.router(e16.to(dev), e8.to(dev), c, m, per_image=Tru
 hc, hm, hf = (t.to(dev) for t in workload.heads(B, H, W, cbk, 1000))
 z = cg.ops.mask_mix(hc, hm, hf, mc, mm, mf)
 flush = torch.empty(1 << 28, dtype=torch.uint8, device=dev)
+pc = cg.ops.Codebook(cb)
 for _ in range(3):
     flush.zero_()
-    cg.ops.vq_assign(z, cb)
+    cg.ops.vq_assign(z, pc)
 torch.cuda.synchronize()
 ws = list(cg.ops._ws_cache.values())[0]
-raw = ws[256:].view(torch.int64)[512:512 + 300 * 8].cpu().numpy().reshape(300, 8)[:148]
+raw = ws[256:].view(torch.int64)[512:512 + 300 * 8].cpu().numpy().reshape(300, 8)[:296]
 smid = raw[:, 7]
 st = raw[:, :7].astype(np.float64)
 t0 = st[:, 0].min()
