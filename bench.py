@@ -14,9 +14,10 @@ over ranks with no data-path collective, one all-reduce of {bytes, pixels, sqerr
 
     value     device-resident: inputs already in HBM, each step timed by a CUDA-event pair on the
               launching stream, L2 flushed (256 MiB memset) between steps outside the pairs.
-    e2e       the host-buffer C-ABI call cgic_session_roundtrip_host (= CGIC.compress, model.py:206-401:
+    e2e       the host-buffer C-ABI call cgic_session_roundtrip_arena (= CGIC.compress, model.py:206-401:
               encode + pack + unpack + re-assembly): pinned host inputs -> H2D -> kernels -> D2H of
-              every result (streams, sizes, decoded indices / masks / latents), wall clock, per step.
+              every result (streams, sizes, decoded indices / masks / latents), wall clock, per step;
+              the batch moves as pipelined image ranges, one copy per direction and range.
     roofline  dominant kernel, its duration measured live with the library's per-launch CUDA
               events (cgic_prof_*), against the algorithmic bytes of DESIGN.md and the measured
               HBM peak of MEASURED_PEAKS.json.
@@ -117,7 +118,7 @@ def parse_args():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-parts", type=int, default=0, help="pipeline depth of the host-buffer session (0 = library default)")
+    ap.add_argument("--e2e-parts", type=int, default=0, help="image ranges the pinned-arena round trip is pipelined in (0 = 8)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -285,7 +286,7 @@ def run_b200(args):
         runner()
     torch.cuda.synchronize()
 
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 and not os.environ.get('CGIC_BENCH_NO_SAMPLER') else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     if world > 1:
         dist.barrier()
@@ -315,8 +316,6 @@ def run_b200(args):
 
     # ---- e2e: host buffers through the C-ABI session (H2D + kernels + D2H inside the timed region)
     sess = cg.ops.Session(B, h, w, mode, table, cbk)
-    if args.e2e_parts:
-        sess.set_pipeline(args.e2e_parts)
     zh = z.cpu().pin_memory()
     mh = [t_.cpu().pin_memory() for t_ in (mc, mm, mf)]
     for _ in range(3):
@@ -326,12 +325,23 @@ def run_b200(args):
     for _ in range(3):
         rt = sess.roundtrip(zh, *mh)
     assert torch.equal(rt[1], sizes_first) and torch.equal(rt[5].view(-1), idx.cpu()) and int(rt[7].abs().sum()) == 0
+    # the same call on the session's pinned arenas: one copy per direction and image range, ranges pipelined, CUDA graph
+    views = sess.arena(args.e2e_parts or 8)
+    for v in views:
+        r = v["images"]
+        v["z"].copy_(zh[r.start:r.stop])
+        for name, src in zip(("m_c", "m_m", "m_f"), mh):
+            v[name].copy_(src[r.start:r.stop])
+    for _ in range(5):
+        sess.roundtrip_arena()
+    assert torch.equal(torch.cat([v["sizes"] for v in views]), sizes_first) and int(sum(int(v["status"].abs().sum()) for v in views)) == 0
+    assert torch.equal(torch.cat([v["ind"].reshape(-1) for v in views]), idx.cpu())
     n_e2e = max(10, args.steps)
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for _ in range(n_e2e):
-        sess.roundtrip(zh, *mh)           # = CGIC.compress: encode + pack + unpack + re-assembly, host in / host out
+        sess.roundtrip_arena()            # = CGIC.compress: encode + pack + unpack + re-assembly, pinned host in / pinned host out
     e2e_s = time.perf_counter() - t0
     t_end = time.time()
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -387,7 +397,7 @@ def run_b200(args):
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config_of(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e,
-                    "ms_per_step": 1e3 * e2e_s / n_e2e},
+                    "ms_per_step": 1e3 * e2e_s / n_e2e, "call": "cgic_session_roundtrip_arena", "image_ranges": len(views)},
             "gpu_launches": kernels_per_step * args.steps, "cuda_graph": graph is not None,
             "bpp": bpp, "stream_bytes_per_step": tot_bytes, "clocks": clocks, "roofline": roofline}
 

@@ -63,6 +63,9 @@ _SIGNATURES = {
     "cgic_session_compress_host": (c_int, [c_void_p] * 10),
     "cgic_session_decompress_host": (c_int, [c_void_p] * 9),
     "cgic_session_roundtrip_host": (c_int, [c_void_p] * 16),
+    "cgic_session_arena": (c_int, [c_void_p, c_int]),
+    "cgic_session_arena_tensor": (c_int, [c_void_p, c_int, c_int, C.POINTER(c_void_p), C.POINTER(c_int), C.POINTER(c_int)]),
+    "cgic_session_roundtrip_arena": (c_int, [c_void_p, c_int, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -6,6 +6,7 @@
 // overlap (PCIe is full duplex and the copy engines run beside the SMs).  Mirrors CGIC.compress (CGIC/models/model.py:206-401) minus the CNNs:
 //   compress   = VectorQuantize2.forward (a1) + selection (a7) + 5-stream pack (a9/a11/a12)
 //   decompress = decompress_string x5 (a10/a11) + re-assembly (a13) + codebook gather (a14)
+#include <cstdlib>
 #include <new>
 
 #include "common.cuh"
@@ -29,6 +30,22 @@ struct cgic_session {
     double *sqerr_host = nullptr;  // pinned, [MAX_PARTS]
     unsigned char *ws_vq = nullptr, *ws_un = nullptr;  // MAX_PARTS slices each
     size_t ws_vq_bytes = 0, ws_un_bytes = 0;
+    // ---- pinned-arena round trip (cgic_session_arena / cgic_session_roundtrip_arena)
+    // The batch is cut into `a_parts` image ranges.  Every range has ONE contiguous input block
+    // [z | m_c | m_m | m_f] and ONE contiguous output block [bytes | sizes | status | sqerr | ind | quant |
+    // dmc | dmm | dmf | idx | zq], laid out identically in a pinned host arena and a device arena, so a range
+    // moves with one H2D and one D2H copy; the whole call is a CUDA graph of per-range branches.
+    int a_parts = 0;
+    unsigned char *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr;
+    size_t in_bytes = 0, out_bytes = 0;
+    struct Part {
+        int b0 = 0, nb = 0;
+        size_t in_off = 0, in_len = 0, out_off = 0, out_core = 0, out_idx = 0, out_all = 0;  // D2H lengths by request
+        size_t o[CGIC_ARENA_COUNT] = {};  // offset of every tensor inside its block
+    } part[MAX_PARTS];
+    cudaGraphExec_t graph[4] = {};  // by flags (bit 0: idx, bit 1: zq)
+    cudaEvent_t fork = nullptr, join[MAX_PARTS] = {};
+    bool warmed[4] = {};
 };
 
 extern "C" int cgic_session_create(int B, int h, int w, int mode, const cgic_table *t, const float *codebook_host, int K,
@@ -116,6 +133,15 @@ extern "C" void cgic_session_destroy(cgic_session *s)
     if (!s) return;
     for (cudaStream_t st : s->streams)
         if (st) cudaStreamDestroy(st);
+    for (cudaGraphExec_t g : s->graph)
+        if (g) cudaGraphExecDestroy(g);
+    if (s->fork) cudaEventDestroy(s->fork);
+    for (cudaEvent_t e : s->join)
+        if (e) cudaEventDestroy(e);
+    if (s->h_in) cudaFreeHost(s->h_in);
+    if (s->h_out) cudaFreeHost(s->h_out);
+    if (s->d_in) cudaFree(s->d_in);
+    if (s->d_out) cudaFree(s->d_out);
     if (s->index) cgic_codebook_free(s->index);
     if (s->packed) cudaEventDestroy(s->packed);
     if (s->arena) cudaFree(s->arena);
@@ -241,5 +267,190 @@ extern "C" int cgic_session_roundtrip_host(cgic_session *s, const float *z, cons
     CGIC_CUDA_CHECK(cudaStreamSynchronize(enc));
     CGIC_CUDA_CHECK(cudaStreamSynchronize(dec));
     if (sqerr_out) *sqerr_out = s->sqerr_host[0];
+    return CGIC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pinned-arena round trip
+// ---------------------------------------------------------------------------------------------
+static size_t arena_elem_bytes(int what)
+{
+    switch (what) {
+    case CGIC_ARENA_Z: case CGIC_ARENA_QUANT: case CGIC_ARENA_ZQ: return 16;             // per fine token (4 channels)
+    case CGIC_ARENA_MC: case CGIC_ARENA_MM: case CGIC_ARENA_MF: return 4;
+    case CGIC_ARENA_DMC: case CGIC_ARENA_DMM: case CGIC_ARENA_DMF: case CGIC_ARENA_IND: case CGIC_ARENA_IDX: return 8;
+    default: return 1;
+    }
+}
+
+// number of elements of tensor `what` for `nb` images
+static size_t arena_count(const cgic_session *s, int what, int nb)
+{
+    const size_t i4 = (size_t)s->h * s->w, i8 = i4 / 4, i16 = i4 / 16;
+    switch (what) {
+    case CGIC_ARENA_Z: case CGIC_ARENA_QUANT: case CGIC_ARENA_ZQ: case CGIC_ARENA_MF: case CGIC_ARENA_DMF:
+    case CGIC_ARENA_IND: case CGIC_ARENA_IDX: return nb * i4;
+    case CGIC_ARENA_MM: case CGIC_ARENA_DMM: return nb * i8;
+    case CGIC_ARENA_MC: case CGIC_ARENA_DMC: return nb * i16;
+    case CGIC_ARENA_BYTES: return (size_t)nb * s->L.stride;
+    case CGIC_ARENA_SIZES: return (size_t)nb * 5 * 4;
+    case CGIC_ARENA_STATUS: return (size_t)nb * 4;
+    case CGIC_ARENA_SQERR: return 8;
+    default: return 0;
+    }
+}
+
+extern "C" int cgic_session_arena(cgic_session *s, int parts)
+{
+    CGIC_REQUIRE(s && parts >= 1 && parts <= cgic_session::MAX_PARTS, CGIC_EINVAL, "cgic_session_arena: parts must be in [1, %d]",
+                 cgic_session::MAX_PARTS);
+    if (parts > s->B) parts = s->B;
+    if (parts == s->a_parts) return CGIC_OK;
+    for (cudaGraphExec_t &g : s->graph) {
+        if (g) cudaGraphExecDestroy(g);
+        g = nullptr;
+    }
+    for (bool &w : s->warmed) w = false;
+    static const int in_order[] = {CGIC_ARENA_Z, CGIC_ARENA_MC, CGIC_ARENA_MM, CGIC_ARENA_MF};
+    static const int out_order[] = {CGIC_ARENA_BYTES, CGIC_ARENA_SIZES, CGIC_ARENA_STATUS, CGIC_ARENA_SQERR, CGIC_ARENA_IND, CGIC_ARENA_QUANT,
+                                    CGIC_ARENA_DMC, CGIC_ARENA_DMM, CGIC_ARENA_DMF, CGIC_ARENA_IDX, CGIC_ARENA_ZQ};
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    size_t in_total = 0, out_total = 0;
+    for (int p = 0; p < parts; ++p) {
+        cgic_session::Part &P = s->part[p];
+        P.b0 = (int)((int64_t)s->B * p / parts);
+        P.nb = (int)((int64_t)s->B * (p + 1) / parts) - P.b0;
+        P.in_off = in_total;
+        size_t o = 0;
+        for (int what : in_order) {
+            P.o[what] = o;
+            o += up(arena_count(s, what, P.nb) * arena_elem_bytes(what));
+        }
+        P.in_len = o;
+        in_total += o;
+        P.out_off = out_total;
+        o = 0;
+        for (int what : out_order) {
+            if (what == CGIC_ARENA_IDX) P.out_core = o;
+            if (what == CGIC_ARENA_ZQ) P.out_idx = o;
+            P.o[what] = o;
+            o += up(arena_count(s, what, P.nb) * arena_elem_bytes(what));
+        }
+        P.out_all = o;
+        out_total += o;
+    }
+    if (in_total > s->in_bytes || out_total > s->out_bytes || !s->h_in) {
+        if (s->h_in) cudaFreeHost(s->h_in);
+        if (s->h_out) cudaFreeHost(s->h_out);
+        if (s->d_in) cudaFree(s->d_in);
+        if (s->d_out) cudaFree(s->d_out);
+        s->h_in = s->h_out = s->d_in = s->d_out = nullptr;
+        cudaError_t e = cudaMallocHost(&s->h_in, in_total);
+        if (e == cudaSuccess) e = cudaMallocHost(&s->h_out, out_total);
+        if (e == cudaSuccess) e = cudaMalloc(&s->d_in, in_total);
+        if (e == cudaSuccess) e = cudaMalloc(&s->d_out, out_total);
+        if (e == cudaSuccess) e = cudaMemset(s->d_out, 0, out_total);
+        if (e != cudaSuccess) {
+            cgic::set_error("cgic_session_arena: %s", cudaGetErrorString(e));
+            return e == cudaErrorMemoryAllocation ? CGIC_ENOMEM : CGIC_ECUDA;
+        }
+        s->in_bytes = in_total;
+        s->out_bytes = out_total;
+    }
+    if (!s->fork) {
+        CGIC_CUDA_CHECK(cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming));
+        for (cudaEvent_t &e : s->join) CGIC_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    s->a_parts = parts;
+    return CGIC_OK;
+}
+
+extern "C" int cgic_session_arena_tensor(const cgic_session *s, int what, int part, void **host_ptr, int *first_image, int *n_images)
+{
+    CGIC_REQUIRE(s && s->a_parts > 0, CGIC_EINVAL, "cgic_session_arena_tensor: call cgic_session_arena first");
+    CGIC_REQUIRE(what >= 0 && what < CGIC_ARENA_COUNT && part >= 0 && part < s->a_parts && host_ptr, CGIC_EINVAL,
+                 "cgic_session_arena_tensor: bad argument what=%d part=%d", what, part);
+    const cgic_session::Part &P = s->part[part];
+    const bool is_in = what == CGIC_ARENA_Z || what == CGIC_ARENA_MC || what == CGIC_ARENA_MM || what == CGIC_ARENA_MF;
+    *host_ptr = (is_in ? s->h_in + P.in_off : s->h_out + P.out_off) + P.o[what];
+    if (first_image) *first_image = P.b0;
+    if (n_images) *n_images = P.nb;
+    return CGIC_OK;
+}
+
+// enqueues the whole round trip of every part (part p on streams[p]); used eagerly once and then under capture
+static int arena_enqueue(cgic_session *s, int flags)
+{
+    const size_t i4 = (size_t)s->h * s->w;
+    (void)i4;
+    cudaStream_t s0 = s->streams[0];
+    CGIC_CUDA_CHECK(cudaEventRecord(s->fork, s0));
+    for (int p = 0; p < s->a_parts; ++p) {
+        const cgic_session::Part &P = s->part[p];
+        cudaStream_t st = s->streams[p];
+        if (p) CGIC_CUDA_CHECK(cudaStreamWaitEvent(st, s->fork, 0));
+        unsigned char *di = s->d_in + P.in_off, *dout = s->d_out + P.out_off;
+        auto in = [&](int what) { return di + P.o[what]; };
+        auto out = [&](int what) { return dout + P.o[what]; };
+        CGIC_CUDA_CHECK(cudaMemcpyAsync(di, s->h_in + P.in_off, P.in_len, cudaMemcpyHostToDevice, st));
+        int rc = cgic_vq_assign_indexed(reinterpret_cast<const float *>(in(CGIC_ARENA_Z)), P.nb, s->h, s->w, s->index,
+                                        reinterpret_cast<int64_t *>(out(CGIC_ARENA_IDX)),
+                                        (flags & 2) ? reinterpret_cast<float *>(out(CGIC_ARENA_ZQ)) : nullptr,
+                                        reinterpret_cast<double *>(out(CGIC_ARENA_SQERR)), s->ws_vq + p * s->ws_vq_bytes, s->ws_vq_bytes, st);
+        if (rc) return rc;
+        rc = cgic_pack(reinterpret_cast<const int64_t *>(out(CGIC_ARENA_IDX)), reinterpret_cast<const int32_t *>(in(CGIC_ARENA_MC)),
+                       reinterpret_cast<const int32_t *>(in(CGIC_ARENA_MM)), reinterpret_cast<const int32_t *>(in(CGIC_ARENA_MF)), P.nb, s->h,
+                       s->w, s->mode, s->table, out(CGIC_ARENA_BYTES), reinterpret_cast<int32_t *>(out(CGIC_ARENA_SIZES)), st);
+        if (rc) return rc;
+        rc = cgic_unpack(out(CGIC_ARENA_BYTES), reinterpret_cast<const int32_t *>(out(CGIC_ARENA_SIZES)), P.nb, s->h, s->w, s->mode, s->table,
+                         s->codebook, reinterpret_cast<int64_t *>(out(CGIC_ARENA_DMC)), reinterpret_cast<int64_t *>(out(CGIC_ARENA_DMM)),
+                         reinterpret_cast<int64_t *>(out(CGIC_ARENA_DMF)), reinterpret_cast<int64_t *>(out(CGIC_ARENA_IND)),
+                         reinterpret_cast<float *>(out(CGIC_ARENA_QUANT)), reinterpret_cast<int32_t *>(out(CGIC_ARENA_STATUS)),
+                         s->ws_un + p * s->ws_un_bytes, s->ws_un_bytes, st);
+        if (rc) return rc;
+        const size_t len = (flags & 2) ? P.out_all : ((flags & 1) ? P.out_idx : P.out_core);
+        CGIC_CUDA_CHECK(cudaMemcpyAsync(s->h_out + P.out_off, dout, len, cudaMemcpyDeviceToHost, st));
+        if (p) {
+            CGIC_CUDA_CHECK(cudaEventRecord(s->join[p], st));
+            CGIC_CUDA_CHECK(cudaStreamWaitEvent(s0, s->join[p], 0));
+        }
+    }
+    return CGIC_OK;
+}
+
+extern "C" int cgic_session_roundtrip_arena(cgic_session *s, int flags, double *sqerr_out)
+{
+    CGIC_REQUIRE(s && s->a_parts > 0, CGIC_EINVAL, "cgic_session_roundtrip_arena: call cgic_session_arena first");
+    CGIC_REQUIRE(flags >= 0 && flags < 4, CGIC_EINVAL, "cgic_session_roundtrip_arena: flags %d", flags);
+    cudaStream_t s0 = s->streams[0];
+    static const bool no_graph = getenv("CGIC_SESSION_NO_GRAPH") != nullptr;  // diagnosis only
+    if (!s->warmed[flags] || no_graph) {
+        // first call: eager (one-time attribute set-up inside the launchers must not happen under capture)
+        int rc = arena_enqueue(s, flags);
+        if (rc) return rc;
+        s->warmed[flags] = true;
+    } else {
+        if (!s->graph[flags]) {
+            cudaGraph_t g = nullptr;
+            CGIC_CUDA_CHECK(cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal));
+            int rc = arena_enqueue(s, flags);
+            cudaError_t e = cudaStreamEndCapture(s0, &g);
+            if (rc) {
+                if (g) cudaGraphDestroy(g);
+                return rc;
+            }
+            CGIC_CUDA_CHECK(e);
+            e = cudaGraphInstantiate(&s->graph[flags], g, 0);
+            cudaGraphDestroy(g);
+            CGIC_CUDA_CHECK(e);
+        }
+        CGIC_CUDA_CHECK(cudaGraphLaunch(s->graph[flags], s0));
+    }
+    CGIC_CUDA_CHECK(cudaStreamSynchronize(s0));
+    if (sqerr_out) {
+        double tot = 0.0;
+        for (int p = 0; p < s->a_parts; ++p) tot += *reinterpret_cast<const double *>(s->h_out + s->part[p].out_off + s->part[p].o[CGIC_ARENA_SQERR]);
+        *sqerr_out = tot;  // fixed order: deterministic
+    }
     return CGIC_OK;
 }

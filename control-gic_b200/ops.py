@@ -446,6 +446,48 @@ class Session:
                                                  self.status.data_ptr()), "cgic_session_decompress_host")
         return self.mc, self.mm, self.mf, self.ind, self.quant, self.status
 
+    # ---- pinned-arena round trip: buffers owned by the session, one copy per direction and image range,
+    #      ranges pipelined, replayed as a CUDA graph (cgic_session_arena / cgic_session_roundtrip_arena)
+    _ARENA = dict(z=(0, torch.float32), m_c=(1, torch.int32), m_m=(2, torch.int32), m_f=(3, torch.int32), bytes=(4, torch.uint8),
+                  sizes=(5, torch.int32), status=(6, torch.int32), sqerr=(7, torch.float64), ind=(8, torch.int64), quant=(9, torch.float32),
+                  mc=(10, torch.int64), mm=(11, torch.int64), mf=(12, torch.int64), idx=(13, torch.int64), zq=(14, torch.float32))
+
+    def arena(self, parts: int = 8):
+        """Fixes the number of image ranges and returns a list (one entry per range) of dicts of host tensor
+        VIEWS into the session's pinned arenas: inputs z, m_c, m_m, m_f (fill them before roundtrip_arena) and
+        outputs bytes, sizes, status, ind, quant, mc, mm, mf, idx, zq (valid after it), plus `images` = range."""
+        check(lib().cgic_session_arena(self._s, int(parts)), "cgic_session_arena")
+        h, w = self.h, self.w
+        shapes = dict(z=lambda n: (n, 4, h, w), m_c=lambda n: (n, 1, h // 4, w // 4), m_m=lambda n: (n, 1, h // 2, w // 2),
+                      m_f=lambda n: (n, 1, h, w), bytes=lambda n: (n, self.image_stride), sizes=lambda n: (n, 5), status=lambda n: (n,),
+                      sqerr=lambda n: (1,), ind=lambda n: (n, h, w), quant=lambda n: (n, 4, h, w), mc=lambda n: (n, h // 4, w // 4),
+                      mm=lambda n: (n, h // 2, w // 2), mf=lambda n: (n, h, w), idx=lambda n: (n * h * w,), zq=lambda n: (n, 4, h, w))
+        views = []
+        p = 0
+        while True:
+            ptr, b0, nb = C.c_void_p(), C.c_int(), C.c_int()
+            rc = lib().cgic_session_arena_tensor(self._s, 0, p, C.byref(ptr), C.byref(b0), C.byref(nb))
+            if rc != 0:
+                break
+            d = {"images": range(b0.value, b0.value + nb.value)}
+            for name, (what, dtype) in self._ARENA.items():
+                check(lib().cgic_session_arena_tensor(self._s, what, p, C.byref(ptr), None, None), "cgic_session_arena_tensor")
+                shape = shapes[name](nb.value)
+                nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+                buf = (C.c_uint8 * nbytes).from_address(ptr.value)
+                d[name] = torch.frombuffer(buf, dtype=dtype).view(*shape)
+            views.append(d)
+            p += 1
+        self._arena_views = views
+        return views
+
+    def roundtrip_arena(self, want_idx: bool = False, want_zq: bool = False) -> float:
+        """CGIC.compress on the arena contents; returns sum((e - z)^2) over the batch."""
+        sq = C.c_double()
+        check(lib().cgic_session_roundtrip_arena(self._s, int(want_idx) | (int(want_zq) << 1), C.byref(sq)),
+              "cgic_session_roundtrip_arena")
+        return sq.value
+
     def roundtrip(self, z, m_c, m_m, m_f, want_idx: bool = False):
         """CGIC.compress in one call: host z + masks -> (bytes, sizes, mc, mm, mf, ind, quant, status[, idx]) (pinned host)."""
         check(lib().cgic_session_roundtrip_host(self._s, self._host(z, torch.float32, "z"), self._host(m_c, torch.int32, "m_c"),

@@ -224,6 +224,29 @@ CGIC_API int cgic_session_roundtrip_host(cgic_session *s, const float *z, const 
                                 float *zq_out, double *sqerr_out, int64_t *mc_out, int64_t *mm_out, int64_t *mf_out,
                                 int64_t *ind_out, float *quant_out, int32_t *status_out);
 
+/* Pinned-arena round trip: the same call with the host buffers owned by the session.  The batch is cut
+ * into `parts` contiguous image ranges; every range has one contiguous input block and one contiguous
+ * output block in pinned host memory (and a mirror on the device), so a range moves with ONE copy per
+ * direction and the ranges pipeline: H2D of range p+1, the kernels of range p and D2H of range p-1 run
+ * at the same time.  After the first (eager) call the whole round trip is replayed as one CUDA graph.
+ *   cgic_session_arena        fixes `parts` (<= 8) and (re)allocates the arenas (init time);
+ *   cgic_session_arena_tensor host pointer of tensor `what` of range `part` (+ its image range);
+ *                             inputs are written there by the caller before the call, outputs read after;
+ *   cgic_session_roundtrip_arena  flags: bit 0 also return idx (VQ indices), bit 1 also z_q.
+ * Tensor shapes per range of nb images: Z/QUANT/ZQ fp32 [nb,4,h,w]; MC/MM/MF int32 [nb,1,.,.]; BYTES
+ * uint8 [nb,image_stride]; SIZES int32 [nb,5]; STATUS int32 [nb]; SQERR double[1]; IND/IDX int64 [nb,h,w];
+ * DMC/DMM/DMF int64 [nb,.,.]. */
+enum {
+    CGIC_ARENA_Z = 0, CGIC_ARENA_MC, CGIC_ARENA_MM, CGIC_ARENA_MF,          /* inputs */
+    CGIC_ARENA_BYTES, CGIC_ARENA_SIZES, CGIC_ARENA_STATUS, CGIC_ARENA_SQERR, /* outputs */
+    CGIC_ARENA_IND, CGIC_ARENA_QUANT, CGIC_ARENA_DMC, CGIC_ARENA_DMM, CGIC_ARENA_DMF,
+    CGIC_ARENA_IDX, CGIC_ARENA_ZQ, CGIC_ARENA_COUNT
+};
+CGIC_API int cgic_session_arena(cgic_session *s, int parts);
+CGIC_API int cgic_session_arena_tensor(const cgic_session *s, int what, int part, void **host_ptr, int *first_image,
+                              int *n_images);
+CGIC_API int cgic_session_roundtrip_arena(cgic_session *s, int flags, double *sqerr_out);
+
 #ifdef __cplusplus
 }
 #endif

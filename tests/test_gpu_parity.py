@@ -432,6 +432,32 @@ def test_session_host_roundtrip(cg, orc):
             for s in range(5):
                 assert torch.equal(rt[0][b, offs[s]: offs[s] + sz[b, s]], packed[b, offs[s]: offs[s] + sz[b, s]].cpu())
                 assert torch.equal(by2[b, offs[s]: offs[s] + sz[b, s]], packed[b, offs[s]: offs[s] + sz[b, s]].cpu())
+    # the pinned-arena round trip: per-range contiguous blocks, ranges pipelined, replayed as a CUDA graph
+    for parts in (1, 3, 4):
+        views = sess.arena(parts)
+        assert sum(len(v["images"]) for v in views) == B and len(views) == min(parts, B)
+        for v in views:
+            r = v["images"]
+            v["z"].copy_(zh[r.start:r.stop])
+            for name, src in zip(("m_c", "m_m", "m_f"), mh):
+                v[name].copy_(src[r.start:r.stop])
+        for rep in range(3):                     # eager call, graph capture, graph replay
+            sq = sess.roundtrip_arena(want_idx=True, want_zq=(rep == 2))
+            for v in views:
+                r = v["images"]
+                sl = slice(r.start, r.stop)
+                assert torch.equal(v["sizes"], sizes.cpu()[sl]) and int(v["status"].abs().sum()) == 0, (parts, rep)
+                assert torch.equal(v["idx"], idx_d.cpu().view(B, -1)[sl].reshape(-1)) and torch.equal(v["ind"].view(len(r), -1), idx_d.cpu().view(B, -1)[sl])
+                assert torch.equal(v["quant"], quant[sl])
+                for got, want in zip((v["mc"], v["mm"], v["mf"]), masks):
+                    assert torch.equal(got, want[sl, 0].long().cpu())
+                for i, b in enumerate(r):
+                    for st in range(5):
+                        assert torch.equal(v["bytes"][i, offs[st]: offs[st] + sz[b, st]], packed[b, offs[st]: offs[st] + sz[b, st]].cpu())
+            _, zq_d, sq_d = cg.ops.vq_assign(z, cb)
+            assert np.isclose(sq, float(sq_d), rtol=1e-12)
+            if rep == 2:
+                assert torch.equal(torch.cat([v["zq"] for v in views]), zq_d.cpu())
     sess.close()
 
 
