@@ -4,12 +4,12 @@ The directory is named `control-gic_b200`; import it as `cgic_b200` (the top-lev
 `cgic_b200.py` aliases it).  Python here is the host-side mirror of the reference's
 operator API; all compute is in libcgic_b200.so (include/cgic_b200.h), loaded with ctypes.
 """
-from . import _lib, ops, dist  # noqa: F401
+from . import _lib, ops, dist, inference  # noqa: F401
 from .codec import BinaryCoding, HuffmanCoding  # noqa: F401
 from .entropy import Entropy, entropy_pair  # noqa: F401
 from .model import CGIC, ReferenceEncoderHeads  # noqa: F401
 from .quantize import VectorQuantize2  # noqa: F401
 from .router import TripleGrainFixedEntropyRouter  # noqa: F401
 
-__all__ = ["ops", "dist", "HuffmanCoding", "BinaryCoding", "Entropy", "entropy_pair", "CGIC", "ReferenceEncoderHeads",
+__all__ = ["ops", "dist", "inference", "HuffmanCoding", "BinaryCoding", "Entropy", "entropy_pair", "CGIC", "ReferenceEncoderHeads",
            "VectorQuantize2", "TripleGrainFixedEntropyRouter"]

@@ -113,7 +113,7 @@ __device__ void pack_index_stream(const PackArgs &a, int s, int b, uint32_t *sta
         if (!mask) {
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) on[i] = pos0 + i < n_pos;
-        } else if (ITEMS % 4 == 0 && pos0 + ITEMS <= n_pos) {
+        } else if (ITEMS % 4 == 0 && pos0 + ITEMS <= n_pos && (reinterpret_cast<uintptr_t>(mask + pos0) & 15) == 0) {
 #pragma unroll
             for (int v = 0; v < ITEMS / 4; ++v) {
                 const int4 m = __ldg(reinterpret_cast<const int4 *>(mask + pos0) + v);
@@ -237,7 +237,7 @@ __device__ void pack_bit_stream(const int32_t *v, int64_t n, uint8_t *out, int64
     for (int64_t j = threadIdx.x; j < nbytes; j += blockDim.x) {
         uint32_t byte = 0;
         const int64_t base = j * 8;
-        if (base + 8 <= n) {
+        if (base + 8 <= n && (reinterpret_cast<uintptr_t>(v) & 15) == 0) {
             const int4 lo = *reinterpret_cast<const int4 *>(v + base);
             const int4 hi = *reinterpret_cast<const int4 *>(v + base + 4);
             byte = ((lo.x != 0) << 7) | ((lo.y != 0) << 6) | ((lo.z != 0) << 5) | ((lo.w != 0) << 4) | ((hi.x != 0) << 3) |
@@ -371,9 +371,6 @@ extern "C" int cgic_pack(const int64_t *idx, const int32_t *m_c, const int32_t *
     CGIC_REQUIRE(smem <= 200 * 1024, CGIC_EINVAL, "cgic_pack: code length %d needs %zu bytes of staging", a.T.max_len, smem);
     rc = ensure_smem(items == 8 ? (const void *)pack_kernel<8> : (const void *)pack_kernel<1>, smem);
     if (rc) return rc;
-    // the coarse-mask payload must stay int4-loadable per image: (h/4)*(w/4) ints per image
-    CGIC_REQUIRE(((int64_t)(h / 4) * (w / 4)) % 4 == 0 || B == 1, CGIC_EINVAL,
-                 "cgic_pack: (h/4)*(w/4) must be a multiple of 4 for batched masks");
     {
         CGIC_PROF("pack_kernel", as_stream(stream));
         if (items == 8) CGIC_CUDA_CHECK(launch_pdl(pack_kernel<8>, dim3(5, B), dim3(PK_THREADS), smem, as_stream(stream), a));

@@ -1,0 +1,57 @@
+"""Host logic of the tiling driver / CLI mirror (cgic_b200.inference) against vectors generated from the
+unmodified reference (tests/golden/make_tiling_golden.py).  No GPU needed: geometry, weights, parser."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import torch
+
+from conftest import GOLDEN
+
+
+def _kats():
+    with open(os.path.join(GOLDEN, "tiling_kats.json")) as f:
+        return json.load(f)
+
+
+def test_tiling_geometry_matches_reference():
+    import cgic_b200 as cg
+    inf = cg.inference
+    for s in _kats()["shapes"]:
+        pad, unpad = inf.compute_padding(s["H"], s["W"], min_div=16)
+        assert list(pad) == s["pad"] and list(unpad) == s["unpad"], s
+        Hp, Wp = s["H"] + pad[2] + pad[3], s["W"] + pad[0] + pad[1]
+        h_list, w_list, th, tw = inf.nonoverlapping_grid_indices(torch.zeros(1, 3, Hp, Wp))
+        assert (h_list, w_list, th, tw) == (s["h_list"], s["w_list"], s["tile_h"], s["tile_w"]), s
+        plan = inf.tile_plan(Hp, Wp)
+        assert len(plan) == len(h_list) * len(w_list) and sum(t[2] * t[3] for t in plan) == Hp * Wp
+        groups = inf.group_tiles(plan)
+        assert sorted(i for g in groups.values() for i in g) == list(range(len(plan)))
+
+
+def test_div2k_shape_is_the_six_tiles_of_the_survey():
+    import cgic_b200 as cg
+    plan = cg.inference.tile_plan(1344, 2032)          # DIV2K 2040x1356 after the dataset's x16 centre crop
+    assert [(t[2], t[3]) for t in plan] == [(768, 768), (768, 768), (768, 496), (576, 768), (576, 768), (576, 496)]
+
+
+def test_gaussian_weights_match_reference():
+    import cgic_b200 as cg
+    for w in _kats()["weights"]:
+        got = cg.inference.gaussian_weights(w["tile_w"], w["tile_h"], 1, "cpu")
+        assert list(got.shape) == w["shape"] and str(got.dtype) == w["dtype"]
+        assert hashlib.sha256(np.ascontiguousarray(got.numpy()).tobytes()).hexdigest() == w["sha256"], w
+
+
+def test_parsers_and_config_keys():
+    import cgic_b200 as cg
+    k = _kats()
+    for hr, want in ((False, k["parser"]), (True, k["parser_hr"])):
+        got = {a: (list(v) if isinstance(v, tuple) else v) for a, v in vars(cg.inference.get_parser(high_resolution=hr).parse_args([])).items()}
+        assert got == want
+    args = cg.inference.get_parser().parse_args(["-i", "d", "-b", "2", "-n", "3", "-s", "256", "-o", "o", "-w", "-r", "4", "9"])
+    assert (args.images_dir, args.batch_size, args.num_workers, args.image_size, args.output_dir, args.write_partiton_map,
+            list(args.images_range)) == ("d", 2, 3, 256, "o", True, [4, 9])
+    cfg = cg.inference._Cfg({"model": {"params": {"ddconfig": {"router_config": {"params": {"coarse_grain_ratio": 0.1}}}}}})
+    assert cfg.model.params.ddconfig.router_config.params.coarse_grain_ratio == 0.1
