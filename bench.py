@@ -256,7 +256,7 @@ def run_b200(args):
         packed, sizes = cg.ops.pack(idx, mc, mm, mf, mode, table, h, w)
         dmc, dmm, dmf, ind, quant, status = cg.ops.unpack(packed, sizes, mode, table, cb, h, w)
         return idx, sq, sizes, ind, quant, status
-    kernels_per_step = 4    # vq_indexed, pack, unpack_decode, unpack_assemble
+    kernels_per_step = 4    # vq_warp, pack, unpack_decode, unpack_assemble
 
     # correctness gate of the run itself (round trip + status), before any timing
     idx, sq, sizes, ind, quant, status = step()

@@ -65,7 +65,7 @@ __device__ __forceinline__ int block_exscan(int v, int *s_warp, int *total)
 // code table is read from shared memory (s_enc: (code bits left aligned, length) per symbol) when
 // every code fits 32 bits, else from the global code pool.  `stage` holds one tile of output bits.
 template <int ITEMS>
-__device__ void pack_index_stream(const PackArgs &a, int s, int b, uint32_t *stage, const uint2 *s_enc)
+__device__ void pack_index_stream(const PackArgs &a, int s, int b, uint32_t *stage, const uint2 *s_enc, unsigned long long *mbar)
 {
     constexpr int TILE = PK_THREADS * ITEMS;
     __shared__ int s_warp[PK_THREADS / 32];
@@ -126,25 +126,37 @@ __device__ void pack_index_stream(const PackArgs &a, int s, int b, uint32_t *sta
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) on[i] = pos0 + i < n_pos && mask[pos0 + i] == 1;
         }
-        // ---- symbols: the block's top-left token (model.py:219-221)
+        // ---- symbols: the block's top-left token (model.py:219-221).  The loads do not wait for the mask
+        //      values (issued for every in-range position), so mask and index latencies overlap.
         int y = 0, x = 0;
         if (mask) {
             y = (int)(pos0 / gw);
             x = (int)(pos0 - (int64_t)y * gw);
         }
+        int64_t val[ITEMS];
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
-            sym[i] = -1;
-            if (on[i]) {
+            val[i] = 0;
+            if (pos0 + i < n_pos) {
                 const int64_t at = mask ? (int64_t)(y * step) * a.w + x * step : pos0 + i;
-                const int64_t v = src[at];
-                if (v < 0 || v >= a.T.K) s_bad = 1;
-                else sym[i] = (int)v;
+                val[i] = src[at];
             }
             if (++x == gw) {
                 x = 0;
                 ++y;
             }
+        }
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            sym[i] = -1;
+            if (on[i]) {
+                if (val[i] < 0 || val[i] >= a.T.K) s_bad = 1;
+                else sym[i] = (int)val[i];
+            }
+        }
+        if (mbar) {  // the code table's bulk copy was started before the loads above; first use is below
+            mbar_wait(mbar, 0);
+            mbar = nullptr;
         }
         int tsum = 0;
 #pragma unroll
@@ -197,6 +209,7 @@ __device__ void pack_index_stream(const PackArgs &a, int s, int b, uint32_t *sta
         P += tot;
         __syncthreads();
     }
+    if (mbar) mbar_wait(mbar, 0);  // empty stream: never leave with the bulk copy in flight
     // tail: bytes not yet written, pad, header
     const int64_t nbits = P - 8;
     if (nbits == 0 || s_bad) {
@@ -259,17 +272,18 @@ __device__ __forceinline__ void pack_stream_entry(const PackArgs &a, int s, int 
 {
     const uint2 *s_enc = nullptr;
     uint32_t *stage = reinterpret_cast<uint32_t *>(dyn);
-    if (a.T.enc) {  // stage the code table with one TMA bulk copy
+    bool staged = false;
+    if (a.T.enc) {  // stage the code table with one TMA bulk copy; waited for inside, after the first loads are in flight
         const uint32_t bytes = (uint32_t)((a.T.K + 1) / 2 * 2) * 8u;
         if (threadIdx.x == 0) mbar_init(mbar);
         __syncthreads();
         if (threadIdx.x == 0) tma_load_1d(dyn, a.T.enc, bytes, mbar);
-        mbar_wait(mbar, 0);
         s_enc = reinterpret_cast<const uint2 *>(dyn);
         stage = reinterpret_cast<uint32_t *>(dyn + bytes);
+        staged = true;
     }
     pdl_wait();  // the code table above is immutable; indices and masks come from the predecessor
-    pack_index_stream<ITEMS>(a, s, b, stage, s_enc);
+    pack_index_stream<ITEMS>(a, s, b, stage, s_enc, staged ? mbar : nullptr);
 }
 
 template <int ITEMS>
