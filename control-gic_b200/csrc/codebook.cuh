@@ -6,11 +6,11 @@ namespace cgic {
 
 constexpr int CB_NB = 256;        // fine bins per dimension
 constexpr int CB_PAD = 48;        // bins beyond the codebook's min / max on each side
-constexpr int CB_G = 8;           // cells per dimension
+constexpr int CB_G = 12;          // cells per dimension
 constexpr int CB_RW = 64;         // u16 words per cell record: count + up to 63 candidates
 constexpr int CB_MAX_K = 4096;
 constexpr int CB_NDOM = 20;       // dominators tried per cell: nearest code to the 16 corners + 4 nearest to the centre
-constexpr int CB_HDR = 256;       // header bytes
+constexpr int CB_HDR = 512;       // header bytes
 constexpr int CB_LUT = 4 * CB_NB; // lookup-table bytes
 
 struct CbHeader {

@@ -522,8 +522,10 @@ vq_warp_kernel(const float *__restrict__ z, int h, int w, int tiles_x, int tiles
     uint8_t *lead = list + VQW_TILE;                                     // [128] leader of every token
     const uint4 *recs = reinterpret_cast<const uint4 *>(blob + CL.rec);
 
+    VQ_STAMP(0);
     pdl_launch_dependents();
     pdl_wait();  // the prepared blob and z may come straight from a preceding kernel
+    VQ_STAMP(1);
     if (tid == 0) mbar_init(&mbar);
     __syncthreads();
     if (tid == 0) tma_load_1d(smem, blob, (uint32_t)CL.stage, &mbar);
@@ -532,7 +534,8 @@ vq_warp_kernel(const float *__restrict__ z, int h, int w, int tiles_x, int tiles
     const int64_t plane = (int64_t)h * w;
     const int tpi = tiles_x * tiles_y;
     double sq = 0.0;
-    const int64_t wid = (int64_t)blockIdx.x * VQW_WARPS + warp, nwarps = (int64_t)gridDim.x * VQW_WARPS;
+    // tiles are dealt round-robin over the CTAs (tile i -> CTA i % grid), so every SM gets the same number of busy warps
+    const int64_t wid = (int64_t)warp * gridDim.x + blockIdx.x, nwarps = (int64_t)gridDim.x * VQW_WARPS;
     for (int64_t tile = wid; tile < n_tiles; tile += nwarps) {
         const int b = (int)(tile / tpi), rt = (int)(tile - (int64_t)b * tpi);
         const int ty = rt / tiles_x, tx = rt - ty * tiles_x;
@@ -556,6 +559,7 @@ vq_warp_kernel(const float *__restrict__ z, int h, int w, int tiles_x, int tiles
             mbar_wait(&mbar, 0);
         }
         __syncwarp();
+        VQ_STAMP(2);
         // ---- classify + compact
         int nlead = 0;
         unsigned lmask[4];
@@ -588,18 +592,31 @@ vq_warp_kernel(const float *__restrict__ z, int h, int w, int tiles_x, int tiles
             nlead += __popc(lmask[r]);
         }
         __syncwarp();
-        // ---- search: one lane per leader
+        VQ_STAMP(3);
+        // ---- search: one lane per leader.  Pass 1 finds every leader's grid cell and prefetches its record, so that
+        //      the memory latency of all rounds overlaps; pass 2 evaluates.
         const bool usable = hdr->valid != 0;
         for (int j = lane; j < nlead; j += 32) {
             const int t = list[j];
             const float4 v = zs[t];
-            int cell = -1;
+            int cell = 0xffff;
             if (usable) {
                 const int b0 = cb_bin(v.x, hdr->lo[0], hdr->inv[0]), b1 = cb_bin(v.y, hdr->lo[1], hdr->inv[1]),
                           b2 = cb_bin(v.z, hdr->lo[2], hdr->inv[2]), b3 = cb_bin(v.w, hdr->lo[3], hdr->inv[3]);
-                if ((b0 | b1 | b2 | b3) >= 0)
+                if ((b0 | b1 | b2 | b3) >= 0) {
                     cell = (((int)lut[b0] * CB_G + (int)lut[CB_NB + b1]) * CB_G + (int)lut[2 * CB_NB + b2]) * CB_G + (int)lut[3 * CB_NB + b3];
+                    const uint4 *rp = recs + (size_t)cell * (CB_RW / 8);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 2));
+                }
             }
+            res[t] = (uint16_t)cell;  // parked here until pass 2 overwrites it with the code
+        }
+        __syncwarp();
+        for (int j = lane; j < nlead; j += 32) {
+            const int t = list[j];
+            const float4 v = zs[t];
+            const int cell = res[t] == 0xffffu ? -1 : (int)res[t];
             unsigned count = 0xffffu;
             uint4 q0, q1, q2, q3;
             const uint4 *rp = recs + (size_t)max(cell, 0) * (CB_RW / 8);
@@ -642,6 +659,7 @@ vq_warp_kernel(const float *__restrict__ z, int h, int w, int tiles_x, int tiles
             res[t] = (uint16_t)bk;
         }
         __syncwarp();
+        VQ_STAMP(4);
         // ---- finalize
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -668,6 +686,7 @@ vq_warp_kernel(const float *__restrict__ z, int h, int w, int tiles_x, int tiles
             }
         }
     }
+    VQ_STAMP(5);
     if (!staged) mbar_wait(&mbar, 0);  // never leave with the bulk copy in flight
     if (!sqerr_out) return;
     // deterministic reduction: warp shuffle -> CTA -> per-CTA partial -> the last CTA sums them in order
@@ -698,8 +717,8 @@ vq_warp_kernel(const float *__restrict__ z, int h, int w, int tiles_x, int tiles
             counters[0] = 0;  // leave the ticket zeroed for the next launch (workspace contract)
         }
     }
+    VQ_STAMP(6);
 }
-
 
 __global__ void vq_count_kernel(const int64_t *__restrict__ idx, int64_t n, float *__restrict__ counters, int K)
 {
@@ -799,9 +818,13 @@ extern "C" int cgic_vq_assign_indexed(const float *z, int B, int h, int w, const
     }
     const int tiles_x = (w + 31) / 32, tiles_y = (h + 3) / 4;
     const int64_t n_tiles = (int64_t)B * tiles_x * tiles_y;
-    // one tile per warp while the grid fits the machine (3 CTAs of 8 warps per SM), persistent beyond that
-    const int64_t want = (n_tiles + VQW_WARPS - 1) / VQW_WARPS, cap = (int64_t)3 * n_sm;
-    const int grid = (int)(want < cap ? want : cap);
+    // one tile per warp while the grid fits the machine (3 CTAs of 8 warps per SM), persistent beyond that; the grid is a
+    // multiple of the SM count so that the round-robin deal leaves every SM with the same load
+    const int64_t want = (n_tiles + VQW_WARPS - 1) / VQW_WARPS;
+    int64_t per_sm = (want + n_sm - 1) / n_sm;
+    if (per_sm > 3) per_sm = 3;
+    const int64_t full = per_sm * n_sm;
+    const int grid = (int)(n_tiles < full ? n_tiles : full);
     {
         CGIC_PROF("vq_warp_kernel", stream);
         CGIC_CUDA_CHECK(launch_pdl(vq_warp_kernel, dim3(grid), dim3(VQW_THREADS), vqw_smem_bytes(K), stream, z, h, w, tiles_x, tiles_y, n_tiles,

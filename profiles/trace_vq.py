@@ -20,12 +20,13 @@ for _ in range(3):
     cg.ops.vq_assign(z, pc)
 torch.cuda.synchronize()
 ws = list(cg.ops._ws_cache.values())[0]
-raw = ws[256:].view(torch.int64)[512:512 + 300 * 8].cpu().numpy().reshape(300, 8)[:296]
+raw = ws[256:].view(torch.int64)[512:512 + 300 * 8].cpu().numpy().reshape(300, 8)
+raw = raw[raw[:, 0] > 0]
 smid = raw[:, 7]
 st = raw[:, :7].astype(np.float64)
 t0 = st[:, 0].min()
 st = (st - t0) / 1e3
-names = ["start", "tile_begin", "loaded", "classified", "searched", "finalized", "end"]
+names = ["start", "pdl_wait", "loaded", "classified", "searched", "finalized", "end"]
 print("per-CTA phase END times (us since first CTA start): min / median / max over the CTAs")
 for k, n in enumerate(names):
     print(f"  {n:11s} {st[:,k].min():7.2f} {np.median(st[:,k]):7.2f} {st[:,k].max():7.2f}")

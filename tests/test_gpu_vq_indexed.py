@@ -95,7 +95,7 @@ def test_indexed_vs_oracle(cg, orc, kind, K):
     assert np.array_equal(zq.cpu().numpy().view(np.uint32), ozq.view(np.uint32))
     assert np.isclose(1.25 * float(sq.item()) / z.numel(), oloss, rtol=LOSS_RTOL)
     st = pc.stats()
-    assert st["valid"] == 1 and st["cells"] == 4096, st
+    assert st["valid"] == 1 and st["cells"] == 12 ** 4, st
 
 
 def test_indexed_golden_cases(cg):
@@ -129,7 +129,7 @@ def test_indexed_bench_workload_stays_in_the_grid(cg):
     import workload
     cbk, _ = workload.codebook_and_counts()
     st = cg.ops.Codebook(cbk.cuda()).stats()
-    assert st == dict(valid=1, cells=4096, max_list=st["max_list"], overflow_cells=0) and 1 <= st["max_list"] <= 63, st
+    assert st == dict(valid=1, cells=12 ** 4, max_list=st["max_list"], overflow_cells=0) and 1 <= st["max_list"] <= 63, st
 
 
 def test_indexed_unusable_codebook_falls_back(cg, orc):
