@@ -4,7 +4,7 @@
 //              HuffmanCoding.compress  CGIC/tools/indices_coding.py:113-126 (78-82, 91-98, 101-110),
 //              BinaryCoding.compress   CGIC/tools/mask_coding.py:40-55.
 //
-// One CTA per (stream, image).  An index stream walks its level's grid in row-major order in
+// One CTA per (index stream, image); the coarse stream's CTA also packs the two mask streams.  An index stream walks its level's grid in row-major order in
 // tiles of 1024 positions: mask test + symbol fetch (the block's top-left token), a block-wide
 // exclusive scan of the code lengths gives every symbol its bit offset, the codes are OR-ed into
 // a shared-memory staging window (atomicOr on 32-bit words), and complete words leave as
@@ -286,6 +286,8 @@ __device__ __forceinline__ void pack_stream_entry(const PackArgs &a, int s, int 
     pack_index_stream<ITEMS>(a, s, b, stage, s_enc, staged ? mbar : nullptr);
 }
 
+// grid (3, B): CTA s packs index stream s of image b; CTA 0 (the coarse stream, by far the shortest) also packs the
+// two mask streams, so that a 64-image batch is 192 CTAs = one wave at two CTAs per SM.
 template <int ITEMS>
 __global__ void __launch_bounds__(PK_THREADS) pack_kernel(const PackArgs a)
 {
@@ -293,20 +295,23 @@ __global__ void __launch_bounds__(PK_THREADS) pack_kernel(const PackArgs a)
     __shared__ __align__(8) unsigned long long mbar;
     const int s = blockIdx.x, b = blockIdx.y;
     pdl_launch_dependents();
-    if (!stream_present(a.mode, s)) {
-        pdl_wait();
-        if (threadIdx.x == 0) a.sizes[b * 5 + s] = 0;
-        return;
-    }
-    if (s < 3) {
-        pack_stream_entry<ITEMS>(a, s, b, dyn, &mbar);
+    if (stream_present(a.mode, s)) {
+        pack_stream_entry<ITEMS>(a, s, b, dyn, &mbar);   // waits for the predecessor grid inside
     } else {
         pdl_wait();
-        const int lvl = s - 3;  // 0 coarse, 1 medium
+        if (threadIdx.x == 0) a.sizes[b * 5 + s] = 0;
+    }
+    if (s != 0) return;
+    for (int ms = 3; ms < 5; ++ms) {
+        if (!stream_present(a.mode, ms)) {
+            if (threadIdx.x == 0) a.sizes[b * 5 + ms] = 0;
+            continue;
+        }
+        const int lvl = ms - 3;  // 0 coarse, 1 medium
         const int div = lvl == 0 ? 4 : 2;
         const int64_t n = (int64_t)(a.h / div) * (a.w / div);
-        pack_bit_stream(a.mask[lvl] + (int64_t)b * n, n, a.out + (int64_t)b * a.image_stride + a.slot_off[s], a.slot_cap[s],
-                        a.sizes + b * 5 + s);
+        pack_bit_stream(a.mask[lvl] + (int64_t)b * n, n, a.out + (int64_t)b * a.image_stride + a.slot_off[ms], a.slot_cap[ms],
+                        a.sizes + b * 5 + ms);
     }
 }
 
@@ -387,8 +392,8 @@ extern "C" int cgic_pack(const int64_t *idx, const int32_t *m_c, const int32_t *
     if (rc) return rc;
     {
         CGIC_PROF("pack_kernel", as_stream(stream));
-        if (items == 8) CGIC_CUDA_CHECK(launch_pdl(pack_kernel<8>, dim3(5, B), dim3(PK_THREADS), smem, as_stream(stream), a));
-        else CGIC_CUDA_CHECK(launch_pdl(pack_kernel<1>, dim3(5, B), dim3(PK_THREADS), smem, as_stream(stream), a));
+        if (items == 8) CGIC_CUDA_CHECK(launch_pdl(pack_kernel<8>, dim3(3, B), dim3(PK_THREADS), smem, as_stream(stream), a));
+        else CGIC_CUDA_CHECK(launch_pdl(pack_kernel<1>, dim3(3, B), dim3(PK_THREADS), smem, as_stream(stream), a));
     }
     CGIC_LAUNCH_CHECK();
     return CGIC_OK;

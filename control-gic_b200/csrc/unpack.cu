@@ -4,14 +4,14 @@
 //              CGIC/tools/indices_coding.py:153-168 (131-138, 140-151);  BinaryCoding
 //              CGIC/tools/mask_coding.py:81-96.
 //
-// Stage 1 (unpack_decode_kernel, one CTA per (stream, image)):
+// Stage 1 (unpack_decode_kernel, four CTAs per image):
 //   streams 0..2  prefix decode of the Huffman payload into a symbol list (table-driven: the
 //                 first lut_bits bits index a LUT that either names the symbol or the tree node
 //                 to continue from, so codes of any length -- the untrained model has 224-bit
 //                 codes -- decode correctly);
 //   stream 3 / 4  granularity masks -> bitmaps (one bit per grid cell) plus an exclusive
-//                 popcount prefix per 32-bit word, for the coarse (CTA 3) and the medium and
-//                 derived fine level (CTA 4): fine = 1 - up2(medium) - up4(coarse).
+//                 popcount prefix per 32-bit word, for the coarse, the medium and the derived
+//                 fine level (all by CTA 3): fine = 1 - up2(medium) - up4(coarse).
 // Stage 2 (unpack_assemble_kernel, one thread per fine token): rank of the token's cell among
 //   the set cells of its level = prefix[word] + popc(bits below) -> the decoded symbol that the
 //   reference's masked assignment puts there (row-major order); ind = fine + up2(medium) +
@@ -694,8 +694,8 @@ __device__ __forceinline__ const uint8_t *stage_bytes(const uint8_t *src, int nb
     return dst;
 }
 
-// grid (5, B): CTAs 0..2 decode the index streams, CTA 3 builds the coarse level, CTA 4 the medium
-// and fine levels.  Dynamic shared memory: decode tables (CTAs 0..2) / mask stream bytes (3, 4).
+// grid (4, B): CTAs 0..2 decode the index streams, CTA 3 builds the coarse, medium and fine mask levels
+// (four CTAs per image keep a 64-image batch within one wave at two CTAs per SM).  Dynamic shared memory: decode tables (CTAs 0..2) / mask stream bytes (3, 4).
 __device__ __forceinline__ void unpack_decode_cta(const UnpackArgs &a, unsigned char *dyn, unsigned long long &mbar_ref)
 {
     unsigned long long *mbar_p = &mbar_ref;
@@ -734,10 +734,11 @@ __device__ __forceinline__ void unpack_decode_cta(const UnpackArgs &a, unsigned 
     // framing check of the mask streams this mode reads
     bool ok_c = true, ok_m = true;
     if (need_c) ok_c = sz[3] == cap_c && img[a.slot_off[3]] == 8 - (int)(g.n16 & 7);
-    if (need_m && s == 4) ok_m = sz[4] == cap_m && img[a.slot_off[4]] == 8 - (int)(g.n8 & 7);
+    if (need_m) ok_m = sz[4] == cap_m && img[a.slot_off[4]] == 8 - (int)(g.n8 & 7);
     if (threadIdx.x == 0) {
-        a.ws.flag[b * 5 + s] = ((s == 3 && !ok_c) || (s == 4 && !ok_m)) ? CGIC_EFORMAT : 0;
-        if (s == 3) a.status[b] = 0;  // the assemble kernel (which runs after this grid) raises it atomically
+        a.ws.flag[b * 5 + 3] = !ok_c ? CGIC_EFORMAT : 0;
+        a.ws.flag[b * 5 + 4] = !ok_m ? CGIC_EFORMAT : 0;
+        a.status[b] = 0;  // the assemble kernel (which runs after this grid) raises it atomically
     }
     // mask bytes: shared copies when they fit (a.mask_stage), else straight from global
     const uint8_t *mc = img + a.slot_off[3];
@@ -745,18 +746,19 @@ __device__ __forceinline__ void unpack_decode_cta(const UnpackArgs &a, unsigned 
     if (a.mask_stage) {
         const int off_m = (cap_c + 15) & ~15;
         if (need_c && ok_c) mc = stage_bytes(mc, cap_c, dyn);
-        if (need_m && ok_m && s == 4) mm = stage_bytes(mm, cap_m, dyn + off_m);
+        if (need_m && ok_m) mm = stage_bytes(mm, cap_m, dyn + off_m);
         __syncthreads();
     }
     uint32_t *bits = a.ws.bits + (int64_t)b * nwt;
     uint32_t *prefix = a.ws.prefix + (int64_t)b * nwt;
     int32_t *pop = a.ws.pop + b * 3;
-    if (s == 3) {
+    {
         if (need_c)
             build_level(g.n16, g.nw16, bits, prefix, pop + 0, [&](int wi) { return word_from_stream(mc, cap_c, wi); });
         else
             build_level(g.n16, g.nw16, bits, prefix, pop + 0, [&](int) { return a.mode == 4 ? 0xFFFFFFFFu : 0u; });
-    } else {
+    }
+    {
         if (need_m)
             build_level(g.n8, g.nw8, bits + g.nw16, prefix + g.nw16, pop + 1, [&](int wi) { return word_from_stream(mm, cap_m, wi); });
         else if (a.mode == 3)
@@ -884,7 +886,7 @@ __device__ __forceinline__ void assemble_quad(const UnpackArgs &a, int b, int64_
     }
 }
 
-// grid (5, B).  Fused form (a.fused): launched as thread-block clusters of 5 CTAs = the five streams of one
+// grid (4, B).  Fused form (a.fused): launched as thread-block clusters of 4 CTAs = the streams of one
 // image; after a cluster barrier the same CTAs re-assemble the image (no second launch, the symbols and
 // bitmaps are still in L2).
 __global__ void __launch_bounds__(UP_THREADS) unpack_decode_kernel(const UnpackArgs a)
@@ -896,7 +898,7 @@ __global__ void __launch_bounds__(UP_THREADS) unpack_decode_kernel(const UnpackA
     __threadfence();
     cluster_sync_all();
     const int64_t nquad = a.g.n4 / 4;
-    for (int64_t quad = (int64_t)blockIdx.x * UP_THREADS + threadIdx.x; quad < nquad; quad += (int64_t)5 * UP_THREADS)
+    for (int64_t quad = (int64_t)blockIdx.x * UP_THREADS + threadIdx.x; quad < nquad; quad += (int64_t)4 * UP_THREADS)
         assemble_quad(a, blockIdx.y, quad);
 }
 
@@ -1009,7 +1011,7 @@ extern "C" int cgic_unpack(const uint8_t *bytes, const int32_t *sizes, int B, in
     a.fused = fuse ? 1 : 0;
     {
         CGIC_PROF("unpack_decode_kernel", stream);
-        CGIC_CUDA_CHECK(launch_pdl_cluster(unpack_decode_kernel, dim3(5, B), dim3(UP_THREADS), smem, stream, a.fused ? 5 : 1, a));
+        CGIC_CUDA_CHECK(launch_pdl_cluster(unpack_decode_kernel, dim3(4, B), dim3(UP_THREADS), smem, stream, a.fused ? 4 : 1, a));
     }
     CGIC_LAUNCH_CHECK();
     if (!a.fused) {

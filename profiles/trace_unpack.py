@@ -29,11 +29,11 @@ torch.cuda.synchronize()
 buf = np.zeros(1024 * 8, np.uint64)
 rc = cg._lib.lib()._handle and ctypes.CDLL(cg._lib.LIB_PATH).cgic_trace_unpack(buf.ctypes.data_as(ctypes.c_void_p))
 assert rc == 0, rc
-st = buf.reshape(1024, 8)[: 5 * B].astype(np.float64)
+st = buf.reshape(1024, 8)[: 4 * B].astype(np.float64)
 t0 = st[:, 0][st[:, 0] > 0].min()
 names = ["start", "tables", "chunk", "staged", "A done", "B done", "end", "A0 done"]
-for s_id, label in ((0, "coarse idx"), (1, "medium idx"), (2, "fine idx"), (3, "mask coarse CTA"), (4, "mask medium+fine CTA")):
-    rows = st[s_id::5]
+for s_id, label in ((0, "coarse idx"), (1, "medium idx"), (2, "fine idx"), (3, "mask CTA")):
+    rows = st[s_id::4]
     print(label)
     if s_id < 3:
         rel = (rows[:, :8] - t0) / 1e3
