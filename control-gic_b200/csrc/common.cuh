@@ -68,41 +68,20 @@ __host__ __device__ inline bool stream_present(int mode, int s)
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-// cluster_x > 1: thread-block clusters of cluster_x CTAs along x (grid.x must be a multiple of it)
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
-                                      Args... args)
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args)
 {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.numAttrs = 1;
-    if (cluster_x > 1) {
-        attr[1].id = cudaLaunchAttributeClusterDimension;
-        attr[1].val.clusterDim.x = (unsigned)cluster_x;
-        attr[1].val.clusterDim.y = 1;
-        attr[1].val.clusterDim.z = 1;
-        cfg.numAttrs = 2;
-    }
     cfg.attrs = attr;
+    cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args)
-{
-    return launch_pdl_cluster(kernel, grid, block, smem, stream, 1, args...);
-}
-
-// cluster-wide barrier with release / acquire ordering (all threads of all CTAs of the cluster)
-__device__ __forceinline__ void cluster_sync_all()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) global -> shared with mbarrier completion ----

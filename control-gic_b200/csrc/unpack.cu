@@ -17,7 +17,6 @@
 //   reference's masked assignment puts there (row-major order); ind = fine + up2(medium) +
 //   up4(coarse); quant = codebook[ind] written NCHW; masks written as int64 like the reference.
 #include <algorithm>
-#include <cstdlib>
 
 #include "common.cuh"
 
@@ -99,7 +98,6 @@ struct UnpackArgs {
     int32_t *status;
     int mask_stage;  // 1: mask CTAs copy the mask streams to shared memory first
     int ch;          // subsequences per chunk of the candidate decoder (shared-memory budget)
-    int fused;       // 1: launched as clusters of 5 CTAs (one image each) that re-assemble the image after a cluster barrier
 };
 
 // ---- parallel prefix decoder (whole CTA, one stream) ------------------------------------------
@@ -886,23 +884,15 @@ __device__ __forceinline__ void assemble_quad(const UnpackArgs &a, int b, int64_
     }
 }
 
-// grid (4, B).  Fused form (a.fused): launched as thread-block clusters of 4 CTAs = the streams of one
-// image; after a cluster barrier the same CTAs re-assemble the image (no second launch, the symbols and
-// bitmaps are still in L2).
+// grid (4, B)
 __global__ void __launch_bounds__(UP_THREADS) unpack_decode_kernel(const UnpackArgs a)
 {
     extern __shared__ __align__(128) unsigned char dyn[];
     __shared__ __align__(8) unsigned long long mbar;
     unpack_decode_cta(a, dyn, mbar);
-    if (!a.fused) return;
-    __threadfence();
-    cluster_sync_all();
-    const int64_t nquad = a.g.n4 / 4;
-    for (int64_t quad = (int64_t)blockIdx.x * UP_THREADS + threadIdx.x; quad < nquad; quad += (int64_t)4 * UP_THREADS)
-        assemble_quad(a, blockIdx.y, quad);
 }
 
-// stand-alone re-assembly (the default; see cgic_unpack): one thread per quad
+// re-assembly: one thread per quad, its own PDL-chained launch (see the note in cgic_unpack)
 __global__ void __launch_bounds__(256) unpack_assemble_kernel(const UnpackArgs a)
 {
     pdl_launch_dependents();
@@ -1005,20 +995,20 @@ extern "C" int cgic_unpack(const uint8_t *bytes, const int32_t *sizes, int B, in
         CGIC_CUDA_CHECK(cudaFuncSetAttribute(unpack_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         smem_opt_in = true;
     }
-    // Measured on B200 (B = 64, 256^2): the cluster form takes 36.5 us against 29.6 us for the two PDL-chained
-    // launches (cluster launch latency + every CTA of an image waiting for its slowest stream), so it is opt-in.
-    static const bool fuse = getenv("CGIC_UNPACK_CLUSTER") != nullptr;
-    a.fused = fuse ? 1 : 0;
+    // Two PDL-chained launches.  Fusing the re-assembly into the decode kernel was measured on B200 (B = 64, 256^2,
+    // decode + re-assembly per step) and lost both ways: as thread-block clusters of one image's CTAs with a cluster
+    // barrier 36.5 us, as "the last CTA of an image to finish re-assembles it" (ticket) 30.2 us, against 27.9 us here --
+    // the re-assembly wants many SMs per image, not the one that happens to finish last.
     {
         CGIC_PROF("unpack_decode_kernel", stream);
-        CGIC_CUDA_CHECK(launch_pdl_cluster(unpack_decode_kernel, dim3(4, B), dim3(UP_THREADS), smem, stream, a.fused ? 4 : 1, a));
+        CGIC_CUDA_CHECK(launch_pdl(unpack_decode_kernel, dim3(4, B), dim3(UP_THREADS), smem, stream, a));
     }
     CGIC_LAUNCH_CHECK();
-    if (!a.fused) {
+    {
         CGIC_PROF("unpack_assemble_kernel", stream);
         CGIC_CUDA_CHECK(launch_pdl(unpack_assemble_kernel, dim3((unsigned)((a.g.n4 / 4 + 255) / 256), B), dim3(256), 0, stream, a));
-        CGIC_LAUNCH_CHECK();
     }
+    CGIC_LAUNCH_CHECK();
     return CGIC_OK;
 }
 

@@ -11,8 +11,12 @@ hdr_i = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
 h = rows[hdr_i]
 ki, vi, ui = h.index('Kernel Name'), h.index('Metric Value'), h.index('Metric Unit')
 acc = collections.OrderedDict()
+other = 0
 for r in rows[hdr_i + 1:]:
     if len(r) > vi:
+        if 'cgic::' not in r[ki]:      # torch's own kernels in the captured command (L2 flush memset, set-up): not part of the step
+            other += 1
+            continue
         name = r[ki].split('(')[0].split('::')[-1]
         acc.setdefault(name, []).append(float(r[vi].replace(',', '')) / (1000 if r[ui] == 'ns' else 1))
 tot = sum(sum(v) / len(v) for v in acc.values())
@@ -20,7 +24,7 @@ with open(os.path.join(out_dir, f"{tag}_launches.txt"), "w") as f:
     f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised): compare SHARES\n# source: {os.path.basename(launches)}\n")
     for k, v in acc.items():
         f.write(f"{k:28s} launches={len(v):3d} mean_us={sum(v)/len(v):8.2f} share={sum(v)/len(v)/tot:.3f}\n")
-    f.write(f"{'sum of kernel means':28s} {tot:.2f} us per step\n")
+    f.write(f"{'sum of kernel means':28s} {tot:.2f} us per step   ({other} launches of non-library kernels -- L2 flush, set-up -- left out)\n")
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rr = list(csv.reader(raw.splitlines()))
 hh = rr[0]
