@@ -5,6 +5,7 @@
    profiles/<tag>_kernels.txt  (per-kernel dram bytes, duration, pipe utilisation from --set full)"""
 import collections, csv, subprocess, sys, os
 launches, rep, tag = sys.argv[1:4]
+step = (sys.argv[4] if len(sys.argv) > 4 else 'vq_warp_kernel,pack_kernel<8>,unpack_decode_kernel,unpack_assemble_kernel').split(',')
 out_dir = os.path.dirname(os.path.abspath(__file__))
 rows = list(csv.reader(open(launches)))
 hdr_i = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
@@ -19,11 +20,14 @@ for r in rows[hdr_i + 1:]:
             continue
         name = r[ki].split('(')[0].split('::')[-1]
         acc.setdefault(name, []).append(float(r[vi].replace(',', '')) / (1000 if r[ui] == 'ns' else 1))
-tot = sum(sum(v) / len(v) for v in acc.values())
+tot = sum(sum(v) / len(v) for k, v in acc.items() if k in step)
 with open(os.path.join(out_dir, f"{tag}_launches.txt"), "w") as f:
     f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised): compare SHARES\n# source: {os.path.basename(launches)}\n")
     for k, v in acc.items():
-        f.write(f"{k:28s} launches={len(v):3d} mean_us={sum(v)/len(v):8.2f} share={sum(v)/len(v)/tot:.3f}\n")
+        if k in step:
+            f.write(f"{k:28s} launches={len(v):3d} mean_us={sum(v)/len(v):8.2f} share={sum(v)/len(v)/tot:.3f}\n")
+    f.write("# set-up kernels of the captured command (once, not part of a step): " +
+            ", ".join(f"{k} x{len(v)} {sum(v)/len(v):.1f} us" for k, v in acc.items() if k not in step) + "\n")
     f.write(f"{'sum of kernel means':28s} {tot:.2f} us per step   ({other} launches of non-library kernels -- L2 flush, set-up -- left out)\n")
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rr = list(csv.reader(raw.splitlines()))
