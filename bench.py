@@ -314,6 +314,54 @@ def run_b200(args):
     # the path's only collective: {bytes, pixels, squared error} summed over ranks
     tot_bytes, tot_pix, tot_sq, bpp = cdist.reduce_rate_distortion(float(sizes_first.sum()), float(pixels), float(sq.item()), device=dev)
 
+    # ---- "image-in" figure: the same step preceded by a4 entropy maps + a5 router + a6 mask-mix on the images
+    gimg = torch.Generator().manual_seed(seed + 7 + first)
+    x_img = torch.rand(B, 3, H, W, generator=gimg).to(dev)
+    hc2, hm2, hf2 = (t.to(dev) for t in workload.heads(B, H, W, cbk, seed, first))
+
+    def step_image_in():
+        e8_, e16_ = cg.ops.entropy_maps(x_img)
+        mc_, mm_, mf_, _, mode_ = cg.ops.router(e16_, e8_, c, m, per_image=True)
+        z_ = cg.ops.mask_mix(hc2, hm2, hf2, mc_, mm_, mf_)
+        idx_, zq_, sq_ = cg.ops.vq_assign(z_, prepared)
+        packed_, sizes_ = cg.ops.pack(idx_, mc_, mm_, mf_, mode_, table, h, w)
+        out_ = cg.ops.unpack(packed_, sizes_, mode_, table, cb, h, w)
+        return idx_, out_[3], out_[5]
+    i_idx, i_ind, i_status = step_image_in()
+    torch.cuda.synchronize()
+    assert int(i_status.abs().sum()) == 0 and torch.equal(i_ind.view(-1), i_idx)
+    img_runner = step_image_in
+    if not args.no_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step_image_in()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        img_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(img_graph):
+            step_image_in()
+        img_runner = img_graph.replay
+    for _ in range(3):
+        flush.zero_()
+        img_runner()
+    n_img = max(10, args.steps // 2)
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_img)]
+    torch.cuda.synchronize()
+    for a, b in ev2:
+        flush.zero_()
+        a.record()
+        img_runner()
+        b.record()
+    torch.cuda.synchronize()
+    img_ms = sum(a.elapsed_time(b) for a, b in ev2) / n_img
+    t = torch.tensor([img_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    img_ms = float(t.item())
+    del hc2, hm2, hf2
+
     # ---- e2e: host buffers through the C-ABI session (H2D + kernels + D2H inside the timed region)
     sess = cg.ops.Session(B, h, w, mode, table, cbk)
     zh = z.cpu().pin_memory()
@@ -399,6 +447,8 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e,
                     "ms_per_step": 1e3 * e2e_s / n_e2e, "call": "cgic_session_roundtrip_arena", "image_ranges": len(views)},
             "gpu_launches": kernels_per_step * args.steps, "cuda_graph": graph is not None,
+            "image_in": {"value": world * pixels / 1e6 / (img_ms * 1e-3), "unit": UNIT, "ms_per_step": img_ms, "steps": n_img,
+                         "adds": "a4 entropy maps (12 B/pixel image read) + a5 router + a6 mask-mix in front of the step"},
             "bpp": bpp, "stream_bytes_per_step": tot_bytes, "clocks": clocks, "roofline": roofline}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

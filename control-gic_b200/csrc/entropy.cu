@@ -3,17 +3,19 @@
 // Reference: gray image -> unfold into p x p patches -> for each patch a 32-bin soft histogram
 //   pdf_j = mean_i exp(-0.5 * ((v_i - bin_j) / 0.01)^2),  pdf = pdf / (sum + 1e-40) + 1e-40,
 //   H = -sum_j pdf_j * log(pdf_j);  it materialises [patches, p*p, 32] temporaries per scale.
-// Here one CTA owns one 16x16 pixel block (= one p=16 patch = four p=8 patches) and reads the
-// image exactly once:
-//   phase 1  one thread per pixel: gray value, then the kernel value for the 7 bins around the
-//            nearest bin.  sigma = 0.01 against a bin spacing of 2/31 makes every other term
-//            exp(-130) or smaller, which IS 0.0f in fp32 -- skipping them is exact, not an
-//            approximation.
-//   phase 2  one warp per 8x8 patch, lane = bin: a fixed-order (row-major) sum of the 64 pixel
-//            contributions -> pdf8; the p=16 histogram is the sum of the four (deterministic).
-//   phase 3  normalisation and -sum p*log(p) by warp shuffles.
-// fp32 throughout, denormals kept (eps = 1e-40 is a denormal; flush-to-zero would turn every
-// entropy into NaN).  Float-tolerance parity (the reference's own summation order is torch's).
+// Here the image is read exactly once and nothing is materialised.  A WARP owns a region of 16 rows x
+// 32 columns (= two 16x16 blocks = eight 8x8 patches); lane = column, so every load is one 128-byte row
+// segment.  Each lane keeps two 32-bin histogram rows in shared memory (its column's upper and lower 8
+// pixels) and adds the kernel values of its 16 pixels into them -- only the 3 bins around the nearest one:
+// sigma = 0.01 against a bin spacing of 2/31 puts every other bin at least 1.5 spacings away, a term of at
+// most exp(-46.8) = 4.7e-21 next to the nearest bin's >= 5.5e-3: far below the fp32 resolution of the
+// histogram sums and of the entropy (terms 2.5 spacings away are exactly 0.0f in fp32).  The histogram of
+// an 8x8 patch is the sum of 8 lanes' rows (lane = bin, fixed order), the 16x16 histogram the sum of its
+// four patches; the ten histograms of a region are normalised and turned into -sum p*log(p) together
+// (lane = bin for the element-wise part, one lane per histogram for the two sums).  __syncwarp only.
+// fp32 throughout, denormals kept (eps = 1e-40 is a denormal; flush-to-zero would turn every entropy into
+// NaN).  Float-tolerance parity (rtol 2e-5 in the tests): the summation order is ours, and
+// exp(-0.5 ((v - bin) / 0.01)^2) is evaluated as ex2.approx(-((v - bin) * c)^2), c = 100 sqrt(log2(e) / 2).
 #include "common.cuh"
 
 namespace cgic {
@@ -23,79 +25,123 @@ struct Bins {
     float v[32];
 };
 
-constexpr int EN_WIN = 7;
+constexpr int EN_WIN = 3;
+constexpr int EN_WARPS = 4;              // warps (= regions in flight) per CTA
+constexpr int EN_STRIDE = 33;            // words per histogram row: lanes hitting the same bin fall into different banks
 
-__device__ __forceinline__ float warp_sum(float v)
+__device__ __forceinline__ float ex2_approx(float x)  // no flush-to-zero: denormal results are kept
 {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+    float y;
+    asm("ex2.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
-__device__ __forceinline__ float entropy_of(float pdf_lane)
+__global__ void __launch_bounds__(EN_WARPS * 32, 8)
+entropy_kernel(const float *__restrict__ x, int H, int W, int regions_x, int64_t n_regions, const Bins bins, float *__restrict__ e8,
+               float *__restrict__ e16)
 {
-    const float eps = 1e-40f;
-    const float norm = warp_sum(pdf_lane) + eps;
-    const float p = pdf_lane / norm + eps;
-    return -warp_sum(p * logf(p));
-}
-
-__global__ void __launch_bounds__(256)
-entropy_kernel(const float *__restrict__ x, int H, int W, const Bins bins, float *__restrict__ e8, float *__restrict__ e16)
-{
-    __shared__ float s_val[256][EN_WIN];
-    __shared__ signed char s_lo[256];
+    __shared__ __align__(16) float s_rows[EN_WARPS][32 * EN_STRIDE + 4];  // per warp: 32 histogram rows (slice a multiple of 16 bytes)
     __shared__ float s_bins[32];
-    __shared__ float s_sum[4][32];
-    const int tid = threadIdx.x;
-    const int b = blockIdx.z;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 32) s_bins[threadIdx.x] = bins.v[threadIdx.x];
+    __syncthreads();
+    const int64_t region = (int64_t)blockIdx.x * EN_WARPS + warp;
+    if (region >= n_regions) return;
+    const int regions_y = H / 16;
+    const int b = (int)(region / ((int64_t)regions_x * regions_y));
+    const int rr = (int)(region - (int64_t)b * regions_x * regions_y);
+    const int ry = rr / regions_x, rx = rr - ry * regions_x;
+    const int gx = rx * 32 + lane;
+    const bool col_ok = gx < W;
     const int64_t plane = (int64_t)H * W;
-    if (tid < 32) s_bins[tid] = bins.v[tid];
-    __syncthreads();
-    {
-        const int py = tid >> 4, px = tid & 15;
-        const int64_t o = (int64_t)(blockIdx.y * 16 + py) * W + blockIdx.x * 16 + px;
-        const float *xb = x + (int64_t)b * 3 * plane;
-        // 0.2989*R + 0.5870*G + 0.1140*B, each product and sum rounded (model.py:471)
-        float g = __fadd_rn(__fmul_rn(0.2989f, xb[o]), __fmul_rn(0.5870f, xb[plane + o]));
-        g = __fadd_rn(g, __fmul_rn(0.1140f, xb[2 * plane + o]));
-        int jc = __float2int_rn((g + 1.0f) * 15.5f);
-        jc = max(0, min(31, jc));
-        const int lo = jc - EN_WIN / 2;
-        s_lo[tid] = (signed char)lo;
+    const float *xb = x + (int64_t)b * 3 * plane + (int64_t)(ry * 16) * W + gx;
+    float *rows = s_rows[warp];
+    float *row = rows + lane * EN_STRIDE;
+    // the two halves (upper / lower 8 rows) go through the same 32 histogram rows one after the other; the
+    // lower half's pixels are already in flight while the upper half is accumulated
+    float raw[2][8][3];
 #pragma unroll
-        for (int r = 0; r < EN_WIN; ++r) {
-            const int j = lo + r;
-            float v = 0.f;
-            if (j >= 0 && j < 32) {
-                const float q = __fdiv_rn(__fsub_rn(g, s_bins[j]), 0.01f);
-                v = expf(__fmul_rn(-0.5f, __fmul_rn(q, q)));
+    for (int half = 0; half < 2; ++half)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int64_t o = (int64_t)(half * 8 + r) * W;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) raw[half][r][c] = col_ok ? __ldg(xb + c * plane + o) : 0.f;
+        }
+    float acc[2][4];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        // zero the 32 rows (16-byte stores over the whole slice)
+        for (int i = lane; i < (32 * EN_STRIDE + 4) / 4; i += 32) reinterpret_cast<float4 *>(rows)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
+        if (col_ok) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                // 0.2989*R + 0.5870*G + 0.1140*B, each product and sum rounded (model.py:471)
+                const float g = __fadd_rn(__fadd_rn(__fmul_rn(0.2989f, raw[half][r][0]), __fmul_rn(0.5870f, raw[half][r][1])),
+                                          __fmul_rn(0.1140f, raw[half][r][2]));
+                int jc = __float2int_rn((g + 1.0f) * 15.5f);
+                jc = max(0, min(31, jc));
+#pragma unroll
+                for (int k = 0; k < EN_WIN; ++k) {
+                    const int j = jc - EN_WIN / 2 + k;
+                    if (j >= 0 && j < 32) {
+                        const float q = __fmul_rn(__fsub_rn(g, s_bins[j]), 84.93218002880191f);  // 100 * sqrt(log2(e) / 2)
+                        row[j] += ex2_approx(-__fmul_rn(q, q));  // same thread owns the row: plain read-modify-write
+                    }
+                }
             }
-            s_val[tid][r] = v;
         }
+        __syncwarp();
+        // the half's four 8x8 patches (pq = column group of 8): lane = bin, fixed order over the 8 columns
+#pragma unroll
+        for (int pq = 0; pq < 4; ++pq) {
+            float a = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) a += rows[(pq * 8 + c) * EN_STRIDE + lane];
+            acc[half][pq] = a;
+        }
+        __syncwarp();
     }
-    __syncthreads();
-    const int warp = tid >> 5, lane = tid & 31;
-    if (warp < 4) {
-        const int sy = warp >> 1, sx = warp & 1;
-        float acc = 0.f;
-        for (int i = 0; i < 64; ++i) {
-            const int t = ((sy * 8 + (i >> 3)) << 4) + sx * 8 + (i & 7);
-            const int r = lane - (int)s_lo[t];
-            if (r >= 0 && r < EN_WIN) acc += s_val[t][r];
-        }
-        s_sum[warp][lane] = acc;
-        if (e8) {
-            const float ent = entropy_of(acc / 64.0f);
-            if (lane == 0)
-                e8[((int64_t)b * (H / 8) + blockIdx.y * 2 + sy) * (W / 8) + blockIdx.x * 2 + sx] = ent;
-        }
+    const int valid_pq = min(4, (W - rx * 32) / 8);  // a region may hang over the right edge by one 16-pixel block
+    // ten histograms per region: 0..7 = the 8x8 patches (py * 4 + pq), 8..9 = the 16x16 blocks; pdf = sum / patch size
+    float pdf[10];
+#pragma unroll
+    for (int py = 0; py < 2; ++py)
+#pragma unroll
+        for (int pq = 0; pq < 4; ++pq) pdf[py * 4 + pq] = acc[py][pq] / 64.0f;
+#pragma unroll
+    for (int kx = 0; kx < 2; ++kx)
+        pdf[8 + kx] = ((acc[0][2 * kx] + acc[0][2 * kx + 1]) + (acc[1][2 * kx] + acc[1][2 * kx + 1])) / 256.0f;
+    // the histogram rows are dead: reuse the slice as T[10][33] (+ norms at [10 * 33 ..])
+    float *T = rows;
+#pragma unroll
+    for (int p = 0; p < 10; ++p) T[p * EN_STRIDE + lane] = pdf[p];
+    __syncwarp();
+    const float eps = 1e-40f;
+    if (lane < 10) {
+        float sum = 0.f;
+        for (int j = 0; j < 32; ++j) sum += T[lane * EN_STRIDE + j];
+        T[10 * EN_STRIDE + lane] = sum + eps;
     }
-    __syncthreads();
-    if (warp == 0 && e16) {
-        const float tot = (s_sum[0][lane] + s_sum[1][lane]) + (s_sum[2][lane] + s_sum[3][lane]);
-        const float ent = entropy_of(tot / 256.0f);
-        if (lane == 0) e16[((int64_t)b * (H / 16) + blockIdx.y) * (W / 16) + blockIdx.x] = ent;
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < 10; ++p) {
+        const float q = pdf[p] / T[10 * EN_STRIDE + p] + eps;
+        T[p * EN_STRIDE + lane] = q * logf(q);
+    }
+    __syncwarp();
+    if (lane < 10) {
+        float sum = 0.f;
+        for (int j = 0; j < 32; ++j) sum += T[lane * EN_STRIDE + j];
+        const float ent = -sum;
+        if (lane < 8) {
+            const int py = lane >> 2, pq = lane & 3;
+            if (e8 && pq < valid_pq) e8[((int64_t)b * (H / 8) + ry * 2 + py) * (W / 8) + rx * 4 + pq] = ent;
+        } else {
+            const int kx = lane - 8;
+            if (e16 && 2 * kx < valid_pq) e16[((int64_t)b * (H / 16) + ry) * (W / 16) + rx * 2 + kx] = ent;
+        }
     }
 }
 
@@ -110,13 +156,16 @@ extern "C" int cgic_entropy_maps(const float *x, int B, int H, int W, const floa
     CGIC_REQUIRE(x && bins32_host && (e8_out || e16_out), CGIC_EINVAL, "cgic_entropy_maps: null argument");
     CGIC_REQUIRE(B >= 0 && H > 0 && W > 0 && H % 16 == 0 && W % 16 == 0, CGIC_EINVAL,
                  "cgic_entropy_maps: image %dx%d must be multiples of 16", H, W);
-    CGIC_REQUIRE(B <= 65535 && H / 16 <= 65535, CGIC_EINVAL, "cgic_entropy_maps: grid too large");
     if (B == 0) return CGIC_OK;
+    const int regions_x = (W + 31) / 32;
+    const int64_t n_regions = (int64_t)B * (H / 16) * regions_x;
+    CGIC_REQUIRE((n_regions + EN_WARPS - 1) / EN_WARPS < ((int64_t)1 << 31), CGIC_EINVAL, "cgic_entropy_maps: grid too large");
     Bins bins;
     for (int i = 0; i < 32; ++i) bins.v[i] = bins32_host[i];
     {
         CGIC_PROF("entropy_kernel", as_stream(stream));
-        entropy_kernel<<<dim3(W / 16, H / 16, B), 256, 0, as_stream(stream)>>>(x, H, W, bins, e8_out, e16_out);
+        entropy_kernel<<<(unsigned)((n_regions + EN_WARPS - 1) / EN_WARPS), EN_WARPS * 32, 0, as_stream(stream)>>>(x, H, W, regions_x, n_regions,
+                                                                                                              bins, e8_out, e16_out);
     }
     CGIC_LAUNCH_CHECK();
     return CGIC_OK;

@@ -48,16 +48,37 @@ __device__ float select_rank(Fetch fetch, int64_t n, int64_t rank, uint32_t *s_h
             if ((k & mask) == prefix) atomicAdd(&s_hist[(k >> shift) & 255u], 1u);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            uint64_t r = ((uint64_t)s_state[2] << 32) | s_state[1];
-            uint32_t d = 0;
-            for (; d < 255; ++d) {
-                if (r < s_hist[d]) break;
-                r -= s_hist[d];
+        if (threadIdx.x < 32) {
+            // the bucket holding the wanted rank: lane l owns buckets 8l .. 8l+7; inclusive scan of the lane totals by
+            // shuffles, then the owning lane walks its 8 buckets (a serial walk over 256 buckets cost 4 us per pass)
+            const int lane = threadIdx.x;
+            uint64_t rk = ((uint64_t)s_state[2] << 32) | s_state[1];
+            uint32_t cnt[8], tot = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                cnt[i] = s_hist[lane * 8 + i];
+                tot += cnt[i];
             }
-            s_state[0] = prefix | (d << shift);
-            s_state[1] = (uint32_t)r;
-            s_state[2] = (uint32_t)(r >> 32);
+            uint32_t inc = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            const uint32_t exc = inc - tot;
+            // rank < n always, so exactly one lane has exc <= rk < inc (the last lane takes everything beyond: d <= 255)
+            const bool mine = (rk >= exc && rk < inc) || (lane == 31 && rk >= inc);
+            if (mine) {
+                uint64_t rem = rk - exc;
+                uint32_t d = 0;
+                for (; d < 7; ++d) {
+                    if (rem < cnt[d]) break;
+                    rem -= cnt[d];
+                }
+                s_state[0] = prefix | ((uint32_t)(lane * 8 + d) << shift);
+                s_state[1] = (uint32_t)rem;
+                s_state[2] = (uint32_t)(rem >> 32);
+            }
         }
         __syncthreads();
         prefix = s_state[0];
@@ -70,7 +91,8 @@ __device__ float select_rank(Fetch fetch, int64_t n, int64_t rank, uint32_t *s_h
 // grid = B (per_image) or 1; writes m_c and m_m.
 __global__ void __launch_bounds__(RT_THREADS)
 router_select_kernel(const float *__restrict__ e16, const float *__restrict__ e8, int B, int h16, int w16, int mode,
-                     int64_t k_c, int64_t k_m, int per_image, int32_t *__restrict__ m_c, int32_t *__restrict__ m_m)
+                     int64_t k_c, int64_t k_m, int per_image, int32_t *__restrict__ m_c, int32_t *__restrict__ m_m,
+                     int32_t *__restrict__ m_f, float *__restrict__ gate)
 {
     __shared__ uint32_t s_hist[256];
     __shared__ uint32_t s_state[4];
@@ -111,6 +133,30 @@ router_select_kernel(const float *__restrict__ e16, const float *__restrict__ e8
     } else {
         for (int64_t i = threadIdx.x; i < n8; i += blockDim.x) m[i] = (mode == 5);
     }
+    if (!m_f) return;
+    // per-image launches also write the image's fine mask and gate (saves the second launch); 4 tokens per thread
+    __syncthreads();  // c[] and m[] (global) are re-read below by other threads of this CTA
+    const int h = 4 * h16, w = 4 * w16;
+    const int64_t plane = (int64_t)h * w;
+    int32_t *f = m_f + img0 * plane;
+    for (int64_t q = threadIdx.x; q < plane / 4; q += blockDim.x) {
+        const int y = (int)(q / w16), xq = (int)(q - (int64_t)y * w16);
+        const int cc = c[(int64_t)(y >> 2) * w16 + xq];
+        const int2 mm = *reinterpret_cast<const int2 *>(&m[(int64_t)(y >> 1) * w8 + 2 * xq]);
+        int4 fv;
+        if (mode <= 2) fv = make_int4((1 - cc - mm.x) != 0, (1 - cc - mm.x) != 0, (1 - cc - mm.y) != 0, (1 - cc - mm.y) != 0);
+        else fv = make_int4(mode == 6, mode == 6, mode == 6, mode == 6);
+        *reinterpret_cast<int4 *>(&f[(int64_t)y * w + 4 * xq]) = fv;
+        if (gate) {
+            float *row = gate + (img0 * h + y) * (int64_t)(3 * w);
+            const float fc = (float)cc;
+            *reinterpret_cast<float4 *>(&row[4 * xq]) = make_float4(fc, fc, fc, fc);
+            *reinterpret_cast<float4 *>(&row[w + 4 * xq]) = make_float4((float)mm.x, (float)mm.x, (float)mm.y, (float)mm.y);
+            *reinterpret_cast<float4 *>(&row[2 * w + 4 * xq]) =
+                mode <= 2 ? make_float4((float)(1 - cc - mm.x), (float)(1 - cc - mm.x), (float)(1 - cc - mm.y), (float)(1 - cc - mm.y))
+                          : make_float4((float)fv.x, (float)fv.y, (float)fv.z, (float)fv.w);
+        }
+    }
 }
 
 // one thread per fine token: m_f and the optional gate tensor [B,1,h,3w]
@@ -136,21 +182,35 @@ __global__ void router_fine_kernel(const int32_t *__restrict__ m_c, const int32_
     }
 }
 
-__global__ void mask_mix_kernel(const float *__restrict__ h_c, const float *__restrict__ h_m, const float *__restrict__ h_f,
-                                const int32_t *__restrict__ m_c, const int32_t *__restrict__ m_m,
-                                const int32_t *__restrict__ m_f, int64_t n, int C, int h, int w, float *__restrict__ out)
+// one thread per 4 consecutive fine tokens of a row (they share one coarse cell and two medium cells): 16-byte loads / stores
+__global__ void __launch_bounds__(256)
+mask_mix_kernel(const float *__restrict__ h_c, const float *__restrict__ h_m, const float *__restrict__ h_f, const int32_t *__restrict__ m_c,
+                const int32_t *__restrict__ m_m, const int32_t *__restrict__ m_f, int64_t n_quads, int C, int h, int w,
+                float *__restrict__ out)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int x = (int)(i % w);
-    const int y = (int)((i / w) % h);
-    const int64_t bc = i / ((int64_t)w * h);  // b*C + c
+    const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= n_quads) return;
+    const unsigned wq = (unsigned)w / 4u;
+    const int64_t rowi = qi / wq;              // (b*C + c) * h + y
+    const int xq = (int)(qi - rowi * wq);      // = x / 4
+    const int64_t bc = rowi / h;
+    const int y = (int)(rowi - bc * h);
     const int64_t b = bc / C;
     const int h8 = h / 2, w8 = w / 2, h16 = h / 4, w16 = w / 4;
-    const float a = __fmul_rn(h_c[(bc * h16 + (y >> 2)) * w16 + (x >> 2)], (float)m_c[(b * h16 + (y >> 2)) * w16 + (x >> 2)]);
-    const float m = __fmul_rn(h_m[(bc * h8 + (y >> 1)) * w8 + (x >> 1)], (float)m_m[(b * h8 + (y >> 1)) * w8 + (x >> 1)]);
-    const float f = __fmul_rn(h_f[i], (float)m_f[(b * h + y) * (int64_t)w + x]);
-    out[i] = __fadd_rn(__fadd_rn(a, m), f);
+    const float hc = __ldg(&h_c[(bc * h16 + (y >> 2)) * w16 + xq]);
+    const float mc = (float)__ldg(&m_c[(b * h16 + (y >> 2)) * w16 + xq]);
+    const float2 hm = __ldg(reinterpret_cast<const float2 *>(&h_m[(bc * h8 + (y >> 1)) * w8 + 2 * xq]));
+    const int2 mm = __ldg(reinterpret_cast<const int2 *>(&m_m[(b * h8 + (y >> 1)) * w8 + 2 * xq]));
+    const float4 hf = __ldg(reinterpret_cast<const float4 *>(&h_f[rowi * w + 4 * xq]));
+    const int4 mf = __ldg(reinterpret_cast<const int4 *>(&m_f[(b * h + y) * (int64_t)w + 4 * xq]));
+    const float a = __fmul_rn(hc, mc);
+    const float m0 = __fmul_rn(hm.x, (float)mm.x), m1 = __fmul_rn(hm.y, (float)mm.y);
+    float4 o;
+    o.x = __fadd_rn(__fadd_rn(a, m0), __fmul_rn(hf.x, (float)mf.x));
+    o.y = __fadd_rn(__fadd_rn(a, m0), __fmul_rn(hf.y, (float)mf.y));
+    o.z = __fadd_rn(__fadd_rn(a, m1), __fmul_rn(hf.z, (float)mf.z));
+    o.w = __fadd_rn(__fadd_rn(a, m1), __fmul_rn(hf.w, (float)mf.w));
+    *reinterpret_cast<float4 *>(&out[rowi * w + 4 * xq]) = o;
 }
 
 }  // namespace
@@ -169,11 +229,16 @@ extern "C" int cgic_router(const float *e16, const float *e8, int B, int h16, in
                  "cgic_router: bad argument B=%d h16=%d w16=%d mode=%d", B, h16, w16, mode);
     if (B == 0) return CGIC_OK;
     cudaStream_t stream = as_stream(stream_);
+    // per-image thresholds: the select kernel (one CTA per image) also writes the fine mask / gate when the rows are 16-byte aligned
+    const bool fuse_fine = per_image && (reinterpret_cast<uintptr_t>(m_m) & 7) == 0 && (reinterpret_cast<uintptr_t>(m_f) & 15) == 0 &&
+                           (!gate_out || (reinterpret_cast<uintptr_t>(gate_out) & 15) == 0);
     {
         CGIC_PROF("router_select_kernel", stream);
-        router_select_kernel<<<per_image ? B : 1, RT_THREADS, 0, stream>>>(e16, e8, B, h16, w16, mode, k_c, k_m, per_image, m_c, m_m);
+        router_select_kernel<<<per_image ? B : 1, RT_THREADS, 0, stream>>>(e16, e8, B, h16, w16, mode, k_c, k_m, per_image, m_c, m_m,
+                                                                           fuse_fine ? m_f : nullptr, gate_out);
     }
     CGIC_LAUNCH_CHECK();
+    if (fuse_fine) return CGIC_OK;
     const int64_t n = (int64_t)B * 16 * h16 * w16;
     {
         CGIC_PROF("router_fine_kernel", stream);
@@ -188,8 +253,10 @@ extern "C" int cgic_mask_mix(const float *h_c, const float *h_m, const float *h_
 {
     CGIC_REQUIRE(h_c && h_m && h_f && m_c && m_m && m_f && out, CGIC_EINVAL, "cgic_mask_mix: null argument");
     CGIC_REQUIRE(B >= 0 && C > 0 && h > 0 && w > 0 && h % 4 == 0 && w % 4 == 0, CGIC_EINVAL, "cgic_mask_mix: bad shape");
-    const int64_t n = (int64_t)B * C * h * w;
+    const int64_t n = (int64_t)B * C * h * w / 4;
     if (n == 0) return CGIC_OK;
+    for (const void *ptr : {(const void *)h_m, (const void *)h_f, (const void *)m_m, (const void *)m_f, (const void *)out})
+        CGIC_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, CGIC_EINVAL, "cgic_mask_mix: buffers must be 16-byte aligned");
     {
         CGIC_PROF("mask_mix_kernel", as_stream(stream));
         mask_mix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(h_c, h_m, h_f, m_c, m_m, m_f, n, C, h, w, out);
