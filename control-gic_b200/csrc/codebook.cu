@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(256) cb_cells_kernel(unsigned char *__restrict
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *es = reinterpret_cast<float4 *>(smem_raw);                       // [K]
-    unsigned short *list = reinterpret_cast<unsigned short *>(es + K);       // [K]
+    unsigned short *list = reinterpret_cast<unsigned short *>(es + K);       // [2][K]: survivors of stage 1 / stage 2
     __shared__ int s_dom[CB_NDOM];
     __shared__ int s_wcnt[8];
     __shared__ int s_base;
@@ -187,14 +187,84 @@ __global__ void __launch_bounds__(256) cb_cells_kernel(unsigned char *__restrict
     const double margin = 2.0 * 10.0 * u * reach * reach * 1.001 + 1e-40;
     __syncthreads();
 
-    // ---- dominators: the nearest code to each corner (2 per warp), then the 4 codes nearest to the centre (warp 0)
-    auto nearest = [&](const double p[4], const int *excl, int nexcl) {
+    // domination test: is code k worse than dominator j by more than the rounding slack EVERYWHERE in the cell?
+    auto dominated = [&](int k, const int *dom, int ndom) {
+        const float4 ek = es[k];
+        const double e[4] = {ek.x, ek.y, ek.z, ek.w};
+        const double n_k = e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3];
+        for (int i = 0; i < ndom; ++i) {
+            const float4 ejf = es[dom[i]];
+            const double ej[4] = {ejf.x, ejf.y, ejf.z, ejf.w};
+            double mn = n_k - (ej[0] * ej[0] + ej[1] * ej[1] + ej[2] * ej[2] + ej[3] * ej[3]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const double dl = e[c] - ej[c];
+                mn -= fmax(2.0 * lo[c] * dl, 2.0 * hi[c] * dl);  // min over the box of a linear function: per-coordinate extremes
+            }
+            if (mn > margin) return true;
+        }
+        return false;
+    };
+    // ordered compaction of the codes src[0..n) (ascending) that survive `dom` into dst; whole CTA; returns the count
+    auto survivors = [&](const unsigned short *src, int n, const int *dom, int ndom, unsigned short *dst) {
+        if (tid == 0) s_base = 0;
+        __syncthreads();
+        for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+            const int i = i0 + tid;
+            const int k = i < n ? (src ? (int)src[i] : i) : -1;
+            const bool alive = k >= 0 && !dominated(k, dom, ndom);
+            const unsigned m = __ballot_sync(0xffffffffu, alive);
+            if (lane == 0) s_wcnt[warp] = __popc(m);
+            __syncthreads();
+            int before = s_base;
+            for (int w = 0; w < warp; ++w) before += s_wcnt[w];
+            if (alive) dst[before + __popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
+            __syncthreads();
+            if (tid == 0) {
+                int t = s_base;
+                for (int w = 0; w < 8; ++w) t += s_wcnt[w];
+                s_base = t;
+            }
+            __syncthreads();
+        }
+        return s_base;
+    };
+    // nearest code to p among src[0..n) (src == nullptr: all K codes), one warp; ties -> lowest index
+    auto nearest = [&](const double p[4], const unsigned short *src, int n) {
         double bd = 1e300;
         int bk = 0x7fffffff;
-        for (int k = lane; k < K; k += 32) {
-            bool skip = false;
-            for (int i = 0; i < nexcl; ++i) skip |= excl[i] == k;
-            if (skip) continue;
+        for (int i = lane; i < n; i += 32) {
+            const int k = src ? (int)src[i] : i;
+            const float4 e = es[k];
+            const double d0 = e.x - p[0], d1 = e.y - p[1], d2 = e.z - p[2], d3 = e.w - p[3];
+            const double d = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+            if (d < bd || (d == bd && k < bk)) {
+                bd = d;
+                bk = k;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+            const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+            if (od < bd || (od == bd && ok < bk)) {
+                bd = od;
+                bk = ok;
+            }
+        }
+        return bk;
+    };
+
+    // ---- stage 1: eight dominators = each warp's nearest code to the cell centre within its slice of the codebook
+    //      (the global nearest is among them); they already remove all but a few dozen codes
+    {
+        double p[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) p[c] = 0.5 * (lo[c] + hi[c]);
+        const int per = (K + 7) / 8, k0 = warp * per, k1 = min(K, k0 + per);
+        double bd = 1e300;
+        int bk = 0x7fffffff;
+        for (int k = k0 + lane; k < k1; k += 32) {
             const float4 e = es[k];
             const double d0 = e.x - p[0], d1 = e.y - p[1], d2 = e.z - p[2], d3 = e.w - p[3];
             const double d = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
@@ -212,66 +282,23 @@ __global__ void __launch_bounds__(256) cb_cells_kernel(unsigned char *__restrict
                 bk = ok;
             }
         }
-        return bk;
-    };
+        if (lane == 0) s_dom[warp] = bk == 0x7fffffff ? 0 : bk;  // an empty slice (K < 8) repeats code 0: harmless
+    }
+    __syncthreads();
+    unsigned short *list2 = list + K;
+    int count = survivors(nullptr, K, s_dom, 8, list);
+    // ---- stage 2: the nearest survivor to each of the 16 corners (the nearest code to a point of the cell is never
+    //      dominated, so it is among the survivors); a second pass with these dominators
     for (int q = warp; q < 16; q += 8) {
         double p[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) p[c] = ((q >> c) & 1) ? hi[c] : lo[c];
-        const int k = nearest(p, nullptr, 0);
-        if (lane == 0) s_dom[q] = k;
+        const int k = nearest(p, list, count);
+        if (lane == 0) s_dom[q] = k == 0x7fffffff ? 0 : k;  // (no survivor cannot happen; any code is a valid dominator)
     }
-    if (warp == 0) {
-        double p[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) p[c] = 0.5 * (lo[c] + hi[c]);
-        int ex[4];
-        for (int i = 0; i < 4; ++i) {
-            int k = nearest(p, ex, i);
-            if (k == 0x7fffffff) k = ex[0];  // fewer than 4 codes
-            ex[i] = k;
-            if (lane == 0) s_dom[16 + i] = k;
-        }
-    }
-    if (tid == 0) s_base = 0;
     __syncthreads();
-
-    // ---- domination tests + ordered compaction (ascending code index)
-    for (int k0 = 0; k0 < K; k0 += blockDim.x) {
-        const int k = k0 + tid;
-        bool alive = k < K;
-        if (alive) {
-            const float4 ek = es[k];
-            const double e[4] = {ek.x, ek.y, ek.z, ek.w};
-            const double n_k = e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3];
-            for (int i = 0; i < CB_NDOM && alive; ++i) {
-                const int j = s_dom[i];
-                const float4 ejf = es[j];
-                const double ej[4] = {ejf.x, ejf.y, ejf.z, ejf.w};
-                double mn = n_k - (ej[0] * ej[0] + ej[1] * ej[1] + ej[2] * ej[2] + ej[3] * ej[3]);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const double dl = e[c] - ej[c];
-                    mn -= fmax(2.0 * lo[c] * dl, 2.0 * hi[c] * dl);
-                }
-                if (mn > margin) alive = false;  // e_j is closer than e_k by more than the rounding slack everywhere in the cell
-            }
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, alive);
-        if (lane == 0) s_wcnt[warp] = __popc(m);
-        __syncthreads();
-        int before = s_base;
-        for (int i = 0; i < warp; ++i) before += s_wcnt[i];
-        if (alive) list[before + __popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
-        __syncthreads();
-        if (tid == 0) {
-            int t = s_base;
-            for (int i = 0; i < 8; ++i) t += s_wcnt[i];
-            s_base = t;
-        }
-        __syncthreads();
-    }
-    const int count = s_base;
+    count = survivors(list, count, s_dom, 16, list2);
+    list = list2;
     if (count >= 1 && count <= CB_RW - 1) {
         for (int i = tid; i < CB_RW; i += blockDim.x) rec[i] = i == 0 ? (unsigned short)count : list[min(i, count) - 1];
     } else {
@@ -326,10 +353,10 @@ extern "C" int cgic_codebook_update(cgic_codebook *cb, const float *codebook, cg
     CGIC_REQUIRE((reinterpret_cast<uintptr_t>(codebook) & 15) == 0, CGIC_EINVAL, "cgic_codebook_update: codebook must be 16-byte aligned");
     cudaStream_t stream = as_stream(stream_);
     const int K = cb->K;
-    const size_t smem = (size_t)K * (16 + 2);
+    const size_t smem = (size_t)K * (16 + 4);
     static bool attr_done = false;
     if (!attr_done) {
-        CGIC_CUDA_CHECK(cudaFuncSetAttribute(cb_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CB_MAX_K * (16 + 2)));
+        CGIC_CUDA_CHECK(cudaFuncSetAttribute(cb_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CB_MAX_K * (16 + 4)));
         attr_done = true;
     }
     {

@@ -9,7 +9,7 @@ constexpr int CB_PAD = 48;        // bins beyond the codebook's min / max on eac
 constexpr int CB_G = 12;          // cells per dimension
 constexpr int CB_RW = 64;         // u16 words per cell record: count + up to 63 candidates
 constexpr int CB_MAX_K = 4096;
-constexpr int CB_NDOM = 20;       // dominators tried per cell: nearest code to the 16 corners + 4 nearest to the centre
+constexpr int CB_NDOM = 16;       // dominators per stage: 8 nearest-to-centre (one per codebook slice), then the nearest survivor to each corner
 constexpr int CB_HDR = 512;       // header bytes
 constexpr int CB_LUT = 4 * CB_NB; // lookup-table bytes
 

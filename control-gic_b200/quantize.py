@@ -99,11 +99,13 @@ class VectorQuantize2(nn.Module):
 
     def forward(self, z):
         w = self.embedding.weight
-        prepared = self.prepared_codebook()
+        # the index costs ~1.5 ms to build: worth it when the weights stand still (inference), not when every
+        # optimiser step moves them (training) -- there the exhaustive kernel (~37 us per 262 k latents) is used
+        prepared = None if self.training else self.prepared_codebook()
         if torch.is_grad_enabled() and (z.requires_grad or w.requires_grad):
             z_q, loss, idx = _VQFunction.apply(z, w, self.beta, self.legacy, prepared)
         else:
-            idx, z_q, sq = ops.vq_assign(z, prepared)
+            idx, z_q, sq = ops.vq_assign(z, prepared if prepared is not None else w)
             mean = (sq / z.numel()).to(torch.float32)[0]
             loss = mean + self.beta * mean if self.legacy else self.beta * mean + mean
         if self.training:
