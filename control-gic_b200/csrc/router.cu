@@ -27,9 +27,10 @@ __device__ __forceinline__ float key_float(uint32_t k)
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
 }
 
-// value of rank `rank` (0-based) among fetch(0..n-1); whole CTA must call.
+// value of rank `rank` (0-based) among fetch(0..n-1); whole CTA must call.  s_keys (nullable): room for n keys in
+// shared memory -- the values are fetched and converted once instead of once per pass.
 template <typename Fetch>
-__device__ float select_rank(Fetch fetch, int64_t n, int64_t rank, uint32_t *s_hist, uint32_t *s_state)
+__device__ float select_rank(Fetch fetch, int64_t n, int64_t rank, uint32_t *s_hist, uint32_t *s_state, uint32_t *s_keys)
 {
     uint32_t prefix = 0, mask = 0;
     if (rank > n - 1) rank = n - 1;
@@ -39,13 +40,23 @@ __device__ float select_rank(Fetch fetch, int64_t n, int64_t rank, uint32_t *s_h
         s_state[1] = (uint32_t)rank;
         s_state[2] = (uint32_t)((uint64_t)rank >> 32);
     }
+    if (s_keys)
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = float_key(fetch(i));
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 24 - 8 * pass;
         for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
         __syncthreads();
-        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-            const uint32_t k = float_key(fetch(i));
-            if ((k & mask) == prefix) atomicAdd(&s_hist[(k >> shift) & 255u], 1u);
+        for (int64_t i0 = 0; i0 < n; i0 += blockDim.x) {  // uniform trip count: the warp votes below need every lane
+            const int64_t i = i0 + threadIdx.x;
+            uint32_t digit = 0xFFFFFFFFu;
+            if (i < n) {
+                const uint32_t k = s_keys ? s_keys[i] : float_key(fetch(i));
+                if ((k & mask) == prefix) digit = (k >> shift) & 255u;
+            }
+            // one atomic per distinct digit and warp (entropies share their exponent: the first pass would otherwise
+            // serialise hundreds of increments on one or two counters)
+            const unsigned same = __match_any_sync(0xffffffffu, digit);
+            if (digit != 0xFFFFFFFFu && (threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&s_hist[digit], (uint32_t)__popc(same));
         }
         __syncthreads();
         if (threadIdx.x < 32) {
@@ -68,6 +79,7 @@ __device__ float select_rank(Fetch fetch, int64_t n, int64_t rank, uint32_t *s_h
             const uint32_t exc = inc - tot;
             // rank < n always, so exactly one lane has exc <= rk < inc (the last lane takes everything beyond: d <= 255)
             const bool mine = (rk >= exc && rk < inc) || (lane == 31 && rk >= inc);
+            __syncwarp();  // every lane has read the rank before the owning lane replaces it
             if (mine) {
                 uint64_t rem = rk - exc;
                 uint32_t d = 0;
@@ -92,8 +104,9 @@ __device__ float select_rank(Fetch fetch, int64_t n, int64_t rank, uint32_t *s_h
 __global__ void __launch_bounds__(RT_THREADS)
 router_select_kernel(const float *__restrict__ e16, const float *__restrict__ e8, int B, int h16, int w16, int mode,
                      int64_t k_c, int64_t k_m, int per_image, int32_t *__restrict__ m_c, int32_t *__restrict__ m_m,
-                     int32_t *__restrict__ m_f, float *__restrict__ gate)
+                     int32_t *__restrict__ m_f, float *__restrict__ gate, int key_cache)
 {
+    extern __shared__ uint32_t s_keys_dyn[];  // key cache (n8 keys) when the launch provided it
     __shared__ uint32_t s_hist[256];
     __shared__ uint32_t s_state[4];
     const int h8 = 2 * h16, w8 = 2 * w16;
@@ -106,9 +119,10 @@ router_select_kernel(const float *__restrict__ e16, const float *__restrict__ e8
     int32_t *m = m_m + img0 * n8_img;
     const int64_t n16 = nb * n16_img, n8 = nb * n8_img;
     const bool use_c = mode == 0 || mode == 2 || mode == 3;
+    uint32_t *s_keys = key_cache ? s_keys_dyn : nullptr;
 
     if (use_c) {
-        const float thr = select_rank([&](int64_t i) { return a16[i]; }, n16, k_c != 0 ? k_c - 1 : 0, s_hist, s_state);
+        const float thr = select_rank([&](int64_t i) { return a16[i]; }, n16, k_c != 0 ? k_c - 1 : 0, s_hist, s_state, s_keys);
         for (int64_t i = threadIdx.x; i < n16; i += blockDim.x) c[i] = a16[i] < thr;
     } else {
         for (int64_t i = threadIdx.x; i < n16; i += blockDim.x) c[i] = (mode == 4);
@@ -123,10 +137,10 @@ router_select_kernel(const float *__restrict__ e16, const float *__restrict__ e8
         // entropy of cells under a coarse patch is zeroed before the sort (RouterTriple.py:27)
         const float thr = select_rank(
             [&](int64_t i) { return __fmul_rn(a8[i], __fsub_rn(1.0f, (float)c[parent(i)])); }, n8,
-            k_m != 0 ? k_m - 1 : 0, s_hist, s_state);
+            k_m != 0 ? k_m - 1 : 0, s_hist, s_state, s_keys);
         for (int64_t i = threadIdx.x; i < n8; i += blockDim.x) m[i] = (a8[i] < thr) && !c[parent(i)];
     } else if (mode == 1) {
-        const float thr = select_rank([&](int64_t i) { return a8[i]; }, n8, k_m != 0 ? k_m - 1 : 0, s_hist, s_state);
+        const float thr = select_rank([&](int64_t i) { return a8[i]; }, n8, k_m != 0 ? k_m - 1 : 0, s_hist, s_state, s_keys);
         for (int64_t i = threadIdx.x; i < n8; i += blockDim.x) m[i] = a8[i] < thr;
     } else if (mode == 3) {
         for (int64_t i = threadIdx.x; i < n8; i += blockDim.x) m[i] = 1 - c[parent(i)];
@@ -234,8 +248,10 @@ extern "C" int cgic_router(const float *e16, const float *e8, int B, int h16, in
                            (!gate_out || (reinterpret_cast<uintptr_t>(gate_out) & 15) == 0);
     {
         CGIC_PROF("router_select_kernel", stream);
-        router_select_kernel<<<per_image ? B : 1, RT_THREADS, 0, stream>>>(e16, e8, B, h16, w16, mode, k_c, k_m, per_image, m_c, m_m,
-                                                                           fuse_fine ? m_f : nullptr, gate_out);
+        const int64_t n8_cta = (int64_t)(per_image ? 1 : B) * 4 * h16 * w16;
+        const int key_cache = n8_cta <= 12288;  // 48 KB of keys
+        router_select_kernel<<<per_image ? B : 1, RT_THREADS, key_cache ? (size_t)n8_cta * 4 : 0, stream>>>(
+            e16, e8, B, h16, w16, mode, k_c, k_m, per_image, m_c, m_m, fuse_fine ? m_f : nullptr, gate_out, key_cache);
     }
     CGIC_LAUNCH_CHECK();
     if (fuse_fine) return CGIC_OK;
