@@ -32,6 +32,8 @@ struct UnpackWs {
     int32_t *count;    // [B][3]  decoded symbols per index stream (-1: empty stream)
     int32_t *pop;      // [B][3]  population of each mask level
     int32_t *flag;     // [B][5]  per decode CTA: 0 or CGIC_EFORMAT (no zeroing needed: every CTA writes its slot)
+    unsigned long long *chain;  // [B][3][max_chunks] chunk hand-over records (zero between launches)
+    int max_chunks;
     uint32_t *bits;    // [B][nw16 + nw8 + nw4] bitmaps
     uint32_t *prefix;  // same shape: exclusive popcount prefix
     size_t bytes;
@@ -61,12 +63,18 @@ __host__ __device__ inline Geo make_geo(int h, int w)
     return g;
 }
 
+// chunk records per stream: enough for a stream of `n4` symbols of 64 bits each in chunks of 128 subsequences
+__host__ __device__ inline int unpack_max_chunks(const Geo &g) { return (int)(g.n4 * 64 / (128 * 128)) + 2; }
+
 UnpackWs carve_unpack(void *ws, int B, const Geo &g)
 {
     auto up = [](size_t v) { return (v + 255) / 256 * 256; };
     UnpackWs c{};
     unsigned char *p = static_cast<unsigned char *>(ws);
     size_t o = 0;
+    c.max_chunks = unpack_max_chunks(g);
+    c.chain = reinterpret_cast<unsigned long long *>(p + o);  // first: the part of the workspace that must start zeroed
+    o += up((size_t)B * 3 * c.max_chunks * 8);
     c.count = reinterpret_cast<int32_t *>(p + o);
     o += up((size_t)B * 3 * 4);
     c.pop = reinterpret_cast<int32_t *>(p + o);
@@ -98,6 +106,7 @@ struct UnpackArgs {
     int32_t *status;
     int mask_stage;  // 1: mask CTAs copy the mask streams to shared memory first
     int ch;          // subsequences per chunk of the candidate decoder (shared-memory budget)
+    int nslots;      // CTAs per index stream (chunks dealt round-robin, chained through ws.chain)
 };
 
 // ---- parallel prefix decoder (whole CTA, one stream) ------------------------------------------
@@ -336,6 +345,33 @@ __device__ __forceinline__ int decode_write_smem(const uint32_t *s_words, uint32
     return cnt;
 }
 
+// Chunks of one stream may be spread over `nslots` CTAs (slot j takes chunks j, j + nslots, ...).  What a chunk
+// needs from its predecessor -- the offset of its first codeword and the number of symbols decoded so far -- travels
+// through one 64-bit record per chunk in global memory: bit 63 = valid, bits 32..39 = start offset of the NEXT chunk,
+// bits 0..31 = symbols up to and including this chunk.  The reader clears the record after use, so the records are
+// all zero again when the kernel ends (workspace contract: zero before the first launch).
+struct DecChain {
+    unsigned long long *rec;  // [max chunks] of this stream; null = single CTA per stream
+    int slot, nslots;
+};
+constexpr int DEC_NOT_MINE = -2147483647 - 1;  // returned by the CTAs that did not decode a stream's last chunk
+
+__device__ __forceinline__ unsigned long long chain_wait_and_clear(unsigned long long *p)
+{
+    unsigned long long v;
+    do {
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        if (!(v >> 63)) __nanosleep(40);
+    } while (!(v >> 63));
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(0ull) : "memory");
+    return v;
+}
+__device__ __forceinline__ void chain_publish(unsigned long long *p, uint32_t next_start, uint32_t symbols)
+{
+    const unsigned long long v = (1ull << 63) | ((unsigned long long)(next_start & 0xFFu) << 32) | symbols;
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 // Phase A of the candidate decoder: NCH chains per thread in lock step (each step is one dependent
 // shared-memory load, no branches); pairs tid, tid + DEC_THREADS, ... ; pair = subsequence * D + candidate offset.
 template <int NCH>
@@ -543,6 +579,227 @@ __device__ int decode_stream_cta_cand(const uint8_t *in, int64_t nbytes, const D
     return (int)total;
 }
 
+// The same decoder for streams whose chunks are spread over several CTAs (MULTI) -- kept as a separate function so
+// that the single-CTA decoder above stays exactly the code that was tuned on the small-grid batch.
+template <bool LUT2S, bool MULTI, typename Out>
+__device__ int decode_stream_cta_chain(const uint8_t *in, int64_t nbytes, const DevTable &T, const uint32_t *s_lut, const uint32_t *lut2,
+                                      uint32_t *s_words, uint8_t *s_len, uint16_t *s_fn, int ch, Out *out, int64_t cap, const DecChain chain)
+{
+    __shared__ uint8_t s_blockfn[32 * DEC_MAX_D];
+    // chained streams only: symbols of a block per candidate start, chunk exit offset / symbol count per candidate start
+    __shared__ uint16_t s_blockcnt[MULTI ? 32 * DEC_MAX_D : 1];
+    __shared__ uint8_t s_aggx[MULTI ? DEC_MAX_D : 1];
+    __shared__ uint32_t s_aggn[MULTI ? DEC_MAX_D : 1];
+    __shared__ uint8_t s_blkstart[32];
+    __shared__ uint8_t s_substart[DEC_MAX_CH];
+    __shared__ int s_wsum[DEC_THREADS / 32];
+    __shared__ uint32_t s_next, s_start, s_base;
+    constexpr bool multi = MULTI;
+    bool overflow = false;
+    if (nbytes <= 0) return chain.slot == 0 ? -1 : DEC_NOT_MINE;
+    const int tid = threadIdx.x;
+    const int pad = in[0];
+    int64_t nbits = (nbytes - 1) * 8 - pad;
+    if (pad == 0 || nbits < 0) nbits = 0;
+    const int64_t q_end_abs = 8 + nbits;  // stream bit coordinates (header byte = bits 0..7)
+    const int D = T.max_len, L = T.lut_bits;
+    const int64_t nsub_total = (nbits + DEC_SUB_BITS - 1) / DEC_SUB_BITS;
+    uint32_t start_off = 0;
+    int64_t total = 0;
+    const int64_t nchunks = (nsub_total + ch - 1) / ch;
+    const int nslots = multi ? chain.nslots : 1, slot = multi ? chain.slot : 0;
+    // the CTA that decodes the last chunk reports the stream's symbol count (slot 0 when there is no chunk at all)
+    const bool mine_last = nchunks == 0 ? slot == 0 : (int)((nchunks - 1) % nslots) == slot;
+    for (int64_t chunk = slot; chunk < nchunks && start_off != DEC_OFF_STOP; chunk += nslots) {
+        const int64_t c0 = chunk * ch;
+        const int nsub = (int)min((int64_t)ch, nsub_total - c0);
+        CGIC_STAMP(unpack, 2);
+        // ---- stage the chunk: bytes [c0 * 16, ...) of the stream as big-endian words, zero past the end
+        const int npos_words = nsub * (DEC_SUB_BITS / 32) + (DEC_MAX_D + 8 + 31) / 32;  // positions a chain can visit
+        {
+            const int64_t byte0 = c0 * (DEC_SUB_BITS / 8);
+            const int nw = nsub * (DEC_SUB_BITS / 32) + DEC_LOOKAHEAD_WORDS;
+            for (int wi = tid; wi < nw; wi += DEC_THREADS) {
+                const int64_t bo = byte0 + (int64_t)wi * 4;
+                uint32_t v = 0;
+                if (bo + 4 <= nbytes) {
+                    v = __byte_perm(__ldg(reinterpret_cast<const uint32_t *>(in + bo)), 0, 0x0123);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (bo + k < nbytes) v |= (uint32_t)in[bo + k] << (24 - 8 * k);
+                }
+                s_words[wi] = v;
+            }
+        }
+        __syncthreads();
+        const int64_t rel_end = q_end_abs - c0 * DEC_SUB_BITS;  // payload end, local to the chunk
+        const uint32_t q_end = (uint32_t)min(rel_end, (int64_t)(nsub * DEC_SUB_BITS + 8 + DEC_MAX_D + 64));
+        CGIC_STAMP(unpack, 3);
+        // ---- A0: code length at EVERY bit position (independent lookups: 32 positions per thread and
+        //      pass sharing one word pair); 0 where the codeword would run past the payload.  Fast path:
+        //      the first-level entry's low byte IS the length; positions whose entry carries the
+        //      second-level / tree-walk flag (bit 7), and the few words near the payload end, are
+        //      resolved by a second sweep with the full decode.
+        for (int it = tid; it < npos_words * 4; it += DEC_THREADS) {  // work item: 8 positions of one word
+            const int wi = it >> 2, qtr = it & 3;
+            const uint32_t w0 = s_words[wi], w1 = s_words[wi + 1];
+            uint32_t *dst = reinterpret_cast<uint32_t *>(s_len) + wi * 8 + qtr * 2;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int p0 = qtr * 8 + j * 4;
+                uint32_t f[4], e[4], win[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    win[k] = __funnelshift_l(w1, w0, p0 + k);
+                    e[k] = s_lut[win[k] >> (32 - L)];
+                    f[k] = e[k] & 0xFFu;
+                }
+                if ((f[0] | f[1] | f[2] | f[3]) & 0x80u) {  // uncommon: second-level table, rare: tree walk
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (f[k] & 0x80u) {
+                            if (f[k] != 0xFFu) {
+                                const uint32_t hgt = f[k] & 0x7Fu;
+                                const uint32_t i2 = (e[k] >> 8) + ((win[k] << L) >> (32 - hgt));  // win holds 32 bits from the position on
+                                f[k] = ((LUT2S ? lut2[i2] : __ldg(&lut2[i2])) & 0xFFu) + (uint32_t)L;
+                            } else {
+                                f[k] = decode_one<LUT2S>(s_words, (uint32_t)wi * 32u + (uint32_t)(p0 + k), s_lut, lut2, T, L) & 0xFFu;
+                                if (f[k] == 0xFFu) f[k] = 0;  // (DEC_MAX_D = 128 < 0xFF)
+                            }
+                        }
+                }
+                dst[j] = f[0] | (f[1] << 8) | (f[2] << 16) | (f[3] << 24);
+            }
+        }
+        __syncthreads();
+        // no codeword may run past the payload: only positions within D bits of its end can
+        for (uint32_t q = (q_end > (uint32_t)D ? q_end - (uint32_t)D : 0u) + (uint32_t)tid; q < (uint32_t)npos_words * 32u; q += DEC_THREADS)
+            if (q + s_len[q] > q_end) s_len[q] = 0;
+        __syncthreads();
+        CGIC_STAMP(unpack, 7);
+        // ---- A: every (subsequence, candidate offset) pair follows its chain through len8[];
+        //      four chains per thread in lock step (each step is one dependent shared-memory load, no branches)
+        {
+            const int npairs = nsub * D;
+            const int per = (npairs + DEC_THREADS - 1) / DEC_THREADS;
+            if (per <= 1) follow_chains<1>(s_len, s_fn, npairs, D, tid);
+            else if (per == 2) follow_chains<2>(s_len, s_fn, npairs, D, tid);
+            else if (per == 3) follow_chains<3>(s_len, s_fn, npairs, D, tid);
+            else follow_chains<4>(s_len, s_fn, npairs, D, tid);
+        }
+        __syncthreads();
+        CGIC_STAMP(unpack, 4);
+        // ---- B: true start offset of every subsequence
+        const int bs = nsub <= 128 ? 8 : 32;  // subsequences per block; at most 32 blocks either way
+        const int nblk = (nsub + bs - 1) / bs;
+        for (int item = tid; item < nblk * D; item += DEC_THREADS) {
+            const int blk = item / D, c = item - blk * D;
+            uint32_t x = (uint32_t)c;
+            const int j1 = min(nsub, (blk + 1) * bs);
+            uint32_t nsym = 0;
+            for (int j = blk * bs; j < j1 && x != DEC_OFF_STOP; ++j) {
+                const uint32_t e = s_fn[j * D + x];
+                nsym += e & 0xFFu;
+                x = e >> 8;
+            }
+            s_blockfn[item] = (uint8_t)x;
+            if (multi) s_blockcnt[item] = (uint16_t)nsym;
+        }
+        __syncthreads();
+        if (multi) {
+            // what this chunk does to EVERY possible start offset, ready before the predecessor's answer arrives
+            if (tid < D) {
+                uint32_t x = (uint32_t)tid, nsym = 0;
+                for (int blk = 0; blk < nblk && x != DEC_OFF_STOP; ++blk) {
+                    nsym += s_blockcnt[blk * D + x];
+                    x = s_blockfn[blk * D + x];
+                }
+                s_aggx[tid] = (uint8_t)x;
+                s_aggn[tid] = nsym;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t st = 0, base = 0;
+                if (chunk > 0) {
+                    const unsigned long long r = chain_wait_and_clear(chain.rec + (chunk - 1));
+                    st = (uint32_t)(r >> 32) & 0xFFu;
+                    base = (uint32_t)r;
+                }
+                if (chunk + 1 < nchunks)  // the last chunk has no reader
+                    chain_publish(chain.rec + chunk, st == DEC_OFF_STOP ? DEC_OFF_STOP : s_aggx[st], base + (st == DEC_OFF_STOP ? 0u : s_aggn[st]));
+                s_start = st;
+                s_base = base;
+            }
+            __syncthreads();
+            start_off = s_start;
+            total = s_base;
+            if (start_off == DEC_OFF_STOP) {  // decoding ended in an earlier chunk: nothing here (and nothing after)
+                start_off = 0;                // (keeps the loop going so that this slot's later chunks pass the chain on)
+                continue;
+            }
+        }
+        if (tid == 0) {
+            uint32_t x = start_off;
+            for (int blk = 0; blk < nblk; ++blk) {
+                s_blkstart[blk] = (uint8_t)x;
+                if (x != DEC_OFF_STOP) x = s_blockfn[blk * D + x];
+            }
+            s_next = x;
+        }
+        __syncthreads();
+        if (tid < nblk) {
+            uint32_t x = s_blkstart[tid];
+            const int j1 = min(nsub, (tid + 1) * bs);
+            for (int j = tid * bs; j < j1; ++j) {
+                s_substart[j] = (uint8_t)x;
+                if (x != DEC_OFF_STOP) x = s_fn[j * D + x] >> 8;
+            }
+        }
+        __syncthreads();
+        CGIC_STAMP(unpack, 5);
+        // ---- C: counts -> offsets -> symbols
+        for (int base = 0; base < nsub; base += DEC_THREADS) {
+            const int i = base + tid;
+            uint32_t st = DEC_OFF_STOP;
+            int cnt = 0;
+            if (i < nsub) {
+                st = s_substart[i];
+                if (st != DEC_OFF_STOP) cnt = s_fn[i * D + st] & 0xFF;
+            }
+            const int lane = tid & 31, wid = tid >> 5;
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += n;
+            }
+            if (lane == 31) s_wsum[wid] = inc;
+            __syncthreads();
+            int woff = 0, ctot = 0;
+#pragma unroll
+            for (int k = 0; k < DEC_THREADS / 32; ++k) {
+                const int v = s_wsum[k];
+                if (k < wid) woff += v;
+                ctot += v;
+            }
+            if (total + ctot > cap) {
+                if (!multi) return -2;
+                overflow = true;  // a chained CTA must keep passing the chain on; the stream's last CTA sees the overflow too
+            }
+            if (cnt && !overflow) {
+                const uint32_t sub0 = 8u + (uint32_t)i * DEC_SUB_BITS;
+                decode_write_smem<LUT2S, Out>(s_words, sub0 + st, sub0 + DEC_SUB_BITS, q_end, s_lut, lut2, T, out + total + woff + inc - cnt);
+            }
+            total += ctot;
+            __syncthreads();
+        }
+        start_off = multi ? 0u : s_next;
+    }
+    if (overflow) return -2;
+    return mine_last ? (int)total : DEC_NOT_MINE;
+}
+
 // subsequences per chunk for a table: words 16 B + len8[] 128 B + f[] 2 D bytes per subsequence, <= 48 KB
 // Small token grids (<= 4096 fine tokens: the typical stream fits 128 subsequences) take half the budget so
 // that three decode CTAs fit one SM and the whole (5, B) grid of a 64-image batch is resident at once.
@@ -556,19 +813,25 @@ __host__ __device__ inline int cand_chunk_subs(int max_len, int64_t n4 = (int64_
 __host__ __device__ inline int cand_words(int ch) { return ch * (DEC_SUB_BITS / 32) + DEC_LOOKAHEAD_WORDS; }
 __host__ __device__ inline int cand_len_bytes(int ch) { return (ch * (DEC_SUB_BITS / 32) + (DEC_MAX_D + 8 + 31) / 32 + 1) * 32; }
 
-template <typename Out>
+template <typename Out, bool MULTI = false>
 __device__ __forceinline__ int decode_stream_any(const uint8_t *in, int64_t nbytes, const DevTable &T, const uint32_t *s_dec,
-                                                 const uint32_t *lut2, Out *out, int64_t cap, int ch)
+                                                 const uint32_t *lut2, Out *out, int64_t cap, int ch, const DecChain chain = DecChain{nullptr, 0, 1})
 {
     if (T.max_len <= DEC_MAX_D) {
         // f[] lives right behind the staged tables in dynamic shared memory
         uint32_t *s_words = const_cast<uint32_t *>(s_dec) + T.dec_stage_words;
         uint8_t *s_len = reinterpret_cast<uint8_t *>(s_words + cand_words(ch));
         uint16_t *s_fn = reinterpret_cast<uint16_t *>(s_len + cand_len_bytes(ch));
+        if (MULTI) {
+            if (T.dec_stage_words > T.lut_pad)
+                return decode_stream_cta_chain<true, MULTI, Out>(in, nbytes, T, s_dec, lut2, s_words, s_len, s_fn, ch, out, cap, chain);
+            return decode_stream_cta_chain<false, MULTI, Out>(in, nbytes, T, s_dec, lut2, s_words, s_len, s_fn, ch, out, cap, chain);
+        }
         if (T.dec_stage_words > T.lut_pad)
             return decode_stream_cta_cand<true, Out>(in, nbytes, T, s_dec, lut2, s_words, s_len, s_fn, ch, out, cap);
         return decode_stream_cta_cand<false, Out>(in, nbytes, T, s_dec, lut2, s_words, s_len, s_fn, ch, out, cap);
     }
+    if (chain.slot != 0) return DEC_NOT_MINE;  // codes longer than a subsequence: one CTA per stream
     return decode_stream_cta<Out>(in, nbytes, T, s_dec, lut2, out, cap);
 }
 
@@ -694,10 +957,12 @@ __device__ __forceinline__ const uint8_t *stage_bytes(const uint8_t *src, int nb
 
 // grid (4, B): CTAs 0..2 decode the index streams, CTA 3 builds the coarse, medium and fine mask levels
 // (four CTAs per image keep a 64-image batch within one wave at two CTAs per SM).  Dynamic shared memory: decode tables (CTAs 0..2) / mask stream bytes (3, 4).
+template <bool MULTI>
 __device__ __forceinline__ void unpack_decode_cta(const UnpackArgs &a, unsigned char *dyn, unsigned long long &mbar_ref)
 {
     unsigned long long *mbar_p = &mbar_ref;
-    const int s = blockIdx.x, b = blockIdx.y;
+    const int nslots = MULTI ? a.nslots : 1;
+    const int s = (int)blockIdx.x < 3 * nslots ? (int)blockIdx.x / nslots : 3, slot = (int)blockIdx.x - s * nslots, b = blockIdx.y;
     const Geo &g = a.g;
     CGIC_STAMP(unpack, 0);
     pdl_launch_dependents();
@@ -715,13 +980,23 @@ __device__ __forceinline__ void unpack_decode_cta(const UnpackArgs &a, unsigned 
         pdl_wait();
         const int nbytes = stream_present(a.mode, s) ? sz[s] : 0;
         CGIC_STAMP(unpack, 1);
-        if (nbytes > 0)
-            cnt = decode_stream_any<uint16_t>(img + a.slot_off[s], nbytes, a.T, s_dec, lut2,
-                                              a.ws.sym + (int64_t)b * (g.n16 + g.n8 + g.n4) + soff, cap, a.ch);
+        if (nbytes > 0) {
+            // a stream whose payload may exceed the chain's capacity (only a corrupt size can) is decoded by slot 0 alone
+            const bool chained = MULTI && nslots > 1 && ((int64_t)nbytes * 8 + DEC_SUB_BITS - 1) / DEC_SUB_BITS <= (int64_t)a.ws.max_chunks * a.ch;
+            const DecChain chain{chained ? a.ws.chain + ((int64_t)b * 3 + s) * a.ws.max_chunks : nullptr, chained ? slot : 0, chained ? nslots : 1};
+            if (chained || slot == 0)
+                cnt = decode_stream_any<uint16_t, MULTI>(img + a.slot_off[s], nbytes, a.T, s_dec, lut2,
+                                                         a.ws.sym + (int64_t)b * (g.n16 + g.n8 + g.n4) + soff, cap, a.ch, chain);
+            else
+                cnt = DEC_NOT_MINE;
+        } else if (slot != 0) {
+            cnt = DEC_NOT_MINE;
+        }
         CGIC_STAMP(unpack, 6);
         if (threadIdx.x == 0) {
-            a.ws.count[b * 3 + s] = cnt;
-            a.ws.flag[b * 5 + s] = cnt == -2 ? CGIC_EFORMAT : 0;
+            if (cnt == -2) a.ws.flag[b * 5 + s] = CGIC_EFORMAT;  // symbol capacity exceeded (any of the stream's CTAs may see it)
+            else if (cnt != DEC_NOT_MINE) a.ws.flag[b * 5 + s] = 0;
+            if (cnt != DEC_NOT_MINE) a.ws.count[b * 3 + s] = cnt;
         }
         return;
     }
@@ -884,12 +1159,22 @@ __device__ __forceinline__ void assemble_quad(const UnpackArgs &a, int b, int64_
     }
 }
 
-// grid (4, B)
+// grid (4, B): one CTA per index stream, then the mask CTA
 __global__ void __launch_bounds__(UP_THREADS) unpack_decode_kernel(const UnpackArgs a)
 {
     extern __shared__ __align__(128) unsigned char dyn[];
     __shared__ __align__(8) unsigned long long mbar;
-    unpack_decode_cta(a, dyn, mbar);
+    unpack_decode_cta<false>(a, dyn, mbar);
+}
+
+// grid (3 * nslots + 1, B): nslots CTAs per index stream (consecutive block ids), then the mask CTA.  Large token grids
+// only -- a separate kernel so that the hand-over code does not weigh on the small-grid kernel's instruction footprint
+// (measured: +2 us on the 256 x 256 batch when both lived in one kernel).
+__global__ void __launch_bounds__(UP_THREADS, 3) unpack_decode_chained_kernel(const UnpackArgs a)  // <= 42 registers: three CTAs per SM
+{
+    extern __shared__ __align__(128) unsigned char dyn[];
+    __shared__ __align__(8) unsigned long long mbar;
+    unpack_decode_cta<true>(a, dyn, mbar);
 }
 
 // re-assembly: one thread per quad, its own PDL-chained launch (see the note in cgic_unpack)
@@ -986,13 +1271,19 @@ extern "C" int cgic_unpack(const uint8_t *bytes, const int32_t *sizes, int B, in
         CGIC_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, CGIC_EINVAL, "cgic_unpack: buffers must be 16-byte aligned");
     // dynamic shared memory: decode tables for the stream CTAs, mask stream bytes for the mask CTAs
     a.ch = cand_chunk_subs(a.T.max_len, a.g.n4);
+    // CTAs per index stream: one chunk holds ch * 128 bits; a fine stream carries up to ~12 bits per token
+    {
+        const int64_t chunks = (a.g.n4 * 12 / DEC_SUB_BITS + a.ch - 1) / a.ch;
+        a.nslots = a.g.n4 <= 4096 || a.T.max_len > DEC_MAX_D ? 1 : (int)std::min<int64_t>(8, std::max<int64_t>(1, chunks));
+    }
     const size_t dec_bytes = decode_smem_bytes(a.T, a.ch);
     const size_t mask_bytes = (size_t)(((a.g.n16 / 8 + 2 + 15) & ~15) + ((a.g.n8 / 8 + 2 + 15) & ~15));
     a.mask_stage = mask_bytes <= 96 * 1024;
     const size_t smem = std::max(dec_bytes, a.mask_stage ? mask_bytes : (size_t)0);
     static bool smem_opt_in = false;  // static + dynamic shared memory may exceed the 48 KB default
     if (!smem_opt_in) {
-        CGIC_CUDA_CHECK(cudaFuncSetAttribute(unpack_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CGIC_CUDA_CHECK(cudaFuncSetAttribute(unpack_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
+        CGIC_CUDA_CHECK(cudaFuncSetAttribute(unpack_decode_chained_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
         smem_opt_in = true;
     }
     // Two PDL-chained launches.  Fusing the re-assembly into the decode kernel was measured on B200 (B = 64, 256^2,
@@ -1001,7 +1292,8 @@ extern "C" int cgic_unpack(const uint8_t *bytes, const int32_t *sizes, int B, in
     // the re-assembly wants many SMs per image, not the one that happens to finish last.
     {
         CGIC_PROF("unpack_decode_kernel", stream);
-        CGIC_CUDA_CHECK(launch_pdl(unpack_decode_kernel, dim3(4, B), dim3(UP_THREADS), smem, stream, a));
+        if (a.nslots > 1) CGIC_CUDA_CHECK(launch_pdl(unpack_decode_chained_kernel, dim3(3 * a.nslots + 1, B), dim3(UP_THREADS), smem, stream, a));
+        else CGIC_CUDA_CHECK(launch_pdl(unpack_decode_kernel, dim3(4, B), dim3(UP_THREADS), smem, stream, a));
     }
     CGIC_LAUNCH_CHECK();
     {
@@ -1025,7 +1317,7 @@ extern "C" int cgic_huff_decode(const uint8_t *bytes, int64_t nbytes, const cgic
     const size_t smem = decode_smem_bytes(T, ch);
     static bool smem_opt_in = false;
     if (!smem_opt_in) {
-        CGIC_CUDA_CHECK(cudaFuncSetAttribute(huff_decode_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CGIC_CUDA_CHECK(cudaFuncSetAttribute(huff_decode_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
         smem_opt_in = true;
     }
     huff_decode_single_kernel<<<1, DEC_THREADS, smem, as_stream(stream)>>>(bytes, nbytes, T, symbols_out, cap, count_out, ch);

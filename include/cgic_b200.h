@@ -171,6 +171,8 @@ CGIC_API int cgic_pack(const int64_t *idx, const int32_t *m_c, const int32_t *m_
  *     ind_out int64 [B,h,w], quant_out fp32 [B,4,h,w] = codebook[ind] (exact rows, NCHW)
  *     status_out int32 [B]: 0 ok, else CGIC_EFORMAT (symbol count != mask population, bad
  *     framing, ...) -- the cases in which the reference raises.
+ *     workspace: cgic_unpack_workspace_bytes() bytes, ZERO-filled before the first use (the kernels
+ *     leave the chunk hand-over records in it zeroed); one workspace per concurrently running call.
  * ------------------------------------------------------------------------------------------ */
 CGIC_API size_t cgic_unpack_workspace_bytes(int B, int h, int w);
 CGIC_API int cgic_unpack(const uint8_t *bytes, const int32_t *sizes, int B, int h, int w, int mode,
