@@ -476,3 +476,59 @@ def test_errors_are_loud(cg):
     bad[0, 2] = max(int(bad[0, 2]) // 2, 3)
     *_, status = cg.ops.unpack(packed, bad, mode, t, cb, 16, 16)
     assert int(status[0]) != 0
+
+
+# ------------------------------------------------- large token grids: chunks of a stream chained over several CTAs
+@pytest.mark.parametrize("c,m", [(0.0, 0.0), (0.0, 0.5), (0.2, 0.8), (1.0, 0.0), (0.05, 0.05)])
+def test_large_grid_all_modes_vs_oracle(cg, orc, c, m):
+    """512 x 768 images (24 576 fine tokens: the decoder spreads a stream's chunks over several CTAs and hands the
+    codeword offset / symbol count from chunk to chunk) in modes 6, 1, 3, 4 and 0: byte-exact streams, exact decode."""
+    import workload
+    B, H, W = 3, 512, 768
+    cb, t, z, masks, mode = _synthetic(cg, B, H, W, c, m, seed=71)
+    h, w = H // 4, W // 4
+    idx, zq, sq = cg.ops.vq_assign(z, cb)
+    packed, sizes = cg.ops.pack(idx, *masks, mode, t, h, w)
+    mc, mm, mf, ind, quant, status = cg.ops.unpack(packed, sizes, mode, t, cb, h, w)
+    assert int(status.abs().sum()) == 0
+    cbk, counts = workload.codebook_and_counts()
+    ot = orc.huff_build(counts.numpy(), workload.lexicographic_order())
+    offs, _, _ = t.layout(h, w)
+    b = B - 1
+    omask = [mk[b, 0].cpu().numpy() for mk in masks]
+    streams = orc.pack_image(ot, idx.view(B, h, w)[b].cpu().numpy(), *omask, mode)
+    blob, sz = packed[b].cpu().numpy(), sizes[b].cpu().numpy()
+    for s in range(5):
+        assert blob[offs[s]: offs[s] + sz[s]].tobytes() == streams[s], (mode, s)
+    umc, umm, umf, uind, uq = orc.unpack_image(ot, streams, h, w, mode, cbk.numpy())
+    assert np.array_equal(ind[b].cpu().numpy(), uind) and np.array_equal(quant[b].cpu().numpy(), uq)
+    for got, want in zip((mc, mm, mf), (umc, umm, umf)):
+        assert np.array_equal(got[b].cpu().numpy(), want)
+    # every image decodes to what the reference's masked assignment gives: idx at the kept positions
+    for got, want in zip((mc, mm, mf), masks):
+        assert torch.equal(got, want[:, 0].long())
+
+
+def test_large_grid_corrupt_and_long_codes(cg, orc):
+    """Chained decode must terminate and flag a corrupt stream; 224-bit codes (untrained table) take the
+    one-CTA-per-stream decoder on a large grid."""
+    B, H, W = 2, 512, 768
+    cb, t, z, masks, mode = _synthetic(cg, B, H, W, 0.05, 0.05, seed=73)
+    h, w = H // 4, W // 4
+    idx, _, _ = cg.ops.vq_assign(z, cb)
+    packed, sizes = cg.ops.pack(idx, *masks, mode, t, h, w)
+    bad = sizes.clone()
+    bad[0, 2] = int(bad[0, 2]) // 2          # truncated fine stream of image 0
+    noisy = packed.clone()
+    offs, _, _ = t.layout(h, w)
+    noisy[1, offs[2] + 100: offs[2] + 4000] ^= 0x5A          # scrambled payload of image 1 (same length)
+    *_, status = cg.ops.unpack(noisy, bad, mode, t, cb, h, w)
+    torch.cuda.synchronize()
+    assert int(status[0]) != 0
+    *_, ind_ok, _, status_ok = cg.ops.unpack(packed, sizes, mode, t, cb, h, w)    # the workspace is clean again afterwards
+    assert int(status_ok.abs().sum()) == 0 and torch.equal(ind_ok.view(-1), idx)
+    zero_t = cg.ops.HuffTable([0] * 1024)
+    assert zero_t.max_len > 128
+    packed2, sizes2 = cg.ops.pack(idx, *masks, mode, zero_t, h, w)
+    *_, ind2, _, status2 = cg.ops.unpack(packed2, sizes2, mode, zero_t, cb, h, w)
+    assert int(status2.abs().sum()) == 0 and torch.equal(ind2.view(-1), idx)
