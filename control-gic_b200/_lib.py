@@ -48,6 +48,9 @@ _SIGNATURES = {
     "cgic_pack_layout": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "cgic_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                           c_void_p]),
+    "cgic_pack_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "cgic_pack_ws": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_size_t, c_void_p]),
     "cgic_unpack_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "cgic_unpack": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                             c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

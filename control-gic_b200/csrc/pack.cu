@@ -33,6 +33,10 @@ struct PackArgs {
     int64_t slot_off[5];
     int64_t slot_cap[5];
     int32_t *sizes;
+    // large token grids: the tiles of a stream are dealt over `nslots` CTAs and chained through two self-clearing
+    // 64-bit records per tile in the workspace (bit position / carry word), see pack_index_stream_chained
+    unsigned long long *chain;  // [B][3][2][max_tiles]
+    int max_tiles, nslots;
 };
 
 __device__ __forceinline__ uint32_t to_big_endian(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
@@ -234,6 +238,187 @@ __device__ void pack_index_stream(const PackArgs &a, int s, int b, uint32_t *sta
     }
 }
 
+// ---- the same for one stream spread over several CTAs (large token grids) -----------------------------------------
+// Slot j of a stream packs tiles j, j + nslots, ...  A tile needs two things from its predecessor: the bit position
+// where it starts (known as soon as the predecessor has scanned its code lengths) and the bits of the 32-bit word the
+// two tiles share (known once the predecessor has staged its codes).  Both travel through self-clearing records:
+//   recA[t]: bit 63 valid, bit 62 "a symbol was outside the table so far", bits 0..47 bit position after tile t
+//   recB[t]: bit 63 valid, bits 0..31 the partial last word of tile t (0 when it ended on a word boundary)
+// The boundary word is written by the LATER tile.  The CTA that packs the last tile finishes the stream (pad, header,
+// size).  Tiles are handed out in block-id order, so a CTA only ever waits for CTAs dispatched before it.
+__device__ __forceinline__ unsigned long long pk_wait_clear(unsigned long long *p)
+{
+    unsigned long long v;
+    do {
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        if (!(v >> 63)) __nanosleep(40);
+    } while (!(v >> 63));
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(0ull) : "memory");
+    return v;
+}
+__device__ __forceinline__ void pk_publish(unsigned long long *p, unsigned long long payload)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"((1ull << 63) | payload) : "memory");
+}
+
+template <int ITEMS>
+__device__ void pack_index_stream_chained(const PackArgs &a, int s, int b, int slot, uint32_t *stage, const uint2 *s_enc, unsigned long long *mbar)
+{
+    constexpr int TILE = PK_THREADS * ITEMS;
+    __shared__ int s_warp[PK_THREADS / 32];
+    __shared__ uint32_t s_carry;
+    __shared__ int s_bad, s_badall;
+    __shared__ unsigned long long s_P;
+    const int tid = threadIdx.x;
+    const int step = 4 >> s;
+    const int gw = a.w / step;
+    const int64_t n_pos = (int64_t)(a.h / step) * gw;
+    const int32_t *mask = a.mask[s] + (int64_t)b * n_pos;
+    const int64_t *src = a.idx + (int64_t)b * a.h * a.w;
+    uint8_t *out = a.out + (int64_t)b * a.image_stride + a.slot_off[s];
+    int32_t *size_out = a.sizes + b * 5 + s;
+    const int64_t cap = a.slot_cap[s];
+    uint32_t *out32 = reinterpret_cast<uint32_t *>(out);
+    unsigned long long *recA = a.chain + (((int64_t)b * 3 + s) * 2) * a.max_tiles, *recB = recA + a.max_tiles;
+    const int n_tiles = (int)((n_pos + TILE - 1) / TILE);
+    const bool mine_last = (n_tiles - 1) % a.nslots == slot;
+    if (tid == 0) {
+        s_carry = 0;
+        s_bad = 0;
+        s_badall = 0;
+    }
+    __syncthreads();
+    int64_t P_end = 8;
+    for (int t = slot; t < n_tiles; t += a.nslots) {
+        const int64_t tile = (int64_t)t * TILE;
+        int sym[ITEMS];
+        uint32_t len[ITEMS], code[ITEMS];
+        const int64_t pos0 = tile + (int64_t)tid * ITEMS;
+        bool on[ITEMS];
+        if (ITEMS % 4 == 0 && pos0 + ITEMS <= n_pos && (reinterpret_cast<uintptr_t>(mask + pos0) & 15) == 0) {
+#pragma unroll
+            for (int v = 0; v < ITEMS / 4; ++v) {
+                const int4 m = __ldg(reinterpret_cast<const int4 *>(mask + pos0) + v);
+                on[4 * v] = m.x == 1;
+                on[4 * v + 1] = m.y == 1;
+                on[4 * v + 2] = m.z == 1;
+                on[4 * v + 3] = m.w == 1;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) on[i] = pos0 + i < n_pos && mask[pos0 + i] == 1;
+        }
+        int y = (int)(pos0 / gw), x = (int)(pos0 - (int64_t)y * gw);
+        int64_t val[ITEMS];
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            val[i] = 0;
+            if (pos0 + i < n_pos) val[i] = src[(int64_t)(y * step) * a.w + x * step];
+            if (++x == gw) {
+                x = 0;
+                ++y;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            sym[i] = -1;
+            if (on[i]) {
+                if (val[i] < 0 || val[i] >= a.T.K) s_bad = 1;
+                else sym[i] = (int)val[i];
+            }
+        }
+        if (mbar) {
+            mbar_wait(mbar, 0);
+            mbar = nullptr;
+        }
+        int tsum = 0;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            len[i] = 0;
+            code[i] = 0;
+            if (sym[i] >= 0) {
+                const uint2 e = s_enc[sym[i]];
+                code[i] = e.x;
+                len[i] = e.y;
+            }
+            tsum += (int)len[i];
+        }
+        int tot;
+        int o = block_exscan(tsum, s_warp, &tot);  // (its barriers also order the s_bad writes above before the read below)
+        if (tid == 0) {
+            unsigned long long P = 8, bad = (unsigned long long)(s_bad != 0);
+            if (t > 0) {
+                const unsigned long long r = pk_wait_clear(recA + (t - 1));
+                P = r & 0xFFFFFFFFFFFFull;
+                bad |= (r >> 62) & 1ull;
+            }
+            if (t + 1 < n_tiles) pk_publish(recA + t, (bad << 62) | (P + (unsigned long long)tot));
+            s_P = P;
+            s_badall = (int)bad;
+        }
+        __syncthreads();
+        const int64_t P = (int64_t)s_P;
+        const int r0 = (int)(P & 31);
+        const int nwords = (r0 + tot + 31) >> 5;
+        for (int j = tid; j < nwords; j += PK_THREADS) stage[j] = 0u;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            if (len[i]) {
+                const int q = r0 + o;
+                const int sh = q & 31, wi = q >> 5;
+                atomicOr(&stage[wi], code[i] >> sh);
+                if (sh + (int)len[i] > 32) atomicOr(&stage[wi + 1], code[i] << (32 - sh));
+                o += (int)len[i];
+            }
+        }
+        __syncthreads();
+        const int full = (r0 + tot) >> 5;
+        const int64_t w0 = P >> 5;
+        if (tid == 0) {
+            const bool partial = ((r0 + tot) & 31) != 0;
+            // a tile that completes at least one word knows its own last partial word without its predecessor
+            if (full > 0 && t + 1 < n_tiles) pk_publish(recB + t, partial ? stage[full] : 0u);
+            uint32_t carry_in = 0;
+            if (t > 0) carry_in = (uint32_t)pk_wait_clear(recB + (t - 1));  // (0 when this tile starts on a word boundary)
+            stage[0] |= carry_in;
+            if (full == 0 && t + 1 < n_tiles) pk_publish(recB + t, partial ? stage[0] : 0u);  // everything so far sits in one word
+            s_carry = partial ? stage[full] : 0u;
+        }
+        __syncthreads();
+        if ((w0 + full) * 4 <= cap)
+            for (int j = tid; j < full; j += PK_THREADS) out32[w0 + j] = to_big_endian(stage[j]);
+        P_end = P + tot;
+        __syncthreads();
+    }
+    if (mbar) mbar_wait(mbar, 0);
+    if (!mine_last) return;
+    // tail by the CTA of the last tile: bytes not yet written, pad, header
+    const int64_t P = P_end;
+    const int64_t nbits = P - 8;
+    const bool bad = s_badall != 0 || s_bad != 0;
+    if (nbits == 0 || bad) {
+        if (tid == 0) *size_out = bad ? -1 : 0;
+        return;
+    }
+    const int64_t total = nbits / 8 + 2;
+    const int64_t written = (P >> 5) * 4;
+    const uint32_t carry = (P & 31) ? s_carry : 0u;
+    if (total > cap) {
+        if (tid == 0) *size_out = -2;
+        return;
+    }
+    if (tid < 8) {
+        const int64_t i = written + tid;
+        if (i < total) out[i] = tid < 4 ? (uint8_t)(carry >> (24 - 8 * tid)) : (uint8_t)0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        out[0] = (uint8_t)(8 - (int)(nbits & 7));
+        *size_out = (int32_t)total;
+    }
+}
+
 // mask / raw bit stream: one output byte per thread
 __device__ void pack_bit_stream(const int32_t *v, int64_t n, uint8_t *out, int64_t cap, int32_t *size_out)
 {
@@ -315,6 +500,39 @@ __global__ void __launch_bounds__(PK_THREADS) pack_kernel(const PackArgs a)
     }
 }
 
+// grid (3 * nslots, B): nslots CTAs per index stream (consecutive block ids); large token grids with <= 32-bit codes only
+template <int ITEMS>
+__global__ void __launch_bounds__(PK_THREADS) pack_chained_kernel(const PackArgs a)
+{
+    extern __shared__ __align__(128) unsigned char dyn[];
+    __shared__ __align__(8) unsigned long long mbar;
+    const int s = blockIdx.x / a.nslots, slot = blockIdx.x - s * a.nslots, b = blockIdx.y;
+    pdl_launch_dependents();
+    if (stream_present(a.mode, s)) {
+        const uint32_t bytes = (uint32_t)((a.T.K + 1) / 2 * 2) * 8u;
+        if (threadIdx.x == 0) mbar_init(&mbar);
+        __syncthreads();
+        if (threadIdx.x == 0) tma_load_1d(dyn, a.T.enc, bytes, &mbar);
+        pdl_wait();
+        pack_index_stream_chained<ITEMS>(a, s, b, slot, reinterpret_cast<uint32_t *>(dyn + bytes), reinterpret_cast<const uint2 *>(dyn), &mbar);
+    } else {
+        pdl_wait();
+        if (threadIdx.x == 0 && slot == 0) a.sizes[b * 5 + s] = 0;
+    }
+    if (blockIdx.x != 0) return;
+    for (int ms = 3; ms < 5; ++ms) {
+        if (!stream_present(a.mode, ms)) {
+            if (threadIdx.x == 0) a.sizes[b * 5 + ms] = 0;
+            continue;
+        }
+        const int lvl = ms - 3;
+        const int div = lvl == 0 ? 4 : 2;
+        const int64_t n = (int64_t)(a.h / div) * (a.w / div);
+        pack_bit_stream(a.mask[lvl] + (int64_t)b * n, n, a.out + (int64_t)b * a.image_stride + a.slot_off[ms], a.slot_cap[ms],
+                        a.sizes + b * 5 + ms);
+    }
+}
+
 template <int ITEMS>
 __global__ void __launch_bounds__(PK_THREADS) pack_single_kernel(const PackArgs a)
 {
@@ -356,8 +574,23 @@ int ensure_smem(const void *fn, size_t bytes)
 
 using namespace cgic;
 
+static int pack_max_tiles(int h, int w) { return (int)(((int64_t)h * w + PK_THREADS * 8 - 1) / (PK_THREADS * 8)) + 1; }
+
+extern "C" size_t cgic_pack_workspace_bytes(int B, int h, int w)
+{
+    if (B <= 0 || h <= 0 || w <= 0) return 256;
+    return ((size_t)B * 3 * 2 * pack_max_tiles(h, w) * 8 + 255) / 256 * 256;
+}
+
 extern "C" int cgic_pack(const int64_t *idx, const int32_t *m_c, const int32_t *m_m, const int32_t *m_f, int B, int h, int w,
                          int mode, const cgic_table *t, uint8_t *bytes_out, int32_t *sizes_out, cgic_stream_t stream)
+{
+    return cgic_pack_ws(idx, m_c, m_m, m_f, B, h, w, mode, t, bytes_out, sizes_out, nullptr, 0, stream);
+}
+
+extern "C" int cgic_pack_ws(const int64_t *idx, const int32_t *m_c, const int32_t *m_m, const int32_t *m_f, int B, int h, int w,
+                            int mode, const cgic_table *t, uint8_t *bytes_out, int32_t *sizes_out, void *workspace,
+                            size_t workspace_bytes, cgic_stream_t stream)
 {
     CGIC_REQUIRE(idx && m_c && m_m && m_f && bytes_out && sizes_out, CGIC_EINVAL, "cgic_pack: null argument");
     CGIC_REQUIRE(B >= 0 && h > 0 && w > 0 && h % 4 == 0 && w % 4 == 0, CGIC_EINVAL, "cgic_pack: token grid %dx%d must be multiples of 4", h, w);
@@ -390,6 +623,21 @@ extern "C" int cgic_pack(const int64_t *idx, const int32_t *m_c, const int32_t *
     CGIC_REQUIRE(smem <= 200 * 1024, CGIC_EINVAL, "cgic_pack: code length %d needs %zu bytes of staging", a.T.max_len, smem);
     rc = ensure_smem(items == 8 ? (const void *)pack_kernel<8> : (const void *)pack_kernel<1>, smem);
     if (rc) return rc;
+    // large token grids (more than one tile per fine stream) with a workspace: tiles chained over several CTAs per stream
+    const int fine_tiles = (int)(((int64_t)h * w + PK_THREADS * 8 - 1) / (PK_THREADS * 8));
+    if (items == 8 && fine_tiles > 1 && workspace && workspace_bytes >= cgic_pack_workspace_bytes(B, h, w)) {
+        a.chain = static_cast<unsigned long long *>(workspace);
+        a.max_tiles = pack_max_tiles(h, w);
+        a.nslots = fine_tiles < 8 ? fine_tiles : 8;
+        rc = ensure_smem((const void *)pack_chained_kernel<8>, smem);
+        if (rc) return rc;
+        {
+            CGIC_PROF("pack_chained_kernel", as_stream(stream));
+            CGIC_CUDA_CHECK(launch_pdl(pack_chained_kernel<8>, dim3(3 * a.nslots, B), dim3(PK_THREADS), smem, as_stream(stream), a));
+        }
+        CGIC_LAUNCH_CHECK();
+        return CGIC_OK;
+    }
     {
         CGIC_PROF("pack_kernel", as_stream(stream));
         if (items == 8) CGIC_CUDA_CHECK(launch_pdl(pack_kernel<8>, dim3(3, B), dim3(PK_THREADS), smem, as_stream(stream), a));

@@ -28,8 +28,8 @@ struct cgic_session {
     uint8_t *bytes = nullptr;
     double *sqerr = nullptr;  // [MAX_PARTS]
     double *sqerr_host = nullptr;  // pinned, [MAX_PARTS]
-    unsigned char *ws_vq = nullptr, *ws_un = nullptr;  // MAX_PARTS slices each
-    size_t ws_vq_bytes = 0, ws_un_bytes = 0;
+    unsigned char *ws_vq = nullptr, *ws_un = nullptr, *ws_pk = nullptr;  // MAX_PARTS slices each
+    size_t ws_vq_bytes = 0, ws_un_bytes = 0, ws_pk_bytes = 0;
     // ---- pinned-arena round trip (cgic_session_arena / cgic_session_roundtrip_arena)
     // The batch is cut into `a_parts` image ranges.  Every range has ONE contiguous input block
     // [z | m_c | m_m | m_f] and ONE contiguous output block [bytes | sizes | status | sqerr | ind | quant |
@@ -70,6 +70,7 @@ extern "C" int cgic_session_create(int B, int h, int w, int mode, const cgic_tab
     const size_t n4 = (size_t)B * h * w, n8 = n4 / 4, n16 = n4 / 16;
     s->ws_vq_bytes = cgic_vq_workspace_bytes((int64_t)n4);
     s->ws_un_bytes = cgic_unpack_workspace_bytes(B, h, w);
+    s->ws_pk_bytes = cgic_pack_workspace_bytes(B, h, w);
     size_t o = 0;
     auto take = [&](size_t bytes) {
         const size_t at = o;
@@ -80,7 +81,8 @@ extern "C" int cgic_session_create(int B, int h, int w, int mode, const cgic_tab
                  o_mc = take(n16 * 4), o_mm = take(n8 * 4), o_mf = take(n4 * 4), o_sizes = take((size_t)B * 5 * 4),
                  o_status = take((size_t)B * 4), o_idx = take(n4 * 8), o_dmc = take(n16 * 8), o_dmm = take(n8 * 8),
                  o_dmf = take(n4 * 8), o_ind = take(n4 * 8), o_bytes = take((size_t)B * s->L.stride), o_sq = take(8 * cgic_session::MAX_PARTS),
-                 o_wv = take(s->ws_vq_bytes * cgic_session::MAX_PARTS), o_wu = take(s->ws_un_bytes * cgic_session::MAX_PARTS);
+                 o_wv = take(s->ws_vq_bytes * cgic_session::MAX_PARTS), o_wu = take(s->ws_un_bytes * cgic_session::MAX_PARTS),
+                 o_wp = take(s->ws_pk_bytes * cgic_session::MAX_PARTS);
     cudaError_t e = cudaMalloc(&s->arena, o);
     for (int i = 0; i < cgic_session::MAX_PARTS && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&s->streams[i], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->packed, cudaEventDisableTiming);
@@ -111,6 +113,8 @@ extern "C" int cgic_session_create(int B, int h, int w, int mode, const cgic_tab
     s->sqerr = reinterpret_cast<double *>(a + o_sq);
     s->ws_vq = a + o_wv;
     s->ws_un = a + o_wu;
+    s->ws_pk = a + o_wp;
+    s->ws_pk_bytes = (s->ws_pk_bytes + 255) / 256 * 256;
     s->ws_vq_bytes = (s->ws_vq_bytes + 255) / 256 * 256;
     s->ws_un_bytes = (s->ws_un_bytes + 255) / 256 * 256;
     rc = cgic_codebook_create(K, &s->index);
@@ -177,8 +181,8 @@ extern "C" int cgic_session_compress_host(cgic_session *s, const float *z, const
         int rc = cgic_vq_assign_indexed(s->z + b0 * i4 * 4, nb, s->h, s->w, s->index, s->idx + b0 * i4, zq_out ? s->zq + b0 * i4 * 4 : nullptr,
                                 sqerr_out ? s->sqerr + p : nullptr, s->ws_vq + p * s->ws_vq_bytes, s->ws_vq_bytes, st);
         if (rc) return rc;
-        rc = cgic_pack(s->idx + b0 * i4, s->mc + b0 * i16, s->mm + b0 * i8, s->mf + b0 * i4, nb, s->h, s->w, s->mode, s->table,
-                       s->bytes + (size_t)b0 * s->L.stride, s->sizes + b0 * 5, st);
+        rc = cgic_pack_ws(s->idx + b0 * i4, s->mc + b0 * i16, s->mm + b0 * i8, s->mf + b0 * i4, nb, s->h, s->w, s->mode, s->table,
+                          s->bytes + (size_t)b0 * s->L.stride, s->sizes + b0 * 5, s->ws_pk + p * s->ws_pk_bytes, s->ws_pk_bytes, st);
         if (rc) return rc;
         CGIC_CUDA_CHECK(cudaMemcpyAsync(bytes_out + (size_t)b0 * s->L.stride, s->bytes + (size_t)b0 * s->L.stride, (size_t)nb * s->L.stride,
                                         cudaMemcpyDeviceToHost, st));
@@ -245,7 +249,7 @@ extern "C" int cgic_session_roundtrip_host(cgic_session *s, const float *z, cons
     int rc = cgic_vq_assign_indexed(s->z, s->B, s->h, s->w, s->index, s->idx, zq_out ? s->zq : nullptr,
                             sqerr_out ? s->sqerr : nullptr, s->ws_vq, s->ws_vq_bytes, enc);
     if (rc) return rc;
-    rc = cgic_pack(s->idx, s->mc, s->mm, s->mf, s->B, s->h, s->w, s->mode, s->table, s->bytes, s->sizes, enc);
+    rc = cgic_pack_ws(s->idx, s->mc, s->mm, s->mf, s->B, s->h, s->w, s->mode, s->table, s->bytes, s->sizes, s->ws_pk, s->ws_pk_bytes, enc);
     if (rc) return rc;
     CGIC_CUDA_CHECK(cudaEventRecord(s->packed, enc));
     CGIC_CUDA_CHECK(cudaStreamWaitEvent(dec, s->packed, 0));
@@ -398,9 +402,10 @@ static int arena_enqueue(cgic_session *s, int flags)
                                         (flags & 2) ? reinterpret_cast<float *>(out(CGIC_ARENA_ZQ)) : nullptr,
                                         reinterpret_cast<double *>(out(CGIC_ARENA_SQERR)), s->ws_vq + p * s->ws_vq_bytes, s->ws_vq_bytes, st);
         if (rc) return rc;
-        rc = cgic_pack(reinterpret_cast<const int64_t *>(out(CGIC_ARENA_IDX)), reinterpret_cast<const int32_t *>(in(CGIC_ARENA_MC)),
+        rc = cgic_pack_ws(reinterpret_cast<const int64_t *>(out(CGIC_ARENA_IDX)), reinterpret_cast<const int32_t *>(in(CGIC_ARENA_MC)),
                        reinterpret_cast<const int32_t *>(in(CGIC_ARENA_MM)), reinterpret_cast<const int32_t *>(in(CGIC_ARENA_MF)), P.nb, s->h,
-                       s->w, s->mode, s->table, out(CGIC_ARENA_BYTES), reinterpret_cast<int32_t *>(out(CGIC_ARENA_SIZES)), st);
+                       s->w, s->mode, s->table, out(CGIC_ARENA_BYTES), reinterpret_cast<int32_t *>(out(CGIC_ARENA_SIZES)),
+                       s->ws_pk + p * s->ws_pk_bytes, s->ws_pk_bytes, st);
         if (rc) return rc;
         rc = cgic_unpack(out(CGIC_ARENA_BYTES), reinterpret_cast<const int32_t *>(out(CGIC_ARENA_SIZES)), P.nb, s->h, s->w, s->mode, s->table,
                          s->codebook, reinterpret_cast<int64_t *>(out(CGIC_ARENA_DMC)), reinterpret_cast<int64_t *>(out(CGIC_ARENA_DMM)),

@@ -283,8 +283,9 @@ def pack(idx: torch.Tensor, m_c, m_m, m_f, mode: int, table: HuffTable, h: int, 
     _, _, stride = table.layout(h, w)
     out = torch.empty(B, stride, dtype=torch.uint8, device=idx.device)
     sizes = torch.empty(B, 5, dtype=torch.int32, device=idx.device)
-    check(lib().cgic_pack(idx.data_ptr(), m_c.data_ptr(), m_m.data_ptr(), m_f.data_ptr(), B, h, w, mode, table.handle,
-                          out.data_ptr(), sizes.data_ptr(), _stream()), "cgic_pack")
+    ws = _workspace("pack", lib().cgic_pack_workspace_bytes(B, h, w), idx.device)
+    check(lib().cgic_pack_ws(idx.data_ptr(), m_c.data_ptr(), m_m.data_ptr(), m_f.data_ptr(), B, h, w, mode, table.handle,
+                             out.data_ptr(), sizes.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "cgic_pack_ws")
     return out, sizes
 
 

@@ -162,6 +162,13 @@ CGIC_API int cgic_pack_layout(const cgic_table *t, int h, int w, int64_t slot_of
 CGIC_API int cgic_pack(const int64_t *idx, const int32_t *m_c, const int32_t *m_m, const int32_t *m_f, int B, int h,
               int w, int mode, const cgic_table *t, uint8_t *bytes_out, int32_t *sizes_out,
               cgic_stream_t stream);
+/* The same with a workspace (cgic_pack_workspace_bytes() bytes, ZERO-filled before the first use; the kernels leave
+ * it zeroed): on token grids with more than one 4096-position tile per stream the tiles of a stream are packed by
+ * several CTAs, chained through hand-over records in the workspace.  Identical bytes. */
+CGIC_API size_t cgic_pack_workspace_bytes(int B, int h, int w);
+CGIC_API int cgic_pack_ws(const int64_t *idx, const int32_t *m_c, const int32_t *m_m, const int32_t *m_f, int B, int h,
+                 int w, int mode, const cgic_table *t, uint8_t *bytes_out, int32_t *sizes_out, void *workspace,
+                 size_t workspace_bytes, cgic_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * a10 + a11 + a13 + a14  unpack + mask / index re-assembly + codebook gather
