@@ -43,8 +43,10 @@ entropy_kernel(const float *__restrict__ x, int H, int W, int regions_x, int64_t
     __shared__ __align__(16) float s_rows[EN_WARPS][32 * EN_STRIDE + 4];  // per warp: 32 histogram rows (slice a multiple of 16 bytes)
     __shared__ float s_bins[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_launch_dependents();
     if (threadIdx.x < 32) s_bins[threadIdx.x] = bins.v[threadIdx.x];
     __syncthreads();
+    pdl_wait();  // the image may come straight from a preceding kernel
     const int64_t region = (int64_t)blockIdx.x * EN_WARPS + warp;
     if (region >= n_regions) return;
     const int regions_y = H / 16;
@@ -164,8 +166,8 @@ extern "C" int cgic_entropy_maps(const float *x, int B, int H, int W, const floa
     for (int i = 0; i < 32; ++i) bins.v[i] = bins32_host[i];
     {
         CGIC_PROF("entropy_kernel", as_stream(stream));
-        entropy_kernel<<<(unsigned)((n_regions + EN_WARPS - 1) / EN_WARPS), EN_WARPS * 32, 0, as_stream(stream)>>>(x, H, W, regions_x, n_regions,
-                                                                                                              bins, e8_out, e16_out);
+        CGIC_CUDA_CHECK(launch_pdl(entropy_kernel, dim3((unsigned)((n_regions + EN_WARPS - 1) / EN_WARPS)), dim3(EN_WARPS * 32), 0, as_stream(stream), x,
+                                   H, W, regions_x, n_regions, bins, e8_out, e16_out));
     }
     CGIC_LAUNCH_CHECK();
     return CGIC_OK;

@@ -120,6 +120,8 @@ router_select_kernel(const float *__restrict__ e16, const float *__restrict__ e8
     const int64_t n16 = nb * n16_img, n8 = nb * n8_img;
     const bool use_c = mode == 0 || mode == 2 || mode == 3;
     uint32_t *s_keys = key_cache ? s_keys_dyn : nullptr;
+    pdl_launch_dependents();
+    pdl_wait();  // the entropy maps usually come straight from entropy_kernel
 
     if (use_c) {
         const float thr = select_rank([&](int64_t i) { return a16[i]; }, n16, k_c != 0 ? k_c - 1 : 0, s_hist, s_state, s_keys);
@@ -178,6 +180,8 @@ __global__ void router_fine_kernel(const int32_t *__restrict__ m_c, const int32_
                                    int w, int mode, int32_t *__restrict__ m_f, float *__restrict__ gate)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     if (t >= n_tokens) return;
     const int64_t plane = (int64_t)h * w;
     const int64_t b = t / plane, p = t - b * plane;
@@ -203,6 +207,8 @@ mask_mix_kernel(const float *__restrict__ h_c, const float *__restrict__ h_m, co
                 float *__restrict__ out)
 {
     const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();  // masks (and usually the heads) come from preceding kernels
     if (qi >= n_quads) return;
     const unsigned wq = (unsigned)w / 4u;
     const int64_t rowi = qi / wq;              // (b*C + c) * h + y
@@ -250,15 +256,16 @@ extern "C" int cgic_router(const float *e16, const float *e8, int B, int h16, in
         CGIC_PROF("router_select_kernel", stream);
         const int64_t n8_cta = (int64_t)(per_image ? 1 : B) * 4 * h16 * w16;
         const int key_cache = n8_cta <= 12288;  // 48 KB of keys
-        router_select_kernel<<<per_image ? B : 1, RT_THREADS, key_cache ? (size_t)n8_cta * 4 : 0, stream>>>(
-            e16, e8, B, h16, w16, mode, k_c, k_m, per_image, m_c, m_m, fuse_fine ? m_f : nullptr, gate_out, key_cache);
+        CGIC_CUDA_CHECK(launch_pdl(router_select_kernel, dim3(per_image ? B : 1), dim3(RT_THREADS), key_cache ? (size_t)n8_cta * 4 : 0, stream, e16, e8, B,
+                                   h16, w16, mode, k_c, k_m, per_image, m_c, m_m, fuse_fine ? m_f : (int32_t *)nullptr, gate_out, key_cache));
     }
     CGIC_LAUNCH_CHECK();
     if (fuse_fine) return CGIC_OK;
     const int64_t n = (int64_t)B * 16 * h16 * w16;
     {
         CGIC_PROF("router_fine_kernel", stream);
-        router_fine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(m_c, m_m, n, 4 * h16, 4 * w16, mode, m_f, gate_out);
+        CGIC_CUDA_CHECK(launch_pdl(router_fine_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, (const int32_t *)m_c, (const int32_t *)m_m, n,
+                                   4 * h16, 4 * w16, mode, m_f, gate_out));
     }
     CGIC_LAUNCH_CHECK();
     return CGIC_OK;
@@ -275,7 +282,8 @@ extern "C" int cgic_mask_mix(const float *h_c, const float *h_m, const float *h_
         CGIC_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, CGIC_EINVAL, "cgic_mask_mix: buffers must be 16-byte aligned");
     {
         CGIC_PROF("mask_mix_kernel", as_stream(stream));
-        mask_mix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(h_c, h_m, h_f, m_c, m_m, m_f, n, C, h, w, out);
+        CGIC_CUDA_CHECK(launch_pdl(mask_mix_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, as_stream(stream), h_c, h_m, h_f, m_c, m_m, m_f, n, C, h,
+                                   w, out));
     }
     CGIC_LAUNCH_CHECK();
     return CGIC_OK;

@@ -26,7 +26,7 @@ with open(os.path.join(out_dir, f"{tag}_launches.txt"), "w") as f:
     for k, v in acc.items():
         if k in step:
             f.write(f"{k:28s} launches={len(v):3d} mean_us={sum(v)/len(v):8.2f} share={sum(v)/len(v)/tot:.3f}\n")
-    f.write("# set-up kernels of the captured command (once, not part of a step): " +
+    f.write("# other library kernels of the captured command (image-in head of bench.py: entropy / router / mask-mix; codebook index build): " +
             ", ".join(f"{k} x{len(v)} {sum(v)/len(v):.1f} us" for k, v in acc.items() if k not in step) + "\n")
     f.write(f"{'sum of kernel means':28s} {tot:.2f} us per step   ({other} launches of non-library kernels -- L2 flush, set-up -- left out)\n")
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
