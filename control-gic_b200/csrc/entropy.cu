@@ -84,12 +84,21 @@ entropy_kernel(const float *__restrict__ x, int H, int W, int regions_x, int64_t
                                           __fmul_rn(0.1140f, raw[half][r][2]));
                 int jc = __float2int_rn((g + 1.0f) * 15.5f);
                 jc = max(0, min(31, jc));
+                if (jc >= EN_WIN / 2 && jc < 32 - EN_WIN / 2) {  // the whole window is inside the histogram (always, for images in [0, 1])
 #pragma unroll
-                for (int k = 0; k < EN_WIN; ++k) {
-                    const int j = jc - EN_WIN / 2 + k;
-                    if (j >= 0 && j < 32) {
+                    for (int k = 0; k < EN_WIN; ++k) {
+                        const int j = jc - EN_WIN / 2 + k;
                         const float q = __fmul_rn(__fsub_rn(g, s_bins[j]), 84.93218002880191f);  // 100 * sqrt(log2(e) / 2)
                         row[j] += ex2_approx(-__fmul_rn(q, q));  // same thread owns the row: plain read-modify-write
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < EN_WIN; ++k) {
+                        const int j = jc - EN_WIN / 2 + k;
+                        if (j >= 0 && j < 32) {
+                            const float q = __fmul_rn(__fsub_rn(g, s_bins[j]), 84.93218002880191f);
+                            row[j] += ex2_approx(-__fmul_rn(q, q));
+                        }
                     }
                 }
             }

@@ -532,3 +532,20 @@ def test_large_grid_corrupt_and_long_codes(cg, orc):
     packed2, sizes2 = cg.ops.pack(idx, *masks, mode, zero_t, h, w)
     *_, ind2, _, status2 = cg.ops.unpack(packed2, sizes2, mode, zero_t, cb, h, w)
     assert int(status2.abs().sum()) == 0 and torch.equal(ind2.view(-1), idx)
+
+
+def test_entropy_low_entropy_patches(cg, orc):
+    """Smooth and flat images give entropies of 1e-5 .. 1e-3 whose fp32 value hinges on ln(p) for p ~ 1 - 1e-5 (the
+    reference formula itself is then ~1e-3 away from a float64 evaluation); the kernel has to follow the reference's
+    fp32 arithmetic closely enough to stay within the stated tolerance there too, and on inputs outside [0, 1]."""
+    g = torch.Generator().manual_seed(3)
+    smooth = torch.rand(2, 3, 8, 10, generator=g).repeat_interleave(16, -1).repeat_interleave(16, -2) * 0.9 \
+        + 0.05 * torch.rand(2, 3, 128, 160, generator=g)
+    cases = {"smooth": smooth, "flat": torch.full((1, 3, 64, 64), 0.37), "signed": torch.rand(1, 3, 64, 96, generator=g) * 2 - 1,
+             "edges": torch.cat([torch.full((1, 3, 32, 64), -1.0), torch.full((1, 3, 32, 64), 1.0)], 2)}
+    for name, x in cases.items():
+        e8, e16 = cg.entropy_pair(x.cuda())
+        for p, e in ((8, e8), (16, e16)):
+            o = orc.entropy(x.numpy(), p)
+            assert torch.isfinite(e).all(), name
+            assert np.allclose(e.cpu().numpy(), o, rtol=ENTROPY_RTOL, atol=1e-9), (name, p, np.abs(e.cpu().numpy() - o).max())
