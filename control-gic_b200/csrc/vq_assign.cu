@@ -500,7 +500,66 @@ constexpr int VQW_WARPS = VQW_THREADS / 32;
 constexpr int VQW_TILE = 128;  // tokens per warp tile
 __host__ __device__ inline size_t vqw_smem_bytes(int K) { return vq_stage_bytes(K) + (size_t)VQW_WARPS * VQW_TILE * (16 + 2 + 1 + 1); }
 
-__global__ void __launch_bounds__(VQW_THREADS, 3)
+// Leaders the index could not serve (bits of `todo` = positions in list[]): the WARP searches all K codes, up to four
+// leaders per sweep (every code row is loaded once for all of them; lane k, k + 32, ...; per-lane ascending order + an
+// index tie-break in the reduction = the lowest index among equal minima; no finite distance at all leaves index 0,
+// like vq_fused_kernel).  Out of line: its registers must not weigh on the indexed path.
+__device__ __noinline__ void vq_exhaustive_sweep(unsigned todo, const uint8_t *list, const float4 *zs, uint16_t *res, const float4 *cbs,
+                                          const float *e2s, int K, int lane)
+{
+    while (todo) {
+        // up to four leaders per sweep over the codebook: every code row is loaded once for all of them
+        int tq[4];
+        float4 vq[4];
+        float z2q[4], bdq[4];
+        int bkq[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            tq[i] = -1;
+            if (todo) {
+                tq[i] = list[__ffs(todo) - 1];
+                todo &= todo - 1;
+            }
+            vq[i] = zs[tq[i] >= 0 ? tq[i] : 0];
+            z2q[i] = sumsq4(vq[i].x, vq[i].y, vq[i].z, vq[i].w);
+            bdq[i] = __int_as_float(0x7f800000);
+            bkq[i] = 0x7fffffff;
+        }
+        for (int k = lane; k < K; k += 32) {
+            const float4 e = cbs[k];
+            const float e2 = e2s[k];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float dot = __fmul_rn(vq[i].x, e.x);
+                dot = __fmaf_rn(vq[i].y, e.y, dot);
+                dot = __fmaf_rn(vq[i].z, e.z, dot);
+                dot = __fmaf_rn(vq[i].w, e.w, dot);
+                const float d = __fmaf_rn(dot, -2.f, __fadd_rn(z2q[i], e2));
+                if (d < bdq[i]) {
+                    bdq[i] = d;
+                    bkq[i] = k;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float bd = bdq[i];
+            int bk = bkq[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+                const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+                if (od < bd || (od == bd && ok < bk)) {
+                    bd = od;
+                    bk = ok;
+                }
+            }
+            if (lane == 0 && tq[i] >= 0) res[tq[i]] = (uint16_t)(bk == 0x7fffffff ? 0 : bk);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(VQW_THREADS, 2)
 vq_warp_kernel(const float *__restrict__ z, int h, int w, int tiles_x, int tiles_y, int64_t n_tiles, const unsigned char *__restrict__ blob,
                int K, int64_t *__restrict__ idx_out, float *__restrict__ zq_out, double *__restrict__ partials,
                int32_t *__restrict__ counters, double *__restrict__ sqerr_out)
@@ -641,22 +700,18 @@ vq_warp_kernel(const float *__restrict__ z, int h, int w, int tiles_x, int tiles
                 if (count > 23) eval_piece(q3, v, z2, cbs, e2s, bd, bk);
                 for (unsigned pc = 4; pc * 8 < count + 1; ++pc) eval_piece(__ldg(rp + pc), v, z2, cbs, e2s, bd, bk);
             } else {
-                // outside the grid / overflowing cell / no usable index: every code, ascending (lowest index wins ties;
-                // no finite distance at all leaves index 0, like vq_fused_kernel)
-                for (int k = 0; k < K; ++k) {
-                    const float4 e = cbs[k];
-                    float dot = __fmul_rn(v.x, e.x);
-                    dot = __fmaf_rn(v.y, e.y, dot);
-                    dot = __fmaf_rn(v.z, e.z, dot);
-                    dot = __fmaf_rn(v.w, e.w, dot);
-                    const float d = __fmaf_rn(dot, -2.f, __fadd_rn(z2, sumsq4(e.x, e.y, e.z, e.w)));
-                    if (d < bd) {
-                        bd = d;
-                        bk = k;
-                    }
-                }
+                bk = 0xffff;  // outside the grid / overflowing cell / no usable index: searched exhaustively by the whole warp below
             }
             res[t] = (uint16_t)bk;
+        }
+        __syncwarp();
+        // ---- leaders the index could not serve: the WARP searches all K codes for one leader at a time (lane k, k + 32, ...;
+        //      per-lane ascending order + an index tie-break in the reduction = the lowest index among equal minima; no finite
+        //      distance at all leaves index 0, like vq_fused_kernel)
+        for (int j0 = 0; j0 < nlead; j0 += 32) {
+            const int j = j0 + lane;
+            unsigned todo = __ballot_sync(0xffffffffu, j < nlead && res[list[j < nlead ? j : 0]] == 0xffffu);
+            if (todo) vq_exhaustive_sweep(todo, list + j0, zs, res, cbs, e2s, K, lane);  // rare: kept out of line
         }
         __syncwarp();
         VQ_STAMP(4);
@@ -818,11 +873,11 @@ extern "C" int cgic_vq_assign_indexed(const float *z, int B, int h, int w, const
     }
     const int tiles_x = (w + 31) / 32, tiles_y = (h + 3) / 4;
     const int64_t n_tiles = (int64_t)B * tiles_x * tiles_y;
-    // one tile per warp while the grid fits the machine (3 CTAs of 8 warps per SM), persistent beyond that; the grid is a
+    // one tile per warp while the grid fits the machine (2 CTAs of 8 warps per SM), persistent beyond that; the grid is a
     // multiple of the SM count so that the round-robin deal leaves every SM with the same load
     const int64_t want = (n_tiles + VQW_WARPS - 1) / VQW_WARPS;
     int64_t per_sm = (want + n_sm - 1) / n_sm;
-    if (per_sm > 3) per_sm = 3;
+    if (per_sm > 2) per_sm = 2;
     const int64_t full = per_sm * n_sm;
     const int grid = (int)(n_tiles < full ? n_tiles : full);
     {
