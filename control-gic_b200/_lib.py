@@ -45,6 +45,8 @@ _SIGNATURES = {
                             c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cgic_mask_mix": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                               c_void_p, c_void_p]),
+    "cgic_decoder_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                   c_void_p, c_void_p]),
     "cgic_pack_layout": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "cgic_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                           c_void_p]),

@@ -233,10 +233,81 @@ mask_mix_kernel(const float *__restrict__ h_c, const float *__restrict__ h_m, co
     *reinterpret_cast<float4 *>(&out[rowi * w + 4 * xq]) = o;
 }
 
+// f4  decoder entry (CGIC/modules/vqvae/decoder.py:373-382): mask-gated merge of the decoder's branches, two elements per thread.
+//   LEVEL 2: out = h * up2(m_c) + other * m_m                       tensors [B,C,hh,ww], m_c [B,1,hh/2,ww/2], m_m [B,1,hh,ww]
+//   LEVEL 3: out = (h * up4(m_c) + h * up2(m_m)) + other * m_f      tensors [B,C,hh,ww], m_c [B,1,hh/4,ww/4], m_m [B,1,hh/2,ww/2], m_f [B,1,hh,ww]
+// Products and sums rounded one by one in torch's order; masks int32, int64 or float32 (converted like `.float()`).
+template <typename M, int LEVEL>
+__global__ void __launch_bounds__(256)
+decoder_merge_kernel(const float *__restrict__ h, const float *__restrict__ other, const M *__restrict__ m_c, const M *__restrict__ m_m,
+                     const M *__restrict__ m_f, int64_t n_pairs, int C, int hh, int ww, float *__restrict__ out)
+{
+    const int64_t pi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
+    if (pi >= n_pairs) return;
+    const unsigned wp = (unsigned)ww / 2u;
+    const int64_t rowi = pi / wp;              // (b*C + c) * hh + y
+    const int xp = (int)(pi - rowi * wp);      // x / 2
+    const int64_t bc = rowi / hh;
+    const int y = (int)(rowi - bc * hh);
+    const int64_t b = bc / C;
+    const float2 hv = __ldg(reinterpret_cast<const float2 *>(&h[rowi * ww + 2 * xp]));
+    const float2 ov = __ldg(reinterpret_cast<const float2 *>(&other[rowi * ww + 2 * xp]));
+    float2 o;
+    if (LEVEL == 2) {
+        const float mc = (float)m_c[(b * (hh / 2) + (y >> 1)) * (ww / 2) + xp];
+        const float m0 = (float)m_m[(b * hh + y) * (int64_t)ww + 2 * xp], m1 = (float)m_m[(b * hh + y) * (int64_t)ww + 2 * xp + 1];
+        o.x = __fadd_rn(__fmul_rn(hv.x, mc), __fmul_rn(ov.x, m0));
+        o.y = __fadd_rn(__fmul_rn(hv.y, mc), __fmul_rn(ov.y, m1));
+    } else {
+        const float mc = (float)m_c[(b * (hh / 4) + (y >> 2)) * (ww / 4) + (xp >> 1)];
+        const float mm = (float)m_m[(b * (hh / 2) + (y >> 1)) * (ww / 2) + xp];
+        const float f0 = (float)m_f[(b * hh + y) * (int64_t)ww + 2 * xp], f1 = (float)m_f[(b * hh + y) * (int64_t)ww + 2 * xp + 1];
+        o.x = __fadd_rn(__fadd_rn(__fmul_rn(hv.x, mc), __fmul_rn(hv.x, mm)), __fmul_rn(ov.x, f0));
+        o.y = __fadd_rn(__fadd_rn(__fmul_rn(hv.y, mc), __fmul_rn(hv.y, mm)), __fmul_rn(ov.y, f1));
+    }
+    *reinterpret_cast<float2 *>(&out[rowi * ww + 2 * xp]) = o;
+}
+
 }  // namespace
 }  // namespace cgic
 
 using namespace cgic;
+
+template <typename M>
+static int decoder_merge_launch(const float *h, const float *other, const void *m_c, const void *m_m, const void *m_f, int level, int64_t n_pairs,
+                                int C, int hh, int ww, float *out, cudaStream_t stream)
+{
+    const M *c = static_cast<const M *>(m_c), *m = static_cast<const M *>(m_m), *f = static_cast<const M *>(m_f);
+    const dim3 grid((unsigned)((n_pairs + 255) / 256)), block(256);
+    CGIC_PROF("decoder_merge_kernel", stream);
+    if (level == 2) CGIC_CUDA_CHECK(launch_pdl(decoder_merge_kernel<M, 2>, grid, block, 0, stream, h, other, c, m, f, n_pairs, C, hh, ww, out));
+    else CGIC_CUDA_CHECK(launch_pdl(decoder_merge_kernel<M, 3>, grid, block, 0, stream, h, other, c, m, f, n_pairs, C, hh, ww, out));
+    return CGIC_OK;
+}
+
+extern "C" int cgic_decoder_merge(const float *h, const float *other, const void *m_c, const void *m_m, const void *m_f, int mask_elem,
+                                  int level, int B, int C, int hh, int ww, float *out, cgic_stream_t stream_)
+{
+    CGIC_REQUIRE(h && other && m_c && m_m && out && (level == 2 || (level == 3 && m_f)), CGIC_EINVAL, "cgic_decoder_merge: null argument or level %d", level);
+    const int div = level == 2 ? 2 : 4;
+    CGIC_REQUIRE(B >= 0 && C > 0 && hh > 0 && ww > 0 && hh % div == 0 && ww % div == 0, CGIC_EINVAL,
+                 "cgic_decoder_merge: %dx%d must be multiples of %d at level %d", hh, ww, div, level);
+    CGIC_REQUIRE(mask_elem == 4 || mask_elem == 8 || mask_elem == -4, CGIC_EINVAL, "cgic_decoder_merge: mask_elem must be 4, 8 or -4 (float)");
+    for (const void *ptr : {(const void *)h, (const void *)other, (const void *)out})
+        CGIC_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 7) == 0, CGIC_EINVAL, "cgic_decoder_merge: tensors must be 8-byte aligned");
+    const int64_t n_pairs = (int64_t)B * C * hh * ww / 2;
+    if (n_pairs == 0) return CGIC_OK;
+    cudaStream_t stream = as_stream(stream_);
+    int rc;
+    if (mask_elem == 4) rc = decoder_merge_launch<int32_t>(h, other, m_c, m_m, m_f, level, n_pairs, C, hh, ww, out, stream);
+    else if (mask_elem == 8) rc = decoder_merge_launch<int64_t>(h, other, m_c, m_m, m_f, level, n_pairs, C, hh, ww, out, stream);
+    else rc = decoder_merge_launch<float>(h, other, m_c, m_m, m_f, level, n_pairs, C, hh, ww, out, stream);
+    if (rc) return rc;
+    CGIC_LAUNCH_CHECK();
+    return CGIC_OK;
+}
 
 extern "C" size_t cgic_router_workspace_bytes(int, int, int) { return 256; }
 

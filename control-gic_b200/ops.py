@@ -271,6 +271,29 @@ def mask_mix(h_c, h_m, h_f, m_c, m_m, m_f) -> torch.Tensor:
     return out
 
 
+def decoder_merge(h: torch.Tensor, other: torch.Tensor, masks, level: int) -> torch.Tensor:
+    """decoder.py:373-382, the mask-gated merge at the decoder's entry: level 2: h*up2(mask[0]) + other*mask[1];
+    level 3: h*up4(mask[0]) + h*up2(mask[1]) + other*mask[2].  masks: [B,1,.,.] int32 / int64 / float32, one dtype."""
+    h = _cuda(h, torch.float32, "h")
+    other = _cuda(other, torch.float32, "other")
+    if h.shape != other.shape or h.dim() != 4 or level not in (2, 3):
+        raise ValueError("decoder_merge: h and other must be [B,C,hh,ww] tensors of one shape, level 2 or 3")
+    dt = masks[0].dtype
+    elem = {torch.int32: 4, torch.int64: 8, torch.float32: -4}.get(dt)
+    if elem is None or any(m.dtype != dt for m in masks[:level]):
+        raise TypeError("decoder_merge: masks must all be int32, int64 or float32")
+    ms = [_cuda(m, dt, "mask") for m in masks[:level]]
+    B, Cc, hh, ww = h.shape
+    div = 2 if level == 2 else 4
+    want = [(B, 1, hh // div, ww // div), (B, 1, hh // (div // 2), ww // (div // 2))] + ([(B, 1, hh, ww)] if level == 3 else [])
+    if [tuple(m.shape) for m in ms] != want:
+        raise ValueError(f"decoder_merge: mask shapes {[tuple(m.shape) for m in ms]} do not match {want}")
+    out = torch.empty_like(h)
+    check(lib().cgic_decoder_merge(h.data_ptr(), other.data_ptr(), ms[0].data_ptr(), ms[1].data_ptr(), ms[2].data_ptr() if level == 3 else None,
+                                   elem, level, B, Cc, hh, ww, out.data_ptr(), _stream()), "cgic_decoder_merge")
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # a7/a9/a11/a12 pack and a10/a13/a14 unpack (batched, B independent images)
 # --------------------------------------------------------------------------------------------

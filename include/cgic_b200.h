@@ -149,6 +149,14 @@ CGIC_API int cgic_mask_mix(const float *h_c, const float *h_m, const float *h_f,
                   const int32_t *m_m, const int32_t *m_f, int B, int C, int h, int w, float *out,
                   cgic_stream_t stream);
 
+/* f4  decoder entry, CGIC/modules/vqvae/decoder.py:373-382: the mask-gated merge of the decoder's branches
+ *     level 2: out = h*up2(m_c) + other*m_m                     h, other, out [B,C,hh,ww]; m_c [B,1,hh/2,ww/2], m_m [B,1,hh,ww]
+ *     level 3: out = h*up4(m_c) + h*up2(m_m) + other*m_f        m_c [B,1,hh/4,ww/4], m_m [B,1,hh/2,ww/2], m_f [B,1,hh,ww]
+ *     (products and sums rounded in torch's order: bit-identical to the eager expression)
+ *     mask_elem: 4 = int32 masks (router output), 8 = int64 (decoded masks), -4 = float32. */
+CGIC_API int cgic_decoder_merge(const float *h, const float *other, const void *m_c, const void *m_m, const void *m_f,
+                       int mask_elem, int level, int B, int C, int hh, int ww, float *out, cgic_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * a7 + a9 + a11 + a12  index selection + 5-stream pack     CGIC/models/model.py:217-260,
  *     HuffmanCoding.compress indices_coding.py:113-126, BinaryCoding.compress mask_coding.py:40-55.

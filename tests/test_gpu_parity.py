@@ -549,3 +549,23 @@ def test_entropy_low_entropy_patches(cg, orc):
             o = orc.entropy(x.numpy(), p)
             assert torch.isfinite(e).all(), name
             assert np.allclose(e.cpu().numpy(), o, rtol=ENTROPY_RTOL, atol=1e-9), (name, p, np.abs(e.cpu().numpy() - o).max())
+
+
+@pytest.mark.parametrize("mdtype", [torch.int32, torch.int64, torch.float32])
+def test_decoder_entry_merge(cg, mdtype):
+    """f4, decoder.py:373-382: the mask-gated merges at the decoder's entry against the reference's own eager expressions
+    (bit-exact: the same products and sums in the same order)."""
+    g = torch.Generator().manual_seed(17)
+    B, C, H, W = 2, 6, 128, 96
+    e16, e8 = torch.rand(B, H // 16, W // 16, generator=g).cuda(), torch.rand(B, H // 8, W // 8, generator=g).cuda()
+    mc, mm, mf, _, _ = cg.ops.router(e16, e8, 0.2, 0.5, per_image=True)
+    mask = [m.to(mdtype) for m in (mc, mm, mf)]
+    up2, up4 = torch.nn.Upsample(scale_factor=2, mode="nearest"), torch.nn.Upsample(scale_factor=4, mode="nearest")
+    h8, hm = torch.randn(B, C, H // 8, W // 8, generator=g).cuda(), torch.randn(B, C, H // 8, W // 8, generator=g).cuda()
+    want2 = h8 * up2(mask[0].float()) + hm * mask[1]                                                   # decoder.py:375-376
+    got2 = cg.ops.decoder_merge(h8, hm, mask, 2)
+    assert torch.equal(got2.view(torch.int32), want2.view(torch.int32))
+    h4, hf = torch.randn(B, C, H // 4, W // 4, generator=g).cuda(), torch.randn(B, C, H // 4, W // 4, generator=g).cuda()
+    want3 = h4 * up4(mask[0].float()) + h4 * up2(mask[1].float()) + hf * mask[2]                       # decoder.py:378-380
+    got3 = cg.ops.decoder_merge(h4, hf, mask, 3)
+    assert torch.equal(got3.view(torch.int32), want3.view(torch.int32))
