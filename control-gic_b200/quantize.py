@@ -76,12 +76,25 @@ class VectorQuantize2(nn.Module):
         flat[torch.as_tensor(self.counter_order(), device=vals.device)] = vals
         return flat
 
+    def _flat_counter_storage(self, device) -> torch.Tensor:
+        """One fp32 [n_e] tensor (indexed by symbol) that the 1024 `embedding_counter.<i>` parameters are VIEWS of, so
+        that the histogram kernel updates all of them in one launch.  `.to()` / `.cuda()` / `load_state_dict` give the
+        parameters storage of their own again; the aliasing is then re-established here (metadata only, no kernels
+        beyond one gather)."""
+        flat = getattr(self, "_counter_flat", None)
+        params = self.embedding_counter
+        ok = flat is not None and flat.device == device and all(
+            p.device == device and p.data_ptr() == flat.data_ptr() + 4 * int(k) for k, p in params.items())
+        if not ok:
+            flat = self.counters_flat().to(device=device, dtype=torch.float32).contiguous()
+            for k, p in params.items():
+                p.data = flat[int(k): int(k) + 1]
+            self._counter_flat = flat
+        return flat
+
     @torch.no_grad()
     def _bump_counters(self, idx: torch.Tensor) -> None:                                 # quantize.py:79-81
-        flat = self.counters_flat().to(idx.device).contiguous()
-        ops.vq_count(idx, flat)
-        for k, p in self.embedding_counter.items():
-            p.copy_(flat[int(k): int(k) + 1])
+        ops.vq_count(idx, self._flat_counter_storage(idx.device))
 
     def prepared_codebook(self) -> "ops.Codebook":
         """The search index of `embedding.weight` (ops.Codebook), rebuilt on the current stream whenever the

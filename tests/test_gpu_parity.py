@@ -569,3 +569,24 @@ def test_decoder_entry_merge(cg, mdtype):
     want3 = h4 * up4(mask[0].float()) + h4 * up2(mask[1].float()) + hf * mask[2]                       # decoder.py:378-380
     got3 = cg.ops.decoder_merge(h4, hf, mask, 3)
     assert torch.equal(got3.view(torch.int32), want3.view(torch.int32))
+
+
+def test_vq_training_counters_stay_views(cg):
+    """f3: the training-mode counter update is one histogram launch into a flat buffer the 1024 `embedding_counter.<i>`
+    parameters alias; the state dict keeps the reference's keys and shapes, and loading / moving the module re-links."""
+    vq = cg.VectorQuantize2(1024, 4, 0.25).cuda().train()
+    z = (torch.randn(2, 4, 16, 16) * 1e-3).cuda()
+    total = torch.zeros(1024)
+    for _ in range(3):
+        _, _, idx = vq(z)
+        total += torch.bincount(idx.cpu(), minlength=1024).float()
+        assert torch.equal(vq.counters_flat().cpu(), total)
+    sd = vq.state_dict()
+    assert sd["embedding_counter.7"].shape == (1,) and float(sd["embedding_counter.7"]) == float(total[7])
+    vq2 = cg.VectorQuantize2(1024, 4, 0.25)
+    vq2.load_state_dict(sd)
+    vq2 = vq2.cuda().train()
+    _, _, idx = vq2(z)
+    total += torch.bincount(idx.cpu(), minlength=1024).float()
+    assert torch.equal(vq2.counters_flat().cpu(), total)
+    assert list(vq2.embedding_counter.keys())[:4] == ["0", "1", "10", "100"]
