@@ -1097,18 +1097,20 @@ __device__ __forceinline__ void assemble_quad(const UnpackArgs &a, int b, int64_
     const int cnt0 = cntp[0], cnt1 = cntp[1], cnt2 = cntp[2];
     const int64_t p16 = (int64_t)(y >> 2) * g.w16 + (x >> 2);
     const int64_t p8 = (int64_t)(y >> 1) * g.w8 + (x >> 1);  // even: p8 and p8 + 1 share a word
+    // bitmap words, popcount prefixes and counts are all independent loads: issued together, one round trip
     const uint32_t wc = bits[p16 >> 5], wm = bits[g.nw16 + (p8 >> 5)], wf = bits[g.nw16 + g.nw8 + (p >> 5)];
+    const uint32_t pre_c = prefix[p16 >> 5], pre_m = prefix[g.nw16 + (p8 >> 5)], pre_f = prefix[g.nw16 + g.nw8 + (p >> 5)];
     const int sc = (int)(p16 & 31), sm = (int)(p8 & 31), sf = (int)(p & 31);
     const int cbit = (wc >> sc) & 1;
     int64_t base = 0;
     if (cbit && cnt0 > 0) {
-        const int r = prefix[p16 >> 5] + __popc(wc & ((1u << sc) - 1u));
+        const int r = pre_c + __popc(wc & ((1u << sc) - 1u));
         if (r < cnt0) base = sym[r];
     }
     int mbit[2];
     int64_t mval[2] = {0, 0};
     {
-        const uint32_t pre = prefix[g.nw16 + (p8 >> 5)];
+        const uint32_t pre = pre_m;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             mbit[j] = (wm >> (sm + j)) & 1;
@@ -1121,7 +1123,7 @@ __device__ __forceinline__ void assemble_quad(const UnpackArgs &a, int b, int64_
     int fbit[4];
     int64_t ind[4];
     {
-        const uint32_t pre = prefix[g.nw16 + g.nw8 + (p >> 5)];
+        const uint32_t pre = pre_f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             fbit[i] = (wf >> (sf + i)) & 1;
