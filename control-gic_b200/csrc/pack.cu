@@ -478,7 +478,10 @@ __global__ void __launch_bounds__(PK_THREADS) pack_kernel(const PackArgs a)
 {
     extern __shared__ __align__(128) unsigned char dyn[];
     __shared__ __align__(8) unsigned long long mbar;
-    const int s = blockIdx.x, b = blockIdx.y;
+    // linear block order = hand-out order: the fine streams (4096 grid positions each) first, then medium, then the
+    // coarse + mask CTAs, so that the second CTA of an SM is a short one
+    const int lin = (int)(blockIdx.y * gridDim.x + blockIdx.x), nb = (int)gridDim.y;
+    const int k = lin / nb, s = 2 - k, b = lin - k * nb;
     pdl_launch_dependents();
     if (stream_present(a.mode, s)) {
         pack_stream_entry<ITEMS>(a, s, b, dyn, &mbar);   // waits for the predecessor grid inside

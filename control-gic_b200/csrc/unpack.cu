@@ -326,21 +326,60 @@ __device__ __forceinline__ uint32_t decode_one(const uint32_t *s_words, uint32_t
     return two ? e2 + (uint32_t)L : e;  // second-level entries hold the bits used beyond L
 }
 
-// Codewords starting in [q, q_sub_end); returns their number, *q_next = start of the next
-// codeword or DEC_QSTOP once the payload end q_end is reached (a trailing incomplete code, or one
-// completed only by bits past the payload, is dropped like in the reference).
+// Codewords starting in [q, q_sub_end) of a chunk whose length table len8[] is ready (candidate decoder, phase C);
+// returns their number.  A trailing incomplete code, or one completed only by bits past the payload, is dropped like in
+// the reference: len8[] is 0 there.  The walk from codeword to codeword goes through len8[] alone -- one dependent
+// shared-memory byte load per codeword instead of the whole window -> first-level -> second-level lookup chain --
+// and the symbol lookups of four codewords at a time are independent of each other and of the next group's walk, so
+// their latencies overlap.
 template <bool LUT2S, typename Out>
-__device__ __forceinline__ int decode_write_smem(const uint32_t *s_words, uint32_t q, uint32_t q_sub_end, uint32_t q_end,
-                                                 const uint32_t *s_lut, const uint32_t *lut2, const DevTable &T, Out *out)
+__device__ __forceinline__ int decode_write_len(const uint32_t *s_words, const uint8_t *s_len, uint32_t q, uint32_t q_sub_end,
+                                                const uint32_t *s_lut, const uint32_t *lut2, const DevTable &T, Out *out)
 {
-    int cnt = 0;
+    constexpr int G = 4;
+    constexpr uint32_t DEAD = 0xFFFFFFFFu;
     const int L = T.lut_bits;
-    while (q < q_sub_end) {
-        const uint32_t r = decode_one<LUT2S>(s_words, q, s_lut, lut2, T, L);
-        const uint32_t len = r & 0xFFu;
-        if (q + len > q_end) break;
-        out[cnt++] = (Out)(r >> 8);
-        q += len;
+    int cnt = 0;
+    uint32_t qn[G];
+    auto walk = [&]() {
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            const uint32_t len = q < q_sub_end ? (uint32_t)s_len[q] : 0u;
+            qn[k] = len ? q : DEAD;
+            q = len ? q + len : q_sub_end;  // frozen once the subsequence (or the payload) is over
+        }
+    };
+    walk();
+    while (qn[0] != DEAD) {
+        uint32_t qc[G], r[G];
+#pragma unroll
+        for (int k = 0; k < G; ++k) qc[k] = qn[k];
+        walk();
+        bool deep = false;
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            const uint32_t pos = qc[k] != DEAD ? qc[k] : 8u;
+            const uint32_t i = pos >> 5;
+            const uint32_t win = __funnelshift_l(s_words[i + 1], s_words[i], pos & 31);
+            const uint32_t e = s_lut[win >> (32 - L)];
+            const uint32_t f = e & 0xFFu;
+            const bool two = (f & 0x80u) != 0 && f != 0xFFu;
+            const uint32_t hgt = two ? (f & 0x7Fu) : 1u;
+            const uint32_t i2 = two ? (e >> 8) + ((win << L) >> (32 - hgt)) : 0u;
+            const uint32_t e2 = LUT2S ? lut2[i2] : __ldg(&lut2[i2]);
+            r[k] = two ? e2 : e;
+            deep |= f == 0xFFu && qc[k] != DEAD;
+        }
+        if (deep) {  // rare: a code deeper than the second level
+#pragma unroll
+            for (int k = 0; k < G; ++k)
+                if (qc[k] != DEAD) r[k] = decode_one<LUT2S>(s_words, qc[k], s_lut, lut2, T, L);
+        }
+#pragma unroll
+        for (int k = 0; k < G; ++k)
+            if (qc[k] != DEAD) out[cnt + k] = (Out)(r[k] >> 8);
+#pragma unroll
+        for (int k = 0; k < G; ++k) cnt += qc[k] != DEAD;
     }
     return cnt;
 }
@@ -569,7 +608,7 @@ __device__ int decode_stream_cta_cand(const uint8_t *in, int64_t nbytes, const D
             if (total + ctot > cap) return -2;
             if (cnt) {
                 const uint32_t sub0 = 8u + (uint32_t)i * DEC_SUB_BITS;
-                decode_write_smem<LUT2S, Out>(s_words, sub0 + st, sub0 + DEC_SUB_BITS, q_end, s_lut, lut2, T, out + total + woff + inc - cnt);
+                decode_write_len<LUT2S, Out>(s_words, s_len, sub0 + st, sub0 + DEC_SUB_BITS, s_lut, lut2, T, out + total + woff + inc - cnt);
             }
             total += ctot;
             __syncthreads();
@@ -789,7 +828,7 @@ __device__ int decode_stream_cta_chain(const uint8_t *in, int64_t nbytes, const 
             }
             if (cnt && !overflow) {
                 const uint32_t sub0 = 8u + (uint32_t)i * DEC_SUB_BITS;
-                decode_write_smem<LUT2S, Out>(s_words, sub0 + st, sub0 + DEC_SUB_BITS, q_end, s_lut, lut2, T, out + total + woff + inc - cnt);
+                decode_write_len<LUT2S, Out>(s_words, s_len, sub0 + st, sub0 + DEC_SUB_BITS, s_lut, lut2, T, out + total + woff + inc - cnt);
             }
             total += ctot;
             __syncthreads();
@@ -962,7 +1001,17 @@ __device__ __forceinline__ void unpack_decode_cta(const UnpackArgs &a, unsigned 
 {
     unsigned long long *mbar_p = &mbar_ref;
     const int nslots = MULTI ? a.nslots : 1;
-    const int s = (int)blockIdx.x < 3 * nslots ? (int)blockIdx.x / nslots : 3, slot = (int)blockIdx.x - s * nslots, b = blockIdx.y;
+    int s, slot, b;
+    if (MULTI) {
+        s = (int)blockIdx.x < 3 * nslots ? (int)blockIdx.x / nslots : 3, slot = (int)blockIdx.x - s * nslots, b = blockIdx.y;
+    } else {
+        // CTAs are handed to the SMs in linear block order, breadth first: the first 148 get an SM of their own.  Long streams
+        // first (all medium, then all fine), the short coarse streams and the mask CTAs last, so that at two CTAs per SM a long
+        // stream shares its SM with a short one instead of with another long one (block b*4+s pairs equal s: 148 % 4 == 0).
+        const int lin = (int)(blockIdx.y * gridDim.x + blockIdx.x), nb = (int)gridDim.y;
+        const int k = lin / nb;
+        s = k == 0 ? 1 : (k == 1 ? 2 : (k == 2 ? 0 : 3)), slot = 0, b = lin - k * nb;
+    }
     const Geo &g = a.g;
     CGIC_STAMP(unpack, 0);
     pdl_launch_dependents();

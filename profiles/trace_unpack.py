@@ -32,10 +32,11 @@ assert rc == 0, rc
 st = buf.reshape(1024, 8)[: 4 * B].astype(np.float64)
 t0 = st[:, 0][st[:, 0] > 0].min()
 names = ["start", "tables", "chunk", "staged", "A done", "B done", "end", "A0 done"]
-for s_id, label in ((0, "coarse idx"), (1, "medium idx"), (2, "fine idx"), (3, "mask CTA")):
-    rows = st[s_id::4]
+# linear block id = k * B + b with k -> stream (medium, fine, coarse, masks): see unpack_decode_cta
+for s_id, label in ((2, "coarse idx"), (0, "medium idx"), (1, "fine idx"), (3, "mask CTA")):
+    rows = st[s_id * B:(s_id + 1) * B]
     print(label)
-    if s_id < 3:
+    if label != 'mask CTA':
         rel = (rows[:, :8] - t0) / 1e3
         for k, n in enumerate(names):
             print(f"   {n:8s} min/median/max {rel[:,k].min():7.2f} {np.median(rel[:,k]):7.2f} {rel[:,k].max():7.2f}")
