@@ -49,6 +49,9 @@ WORKLOADS = {
     "c3_b24_512x768_r0.3-0.6-0.1": (24, 512, 768, 0.3, 0.6),
     "c3_b24_512x768_r0.1-0.8-0.1": (24, 512, 768, 0.1, 0.8),
     "c3_b24_512x768_r0.05-0.05-0.9": (24, 512, 768, 0.05, 0.05),
+    # not BASELINE configs: the c2 workload at larger batches (how the kernels behave once the grid fills the machine)
+    "x_b512_256x256_r0.1-0.8-0.1": (512, 256, 256, 0.1, 0.8),
+    "x_b2048_256x256_r0.1-0.8-0.1": (2048, 256, 256, 0.1, 0.8),
 }
 DEFAULT_WORKLOAD = "c2_b64_256x256_r0.1-0.8-0.1"
 

@@ -6,10 +6,11 @@ operator API; all compute is in libcgic_b200.so (include/cgic_b200.h), loaded wi
 """
 from . import _lib, ops, dist, inference  # noqa: F401
 from .codec import BinaryCoding, HuffmanCoding  # noqa: F401
+from .decoder import Normalize, SpatialNorm  # noqa: F401
 from .entropy import Entropy, entropy_pair  # noqa: F401
 from .model import CGIC, ReferenceEncoderHeads  # noqa: F401
 from .quantize import VectorQuantize2  # noqa: F401
 from .router import TripleGrainFixedEntropyRouter  # noqa: F401
 
 __all__ = ["ops", "dist", "inference", "HuffmanCoding", "BinaryCoding", "Entropy", "entropy_pair", "CGIC", "ReferenceEncoderHeads",
-           "VectorQuantize2", "TripleGrainFixedEntropyRouter"]
+           "VectorQuantize2", "TripleGrainFixedEntropyRouter", "SpatialNorm", "Normalize"]

@@ -47,6 +47,8 @@ _SIGNATURES = {
                               c_void_p, c_void_p]),
     "cgic_decoder_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_void_p, c_void_p]),
+    "cgic_spatial_norm_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "cgic_spatial_norm": (c_int, [c_void_p] * 8 + [c_int] * 8 + [C.c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cgic_pack_layout": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "cgic_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                           c_void_p]),

@@ -294,6 +294,32 @@ def decoder_merge(h: torch.Tensor, other: torch.Tensor, masks, level: int) -> to
     return out
 
 
+def spatial_norm(f: torch.Tensor, zq: torch.Tensor, gn_weight: Optional[torch.Tensor], gn_bias: Optional[torch.Tensor],
+                 wy: torch.Tensor, by: Optional[torch.Tensor], wb: torch.Tensor, bb: Optional[torch.Tensor],
+                 groups: int, eps: float) -> torch.Tensor:
+    """decoder.py:47-53 (SpatialNorm.forward without the optional 3x3 conv): GroupNorm(f) * conv_y(nearest(zq)) + conv_b(nearest(zq)).
+    f [B,C,H,W], zq [B,Cz,hz,wz] fp32; wy / wb [C,Cz] or [C,Cz,1,1]; by / bb / gn_weight / gn_bias [C] or None."""
+    f = _cuda(f, torch.float32, "f")
+    zq = _cuda(zq, torch.float32, "zq")
+    if f.dim() != 4 or zq.dim() != 4 or zq.shape[0] != f.shape[0]:
+        raise ValueError(f"spatial_norm: f {tuple(f.shape)} / zq {tuple(zq.shape)} must be [B,C,H,W] / [B,Cz,hz,wz]")
+    B, Cc, H, W = f.shape
+    _, Cz, hz, wz = zq.shape
+    wy = _cuda(wy.reshape(wy.shape[0], -1), torch.float32, "wy")
+    wb = _cuda(wb.reshape(wb.shape[0], -1), torch.float32, "wb")
+    if tuple(wy.shape) != (Cc, Cz) or tuple(wb.shape) != (Cc, Cz):
+        raise ValueError(f"spatial_norm: 1x1 conv weights must be [{Cc},{Cz}], got {tuple(wy.shape)} / {tuple(wb.shape)}")
+    vecs = [None if t is None else _cuda(t.reshape(-1), torch.float32, n) for t, n in ((gn_weight, "gn_weight"), (gn_bias, "gn_bias"), (by, "by"), (bb, "bb"))]
+    if any(t is not None and t.numel() != Cc for t in vecs):
+        raise ValueError(f"spatial_norm: per-channel vectors must have {Cc} elements")
+    out = torch.empty_like(f)
+    ws = _workspace("spatial_norm", lib().cgic_spatial_norm_workspace_bytes(B, groups), f.device)
+    check(lib().cgic_spatial_norm(f.data_ptr(), zq.data_ptr(), _p(vecs[0]), _p(vecs[1]), wy.data_ptr(), _p(vecs[2]), wb.data_ptr(), _p(vecs[3]),
+                                  B, Cc, H, W, Cz, hz, wz, groups, float(eps), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+          "cgic_spatial_norm")
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # a7/a9/a11/a12 pack and a10/a13/a14 unpack (batched, B independent images)
 # --------------------------------------------------------------------------------------------

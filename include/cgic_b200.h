@@ -157,6 +157,18 @@ CGIC_API int cgic_mask_mix(const float *h_c, const float *h_m, const float *h_f,
 CGIC_API int cgic_decoder_merge(const float *h, const float *other, const void *m_c, const void *m_m, const void *m_f,
                        int mask_elem, int level, int B, int C, int hh, int ww, float *out, cgic_stream_t stream);
 
+/* f4  SpatialNorm, CGIC/modules/vqvae/decoder.py:34-53 (the conditioning of every decoder block on the decoded latents):
+ *     new_f = GroupNorm(f; groups, eps, gn_weight, gn_bias) * conv_y(zq_up) + conv_b(zq_up),  zq_up = nearest(zq -> H x W)
+ *     f, out [B,C,H,W] fp32; zq [B,Cz,hz,wz] fp32 (Cz <= 8; any hz, wz: torch's nearest index rule); conv_y / conv_b are the
+ *     1x1 convolutions' weights wy, wb [C,Cz] and biases by, bb [C] (nullable = no bias); gn_weight / gn_bias [C] nullable
+ *     (affine=False).  Neither zq_up nor the two convolution outputs are materialised.  Floating point: group statistics
+ *     are accumulated in a different order than torch's -- tolerance, not bit parity (tests: rtol 1e-5, atol 1e-5).
+ *     workspace: cgic_spatial_norm_workspace_bytes(B, groups) bytes, 16-byte aligned, any content. */
+CGIC_API size_t cgic_spatial_norm_workspace_bytes(int B, int groups);
+CGIC_API int cgic_spatial_norm(const float *f, const float *zq, const float *gn_weight, const float *gn_bias, const float *wy,
+                      const float *by, const float *wb, const float *bb, int B, int C, int H, int W, int Cz, int hz, int wz,
+                      int groups, float eps, float *out, void *workspace, size_t workspace_bytes, cgic_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * a7 + a9 + a11 + a12  index selection + 5-stream pack     CGIC/models/model.py:217-260,
  *     HuffmanCoding.compress indices_coding.py:113-126, BinaryCoding.compress mask_coding.py:40-55.

@@ -302,3 +302,30 @@ def entropy(x, psize: int, bins=None):
     rc = lib().orc_entropy(_p(a, C.c_float), B, H, W, psize, _p(bins, C.c_float), _p(out, C.c_float))
     assert rc == 0, rc
     return out
+
+
+# f4  SpatialNorm (decoder.py:34-53), numpy restatement; statistics in float64
+def nearest_index(out_size: int, in_size: int) -> np.ndarray:
+    """torch's nearest rule (F.interpolate(mode="nearest"), decoder.py:49): min(floor(dst * fp32(in / out)), in - 1)."""
+    scale = np.float32(in_size) / np.float32(out_size)
+    return np.minimum(np.floor(np.arange(out_size, dtype=np.float32) * scale).astype(np.int64), in_size - 1)
+
+
+def spatial_norm(f, zq, gn_weight, gn_bias, wy, by, wb, bb, groups: int, eps: float):
+    """decoder.py:47-53 without the optional 3x3 conv: GroupNorm(f) * conv_y(nearest(zq)) + conv_b(nearest(zq)).
+    f [B,C,H,W], zq [B,Cz,hz,wz]; wy / wb [C,Cz]; vectors [C] or None."""
+    f = np.asarray(f, np.float64)
+    zq = np.asarray(zq, np.float64)
+    B, Cc, H, W = f.shape
+    zu = zq[:, :, nearest_index(H, zq.shape[2])][:, :, :, nearest_index(W, zq.shape[3])]
+    g = f.reshape(B, groups, -1)
+    mean = g.mean(axis=2, keepdims=True)
+    var = g.var(axis=2, keepdims=True)                                   # biased (decoder.py:52 -> nn.GroupNorm)
+    n = ((g - mean) / np.sqrt(var + eps)).reshape(B, Cc, H, W)
+    one = np.ones(Cc)
+    zero = np.zeros(Cc)
+    n = n * (one if gn_weight is None else np.asarray(gn_weight, np.float64)).reshape(1, Cc, 1, 1) \
+        + (zero if gn_bias is None else np.asarray(gn_bias, np.float64)).reshape(1, Cc, 1, 1)
+    cy = np.einsum("ck,bkhw->bchw", np.asarray(wy, np.float64).reshape(Cc, -1), zu) + (zero if by is None else np.asarray(by, np.float64)).reshape(1, Cc, 1, 1)
+    cb = np.einsum("ck,bkhw->bchw", np.asarray(wb, np.float64).reshape(Cc, -1), zu) + (zero if bb is None else np.asarray(bb, np.float64)).reshape(1, Cc, 1, 1)
+    return (n * cy + cb).astype(np.float32)

@@ -161,3 +161,28 @@ def test_framing_properties():
             continue
         assert len(data) == n // 8 + 2 and 1 <= data[0] <= 8 and data[0] == 8 - n % 8
         assert orc.bits_decode(data) == bits
+
+
+# ---- f4 SpatialNorm: the numpy restatement against vectors from the reference class (make_spatial_norm_golden.py) ----
+def _sn_cases():
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "spatial_norm.npz"))
+    for name, add_conv in zip(d["cases"], d["add_conv"]):
+        sd = {k[len(name) + 4:]: d[k] for k in d.files if k.startswith(f"{name}.sd.")}
+        yield str(name), bool(add_conv), d[f"{name}.f"], d[f"{name}.zq"], sd, d[f"{name}.out"]
+
+
+def test_spatial_norm_oracle_matches_reference_vectors():
+    import torch
+    from oracle import oracle as orc
+    seen = 0
+    for name, add_conv, f, zq, sd, want in _sn_cases():
+        if add_conv:   # decoder.py:49-51: the 3x3 conv acts on the up-sampled zq; the restatement then sees zq at full size
+            iy, ix = orc.nearest_index(f.shape[2], zq.shape[2]), orc.nearest_index(f.shape[3], zq.shape[3])
+            zu = torch.from_numpy(zq[:, :, iy][:, :, :, ix])
+            zq = torch.nn.functional.conv2d(zu, torch.from_numpy(sd["conv.weight"]), torch.from_numpy(sd["conv.bias"]), padding=1).numpy()
+        got = orc.spatial_norm(f, zq, sd["norm_layer.weight"], sd["norm_layer.bias"], sd["conv_y.weight"], sd["conv_y.bias"],
+                               sd["conv_b.weight"], sd["conv_b.bias"], groups=32, eps=1e-6)
+        # tolerance: the reference computes in fp32 (statistics, 1x1 convs); the restatement in float64
+        np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-5, err_msg=name)
+        seen += 1
+    assert seen == 5
