@@ -137,3 +137,16 @@ def test_workload_counts_formula():
     e16, e8 = workload.entropy_maps(1, 256, 256, 3)
     mc, mm, mf, _ = orc.router(e16.numpy(), e8.numpy(), 0.1, 0.8)
     assert (int(mc.sum()), int(mm.sum()), int(mf.sum())) == (25, 821, 412)
+
+
+def test_spatial_norm_module_host_side():
+    """State-dict keys / shapes of cgic_b200.Normalize == the reference class's (read from the golden file that
+    tests/golden/make_spatial_norm_golden.py wrote from CGIC/modules/vqvae/decoder.py:34-56); no CPU fallback."""
+    d = np.load(os.path.join(ROOT, "tests", "golden", "spatial_norm.npz"))
+    for name, add_conv in zip(d["cases"], d["add_conv"]):
+        ref = {k[len(name) + 4:]: d[k].shape for k in d.files if k.startswith(f"{name}.sd.")}
+        m = cgic_b200.Normalize(d[f"{name}.f"].shape[1], d[f"{name}.zq"].shape[1], bool(add_conv))
+        assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == ref
+        assert m.norm_layer.num_groups == 32 and m.norm_layer.eps == 1e-6
+    with pytest.raises(RuntimeError, match="CUDA"):
+        cgic_b200.Normalize(32, 4, False)(torch.zeros(1, 32, 4, 4), torch.zeros(1, 4, 1, 1))
