@@ -279,7 +279,7 @@ def run_b200(args):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, stream=side):      # the warm-up stream: its workspaces exist, nothing but the 4 kernels is captured
             g_out = step()
         runner = graph.replay
 
@@ -343,7 +343,7 @@ def run_b200(args):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         img_graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(img_graph):
+        with torch.cuda.graph(img_graph, stream=side):
             step_image_in()
         img_runner = img_graph.replay
     for _ in range(3):

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/cgic_b200.h"
 
@@ -66,6 +67,19 @@ __host__ __device__ inline bool stream_present(int mode, int s)
 // every read of data a predecessor may have produced and EVERY global write come after pdl_wait(),
 // which returns once the predecessor grid has completed and its memory is visible.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// The step kernels choose WHEN their dependents may be launched (CGIC_PDL_EARLY: bit 0 VQ, bit 1 pack, bit 2 decode).
+// Early = at the kernel's start: the dependent's CTAs become resident at once, stage their tables and sit in
+// griddepcontrol.wait -- but they are then placed on whatever SMs have room while the primary still runs, not in
+// linear block order on an empty machine.  Late = no explicit trigger: the dependent grid is launched as the primary's
+// CTAs exit (its launch latency still overlaps the primary's drain).
+#ifndef CGIC_PDL_EARLY
+#define CGIC_PDL_EARLY 0
+#endif
+template <int BIT>
+__device__ __forceinline__ void pdl_trigger_step()
+{
+    if (CGIC_PDL_EARLY & BIT) pdl_launch_dependents();
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 template <typename... KArgs, typename... Args>
@@ -76,11 +90,12 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
+    static const bool no_pdl = getenv("CGIC_NO_PDL") != nullptr;  // diagnosis only: plain stream-ordered launches
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = no_pdl ? 0 : 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

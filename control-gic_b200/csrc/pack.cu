@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(PK_THREADS) pack_kernel(const PackArgs a)
     // coarse + mask CTAs, so that the second CTA of an SM is a short one
     const int lin = (int)(blockIdx.y * gridDim.x + blockIdx.x), nb = (int)gridDim.y;
     const int k = lin / nb, s = 2 - k, b = lin - k * nb;
-    pdl_launch_dependents();
+    pdl_trigger_step<2>();
     if (stream_present(a.mode, s)) {
         pack_stream_entry<ITEMS>(a, s, b, dyn, &mbar);   // waits for the predecessor grid inside
     } else {
@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(PK_THREADS) pack_chained_kernel(const PackArgs
     extern __shared__ __align__(128) unsigned char dyn[];
     __shared__ __align__(8) unsigned long long mbar;
     const int s = blockIdx.x / a.nslots, slot = blockIdx.x - s * a.nslots, b = blockIdx.y;
-    pdl_launch_dependents();
+    pdl_trigger_step<2>();
     if (stream_present(a.mode, s)) {
         const uint32_t bytes = (uint32_t)((a.T.K + 1) / 2 * 2) * 8u;
         if (threadIdx.x == 0) mbar_init(&mbar);

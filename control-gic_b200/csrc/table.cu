@@ -250,7 +250,10 @@ int cgic_huff_build(const int64_t *freq, const int32_t *order, int K, cgic_table
     }
     if (t->pool.empty()) t->pool.push_back(0);
     // decode LUT on the first lut_bits bits
-    t->lut_bits = std::min(t->max_len, 12);
+#ifndef CGIC_LUT_BITS
+#define CGIC_LUT_BITS 12
+#endif
+    t->lut_bits = std::min(t->max_len, CGIC_LUT_BITS);
     t->lut.resize((size_t)1 << t->lut_bits);
     for (uint32_t v = 0; v < t->lut.size(); ++v) {
         int node = t->root, used = 0;

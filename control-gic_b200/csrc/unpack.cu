@@ -1014,7 +1014,7 @@ __device__ __forceinline__ void unpack_decode_cta(const UnpackArgs &a, unsigned 
     }
     const Geo &g = a.g;
     CGIC_STAMP(unpack, 0);
-    pdl_launch_dependents();
+    pdl_trigger_step<4>();
     const uint8_t *img = a.bytes + (int64_t)b * a.image_stride;
     const int32_t *sz = a.sizes + b * 5;
     const int nwt = g.nw16 + g.nw8 + g.nw4;

@@ -203,7 +203,7 @@ vq_fused_kernel(const float *__restrict__ z, int B, int h, int w, const VqTiles 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     VQ_STAMP(0);
-    pdl_launch_dependents();
+    pdl_trigger_step<1>();
     pdl_wait();  // the codebook and z may come straight from a preceding kernel
     // --- stage the codebook with one TMA bulk copy (cp.async.bulk -> UBLKCP), mbarrier completion
     if (tid == 0) mbar_init(&mbar);
@@ -582,7 +582,7 @@ vq_warp_kernel(const float *__restrict__ z, int h, int w, int tiles_x, int tiles
     const uint4 *recs = reinterpret_cast<const uint4 *>(blob + CL.rec);
 
     VQ_STAMP(0);
-    pdl_launch_dependents();
+    pdl_trigger_step<1>();
     pdl_wait();  // the prepared blob and z may come straight from a preceding kernel
     VQ_STAMP(1);
     if (tid == 0) mbar_init(&mbar);

@@ -112,10 +112,21 @@ _ws_cache = {}
 
 
 def _workspace(tag: str, nbytes: int, device: torch.device) -> torch.Tensor:
-    """Grow-only scratch buffer per (tag, device, stream); allocation happens off the hot path after warm-up."""
+    """Grow-only scratch buffer per (tag, device, stream), zero-filled when it is created (the kernels leave it clean);
+    allocation happens off the hot path after warm-up.
+
+    Under CUDA-graph capture a miss would put the zero-fill INTO the graph: a ~2 us fill kernel in front of the kernel on
+    every replay, which also severs the programmatic (PDL) edge to its predecessor.  So while capturing, a buffer of the
+    same tag that a warm-up run created on another stream of this device is reused instead (warm up before capturing, as
+    torch asks anyway; do not replay the graph concurrently with eager calls of the same op on that other stream)."""
     key = (tag, device.index, _stream())
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
+        if torch.cuda.is_current_stream_capturing():
+            for (t, d, _), b in reversed(list(_ws_cache.items())):
+                if t == tag and d == device.index and b.numel() >= nbytes:
+                    _ws_cache[key] = b
+                    return b
         buf = torch.zeros(max(nbytes, 256), dtype=torch.uint8, device=device)   # cgic_vq_assign wants its ticket zeroed once
         _ws_cache[key] = buf
     return buf

@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Timeline of the bench step INSIDE the CUDA graph (a -DCGIC_TRACE -DCGIC_VQ_TRACE build: %globaltimer stamps of the VQ
+and decode CTAs): CGIC_B200_LIB=build/variants/lib_trace.so python profiles/trace_graph.py"""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bench, workload
+import cgic_b200 as cg
+B, H, W, c, m = bench.WORKLOADS[bench.DEFAULT_WORKLOAD]
+h, w = H // 4, W // 4
+dev = torch.device("cuda", 0)
+cbk, counts = workload.codebook_and_counts()
+table = cg.ops.HuffTable(counts.numpy(), workload.lexicographic_order()).upload()
+cb = cbk.to(dev)
+prepared = cg.ops.Codebook(cb)
+e16, e8 = workload.entropy_maps(B, H, W, 1000)
+mc, mm, mf, _, mode = cg.ops.router(e16.to(dev), e8.to(dev), c, m, per_image=True)
+hc, hm, hf = (t.to(dev) for t in workload.heads(B, H, W, cbk, 1000))
+z = cg.ops.mask_mix(hc, hm, hf, mc, mm, mf)
+def step():
+    idx, zq, sq = cg.ops.vq_assign(z, prepared)
+    packed, sizes = cg.ops.pack(idx, mc, mm, mf, mode, table, h, w)
+    return cg.ops.unpack(packed, sizes, mode, table, cb, h, w)
+side = torch.cuda.Stream()
+side.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(side):
+    for _ in range(3): step()
+torch.cuda.current_stream().wait_stream(side)
+torch.cuda.synchronize()
+use_graph = "--eager" not in sys.argv
+if use_graph:
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        out = step()
+    run = g.replay
+else:
+    run = step
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+for _ in range(5):
+    flush.zero_(); ev[0].record(); run(); ev[1].record()
+torch.cuda.synchronize()
+print("step (events):", round(1e3 * ev[0].elapsed_time(ev[1]), 2), "us", "graph" if use_graph else "eager")
+buf = np.zeros(1024 * 8, np.uint64)
+assert ctypes.CDLL(cg._lib.LIB_PATH).cgic_trace_unpack(buf.ctypes.data_as(ctypes.c_void_p)) == 0
+un = buf.reshape(1024, 8)[: 4 * B].astype(np.float64)
+ws = [v for k, v in cg.ops._ws_cache.items() if k[0] == "vq"][-1] if not use_graph else None
+# the VQ stamps live in the vq workspace of the stream the kernel ran on: take every cached one and keep the latest stamps
+best = None
+for k, v in cg.ops._ws_cache.items():
+    if k[0] != "vq": continue
+    raw = v[256:].view(torch.int64)[512:512 + 300 * 8].cpu().numpy().reshape(300, 8)
+    raw = raw[raw[:, 0] > 0]
+    if len(raw) and (best is None or raw[:, 0].max() > best[:, 0].max()): best = raw
+vq = best[:, :7].astype(np.float64)
+t0 = vq[:, 0].min()
+rel = lambda a: (a - t0) / 1e3
+print(f"vq     first start 0.00, last start {rel(vq[:,0].max()):.2f}, searched median {rel(np.median(vq[:,4])):.2f}, end median {rel(np.median(vq[:,6])):.2f} max {rel(vq[:,6].max()):.2f}")
+names = {0: "medium", 1: "fine", 2: "coarse", 3: "masks"}
+for k in range(4):
+    rows = un[k * B:(k + 1) * B]
+    s, e = rows[:, 0], rows[:, 6] if k < 3 else rows[:, 0]
+    extra = ""
+    if k < 3:
+        extra = (f" | tables {rel(np.median(rows[:,1])):.2f} chunk {rel(np.median(rows[:,2])):.2f} staged {rel(np.median(rows[:,3])):.2f} A0 {rel(np.median(rows[:,7])):.2f}"
+                 f" A {rel(np.median(rows[:,4])):.2f} B {rel(np.median(rows[:,5])):.2f} end median {rel(np.median(e)):.2f} max {rel(e.max()):.2f}")
+    print(f"decode {names[k]:6s} start min {rel(s.min()):.2f} median {rel(np.median(s)):.2f} max {rel(s.max()):.2f}{extra}")
