@@ -20,6 +20,9 @@
 namespace cgic {
 namespace {
 
+CGIC_TRACE_DECL(pack)
+
+
 constexpr int PK_THREADS = 512;
 
 struct PackArgs {
@@ -468,6 +471,7 @@ __device__ __forceinline__ void pack_stream_entry(const PackArgs &a, int s, int 
         staged = true;
     }
     pdl_wait();  // the code table above is immutable; indices and masks come from the predecessor
+    CGIC_STAMP(pack, 2);
     pack_index_stream<ITEMS>(a, s, b, stage, s_enc, staged ? mbar : nullptr);
 }
 
@@ -482,6 +486,7 @@ __global__ void __launch_bounds__(PK_THREADS) pack_kernel(const PackArgs a)
     // coarse + mask CTAs, so that the second CTA of an SM is a short one
     const int lin = (int)(blockIdx.y * gridDim.x + blockIdx.x), nb = (int)gridDim.y;
     const int k = lin / nb, s = 2 - k, b = lin - k * nb;
+    CGIC_STAMP(pack, 0);
     pdl_trigger_step<2>();
     if (stream_present(a.mode, s)) {
         pack_stream_entry<ITEMS>(a, s, b, dyn, &mbar);   // waits for the predecessor grid inside
@@ -489,6 +494,7 @@ __global__ void __launch_bounds__(PK_THREADS) pack_kernel(const PackArgs a)
         pdl_wait();
         if (threadIdx.x == 0) a.sizes[b * 5 + s] = 0;
     }
+    CGIC_STAMP(pack, 1);
     if (s != 0) return;
     for (int ms = 3; ms < 5; ++ms) {
         if (!stream_present(a.mode, ms)) {

@@ -21,6 +21,7 @@
 #include "common.cuh"
 
 CGIC_TRACE_DECL(unpack)
+CGIC_TRACE_DECL(assemble)
 
 namespace cgic {
 namespace {
@@ -1231,9 +1232,12 @@ __global__ void __launch_bounds__(UP_THREADS, 3) unpack_decode_chained_kernel(co
 // re-assembly: one thread per quad, its own PDL-chained launch (see the note in cgic_unpack)
 __global__ void __launch_bounds__(256) unpack_assemble_kernel(const UnpackArgs a)
 {
+    CGIC_STAMP(assemble, 0);
     pdl_launch_dependents();
     pdl_wait();
+    CGIC_STAMP(assemble, 1);
     assemble_quad(a, blockIdx.y, (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    CGIC_STAMP(assemble, 2);
 }
 
 __global__ void __launch_bounds__(DEC_THREADS)

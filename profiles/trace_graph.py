@@ -65,3 +65,14 @@ for k in range(4):
         extra = (f" | tables {rel(np.median(rows[:,1])):.2f} chunk {rel(np.median(rows[:,2])):.2f} staged {rel(np.median(rows[:,3])):.2f} A0 {rel(np.median(rows[:,7])):.2f}"
                  f" A {rel(np.median(rows[:,4])):.2f} B {rel(np.median(rows[:,5])):.2f} end median {rel(np.median(e)):.2f} max {rel(e.max()):.2f}")
     print(f"decode {names[k]:6s} start min {rel(s.min()):.2f} median {rel(np.median(s)):.2f} max {rel(s.max()):.2f}{extra}")
+
+def unit(name, n):
+    b_ = np.zeros(1024 * 8, np.uint64)
+    assert getattr(ctypes.CDLL(cg._lib.LIB_PATH), "cgic_trace_" + name)(b_.ctypes.data_as(ctypes.c_void_p)) == 0
+    return b_.reshape(1024, 8)[:n].astype(np.float64)
+pk = unit("pack", 3 * B)
+for k, nm in enumerate(("fine", "medium", "coarse+masks")):
+    r = pk[k * B:(k + 1) * B]
+    print(f"pack {nm:13s} start median {rel(np.median(r[:,0])):.2f} max {rel(r[:,0].max()):.2f} | released {rel(np.median(r[:,2])):.2f} | stream done median {rel(np.median(r[:,1])):.2f} max {rel(r[:,1].max()):.2f}")
+asm_ = unit("assemble", 4 * B)
+print(f"assemble start min {rel(asm_[:,0].min()):.2f} median {rel(np.median(asm_[:,0])):.2f} max {rel(asm_[:,0].max()):.2f} | released median {rel(np.median(asm_[:,1])):.2f} max {rel(asm_[:,1].max()):.2f} | thread-0 done median {rel(np.median(asm_[:,2])):.2f} max {rel(asm_[:,2].max()):.2f}")
