@@ -40,6 +40,14 @@ def test_capture_reuses_warmup_workspaces_and_replays_bit_exact():
     for _ in range(2):
         g.replay()
     torch.cuda.synchronize()
-    for a, b in zip(eager, out):
-        assert torch.equal(a, b)
+    for i, (a, b) in enumerate(zip(eager, out)):
+        if i == 2:      # packed slots: only the first sizes[b, s] bytes of a slot are defined (the rest is torch.empty memory)
+            offs, _, _ = table.layout(h, w)
+            sz = out[3].cpu()
+            for img in range(B):
+                for st in range(5):
+                    lo, n = int(offs[st]), int(sz[img, st])
+                    assert torch.equal(a[img, lo:lo + n], b[img, lo:lo + n]), (img, st)
+        else:
+            assert torch.equal(a, b), i
     assert int(out[-1].abs().sum()) == 0
