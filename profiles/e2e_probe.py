@@ -22,8 +22,10 @@ def timeit(fn, n=200):
     t0 = time.perf_counter()
     for _ in range(n): fn()
     return 1e6 * (time.perf_counter() - t0) / n
-print("roundtrip_host us:", round(timeit(lambda: sess.roundtrip(zh, *mh)), 1))
-for parts in (1, 2, 4, 8):
+parts_list = tuple(int(x) for x in sys.argv[1].split(",")) if len(sys.argv) > 1 else (1, 2, 4, 8)
+if len(sys.argv) <= 1:
+    print("roundtrip_host us:", round(timeit(lambda: sess.roundtrip(zh, *mh)), 1))
+for parts in parts_list:
     views = sess.arena(parts)
     for v in views:
         r = v["images"]; v["z"].copy_(zh[r.start:r.stop])
