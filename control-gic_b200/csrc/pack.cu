@@ -475,27 +475,33 @@ __device__ __forceinline__ void pack_stream_entry(const PackArgs &a, int s, int 
     pack_index_stream<ITEMS>(a, s, b, stage, s_enc, staged ? mbar : nullptr);
 }
 
-// grid (3, B): CTA s packs index stream s of image b; CTA 0 (the coarse stream, by far the shortest) also packs the
-// two mask streams, so that a 64-image batch is 192 CTAs = one wave at two CTAs per SM.
+// grid (4, B): per image one CTA for each index stream and one for the two mask streams.  Every index-stream CTA costs
+// about the same whatever its stream's length (one tile: loads, scan, staging, barriers), so the mask streams riding
+// with the coarse CTA made that CTA the kernel's critical path by ~1.7 us (in-graph timeline, profiles/trace_graph.py);
+// a 64-image batch is 256 CTAs = still one wave at two CTAs per SM.
 template <int ITEMS>
 __global__ void __launch_bounds__(PK_THREADS) pack_kernel(const PackArgs a)
 {
     extern __shared__ __align__(128) unsigned char dyn[];
     __shared__ __align__(8) unsigned long long mbar;
-    // linear block order = hand-out order: the fine streams (4096 grid positions each) first, then medium, then the
-    // coarse + mask CTAs, so that the second CTA of an SM is a short one
+    // linear block order = hand-out order: the fine streams (4096 grid positions each) first, then medium, coarse, and
+    // the light mask CTAs last, so that the second CTA of an SM is a short one
     const int lin = (int)(blockIdx.y * gridDim.x + blockIdx.x), nb = (int)gridDim.y;
     const int k = lin / nb, s = 2 - k, b = lin - k * nb;
     CGIC_STAMP(pack, 0);
     pdl_trigger_step<2>();
-    if (stream_present(a.mode, s)) {
-        pack_stream_entry<ITEMS>(a, s, b, dyn, &mbar);   // waits for the predecessor grid inside
-    } else {
-        pdl_wait();
-        if (threadIdx.x == 0) a.sizes[b * 5 + s] = 0;
+    if (k < 3) {
+        if (stream_present(a.mode, s)) {
+            pack_stream_entry<ITEMS>(a, s, b, dyn, &mbar);   // waits for the predecessor grid inside
+        } else {
+            pdl_wait();
+            if (threadIdx.x == 0) a.sizes[b * 5 + s] = 0;
+        }
+        CGIC_STAMP(pack, 1);
+        return;
     }
-    CGIC_STAMP(pack, 1);
-    if (s != 0) return;
+    pdl_wait();
+    CGIC_STAMP(pack, 2);
     for (int ms = 3; ms < 5; ++ms) {
         if (!stream_present(a.mode, ms)) {
             if (threadIdx.x == 0) a.sizes[b * 5 + ms] = 0;
@@ -507,6 +513,7 @@ __global__ void __launch_bounds__(PK_THREADS) pack_kernel(const PackArgs a)
         pack_bit_stream(a.mask[lvl] + (int64_t)b * n, n, a.out + (int64_t)b * a.image_stride + a.slot_off[ms], a.slot_cap[ms],
                         a.sizes + b * 5 + ms);
     }
+    CGIC_STAMP(pack, 1);
 }
 
 // grid (3 * nslots, B): nslots CTAs per index stream (consecutive block ids); large token grids with <= 32-bit codes only
@@ -649,8 +656,8 @@ extern "C" int cgic_pack_ws(const int64_t *idx, const int32_t *m_c, const int32_
     }
     {
         CGIC_PROF("pack_kernel", as_stream(stream));
-        if (items == 8) CGIC_CUDA_CHECK(launch_pdl(pack_kernel<8>, dim3(3, B), dim3(PK_THREADS), smem, as_stream(stream), a));
-        else CGIC_CUDA_CHECK(launch_pdl(pack_kernel<1>, dim3(3, B), dim3(PK_THREADS), smem, as_stream(stream), a));
+        if (items == 8) CGIC_CUDA_CHECK(launch_pdl(pack_kernel<8>, dim3(4, B), dim3(PK_THREADS), smem, as_stream(stream), a));
+        else CGIC_CUDA_CHECK(launch_pdl(pack_kernel<1>, dim3(4, B), dim3(PK_THREADS), smem, as_stream(stream), a));
     }
     CGIC_LAUNCH_CHECK();
     return CGIC_OK;

@@ -70,8 +70,8 @@ def unit(name, n):
     b_ = np.zeros(1024 * 8, np.uint64)
     assert getattr(ctypes.CDLL(cg._lib.LIB_PATH), "cgic_trace_" + name)(b_.ctypes.data_as(ctypes.c_void_p)) == 0
     return b_.reshape(1024, 8)[:n].astype(np.float64)
-pk = unit("pack", 3 * B)
-for k, nm in enumerate(("fine", "medium", "coarse+masks")):
+pk = unit("pack", 4 * B)
+for k, nm in enumerate(("fine", "medium", "coarse", "masks")):
     r = pk[k * B:(k + 1) * B]
     print(f"pack {nm:13s} start median {rel(np.median(r[:,0])):.2f} max {rel(r[:,0].max()):.2f} | released {rel(np.median(r[:,2])):.2f} | stream done median {rel(np.median(r[:,1])):.2f} max {rel(r[:,1].max()):.2f}")
 asm_ = unit("assemble", 4 * B)
