@@ -470,8 +470,8 @@ def run_b200(args):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
 # capture (profiles/), filled in after each capture; None = not captured yet.
 NCU_TRAFFIC = {  # profiles/r1_kernels.txt (round 1; reads only: the writes stay in the 126 MB L2 within the capture)
-    "vq_warp_kernel": 4396800, "vq_fused_kernel": 4260352, "pack_kernel": 3516160, "unpack_decode_kernel": 250368,
-    "unpack_assemble_kernel": 288512}
+    "vq_warp_kernel": 4398080, "vq_fused_kernel": 4260352, "pack_kernel": 3516928, "unpack_decode_kernel": 248832,
+    "unpack_assemble_kernel": 289792}
 
 
 def algorithmic_bytes(B, h, w, stream_bytes):
