@@ -22,6 +22,16 @@ def load_npz(name):
     return dict(np.load(os.path.join(GOLDEN, name), allow_pickle=False))
 
 
+def big_case_names():
+    return sorted(os.path.basename(p)[4:-4] for p in glob.glob(os.path.join(GOLDEN, "big_*.npz")))
+
+
+def unpack_mask_bits(bits, shape):
+    """Inverse of np.packbits(mask.ravel()) for a mask of `shape`."""
+    n = int(np.prod(shape))
+    return np.unpackbits(bits)[:n].reshape(shape)
+
+
 def e2e_case_names():
     return sorted(os.path.basename(p)[4:-4] for p in glob.glob(os.path.join(GOLDEN, "e2e_*.npz")))
 

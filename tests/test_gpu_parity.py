@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import STREAMS, e2e_case_names, load_npz
+from conftest import STREAMS, big_case_names, e2e_case_names, load_npz
 
 pytestmark = pytest.mark.gpu
 
@@ -268,6 +268,47 @@ def test_e2e_golden(cg, tag, tmp_path):
     assert np.array_equal(quant.cpu().numpy(), g["quant_dec"])
     for lvl, arr in enumerate((mc, mm, mf)):
         assert np.array_equal(arr.cpu().numpy().astype(np.uint8), g[f"mask_dec{lvl}"][0])
+
+
+@pytest.mark.parametrize("tag", big_case_names())
+def test_big_golden(cg, tag):
+    """BASELINE-size fixtures from the unmodified reference (make_golden_big.py): config 1 (256x256), config 3 (512x768 at
+    its three ratios), two tiles of config 5.  Router, VQ (exhaustive AND indexed), pack, unpack: bit-exact."""
+    g = load_npz(f"big_{tag}.npz")
+    H, W = map(int, g["shape"])
+    h, w = H // 4, W // 4
+    mode = int(g["mode"])
+    c_ratio, m_ratio = map(float, g["ratios"])
+    masks, gate, ratios, rmode = cg.TripleGrainFixedEntropyRouter(c_ratio, m_ratio)(dev(g["e16"]), dev(g["e8"]))
+    assert rmode == mode
+    for lvl in range(3):
+        assert np.array_equal(np.packbits(masks[lvl].cpu().numpy().astype(np.uint8).ravel()), g[f"mask{lvl}_bits"]), lvl
+    if "x" in g:
+        e8, e16 = cg.entropy_pair(dev(g["x"]))
+        assert np.allclose(e8.cpu().numpy(), g["e8"], rtol=ENTROPY_RTOL, atol=1e-6)
+        assert np.allclose(e16.cpu().numpy(), g["e16"], rtol=ENTROPY_RTOL, atol=1e-6)
+        mixed = cg.ops.mask_mix(dev(g["hc"]), dev(g["hm"]), dev(g["hf"]), *masks)
+        assert hashlib.sha256(mixed.cpu().numpy().tobytes()).digest() == g["h_sha"].tobytes()
+    cb = dev(g["codebook"])
+    z = dev(g["z"])
+    for codebook in (cb, cg.ops.Codebook(cb)):
+        idx, zq, sq = cg.ops.vq_assign(z, codebook)
+        assert np.array_equal(idx.cpu().numpy(), g["ind"].astype(np.int64))
+        assert hashlib.sha256(zq.cpu().numpy().tobytes()).digest() == g["zq_sha"].tobytes()
+        assert np.isclose(1.25 * float(sq.item()) / g["z"].size, g["loss"], rtol=LOSS_RTOL)
+    t = cg.ops.HuffTable(g["counts"], g["order"])
+    packed, sizes = cg.ops.pack(idx, *masks, mode, t, h, w)
+    offs, caps, stride = t.layout(h, w)
+    blob, sz = packed.cpu().numpy()[0], sizes.cpu().numpy()[0]
+    for s, n in enumerate(STREAMS):
+        assert blob[offs[s]: offs[s] + sz[s]].tobytes() == g["file_" + n].tobytes(), n
+    assert int(sz.sum()) * 8 / (H * W) == float(g["bpp"])
+    mc, mm, mf, ind, quant, status = cg.ops.unpack(packed, sizes, mode, t, cb, h, w)
+    assert int(status.abs().sum()) == 0
+    assert np.array_equal(ind.cpu().numpy(), g["ind_dec"].astype(np.int64))
+    assert hashlib.sha256(quant.cpu().numpy().tobytes()).digest() == g["quant_dec_sha"].tobytes()
+    for lvl, arr in enumerate((mc, mm, mf)):
+        assert np.array_equal(np.packbits(arr.cpu().numpy().astype(np.uint8).ravel()), g[f"mask_dec{lvl}_bits"]), lvl
 
 
 class _StubEncoder(torch.nn.Module):

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import STREAMS, e2e_case_names, load_npz
+from conftest import STREAMS, big_case_names, e2e_case_names, load_npz, unpack_mask_bits
 from oracle import oracle as orc
 from oracle import refport
 
@@ -148,6 +148,40 @@ def test_e2e_against_reference_run(tag, tmp_path):
                                                                    masks, table, rev, str(tmp_path))
         assert pbpp == float(g["bpp"]) and sizes == [len(s) for s in streams]
         assert np.array_equal(pind_dec.numpy()[0], uind) and np.array_equal(pq.numpy()[0], uq)
+
+
+@pytest.mark.parametrize("tag", big_case_names())
+def test_big_cases_against_reference_run(tag):
+    """BASELINE-size fixtures (tests/golden/make_golden_big.py: 256x256, 512x768 at the three config-3 ratios, the
+    768x496 / 576x496 tiles of config 5): router, VQ, pack, unpack of the oracle == the unmodified reference's run."""
+    g = load_npz(f"big_{tag}.npz")
+    H, W = map(int, g["shape"])
+    h, w = H // 4, W // 4
+    mode = int(g["mode"])
+    c_ratio, m_ratio = map(float, g["ratios"])
+    mc, mm, mf, omode = orc.router(g["e16"], g["e8"], c_ratio, m_ratio)
+    assert omode == mode
+    for lvl, arr in enumerate((mc, mm, mf)):
+        assert np.array_equal(np.packbits(arr.astype(np.uint8).ravel()), g[f"mask{lvl}_bits"]), lvl
+    if "x" in g:   # the 256x256 case also pins Entropy and the mask-mix
+        assert np.allclose(orc.entropy(g["x"], 8), g["e8"], rtol=2e-5, atol=1e-6)
+        assert np.allclose(orc.entropy(g["x"], 16), g["e16"], rtol=2e-5, atol=1e-6)
+        mix = orc.mask_mix(g["hc"], g["hm"], g["hf"], mc, mm, mf)
+        assert hashlib.sha256(mix.tobytes()).digest() == g["h_sha"].tobytes()
+    zq, loss, idx = orc.vq_assign(g["z"], g["codebook"])
+    assert np.array_equal(idx, g["ind"].astype(np.int64))
+    assert hashlib.sha256(zq.tobytes()).digest() == g["zq_sha"].tobytes()
+    assert np.isclose(loss, g["loss"], rtol=1e-5)
+    t = orc.huff_build(g["counts"], g["order"])
+    streams = orc.pack_image(t, idx.reshape(h, w), mc[0, 0], mm[0, 0], mf[0, 0], mode)
+    for s, n in enumerate(STREAMS):
+        assert streams[s] == g["file_" + n].tobytes(), n
+    assert orc.bpp_of(streams, H, W) == float(g["bpp"])
+    umc, umm, umf, uind, uq = orc.unpack_image(t, streams, h, w, mode, g["codebook"])
+    assert np.array_equal(uind, g["ind_dec"][0].astype(np.int64))
+    assert hashlib.sha256(np.ascontiguousarray(uq[None]).tobytes()).digest() == g["quant_dec_sha"].tobytes()
+    for lvl, arr in enumerate((umc, umm, umf)):
+        assert np.array_equal(np.packbits(arr.astype(np.uint8).ravel()), g[f"mask_dec{lvl}_bits"]), lvl
 
 
 def test_framing_properties():

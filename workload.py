@@ -2,8 +2,10 @@
 
 codebook ~ U(-1/1024, 1/1024) [1024,4] (= the reference's init, quantize.py:26); counters
 floor(-ln(U)*1000) (KAT5 recipe); entropy maps ~ U[0,1); latent heads = codebook[randint] +
-1e-4*N(0,1) mixed per granularity mask exactly like vqvae_blocks.py:364-366, so z has the
-coarse / medium block structure of a real encoder output.  Everything comes from CPU generators
+1e-4*N(0,1) (absolute: about a third of the mean spacing between neighbouring codes, so a latent
+is often nearer to another code than to the one it was drawn around, and ~16 % of the latents
+fall outside the codebook's bounding box -- still inside the search index's padded grid) mixed per granularity mask exactly like
+vqvae_blocks.py:364-366, so z has the coarse / medium block structure of a real encoder output.  Everything comes from CPU generators
 with fixed seeds, so every rank / run / box sees the same numbers.
 """
 from __future__ import annotations
@@ -49,7 +51,7 @@ def heads(B: int, H: int, W: int, codebook: torch.Tensor, seed: int, first_image
         for lvl, div in enumerate((16, 8, 4)):
             h, w = H // div, W // div
             idx = torch.randint(0, codebook.shape[0], (h * w,), generator=g)
-            v = codebook[idx] + 1e-4 * torch.randn(h * w, 4, generator=g) / K
+            v = codebook[idx] + 1e-4 * torch.randn(h * w, 4, generator=g)          # SURVEY.md 8(d), literally
             out[lvl].append(v.view(h, w, 4).permute(2, 0, 1))
     return [torch.stack(v).contiguous() for v in out]
 
