@@ -36,6 +36,8 @@ _SIGNATURES = {
     "cgic_codebook_free": (None, [c_void_p]),
     "cgic_codebook_update": (c_int, [c_void_p, c_void_p, c_void_p]),
     "cgic_codebook_stats_host": (c_int, [c_void_p, c_void_p]),
+    "cgic_codebook_check": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "cgic_codebook_is_stale": (c_int, [c_void_p]),
     "cgic_vq_assign_indexed": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_size_t, c_void_p]),
     "cgic_vq_count": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p]),

@@ -308,6 +308,40 @@ __global__ void __launch_bounds__(256) cb_cells_kernel(unsigned char *__restrict
     if (tid == 0) atomicMax(&hdr->max_count, count);
 }
 
+// ---- staleness guard: is the live weight tensor still the one the index was built from? -------
+// Writes through `weight.data` (the reference's own LitEma.copy_to / restore, CGIC/models/ema.py:51,76) do not move
+// torch's version counter, so the host cannot know.  One CTA compares the live rows with the blob's copy bit for bit;
+// on a mismatch it refreshes the copy and e^2, marks the index unusable (every latent then takes the exhaustive path
+// of vq_warp_kernel -- same results, slower) and raises a flag in mapped host memory that the next call polls.
+__global__ void __launch_bounds__(1024, 1)
+cb_check_kernel(const float *__restrict__ live, int K, unsigned char *__restrict__ blob, int generation, volatile int *stale_flag)
+{
+    __shared__ int s_diff;
+    const CbLayout L = cb_layout(K);
+    CbHeader *hdr = reinterpret_cast<CbHeader *>(blob);
+    uint4 *cb = reinterpret_cast<uint4 *>(blob + L.cb);
+    float *e2 = reinterpret_cast<float *>(blob + L.e2);
+    if (threadIdx.x == 0) s_diff = 0;
+    __syncthreads();
+    bool diff = false;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const uint4 a = reinterpret_cast<const uint4 *>(live)[k], b = cb[k];
+        diff |= a.x != b.x || a.y != b.y || a.z != b.z || a.w != b.w;
+    }
+    if (diff) s_diff = 1;
+    __syncthreads();
+    if (!s_diff) return;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const float4 e = reinterpret_cast<const float4 *>(live)[k];
+        reinterpret_cast<float4 *>(cb)[k] = e;
+        e2[k] = sumsq4f(e.x, e.y, e.z, e.w);
+    }
+    if (threadIdx.x == 0) {
+        hdr->valid = 0;
+        *stale_flag = generation;
+    }
+}
+
 }  // namespace
 }  // namespace cgic
 
@@ -319,6 +353,9 @@ struct cgic_codebook {
     unsigned char *blob = nullptr;
     size_t bytes = 0;
     bool built = false;
+    int generation = 0;          // bumped by every update; a check kernel reports staleness by writing its generation
+    int *stale_host = nullptr;   // mapped, pinned: written by cb_check_kernel, polled by cgic_codebook_is_stale
+    int *stale_dev = nullptr;
 };
 
 extern "C" int cgic_codebook_create(int K, cgic_codebook **out)
@@ -331,8 +368,15 @@ extern "C" int cgic_codebook_create(int K, cgic_codebook **out)
     cb->bytes = cb_layout(K).total;
     cudaError_t e = cudaGetDevice(&cb->device);
     if (e == cudaSuccess) e = cudaMalloc(&cb->blob, cb->bytes);
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&cb->stale_host), sizeof(int), cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+        *cb->stale_host = -1;
+        e = cudaHostGetDevicePointer(reinterpret_cast<void **>(&cb->stale_dev), cb->stale_host, 0);
+    }
     if (e != cudaSuccess) {
         set_error("cgic_codebook_create: %s", cudaGetErrorString(e));
+        if (cb->blob) cudaFree(cb->blob);
+        if (cb->stale_host) cudaFreeHost(cb->stale_host);
         delete cb;
         return e == cudaErrorMemoryAllocation ? CGIC_ENOMEM : CGIC_ECUDA;
     }
@@ -344,6 +388,7 @@ extern "C" void cgic_codebook_free(cgic_codebook *cb)
 {
     if (!cb) return;
     if (cb->blob) cudaFree(cb->blob);
+    if (cb->stale_host) cudaFreeHost(cb->stale_host);
     delete cb;
 }
 
@@ -354,10 +399,9 @@ extern "C" int cgic_codebook_update(cgic_codebook *cb, const float *codebook, cg
     cudaStream_t stream = as_stream(stream_);
     const int K = cb->K;
     const size_t smem = (size_t)K * (16 + 4);
-    static bool attr_done = false;
-    if (!attr_done) {
-        CGIC_CUDA_CHECK(cudaFuncSetAttribute(cb_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CB_MAX_K * (16 + 4)));
-        attr_done = true;
+    {
+        const int rc = ensure_smem((const void *)cb_cells_kernel, CB_MAX_K * (16 + 4));
+        if (rc) return rc;
     }
     {
         CGIC_PROF("cb_grid_kernel", stream);
@@ -370,7 +414,27 @@ extern "C" int cgic_codebook_update(cgic_codebook *cb, const float *codebook, cg
     }
     CGIC_LAUNCH_CHECK();
     cb->built = true;
+    ++cb->generation;  // reports of check kernels launched before this rebuild no longer count
     return CGIC_OK;
+}
+
+extern "C" int cgic_codebook_check(cgic_codebook *cb, const float *codebook, cgic_stream_t stream_)
+{
+    CGIC_REQUIRE(cb && codebook && cb->built, CGIC_EINVAL, "cgic_codebook_check: no built codebook");
+    CGIC_REQUIRE((reinterpret_cast<uintptr_t>(codebook) & 15) == 0, CGIC_EINVAL, "cgic_codebook_check: codebook must be 16-byte aligned");
+    cudaStream_t stream = as_stream(stream_);
+    {
+        CGIC_PROF("cb_check_kernel", stream);
+        cb_check_kernel<<<1, 1024, 0, stream>>>(codebook, cb->K, cb->blob, cb->generation, cb->stale_dev);
+    }
+    CGIC_LAUNCH_CHECK();
+    return CGIC_OK;
+}
+
+extern "C" int cgic_codebook_is_stale(const cgic_codebook *cb)
+{
+    if (!cb || !cb->built) return CGIC_EINVAL;
+    return *reinterpret_cast<volatile int *>(cb->stale_host) == cb->generation ? 1 : 0;
 }
 
 extern "C" int cgic_codebook_stats_host(const cgic_codebook *cb, int32_t out[4])

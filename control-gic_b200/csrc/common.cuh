@@ -161,6 +161,12 @@ PackLayout make_pack_layout(int max_len, int h, int w);
 
 static inline cudaStream_t as_stream(cgic_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Per-DEVICE one-time set-up (cudaFuncSetAttribute and the SM count belong to a device, not to the process):
+// ensure_smem opts kernel `fn` in to `bytes` of dynamic shared memory on the current device (no-op at <= 48 KB or when
+// already granted there); device_sm_count caches cudaDevAttrMultiProcessorCount of the current device.
+int ensure_smem(const void *fn, size_t bytes);
+int device_sm_count(int *n_sm);
+
 // Per-kernel device timing (cgic_prof_*): while enabled, every kernel launch of the library is
 // bracketed by two CUDA events recorded on the launching stream.  Off by default; costs one
 // relaxed load per launch when off.

@@ -12,9 +12,6 @@
 // global memory sees every output word exactly once and needs no pre-zeroing.
 // Framing (must be byte exact): [pad count byte][payload, MSB first][pad zero bits],
 // pad = 8 - nbits % 8 in 1..8, empty symbol list -> 0 bytes.
-#include <map>
-#include <mutex>
-
 #include "common.cuh"
 
 namespace cgic {
@@ -569,20 +566,6 @@ size_t pack_smem_bytes(const DevTable &T, int items)
     size_t b = ((size_t)PK_THREADS * items * T.max_len / 32 + 4) * 4;
     if (T.enc) b += (size_t)((T.K + 1) / 2 * 2) * 8;
     return b;
-}
-
-int ensure_smem(const void *fn, size_t bytes)
-{
-    static std::mutex mu;
-    static std::map<const void *, size_t> granted;
-    if (bytes <= 48 * 1024) return CGIC_OK;
-    std::lock_guard<std::mutex> lock(mu);
-    size_t &g = granted[fn];
-    if (bytes > g) {
-        CGIC_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        g = bytes;
-    }
-    return CGIC_OK;
 }
 
 }  // namespace

@@ -326,7 +326,9 @@ extern "C" int cgic_router(const float *e16, const float *e8, int B, int h16, in
     {
         CGIC_PROF("router_select_kernel", stream);
         const int64_t n8_cta = (int64_t)(per_image ? 1 : B) * 4 * h16 * w16;
-        const int key_cache = n8_cta <= 12288;  // 48 KB of keys
+        // key cache: static (s_hist, s_state) + dynamic shared memory must stay within the 48 KB a kernel gets without
+        // opting in, so 11 776 keys (46 KB) at most -- a 1024 x 768 image has 12 288 medium cells and goes uncached
+        const int key_cache = n8_cta <= 11776;
         CGIC_CUDA_CHECK(launch_pdl(router_select_kernel, dim3(per_image ? B : 1), dim3(RT_THREADS), key_cache ? (size_t)n8_cta * 4 : 0, stream, e16, e8, B,
                                    h16, w16, mode, k_c, k_m, per_image, m_c, m_m, fuse_fine ? m_f : (int32_t *)nullptr, gate_out, key_cache));
     }

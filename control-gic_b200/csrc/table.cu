@@ -62,6 +62,35 @@ ProfScope::~ProfScope()
     cudaEventRecord(g_prof[slot].e1, stream);
 }
 
+int ensure_smem(const void *fn, size_t bytes)
+{
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, size_t> granted;
+    if (bytes <= 48 * 1024) return CGIC_OK;
+    int dev = -1;
+    CGIC_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &g = granted[{dev, fn}];
+    if (bytes > g) {
+        CGIC_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        g = bytes;
+    }
+    return CGIC_OK;
+}
+
+int device_sm_count(int *n_sm)
+{
+    static std::mutex mu;
+    static std::map<int, int> count;
+    int dev = -1;
+    CGIC_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    int &c = count[dev];
+    if (!c) CGIC_CUDA_CHECK(cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev));
+    *n_sm = c;
+    return CGIC_OK;
+}
+
 PackLayout make_pack_layout(int max_len, int h, int w)
 {
     PackLayout L;
@@ -94,11 +123,13 @@ struct cgic_table {
     size_t lut_pad = 0;
     std::vector<int32_t> child;  // 2 * (2K-1)
     std::vector<std::string> code;
-    // device copy (one device per process in this design)
-    std::mutex mu;
-    int device = -1;
-    void *dev_blob = nullptr;
-    cgic::DevTable view{};
+    // device copies, one per device the table was uploaded to (immutable once made)
+    struct DevCopy {
+        void *blob = nullptr;
+        cgic::DevTable view{};
+    };
+    mutable std::mutex mu;
+    std::map<int, DevCopy> dev;
 };
 
 namespace {
@@ -304,7 +335,13 @@ int cgic_huff_build(const int64_t *freq, const int32_t *order, int K, cgic_table
 void cgic_huff_free(cgic_table *t)
 {
     if (!t) return;
-    if (t->dev_blob) cudaFree(t->dev_blob);
+    int cur = -1;
+    const bool have_cur = cudaGetDevice(&cur) == cudaSuccess;
+    for (auto &kv : t->dev) {
+        if (!kv.second.blob) continue;
+        if (cudaSetDevice(kv.first) == cudaSuccess) cudaFree(kv.second.blob);
+    }
+    if (have_cur && !t->dev.empty()) cudaSetDevice(cur);
     delete t;
 }
 
@@ -332,8 +369,7 @@ int cgic_huff_upload(cgic_table *t)
     std::lock_guard<std::mutex> lock(t->mu);
     int dev = -1;
     CGIC_CUDA_CHECK(cudaGetDevice(&dev));
-    if (t->dev_blob && t->device == dev) return CGIC_OK;
-    CGIC_REQUIRE(!t->dev_blob, CGIC_EINVAL, "cgic_huff_upload: table already lives on device %d", t->device);
+    if (t->dev.count(dev)) return CGIC_OK;
     auto pad = [](size_t n) { return (n + 255) / 256 * 256; };
     const size_t b_len = pad(t->len.size() * 2), b_off = pad(t->off.size() * 4), b_pool = pad(t->pool.size() * 4),
                  b_lut = pad(t->dec.size() * 4), b_child = pad(t->child.size() * 4), b_lut2 = pad(t->enc.size() * 8);
@@ -366,22 +402,25 @@ int cgic_huff_upload(cgic_table *t)
         return CGIC_ECUDA;
     }
     auto *base = static_cast<unsigned char *>(blob);
-    t->view.K = t->K;
-    t->view.max_len = t->max_len;
-    t->view.lut_bits = t->lut_bits;
-    t->view.root = t->root;
-    t->view.len = reinterpret_cast<const uint16_t *>(base + o_len);
-    t->view.off = reinterpret_cast<const uint32_t *>(base + o_off);
-    t->view.pool = reinterpret_cast<const uint32_t *>(base + o_pool);
-    t->view.lut = reinterpret_cast<const uint32_t *>(base + o_lut);
-    t->view.child = reinterpret_cast<const int32_t *>(base + o_child);
-    t->view.lut2 = t->view.lut + t->lut_pad;
-    t->view.lut_pad = (uint32_t)t->lut_pad;
+    cgic::DevTable v{};
+    v.K = t->K;
+    v.max_len = t->max_len;
+    v.lut_bits = t->lut_bits;
+    v.root = t->root;
+    v.len = reinterpret_cast<const uint16_t *>(base + o_len);
+    v.off = reinterpret_cast<const uint32_t *>(base + o_off);
+    v.pool = reinterpret_cast<const uint32_t *>(base + o_pool);
+    v.lut = reinterpret_cast<const uint32_t *>(base + o_lut);
+    v.child = reinterpret_cast<const int32_t *>(base + o_child);
+    v.lut2 = v.lut + t->lut_pad;
+    v.lut_pad = (uint32_t)t->lut_pad;
     // stage lut + lut2 together when that stays small, else only the first level
-    t->view.dec_stage_words = (uint32_t)(t->dec.size() * 4 <= 64 * 1024 ? t->dec.size() : t->lut_pad);
-    t->view.enc = t->enc.empty() ? nullptr : reinterpret_cast<const uint2 *>(base + o_lut2);
-    t->dev_blob = blob;
-    t->device = dev;
+    v.dec_stage_words = (uint32_t)(t->dec.size() * 4 <= 64 * 1024 ? t->dec.size() : t->lut_pad);
+    v.enc = t->enc.empty() ? nullptr : reinterpret_cast<const uint2 *>(base + o_lut2);
+    cgic_table::DevCopy copy;
+    copy.blob = blob;
+    copy.view = v;
+    t->dev[dev] = copy;
     return CGIC_OK;
 }
 
@@ -413,9 +452,10 @@ int table_device_view(const cgic_table *t, DevTable *out)
     CGIC_REQUIRE(t, CGIC_EINVAL, "null Huffman table");
     int dev = -1;
     CGIC_CUDA_CHECK(cudaGetDevice(&dev));
-    CGIC_REQUIRE(t->dev_blob && t->device == dev, CGIC_EINVAL,
-                 "Huffman table is not uploaded to device %d (call cgic_huff_upload first)", dev);
-    *out = t->view;
+    std::lock_guard<std::mutex> lock(t->mu);
+    const auto it = t->dev.find(dev);
+    CGIC_REQUIRE(it != t->dev.end(), CGIC_EINVAL, "Huffman table is not uploaded to device %d (call cgic_huff_upload first)", dev);
+    *out = it->second.view;
     return CGIC_OK;
 }
 

@@ -97,6 +97,7 @@ struct UnpackArgs {
     const int32_t *sizes;
     int64_t image_stride;
     int64_t slot_off[5];
+    int64_t slot_cap[5];
     int mode;
     Geo g;
     DevTable T;
@@ -1028,9 +1029,12 @@ __device__ __forceinline__ void unpack_decode_cta(const UnpackArgs &a, unsigned 
         const uint32_t *lut2 = nullptr;
         if (stream_present(a.mode, s)) lut2 = stage_decode_tables(a.T, s_dec, mbar_p);
         pdl_wait();
-        const int nbytes = stream_present(a.mode, s) ? sz[s] : 0;
+        int nbytes = stream_present(a.mode, s) ? sz[s] : 0;
         CGIC_STAMP(unpack, 1);
-        if (nbytes > 0) {
+        if (nbytes < 0 || nbytes > a.slot_cap[s]) {  // a size no packer can have produced: never read past the slot
+            nbytes = 0;
+            cnt = slot == 0 ? -2 : DEC_NOT_MINE;
+        } else if (nbytes > 0) {
             // a stream whose payload may exceed the chain's capacity (only a corrupt size can) is decoded by slot 0 alone
             const bool chained = MULTI && nslots > 1 && ((int64_t)nbytes * 8 + DEC_SUB_BITS - 1) / DEC_SUB_BITS <= (int64_t)a.ws.max_chunks * a.ch;
             const DecChain chain{chained ? a.ws.chain + ((int64_t)b * 3 + s) * a.ws.max_chunks : nullptr, chained ? slot : 0, chained ? nslots : 1};
@@ -1312,7 +1316,10 @@ extern "C" int cgic_unpack(const uint8_t *bytes, const int32_t *sizes, int B, in
     a.bytes = bytes;
     a.sizes = sizes;
     a.image_stride = L.stride;
-    for (int s = 0; s < 5; ++s) a.slot_off[s] = L.off[s];
+    for (int s = 0; s < 5; ++s) {
+        a.slot_off[s] = L.off[s];
+        a.slot_cap[s] = L.cap[s];
+    }
     a.mode = mode;
     a.codebook = codebook;
     a.mc_out = mc_out;
@@ -1335,12 +1342,10 @@ extern "C" int cgic_unpack(const uint8_t *bytes, const int32_t *sizes, int B, in
     const size_t mask_bytes = (size_t)(((a.g.n16 / 8 + 2 + 15) & ~15) + ((a.g.n8 / 8 + 2 + 15) & ~15));
     a.mask_stage = mask_bytes <= 96 * 1024;
     const size_t smem = std::max(dec_bytes, a.mask_stage ? mask_bytes : (size_t)0);
-    static bool smem_opt_in = false;  // static + dynamic shared memory may exceed the 48 KB default
-    if (!smem_opt_in) {
-        CGIC_CUDA_CHECK(cudaFuncSetAttribute(unpack_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
-        CGIC_CUDA_CHECK(cudaFuncSetAttribute(unpack_decode_chained_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
-        smem_opt_in = true;
-    }
+    // static + dynamic shared memory may exceed the 48 KB default
+    rc = ensure_smem((const void *)unpack_decode_kernel, 180 * 1024);
+    if (!rc) rc = ensure_smem((const void *)unpack_decode_chained_kernel, 180 * 1024);
+    if (rc) return rc;
     // Two PDL-chained launches.  Fusing the re-assembly into the decode kernel was measured on B200 (B = 64, 256^2,
     // decode + re-assembly per step) and lost both ways: as thread-block clusters of one image's CTAs with a cluster
     // barrier 36.5 us, as "the last CTA of an image to finish re-assembles it" (ticket) 30.2 us, against 27.9 us here --
@@ -1370,11 +1375,8 @@ extern "C" int cgic_huff_decode(const uint8_t *bytes, int64_t nbytes, const cgic
     if (rc) return rc;
     const int ch = cand_chunk_subs(T.max_len);
     const size_t smem = decode_smem_bytes(T, ch);
-    static bool smem_opt_in = false;
-    if (!smem_opt_in) {
-        CGIC_CUDA_CHECK(cudaFuncSetAttribute(huff_decode_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
-        smem_opt_in = true;
-    }
+    rc = ensure_smem((const void *)huff_decode_single_kernel, 180 * 1024);
+    if (rc) return rc;
     huff_decode_single_kernel<<<1, DEC_THREADS, smem, as_stream(stream)>>>(bytes, nbytes, T, symbols_out, cap, count_out, ch);
     CGIC_LAUNCH_CHECK();
     return CGIC_OK;

@@ -811,13 +811,11 @@ static int vq_launch(const char *who, const float *z, int B, int h, int w, const
     int32_t *counters = static_cast<int32_t *>(workspace);
     double *partials = reinterpret_cast<double *>(static_cast<unsigned char *>(workspace) + 256);
 
-    static int n_sm = 0;
-    if (!n_sm) {
-        int dev = 0, sm = 0;
-        CGIC_CUDA_CHECK(cudaGetDevice(&dev));
-        CGIC_CUDA_CHECK(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
-        CGIC_CUDA_CHECK(cudaFuncSetAttribute(vq_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vq_smem_bytes(VQ_MAX_K)));
-        n_sm = sm;
+    int n_sm = 0;
+    {
+        int rc = device_sm_count(&n_sm);
+        if (!rc) rc = ensure_smem((const void *)vq_fused_kernel, vq_smem_bytes(VQ_MAX_K));
+        if (rc) return rc;
     }
     const int Kpad = (K + VQ_CHUNK - 1) / VQ_CHUNK * VQ_CHUNK;
     const size_t smem = vq_smem_bytes(Kpad);
@@ -863,13 +861,11 @@ extern "C" int cgic_vq_assign_indexed(const float *z, int B, int h, int w, const
                  workspace_bytes, cgic_vq_workspace_bytes(n));
     int32_t *counters = static_cast<int32_t *>(workspace);
     double *partials = reinterpret_cast<double *>(static_cast<unsigned char *>(workspace) + 256);
-    static int n_sm = 0;
-    if (!n_sm) {
-        int dev = 0, sm = 0;
-        CGIC_CUDA_CHECK(cudaGetDevice(&dev));
-        CGIC_CUDA_CHECK(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
-        CGIC_CUDA_CHECK(cudaFuncSetAttribute(vq_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vqw_smem_bytes(VQ_MAX_K)));
-        n_sm = sm;
+    int n_sm = 0;
+    {
+        int rc = device_sm_count(&n_sm);
+        if (!rc) rc = ensure_smem((const void *)vq_warp_kernel, vqw_smem_bytes(VQ_MAX_K));
+        if (rc) return rc;
     }
     const int tiles_x = (w + 31) / 32, tiles_y = (h + 3) / 4;
     const int64_t n_tiles = (int64_t)B * tiles_x * tiles_y;

@@ -54,14 +54,19 @@ class ReferenceEncoderHeads(nn.Module):
         return taps["c"], taps["m"], taps["f"]
 
 
-def _heads(encoder, x, e16, e8):
-    if hasattr(encoder, "forward_heads"):
-        try:
-            return encoder.forward_heads(x, e16, e8)
-        except TypeError:
-            return encoder.forward_heads(x)
-    raise TypeError("encoder must provide forward_heads(x) -> (h_coarse, h_medium, h_fine); wrap a reference "
-                    "Encoder in ReferenceEncoderHeads")
+def _heads_arity(encoder) -> int:
+    """How many positional arguments `encoder.forward_heads` takes: 3 = (x, e16, e8) like the reference Encoder's
+    forward, 1 = (x).  Decided once from the signature (no try / except around the CNN: an error raised inside it
+    must surface as it is, not trigger a second run of the whole encoder)."""
+    import inspect
+    if not hasattr(encoder, "forward_heads"):
+        raise TypeError("encoder must provide forward_heads(x[, e16, e8]) -> (h_coarse, h_medium, h_fine); wrap a reference "
+                        "Encoder in ReferenceEncoderHeads")
+    params = [p for p in inspect.signature(encoder.forward_heads).parameters.values()
+              if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)]
+    if any(p.kind == p.VAR_POSITIONAL for p in inspect.signature(encoder.forward_heads).parameters.values()):
+        return 3
+    return 3 if len(params) >= 3 else 1
 
 
 class CGIC(nn.Module):
@@ -77,6 +82,7 @@ class CGIC(nn.Module):
                              "ReferenceEncoderHeads(Encoder(**ddconfig)) and Decoder(zq_ch=embed_dim, **ddconfig)")
         self.encoder = encoder if hasattr(encoder, "forward_heads") else ReferenceEncoderHeads(encoder)
         self.decoder = decoder
+        self._heads_arity = _heads_arity(self.encoder)
         if learning_rate is not None:
             self.learning_rate = learning_rate
         self.quantize = VectorQuantizer(n_embed, embed_dim, beta=0.25, remap=remap, sane_index_shape=sane_index_shape)
@@ -109,7 +115,10 @@ class CGIC(nn.Module):
 
     def encode(self, x, per_image: bool = False):
         x_entropy_p8, x_entropy_p16 = entropy_pair(x)
-        h_coarse, h_medium, h_fine = _heads(self.encoder, x, x_entropy_p16, x_entropy_p8)
+        if self._heads_arity == 3:
+            h_coarse, h_medium, h_fine = self.encoder.forward_heads(x, x_entropy_p16, x_entropy_p8)
+        else:
+            h_coarse, h_medium, h_fine = self.encoder.forward_heads(x)
         grain_mask, gate, ratios, mode = self._router(per_image)(x_entropy_p16, x_entropy_p8)
         # vqvae_blocks.py:357-359 (quirk Q6: argmax over the width-concatenated axis; kept as is)
         grain_indices = gate.permute(0, 3, 1, 2).argmax(dim=1)

@@ -7,6 +7,7 @@ tensors.  Inputs must be CUDA tensors -- there is no CPU path.
 from __future__ import annotations
 
 import ctypes as C
+import warnings
 from typing import Optional, Sequence, Tuple
 
 import numpy as np
@@ -36,6 +37,25 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _on_tensor_device(fn):
+    """Runs `fn` with the device of its first CUDA tensor argument current, so that the launch, torch's current stream
+    and the per-device set-up inside the library (shared-memory opt-ins, uploaded tables) all refer to the device the
+    data lives on -- not to whatever device happens to be current in the caller."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        for a in args:
+            dev = a.device if isinstance(a, torch.Tensor) else getattr(a, "device", None)
+            if isinstance(dev, torch.device) and dev.type == "cuda":
+                if dev.index is not None and dev.index != torch.cuda.current_device():
+                    with torch.cuda.device(dev):
+                        return fn(*args, **kwargs)
+                break
+        return fn(*args, **kwargs)
+    return wrapper
+
+
 def _p(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -58,7 +78,7 @@ class HuffTable:
         self._free = lib().cgic_huff_free          # bound now: module globals may be gone at interpreter exit
         self.K = int(f.shape[0])
         self.max_len = lib().cgic_huff_max_len(self._h)
-        self._uploaded_on = None
+        self._uploaded_on = set()
         self._layouts = {}
 
     def __del__(self):
@@ -85,9 +105,9 @@ class HuffTable:
 
     def upload(self) -> "HuffTable":
         dev = torch.cuda.current_device()
-        if self._uploaded_on != dev:
+        if dev not in self._uploaded_on:          # one immutable copy per device
             check(lib().cgic_huff_upload(self._h), "cgic_huff_upload")
-            self._uploaded_on = dev
+            self._uploaded_on.add(dev)
         return self
 
     def stream_capacity(self, n_symbols: int) -> int:
@@ -109,6 +129,8 @@ class HuffTable:
 # a1  VQ
 # --------------------------------------------------------------------------------------------
 _ws_cache = {}
+_WS_PER_OP = 8          # scratch buffers kept per (op, device): one per recently used stream
+_warned_alias = False
 
 
 def _workspace(tag: str, nbytes: int, device: torch.device) -> torch.Tensor:
@@ -123,12 +145,22 @@ def _workspace(tag: str, nbytes: int, device: torch.device) -> torch.Tensor:
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         if torch.cuda.is_current_stream_capturing():
-            for (t, d, _), b in reversed(list(_ws_cache.items())):
+            for (t, d, st), b in reversed(list(_ws_cache.items())):
                 if t == tag and d == device.index and b.numel() >= nbytes:
+                    global _warned_alias
+                    if not _warned_alias:
+                        _warned_alias = True
+                        warnings.warn(f"cgic_b200.ops: CUDA-graph capture of '{tag}' reuses the scratch buffer of stream {st:#x}; "
+                                      "do not run that stream's eager calls concurrently with replays of this graph "
+                                      "(warm up on the capture stream to give the graph a buffer of its own)")
                     _ws_cache[key] = b
                     return b
         buf = torch.zeros(max(nbytes, 256), dtype=torch.uint8, device=device)   # cgic_vq_assign wants its ticket zeroed once
         _ws_cache[key] = buf
+        # bounded: streams come and go (torch.cuda.Stream() per request, graph captures); keep the newest few per op and device
+        mine = [k for k in _ws_cache if k[0] == tag and k[1] == device.index]
+        for k in mine[:-_WS_PER_OP]:
+            del _ws_cache[k]
     return buf
 
 
@@ -162,8 +194,19 @@ class Codebook:
         w = _cuda(weight.detach(), torch.float32, "codebook")
         if tuple(w.shape) != (self.K, 4) or w.device != self.device:
             raise ValueError(f"codebook {tuple(w.shape)} on {w.device} does not match the prepared [{self.K}, 4] on {self.device}")
-        check(lib().cgic_codebook_update(self._h, w.data_ptr(), _stream()), "cgic_codebook_update")
+        with torch.cuda.device(self.device):
+            check(lib().cgic_codebook_update(self._h, w.data_ptr(), _stream()), "cgic_codebook_update")
         return self
+
+    def check(self, weight: torch.Tensor) -> None:
+        """Enqueue the staleness guard against the live weights (no sync; see cgic_codebook_check)."""
+        w = _cuda(weight.detach(), torch.float32, "codebook")
+        with torch.cuda.device(self.device):
+            check(lib().cgic_codebook_check(self._h, w.data_ptr(), _stream()), "cgic_codebook_check")
+
+    def is_stale(self) -> bool:
+        """True once a check() since the last update() found the weights changed (host flag, no sync)."""
+        return lib().cgic_codebook_is_stale(self._h) == 1
 
     def stats(self) -> dict:
         """{valid, cells, max_list, overflow_cells} (synchronises)."""
@@ -172,6 +215,7 @@ class Codebook:
         return dict(valid=int(out[0]), cells=int(out[1]), max_list=int(out[2]), overflow_cells=int(out[3]))
 
 
+@_on_tensor_device
 def vq_assign(z: torch.Tensor, codebook, want_zq: bool = True, want_sqerr: bool = True):
     """quantize.py:69-98 -> (idx int64 [B*h*w], z_q fp32 NCHW or None, sqerr float64[1] or None).
     `codebook`: a [K,4] fp32 CUDA tensor (exhaustive search) or a prepared `Codebook` (indexed search,
@@ -197,6 +241,7 @@ def vq_assign(z: torch.Tensor, codebook, want_zq: bool = True, want_sqerr: bool 
     return idx, zq, sq
 
 
+@_on_tensor_device
 def vq_count(idx: torch.Tensor, counters: torch.Tensor) -> None:
     """quantize.py:79-81: counters[idx[i]] += 1, counters fp32 [K] (in place)."""
     idx = _cuda(idx, torch.int64, "idx")
@@ -219,6 +264,7 @@ def linspace_bins() -> np.ndarray:
     return _BINS
 
 
+@_on_tensor_device
 def entropy_maps(x: torch.Tensor, want8: bool = True, want16: bool = True):
     """model.py:440-483 for patch sizes 8 and 16 in one pass -> (e8 [B,H/8,W/8], e16 [B,H/16,W/16])."""
     x = _cuda(x, torch.float32, "x")
@@ -250,6 +296,7 @@ def router_ranks(coarse_ratio: float, medium_ratio: float, n16: int, n8: int, mo
     return int(k_c), int(k_m)
 
 
+@_on_tensor_device
 def router(e16: torch.Tensor, e8: torch.Tensor, coarse_ratio: float, medium_ratio: float, per_image: bool = False,
            want_gate: bool = False):
     """RouterTriple.py:15-96 -> (m_c, m_m, m_f int32 [B,1,.,.], gate fp32 [B,1,h,3w] or None, mode)."""
@@ -271,6 +318,7 @@ def router(e16: torch.Tensor, e8: torch.Tensor, coarse_ratio: float, medium_rati
     return m_c, m_m, m_f, gate, mode
 
 
+@_on_tensor_device
 def mask_mix(h_c, h_m, h_f, m_c, m_m, m_f) -> torch.Tensor:
     """vqvae_blocks.py:361-366: up4(h_c)*up4(m_c) + up2(h_m)*up2(m_m) + h_f*m_f."""
     h_c, h_m, h_f = (_cuda(t, torch.float32, n) for t, n in ((h_c, "h_c"), (h_m, "h_m"), (h_f, "h_f")))
@@ -282,6 +330,7 @@ def mask_mix(h_c, h_m, h_f, m_c, m_m, m_f) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def decoder_merge(h: torch.Tensor, other: torch.Tensor, masks, level: int) -> torch.Tensor:
     """decoder.py:373-382, the mask-gated merge at the decoder's entry: level 2: h*up2(mask[0]) + other*mask[1];
     level 3: h*up4(mask[0]) + h*up2(mask[1]) + other*mask[2].  masks: [B,1,.,.] int32 / int64 / float32, one dtype."""
@@ -305,6 +354,7 @@ def decoder_merge(h: torch.Tensor, other: torch.Tensor, masks, level: int) -> to
     return out
 
 
+@_on_tensor_device
 def spatial_norm(f: torch.Tensor, zq: torch.Tensor, gn_weight: Optional[torch.Tensor], gn_bias: Optional[torch.Tensor],
                  wy: torch.Tensor, by: Optional[torch.Tensor], wb: torch.Tensor, bb: Optional[torch.Tensor],
                  groups: int, eps: float) -> torch.Tensor:
@@ -334,6 +384,7 @@ def spatial_norm(f: torch.Tensor, zq: torch.Tensor, gn_weight: Optional[torch.Te
 # --------------------------------------------------------------------------------------------
 # a7/a9/a11/a12 pack and a10/a13/a14 unpack (batched, B independent images)
 # --------------------------------------------------------------------------------------------
+@_on_tensor_device
 def pack(idx: torch.Tensor, m_c, m_m, m_f, mode: int, table: HuffTable, h: int, w: int):
     """model.py:217-260 for B images -> (bytes uint8 [B, image_stride], sizes int32 [B,5])."""
     idx = _cuda(idx, torch.int64, "idx")
@@ -349,6 +400,7 @@ def pack(idx: torch.Tensor, m_c, m_m, m_f, mode: int, table: HuffTable, h: int, 
     return out, sizes
 
 
+@_on_tensor_device
 def unpack(bytes_: torch.Tensor, sizes: torch.Tensor, mode: int, table: HuffTable, codebook: torch.Tensor, h: int, w: int):
     """model.py:269-392 for B images -> (mc, mm, mf int64, ind int64 [B,h,w], quant fp32 [B,4,h,w], status int32 [B])."""
     bytes_ = _cuda(bytes_, torch.uint8, "bytes")
@@ -377,6 +429,7 @@ def unpack(bytes_: torch.Tensor, sizes: torch.Tensor, mode: int, table: HuffTabl
 # --------------------------------------------------------------------------------------------
 # single-stream codec ops (a9, a10, a11)
 # --------------------------------------------------------------------------------------------
+@_on_tensor_device
 def huff_encode(symbols: torch.Tensor, table: HuffTable) -> bytes:
     """indices_coding.py:113-126 payload: 1-D integer CUDA tensor -> bytes (b'' if empty)."""
     s = _cuda(symbols.reshape(-1), symbols.dtype, "symbols")
@@ -413,6 +466,7 @@ def huff_decode(data: bytes, table: HuffTable, device) -> Optional[list]:
     return out[:n].cpu().tolist()
 
 
+@_on_tensor_device
 def bits_encode(values: torch.Tensor) -> bytes:
     """mask_coding.py:40-55 payload."""
     v = _cuda(values.reshape(-1), values.dtype, "values")

@@ -96,18 +96,33 @@ class VectorQuantize2(nn.Module):
     def _bump_counters(self, idx: torch.Tensor) -> None:                                 # quantize.py:79-81
         ops.vq_count(idx, self._flat_counter_storage(idx.device))
 
+    def invalidate(self) -> None:
+        """Forget the prepared codebook: call after writing `embedding.weight.data` directly."""
+        self._prepared_key = None
+
+    def freeze_codebook(self, frozen: bool = True) -> None:
+        """Promise that `embedding.weight` will not be written through `.data` any more (inference): skips the
+        per-forward staleness guard (one ~2 us kernel).  invalidate() still forces a rebuild."""
+        self._frozen = frozen
+
     def prepared_codebook(self) -> "ops.Codebook":
-        """The search index of `embedding.weight` (ops.Codebook), rebuilt on the current stream whenever the
-        weight tensor was replaced or written in place (its `_version` moved)."""
+        """The search index of `embedding.weight` (ops.Codebook), rebuilt on the current stream whenever the weight
+        tensor was replaced or written in place (its `_version` moved).  Writes through `weight.data` (LitEma.copy_to /
+        restore of the reference, CGIC/models/ema.py:51,76) move neither: unless freeze_codebook() was called, every
+        call also enqueues a device-side comparison of the live weights with the index's copy -- on a mismatch the
+        search of THAT call already runs exhaustively on the live weights (same results), and the next call, which sees
+        the flag the kernel raised, rebuilds the index."""
         w = self.embedding.weight
         key = (w.data_ptr(), w._version, w.device)
-        if getattr(self, "_prepared_key", None) != key:
-            cb = getattr(self, "_prepared", None)
+        cb = getattr(self, "_prepared", None)
+        if getattr(self, "_prepared_key", None) != key or (cb is not None and cb.is_stale()):
             if cb is None or cb.device != w.device or cb.K != w.shape[0]:
                 self._prepared = ops.Codebook(w)
             else:
                 cb.update(w)
             self._prepared_key = key
+        elif not getattr(self, "_frozen", False):
+            cb.check(w)
         return self._prepared
 
     def forward(self, z):

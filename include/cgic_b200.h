@@ -114,6 +114,13 @@ CGIC_API int cgic_codebook_create(int K, cgic_codebook **out);
 CGIC_API void cgic_codebook_free(cgic_codebook *cb);
 CGIC_API int cgic_codebook_update(cgic_codebook *cb, const float *codebook, cgic_stream_t stream);
 CGIC_API int cgic_codebook_stats_host(const cgic_codebook *cb, int32_t out[4]);
+/* Staleness guard for weights written behind torch's back (`weight.data.copy_`, as the reference's LitEma.copy_to /
+ * restore do, CGIC/models/ema.py:51,76): check enqueues one small kernel that compares the live DEVICE codebook with the
+ * copy the index was built from; on a mismatch it refreshes the copy, switches cgic_vq_assign_indexed to its exhaustive
+ * path (results stay those of the live weights) and raises a host-visible flag.  is_stale polls that flag without
+ * synchronising (1 = a check since the last update found a difference: call cgic_codebook_update), 0 otherwise. */
+CGIC_API int cgic_codebook_check(cgic_codebook *cb, const float *codebook, cgic_stream_t stream);
+CGIC_API int cgic_codebook_is_stale(const cgic_codebook *cb);
 CGIC_API int cgic_vq_assign_indexed(const float *z, int B, int h, int w, const cgic_codebook *cb, int64_t *idx_out,
                            float *zq_out, double *sqerr_out, void *workspace, size_t workspace_bytes,
                            cgic_stream_t stream);

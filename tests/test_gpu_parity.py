@@ -225,6 +225,22 @@ def test_router_ties_and_large(cg, orc):
             and np.array_equal(mf.cpu().numpy(), omf), (c, m)
 
 
+@pytest.mark.parametrize("B,h16,w16,per_image", [(1, 64, 48, True), (1, 64, 48, False), (12, 16, 16, False), (3, 32, 32, False),
+                                                 (2, 32, 48, False), (1, 62, 48, True), (1, 46, 64, False)])
+def test_router_key_cache_boundary(cg, orc, B, h16, w16, per_image):
+    """Medium-cell counts around the shared-memory key cache's limit (11 776 keys): a single 1024x768 image (12 288 cells),
+    B=12 of 256x256, B=3 of 512x512, B=2 of 512x768 with batch thresholds, and sizes just below the limit."""
+    g = torch.Generator().manual_seed(1000 + B * h16 + w16)
+    e16 = torch.rand(B, h16, w16, generator=g)
+    e8 = torch.rand(B, 2 * h16, 2 * w16, generator=g)
+    for c, m in ((0.1, 0.8), (0.05, 0.05)):
+        mc, mm, mf, _, mode = cg.ops.router(e16.cuda(), e8.cuda(), c, m, per_image=per_image)
+        torch.cuda.synchronize()
+        omc, omm, omf, omode = orc.router(e16.numpy(), e8.numpy(), c, m)
+        assert mode == omode and np.array_equal(mc.cpu().numpy(), omc) and np.array_equal(mm.cpu().numpy(), omm) \
+            and np.array_equal(mf.cpu().numpy(), omf), (c, m)
+
+
 @pytest.mark.parametrize("tag", e2e_case_names())
 def test_e2e_golden(cg, tag, tmp_path):
     """Every stage against the unmodified reference's run on the same image (all 7 modes)."""
@@ -517,6 +533,14 @@ def test_errors_are_loud(cg):
     bad[0, 2] = max(int(bad[0, 2]) // 2, 3)
     *_, status = cg.ops.unpack(packed, bad, mode, t, cb, 16, 16)
     assert int(status[0]) != 0
+    # a size beyond the slot (corrupt side information): CGIC_EFORMAT in status, never a read past the slot / the buffer
+    offs, caps, stride = t.layout(16, 16)
+    for s_bad, val in ((2, int(caps[2]) + 1), (1, 1 << 30), (0, -7)):
+        bad = sizes.clone()
+        bad[0, s_bad] = val
+        *_, status = cg.ops.unpack(packed, bad, mode, t, cb, 16, 16)
+        torch.cuda.synchronize()
+        assert int(status[0]) == -5, (s_bad, val, int(status[0]))
 
 
 # ------------------------------------------------- large token grids: chunks of a stream chained over several CTAs

@@ -169,3 +169,39 @@ def test_indexed_update_and_ragged_shapes(cg, orc):
         vq.embedding.weight.copy_(cb)
         _, _, i1 = vq(z.cuda())
     assert np.array_equal(i1.cpu().numpy(), oidx) and not torch.equal(i0, i1)
+
+
+def test_module_survives_writes_through_weight_data(cg, orc):
+    """`weight.data.copy_()` / `.data.mul_()` (the reference's LitEma.copy_to / restore, ema.py:51,76) do not
+    move torch's version counter.  The forward right after such a write must already answer for the LIVE weights (the
+    device-side guard switches that call to the exhaustive path); the next one rebuilds the index."""
+    g = torch.Generator().manual_seed(13)
+    vq = cg.VectorQuantize2(1024, 4, 0.25).cuda().eval()
+    z = (torch.rand(2, 4, 16, 24, generator=g) * 2 - 1) / 1024
+    new = torch.randn(1024, 4, generator=g) * 3e-4
+    with torch.no_grad():
+        _, _, i0 = vq(z.cuda())
+        v0 = vq.embedding.weight._version
+        vq.embedding.weight.data.copy_(new.cuda())
+        assert vq.embedding.weight._version == v0                     # the host cannot see the write
+        zq1, _, i1 = vq(z.cuda())                                     # guard: exhaustive on the live weights
+        torch.cuda.synchronize()
+        assert vq._prepared.is_stale()
+        zq2, _, i2 = vq(z.cuda())                                     # rebuilt index
+        torch.cuda.synchronize()
+        assert not vq._prepared.is_stale() and vq._prepared.stats()["valid"] == 1
+    ozq, _, oidx = orc.vq_assign(z.numpy(), new.numpy())
+    for i, q in ((i1, zq1), (i2, zq2)):
+        assert np.array_equal(i.cpu().numpy(), oidx) and np.array_equal(q.cpu().numpy().view(np.uint32), ozq.view(np.uint32))
+    assert not torch.equal(i0, i1)
+    # invalidate(): the explicit hook; freeze_codebook(): no guard kernel any more
+    with torch.no_grad():
+        vq.embedding.weight.data.mul_(2.0)
+        vq.invalidate()
+        _, _, i3 = vq(z.cuda())
+    _, _, oidx3 = orc.vq_assign(z.numpy(), (new * 2.0).numpy())
+    assert np.array_equal(i3.cpu().numpy(), oidx3)
+    vq.freeze_codebook()
+    with torch.no_grad():
+        _, _, i4 = vq(z.cuda())
+    assert torch.equal(i3, i4)
