@@ -57,6 +57,9 @@ _SIGNATURES = {
     "cgic_pack_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "cgic_pack_ws": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_size_t, c_void_p]),
+    "cgic_encode_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "cgic_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                            c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cgic_unpack_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "cgic_unpack": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                             c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -75,6 +78,7 @@ _SIGNATURES = {
     "cgic_session_arena": (c_int, [c_void_p, c_int]),
     "cgic_session_arena_tensor": (c_int, [c_void_p, c_int, c_int, C.POINTER(c_void_p), C.POINTER(c_int), C.POINTER(c_int)]),
     "cgic_session_roundtrip_arena": (c_int, [c_void_p, c_int, c_void_p]),
+    "cgic_session_arena_gather_device": (c_int, [c_void_p, c_int, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -36,6 +36,7 @@ void set_error(const char *fmt, ...);
 struct DevTable {
     int K;
     int max_len;
+    int min_len;
     int lut_bits;
     int root;
     const uint16_t *len;   // [K] code length in bits
@@ -137,7 +138,7 @@ PackLayout make_pack_layout(int max_len, int h, int w);
 // Phase tracing (debug builds only, -DCGIC_TRACE): thread 0 of a CTA stamps %globaltimer into a
 // per-translation-unit device array; cgic_trace_<unit>() copies it out (profiles/trace_*.py).
 #ifdef CGIC_TRACE
-#define CGIC_TRACE_SLOTS 8
+#define CGIC_TRACE_SLOTS 16
 #define CGIC_TRACE_CTAS 1024
 #define CGIC_TRACE_DECL(unit)                                                                        \
     static __device__ unsigned long long g_trace_##unit[CGIC_TRACE_CTAS * CGIC_TRACE_SLOTS];         \

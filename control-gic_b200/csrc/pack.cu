@@ -12,7 +12,9 @@
 // global memory sees every output word exactly once and needs no pre-zeroing.
 // Framing (must be byte exact): [pad count byte][payload, MSB first][pad zero bits],
 // pad = 8 - nbits % 8 in 1..8, empty symbol list -> 0 bytes.
-#include "common.cuh"
+#include <algorithm>
+
+#include "vq_tile.cuh"
 
 namespace cgic {
 namespace {
@@ -560,6 +562,271 @@ bits_single_kernel(const int32_t *v, int64_t n, uint8_t *out, int64_t cap, int32
     pack_bit_stream(v, n, out, cap, size_out);
 }
 
+// ======================================================================================================================
+// Small token grids (<= ES_MAX_N4 fine tokens, codes of at most 32 bits): VectorQuantize2.forward (a1) + index selection
+// (a7) + the five-stream pack (a9, a11, a12) in ONE launch, one CTA per image.  The 32 warps first run the warp-tile
+// search of vq_tile.cuh on the image's 4 x 32 tiles (idx / z_q / sum((e-z)^2) go to global memory as before, the indices
+// also to shared memory as u16), then the CTA packs the three index streams in one pass over the concatenated level
+// grids [coarse | medium | fine]: one exclusive scan of the code lengths serves all three (a stream's bit offsets are
+// relative to the scan value at its first position), codes are OR-ed into per-stream staging windows in shared memory
+// and leave as coalesced big-endian words; header byte and padding are part of the staged words.  The indices never
+// make the round trip through global memory and the step loses one launch and one hand-over.
+#ifndef CGIC_ES_THREADS
+#define CGIC_ES_THREADS 1024
+#endif
+constexpr int ES_THREADS = CGIC_ES_THREADS;
+constexpr int ES_WARPS = ES_THREADS / 32;
+constexpr int ES_MAX_N4 = 4096;
+constexpr int ES_ITEMS = (ES_MAX_N4 + ES_MAX_N4 / 4 + ES_MAX_N4 / 16 + ES_THREADS - 1) / ES_THREADS;  // (n16 + n8 + n4) <= 5376 positions per image
+
+struct EncodeArgs {
+    const float *z;
+    const unsigned char *blob;  // prepared codebook
+    int K, h, w, mode;
+    const int32_t *mask[3];
+    DevTable T;
+    int64_t *idx_out;
+    float *zq_out;
+    double *partials, *sqerr_out;
+    int32_t *counters;
+    uint8_t *out;
+    int64_t image_stride;
+    int64_t slot_off[5];
+    int64_t slot_cap[5];
+    int32_t *sizes;
+};
+
+struct EsLayout {
+    size_t enc, tiles, idx, stage[3], total;
+};
+__host__ __device__ inline EsLayout es_layout(int K, int h, int w, const int64_t cap[5])
+{
+    auto up = [](size_t v) { return (v + 127) / 128 * 128; };
+    EsLayout L;
+    size_t o = up(cb_layout(K).stage);
+    L.enc = o;
+    o += up((size_t)((K + 1) / 2 * 2) * 8);
+    L.idx = o;
+    o += up((size_t)h * w * 2);
+    L.tiles = o;
+    // the staging windows of the pack phase reuse the warps' tile slices
+    size_t so = o;
+    for (int s = 0; s < 3; ++s) {
+        L.stage[s] = so;
+        so += up((size_t)cap[s] + 8);
+    }
+    o += (size_t)ES_WARPS * VQW_TILE_BYTES;
+    L.total = o > so ? o : so;
+    return L;
+}
+
+__global__ void __launch_bounds__(ES_THREADS, 1) encode_small_kernel(const EncodeArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ double s_red[ES_WARPS];
+    __shared__ int s_wsum[ES_WARPS];
+    __shared__ int s_base[4];
+    __shared__ bool s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
+    const int h = a.h, w = a.w, K = a.K;
+    const CbLayout CL = cb_layout(K);
+    const EsLayout SL = es_layout(K, h, w, a.slot_cap);
+    const CbHeader *hdr = reinterpret_cast<const CbHeader *>(smem);
+    const unsigned char *lut = smem + CL.lut;
+    const float4 *cbs = reinterpret_cast<const float4 *>(smem + CL.cb);
+    const float *e2s = reinterpret_cast<const float *>(smem + CL.e2);
+    const uint2 *s_enc = reinterpret_cast<const uint2 *>(smem + SL.enc);
+    uint16_t *idx_s = reinterpret_cast<uint16_t *>(smem + SL.idx);
+    unsigned char *wbase = smem + SL.tiles + (size_t)warp * VQW_TILE_BYTES;
+    float4 *zs = reinterpret_cast<float4 *>(wbase);
+    uint16_t *res = reinterpret_cast<uint16_t *>(zs + VQW_TILE);
+    uint8_t *list = reinterpret_cast<uint8_t *>(res + VQW_TILE);
+    uint8_t *lead = list + VQW_TILE;
+    const uint4 *recs = reinterpret_cast<const uint4 *>(a.blob + CL.rec);
+
+    CGIC_STAMP(pack, 0);
+    pdl_trigger_step<1>();
+    // immutable tables first: the code table of the pack phase may be staged while the predecessor still runs
+    if (tid == 0) mbar_init(&mbar);
+    __syncthreads();
+    const uint32_t enc_bytes = (uint32_t)((a.T.K + 1) / 2 * 2) * 8u;
+    pdl_wait();  // the prepared blob and z may come straight from a preceding kernel
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&mbar)), "r"((uint32_t)CL.stage + enc_bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(smem)),
+                     "l"(a.blob), "r"((uint32_t)CL.stage), "r"(smem_addr(&mbar))
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(smem + SL.enc)),
+                     "l"(a.T.enc), "r"(enc_bytes), "r"(smem_addr(&mbar))
+                     : "memory");
+    }
+    bool staged = false;
+    CGIC_STAMP(pack, 2);
+
+    // ---- a1: warp tiles of this image
+    const int64_t plane = (int64_t)h * w;
+    const int tiles_x = (w + 31) / 32, tiles_y = (h + 3) / 4, n_tiles = tiles_x * tiles_y;
+    double sq = 0.0;
+    const VqTileCtx ctx{hdr, lut, cbs, e2s, recs, K, zs, res, list, lead};
+    for (int tile = warp; tile < n_tiles; tile += ES_WARPS) {
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        vq_process_tile(ctx, a.z + (int64_t)b * 4 * plane, h, w, ty * 4, tx * 32 + lane, lane, a.idx_out + (int64_t)b * plane,
+                        a.zq_out ? a.zq_out + (int64_t)b * 4 * plane : nullptr, a.sqerr_out != nullptr, sq, idx_s, a.counters + 2, [&]() {
+                            if (!staged) {
+                                staged = true;
+                                mbar_wait(&mbar, 0);
+                            }
+                        });
+    }
+    if (!staged) mbar_wait(&mbar, 0);  // (warps without a tile still need the code table below)
+    CGIC_STAMP(pack, 7);
+    // sum((e - z)^2): warp -> CTA partial; the last CTA to arrive adds the partials in image order (deterministic)
+    if (a.sqerr_out) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (lane == 0) s_red[warp] = sq;
+    }
+    __syncthreads();  // idx_s complete; the tile slices are free: the staging windows take their place
+    CGIC_STAMP(pack, 3);
+
+    // ---- a7 + a9: the three index streams in one pass
+    const int n4 = h * w, n8 = n4 / 4, n16 = n4 / 16;
+    const int n_all = n16 + n8 + n4;
+    uint32_t *const stage0 = reinterpret_cast<uint32_t *>(smem + SL.stage[0]), *const stage1 = reinterpret_cast<uint32_t *>(smem + SL.stage[1]),
+                    *const stage2 = reinterpret_cast<uint32_t *>(smem + SL.stage[2]);
+    auto stage_of = [&](int s) { return s == 0 ? stage0 : (s == 1 ? stage1 : stage2); };
+    {
+        // zero the staging windows (16 bytes per thread and pass)
+        const int nz = (int)((SL.stage[2] + ((size_t)a.slot_cap[2] + 8 + 127) / 128 * 128 - SL.stage[0]) / 16);
+        uint4 *zp = reinterpret_cast<uint4 *>(smem + SL.stage[0]);
+        for (int i = tid; i < nz; i += ES_THREADS) zp[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    uint32_t code[ES_ITEMS], len[ES_ITEMS];
+    int lvl[ES_ITEMS];
+    int tsum = 0;
+    const int u0 = tid * ES_ITEMS;
+#pragma unroll
+    for (int i = 0; i < ES_ITEMS; ++i) {
+        const int u = u0 + i;
+        code[i] = 0;
+        len[i] = 0;
+        lvl[i] = u < n16 ? 0 : (u < n16 + n8 ? 1 : 2);
+        if (u < n_all) {
+            const int s = lvl[i];
+            const int p = u - (s == 0 ? 0 : (s == 1 ? n16 : n16 + n8));
+            const int step = 4 >> s, gw = w / step;
+            const int np = s == 0 ? n16 : (s == 1 ? n8 : n4);
+            if (stream_present(a.mode, s) && __ldg(a.mask[s] + (int64_t)b * np + p) == 1) {
+                const int y = p / gw, x = p - y * gw;
+                const uint2 e = s_enc[idx_s[(y * step) * w + x * step]];  // the block's top-left token (model.py:219-221)
+                code[i] = e.x;
+                len[i] = e.y;
+            }
+        }
+        tsum += (int)len[i];
+    }
+    // block-wide exclusive scan of the per-thread bit counts
+    int inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();
+    int woff = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < ES_WARPS; ++i) {
+        const int t = s_wsum[i];
+        if (i < warp) woff += t;
+        total += t;
+    }
+    int o = woff + inc - tsum;
+    // the scan value at a stream's first position = the bits of the streams before it
+    {
+        int run = o;
+#pragma unroll
+        for (int i = 0; i < ES_ITEMS; ++i) {
+            const int u = u0 + i;
+            if (u == 0) s_base[0] = run;
+            if (u == n16) s_base[1] = run;
+            if (u == n16 + n8) s_base[2] = run;
+            run += (int)len[i];
+        }
+        if (tid == 0) s_base[3] = total;
+    }
+    __syncthreads();
+    CGIC_STAMP(pack, 4);
+    const int base0 = s_base[0], base1 = s_base[1], base2 = s_base[2];
+#pragma unroll
+    for (int i = 0; i < ES_ITEMS; ++i) {
+        if (len[i]) {
+            const int s = lvl[i];
+            const int q = 8 + o - (s == 0 ? base0 : (s == 1 ? base1 : base2));  // the header byte is bits 0..7
+            const int sh = q & 31, wi = q >> 5;
+            uint32_t *st = stage_of(s);
+            atomicOr(&st[wi], code[i] >> sh);
+            if (sh + (int)len[i] > 32) atomicOr(&st[wi + 1], code[i] << (32 - sh));
+            o += (int)len[i];
+        }
+    }
+    // header byte (pad count, 1..8) of the non-empty streams
+    if (tid < 3) {
+        const int nbits = s_base[tid + 1] - s_base[tid];
+        if (nbits > 0) atomicOr(stage_of(tid), (uint32_t)(8 - (nbits & 7)) << 24);
+    }
+    __syncthreads();
+    CGIC_STAMP(pack, 5);
+    uint8_t *img = a.out + (int64_t)b * a.image_stride;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        const int nbits = s_base[s + 1] - s_base[s];
+        const int total_bytes = nbits > 0 ? nbits / 8 + 2 : 0;  // empty symbol list -> 0 bytes (the reference's empty file)
+        uint32_t *out32 = reinterpret_cast<uint32_t *>(img + a.slot_off[s]);
+        const uint32_t *st = stage_of(s);
+        for (int j = tid; j < (total_bytes + 3) / 4; j += ES_THREADS) out32[j] = to_big_endian(st[j]);
+        if (tid == 0) a.sizes[b * 5 + s] = total_bytes;
+    }
+    CGIC_STAMP(pack, 6);
+    // ---- a11: the two mask streams
+    for (int ms = 3; ms < 5; ++ms) {
+        if (!stream_present(a.mode, ms)) {
+            if (tid == 0) a.sizes[b * 5 + ms] = 0;
+            continue;
+        }
+        const int lv = ms - 3;
+        const int64_t n = lv == 0 ? n16 : n8;
+        pack_bit_stream(a.mask[lv] + (int64_t)b * n, n, img + a.slot_off[ms], a.slot_cap[ms], a.sizes + b * 5 + ms);
+    }
+    CGIC_STAMP(pack, 1);
+    if (!a.sqerr_out) return;
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int i = 0; i < ES_WARPS; ++i) tot += s_red[i];
+        a.partials[b] = tot;
+        __threadfence();
+        s_last = (atomicAdd(&a.counters[0], 1) == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double tot = 0.0;
+        for (int i = tid; i < (int)gridDim.x; i += ES_THREADS) tot += __ldcg(&a.partials[i]);
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o2);
+        __syncthreads();
+        if (lane == 0) s_red[warp] = tot;
+        __syncthreads();
+        if (tid == 0) {
+            double all = 0.0;
+            for (int i = 0; i < ES_WARPS; ++i) all += s_red[i];
+            *a.sqerr_out = all;
+            a.counters[0] = 0;  // leave the ticket zeroed for the next launch (workspace contract)
+        }
+    }
+}
+
 // tile of PK_THREADS * items positions: output bits + 2 words, plus the staged code table
 size_t pack_smem_bytes(const DevTable &T, int items)
 {
@@ -641,6 +908,83 @@ extern "C" int cgic_pack_ws(const int64_t *idx, const int32_t *m_c, const int32_
         CGIC_PROF("pack_kernel", as_stream(stream));
         if (items == 8) CGIC_CUDA_CHECK(launch_pdl(pack_kernel<8>, dim3(4, B), dim3(PK_THREADS), smem, as_stream(stream), a));
         else CGIC_CUDA_CHECK(launch_pdl(pack_kernel<1>, dim3(4, B), dim3(PK_THREADS), smem, as_stream(stream), a));
+    }
+    CGIC_LAUNCH_CHECK();
+    return CGIC_OK;
+}
+
+namespace cgic {
+const unsigned char *codebook_blob(const cgic_codebook *cb);  // codebook.cu
+int codebook_size(const cgic_codebook *cb);
+}  // namespace cgic
+
+extern "C" size_t cgic_encode_workspace_bytes(int B, int h, int w)
+{
+    const size_t a = cgic_vq_workspace_bytes((int64_t)B * h * w), b = 256 + 8 * (size_t)(B > 0 ? B : 0);
+    return ((a > b ? a : b) + 255) / 256 * 256 + cgic_pack_workspace_bytes(B, h, w);
+}
+
+extern "C" int cgic_encode(const float *z, const int32_t *m_c, const int32_t *m_m, const int32_t *m_f, int B, int h, int w, int mode,
+                           const cgic_codebook *cb, const cgic_table *t, int64_t *idx_out, float *zq_out, double *sqerr_out,
+                           uint8_t *bytes_out, int32_t *sizes_out, void *workspace, size_t workspace_bytes, cgic_stream_t stream_)
+{
+    CGIC_REQUIRE(z && m_c && m_m && m_f && idx_out && bytes_out && sizes_out && workspace, CGIC_EINVAL, "cgic_encode: null argument");
+    CGIC_REQUIRE(B >= 0 && h > 0 && w > 0 && h % 4 == 0 && w % 4 == 0, CGIC_EINVAL, "cgic_encode: token grid %dx%d must be multiples of 4", h, w);
+    CGIC_REQUIRE(mode >= 0 && mode <= 6, CGIC_EINVAL, "cgic_encode: mode %d", mode);
+    CGIC_REQUIRE(workspace_bytes >= cgic_encode_workspace_bytes(B, h, w), CGIC_ESPACE, "cgic_encode: workspace %zu < %zu bytes", workspace_bytes,
+                 cgic_encode_workspace_bytes(B, h, w));
+    const unsigned char *blob = codebook_blob(cb);
+    CGIC_REQUIRE(blob, CGIC_EINVAL, "cgic_encode: no prepared codebook (cgic_codebook_update has not been called)");
+    if (B == 0) return CGIC_OK;
+    EncodeArgs a{};
+    int rc = table_device_view(t, &a.T);
+    if (rc) return rc;
+    const int K = codebook_size(cb);
+    const size_t vq_ws = ((std::max(cgic_vq_workspace_bytes((int64_t)B * h * w), (size_t)256 + 8 * (size_t)B)) + 255) / 256 * 256;
+    cudaStream_t stream = as_stream(stream_);
+    static const bool no_small = getenv("CGIC_NO_SMALL_KERNELS") != nullptr;  // diagnosis / A-B only
+    const PackLayout L = make_pack_layout(a.T.max_len, h, w);
+    bool small = !no_small && (int64_t)h * w <= ES_MAX_N4 && a.T.enc != nullptr && a.T.K == K;
+    size_t smem = 0;
+    if (small) {
+        smem = es_layout(K, h, w, L.cap).total;
+        small = smem <= 200 * 1024;
+    }
+    if (!small) {
+        // large token grids / long codes: the two launches (warp-tile search, then the chained packer)
+        rc = cgic_vq_assign_indexed(z, B, h, w, cb, idx_out, zq_out, sqerr_out, workspace, vq_ws, stream_);
+        if (rc) return rc;
+        return cgic_pack_ws(idx_out, m_c, m_m, m_f, B, h, w, mode, t, bytes_out, sizes_out, static_cast<unsigned char *>(workspace) + vq_ws,
+                            workspace_bytes - vq_ws, stream_);
+    }
+    for (const void *ptr : {(const void *)bytes_out, (const void *)m_c, (const void *)m_m, (const void *)m_f})
+        CGIC_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, CGIC_EINVAL, "cgic_encode: bytes_out and masks must be 16-byte aligned");
+    a.z = z;
+    a.blob = blob;
+    a.K = K;
+    a.h = h;
+    a.w = w;
+    a.mode = mode;
+    a.mask[0] = m_c;
+    a.mask[1] = m_m;
+    a.mask[2] = m_f;
+    a.idx_out = idx_out;
+    a.zq_out = zq_out;
+    a.sqerr_out = sqerr_out;
+    a.counters = static_cast<int32_t *>(workspace);
+    a.partials = reinterpret_cast<double *>(static_cast<unsigned char *>(workspace) + 256);
+    a.out = bytes_out;
+    a.image_stride = L.stride;
+    for (int s = 0; s < 5; ++s) {
+        a.slot_off[s] = L.off[s];
+        a.slot_cap[s] = L.cap[s];
+    }
+    a.sizes = sizes_out;
+    rc = ensure_smem((const void *)encode_small_kernel, smem);
+    if (rc) return rc;
+    {
+        CGIC_PROF("encode_small_kernel", stream);
+        CGIC_CUDA_CHECK(launch_pdl(encode_small_kernel, dim3(B), dim3(ES_THREADS), smem, stream, a));
     }
     CGIC_LAUNCH_CHECK();
     return CGIC_OK;

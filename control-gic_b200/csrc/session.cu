@@ -28,8 +28,8 @@ struct cgic_session {
     uint8_t *bytes = nullptr;
     double *sqerr = nullptr;  // [MAX_PARTS]
     double *sqerr_host = nullptr;  // pinned, [MAX_PARTS]
-    unsigned char *ws_vq = nullptr, *ws_un = nullptr, *ws_pk = nullptr;  // MAX_PARTS slices each
-    size_t ws_vq_bytes = 0, ws_un_bytes = 0, ws_pk_bytes = 0;
+    unsigned char *ws_en = nullptr, *ws_un = nullptr;  // MAX_PARTS slices each
+    size_t ws_en_bytes = 0, ws_un_bytes = 0;
     // ---- pinned-arena round trip (cgic_session_arena / cgic_session_roundtrip_arena)
     // The batch is cut into `a_parts` image ranges.  Every range has ONE contiguous input block
     // [z | m_c | m_m | m_f] and ONE contiguous output block [bytes | sizes | status | sqerr | ind | quant |
@@ -43,9 +43,9 @@ struct cgic_session {
         size_t in_off = 0, in_len = 0, out_off = 0, out_core = 0, out_idx = 0, out_all = 0;  // D2H lengths by request
         size_t o[CGIC_ARENA_COUNT] = {};  // offset of every tensor inside its block
     } part[MAX_PARTS];
-    cudaGraphExec_t graph[4] = {};  // by flags (bit 0: idx, bit 1: zq)
+    cudaGraphExec_t graph[8] = {};  // by flags (bit 0: idx, bit 1: zq, bit 2: decoded tensors stay on the device)
     cudaEvent_t fork = nullptr, join[MAX_PARTS] = {};
-    bool warmed[4] = {};
+    bool warmed[8] = {};
 };
 
 extern "C" int cgic_session_create(int B, int h, int w, int mode, const cgic_table *t, const float *codebook_host, int K,
@@ -68,9 +68,8 @@ extern "C" int cgic_session_create(int B, int h, int w, int mode, const cgic_tab
     s->table = t;
     s->L = cgic::make_pack_layout(cgic::table_max_len(t), h, w);
     const size_t n4 = (size_t)B * h * w, n8 = n4 / 4, n16 = n4 / 16;
-    s->ws_vq_bytes = cgic_vq_workspace_bytes((int64_t)n4);
-    s->ws_un_bytes = cgic_unpack_workspace_bytes(B, h, w);
-    s->ws_pk_bytes = cgic_pack_workspace_bytes(B, h, w);
+    s->ws_en_bytes = (cgic_encode_workspace_bytes(B, h, w) + 255) / 256 * 256;
+    s->ws_un_bytes = (cgic_unpack_workspace_bytes(B, h, w) + 255) / 256 * 256;
     size_t o = 0;
     auto take = [&](size_t bytes) {
         const size_t at = o;
@@ -81,8 +80,7 @@ extern "C" int cgic_session_create(int B, int h, int w, int mode, const cgic_tab
                  o_mc = take(n16 * 4), o_mm = take(n8 * 4), o_mf = take(n4 * 4), o_sizes = take((size_t)B * 5 * 4),
                  o_status = take((size_t)B * 4), o_idx = take(n4 * 8), o_dmc = take(n16 * 8), o_dmm = take(n8 * 8),
                  o_dmf = take(n4 * 8), o_ind = take(n4 * 8), o_bytes = take((size_t)B * s->L.stride), o_sq = take(8 * cgic_session::MAX_PARTS),
-                 o_wv = take(s->ws_vq_bytes * cgic_session::MAX_PARTS), o_wu = take(s->ws_un_bytes * cgic_session::MAX_PARTS),
-                 o_wp = take(s->ws_pk_bytes * cgic_session::MAX_PARTS);
+                 o_we = take(s->ws_en_bytes * cgic_session::MAX_PARTS), o_wu = take(s->ws_un_bytes * cgic_session::MAX_PARTS);
     cudaError_t e = cudaMalloc(&s->arena, o);
     for (int i = 0; i < cgic_session::MAX_PARTS && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&s->streams[i], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->packed, cudaEventDisableTiming);
@@ -111,12 +109,8 @@ extern "C" int cgic_session_create(int B, int h, int w, int mode, const cgic_tab
     s->ind = reinterpret_cast<int64_t *>(a + o_ind);
     s->bytes = a + o_bytes;
     s->sqerr = reinterpret_cast<double *>(a + o_sq);
-    s->ws_vq = a + o_wv;
+    s->ws_en = a + o_we;
     s->ws_un = a + o_wu;
-    s->ws_pk = a + o_wp;
-    s->ws_pk_bytes = (s->ws_pk_bytes + 255) / 256 * 256;
-    s->ws_vq_bytes = (s->ws_vq_bytes + 255) / 256 * 256;
-    s->ws_un_bytes = (s->ws_un_bytes + 255) / 256 * 256;
     rc = cgic_codebook_create(K, &s->index);
     if (rc == CGIC_OK) rc = cgic_codebook_update(s->index, s->codebook, s->streams[0]);
     if (rc == CGIC_OK && cudaStreamSynchronize(s->streams[0]) != cudaSuccess) {
@@ -178,11 +172,9 @@ extern "C" int cgic_session_compress_host(cgic_session *s, const float *z, const
         CGIC_CUDA_CHECK(cudaMemcpyAsync(s->mc + b0 * i16, m_c + b0 * i16, nb * i16 * 4, cudaMemcpyHostToDevice, st));
         CGIC_CUDA_CHECK(cudaMemcpyAsync(s->mm + b0 * i8, m_m + b0 * i8, nb * i8 * 4, cudaMemcpyHostToDevice, st));
         CGIC_CUDA_CHECK(cudaMemcpyAsync(s->mf + b0 * i4, m_f + b0 * i4, nb * i4 * 4, cudaMemcpyHostToDevice, st));
-        int rc = cgic_vq_assign_indexed(s->z + b0 * i4 * 4, nb, s->h, s->w, s->index, s->idx + b0 * i4, zq_out ? s->zq + b0 * i4 * 4 : nullptr,
-                                sqerr_out ? s->sqerr + p : nullptr, s->ws_vq + p * s->ws_vq_bytes, s->ws_vq_bytes, st);
-        if (rc) return rc;
-        rc = cgic_pack_ws(s->idx + b0 * i4, s->mc + b0 * i16, s->mm + b0 * i8, s->mf + b0 * i4, nb, s->h, s->w, s->mode, s->table,
-                          s->bytes + (size_t)b0 * s->L.stride, s->sizes + b0 * 5, s->ws_pk + p * s->ws_pk_bytes, s->ws_pk_bytes, st);
+        int rc = cgic_encode(s->z + b0 * i4 * 4, s->mc + b0 * i16, s->mm + b0 * i8, s->mf + b0 * i4, nb, s->h, s->w, s->mode, s->index, s->table,
+                             s->idx + b0 * i4, zq_out ? s->zq + b0 * i4 * 4 : nullptr, sqerr_out ? s->sqerr + p : nullptr,
+                             s->bytes + (size_t)b0 * s->L.stride, s->sizes + b0 * 5, s->ws_en + p * s->ws_en_bytes, s->ws_en_bytes, st);
         if (rc) return rc;
         CGIC_CUDA_CHECK(cudaMemcpyAsync(bytes_out + (size_t)b0 * s->L.stride, s->bytes + (size_t)b0 * s->L.stride, (size_t)nb * s->L.stride,
                                         cudaMemcpyDeviceToHost, st));
@@ -246,10 +238,8 @@ extern "C" int cgic_session_roundtrip_host(cgic_session *s, const float *z, cons
     CGIC_CUDA_CHECK(cudaMemcpyAsync(s->mc, m_c, n16 * 4, cudaMemcpyHostToDevice, enc));
     CGIC_CUDA_CHECK(cudaMemcpyAsync(s->mm, m_m, n8 * 4, cudaMemcpyHostToDevice, enc));
     CGIC_CUDA_CHECK(cudaMemcpyAsync(s->mf, m_f, n4 * 4, cudaMemcpyHostToDevice, enc));
-    int rc = cgic_vq_assign_indexed(s->z, s->B, s->h, s->w, s->index, s->idx, zq_out ? s->zq : nullptr,
-                            sqerr_out ? s->sqerr : nullptr, s->ws_vq, s->ws_vq_bytes, enc);
-    if (rc) return rc;
-    rc = cgic_pack_ws(s->idx, s->mc, s->mm, s->mf, s->B, s->h, s->w, s->mode, s->table, s->bytes, s->sizes, s->ws_pk, s->ws_pk_bytes, enc);
+    int rc = cgic_encode(s->z, s->mc, s->mm, s->mf, s->B, s->h, s->w, s->mode, s->index, s->table, s->idx, zq_out ? s->zq : nullptr,
+                         sqerr_out ? s->sqerr : nullptr, s->bytes, s->sizes, s->ws_en, s->ws_en_bytes, enc);
     if (rc) return rc;
     CGIC_CUDA_CHECK(cudaEventRecord(s->packed, enc));
     CGIC_CUDA_CHECK(cudaStreamWaitEvent(dec, s->packed, 0));
@@ -382,6 +372,23 @@ extern "C" int cgic_session_arena_tensor(const cgic_session *s, int what, int pa
     return CGIC_OK;
 }
 
+extern "C" int cgic_session_arena_gather_device(cgic_session *s, int what, void *dst_device)
+{
+    CGIC_REQUIRE(s && s->a_parts > 0 && dst_device, CGIC_EINVAL, "cgic_session_arena_gather_device: call cgic_session_arena first");
+    CGIC_REQUIRE(what >= CGIC_ARENA_BYTES && what < CGIC_ARENA_COUNT && what != CGIC_ARENA_SQERR, CGIC_EINVAL,
+                 "cgic_session_arena_gather_device: tensor %d is not a per-image output", what);
+    unsigned char *dst = static_cast<unsigned char *>(dst_device);
+    cudaStream_t s0 = s->streams[0];
+    for (int p = 0; p < s->a_parts; ++p) {
+        const cgic_session::Part &P = s->part[p];
+        const size_t bytes = arena_count(s, what, P.nb) * arena_elem_bytes(what);
+        CGIC_CUDA_CHECK(cudaMemcpyAsync(dst, s->d_out + P.out_off + P.o[what], bytes, cudaMemcpyDeviceToDevice, s0));
+        dst += bytes;
+    }
+    CGIC_CUDA_CHECK(cudaStreamSynchronize(s0));
+    return CGIC_OK;
+}
+
 // enqueues the whole round trip of every part (part p on streams[p]); used eagerly once and then under capture
 static int arena_enqueue(cgic_session *s, int flags)
 {
@@ -397,15 +404,12 @@ static int arena_enqueue(cgic_session *s, int flags)
         auto in = [&](int what) { return di + P.o[what]; };
         auto out = [&](int what) { return dout + P.o[what]; };
         CGIC_CUDA_CHECK(cudaMemcpyAsync(di, s->h_in + P.in_off, P.in_len, cudaMemcpyHostToDevice, st));
-        int rc = cgic_vq_assign_indexed(reinterpret_cast<const float *>(in(CGIC_ARENA_Z)), P.nb, s->h, s->w, s->index,
-                                        reinterpret_cast<int64_t *>(out(CGIC_ARENA_IDX)),
-                                        (flags & 2) ? reinterpret_cast<float *>(out(CGIC_ARENA_ZQ)) : nullptr,
-                                        reinterpret_cast<double *>(out(CGIC_ARENA_SQERR)), s->ws_vq + p * s->ws_vq_bytes, s->ws_vq_bytes, st);
-        if (rc) return rc;
-        rc = cgic_pack_ws(reinterpret_cast<const int64_t *>(out(CGIC_ARENA_IDX)), reinterpret_cast<const int32_t *>(in(CGIC_ARENA_MC)),
-                       reinterpret_cast<const int32_t *>(in(CGIC_ARENA_MM)), reinterpret_cast<const int32_t *>(in(CGIC_ARENA_MF)), P.nb, s->h,
-                       s->w, s->mode, s->table, out(CGIC_ARENA_BYTES), reinterpret_cast<int32_t *>(out(CGIC_ARENA_SIZES)),
-                       s->ws_pk + p * s->ws_pk_bytes, s->ws_pk_bytes, st);
+        int rc = cgic_encode(reinterpret_cast<const float *>(in(CGIC_ARENA_Z)), reinterpret_cast<const int32_t *>(in(CGIC_ARENA_MC)),
+                             reinterpret_cast<const int32_t *>(in(CGIC_ARENA_MM)), reinterpret_cast<const int32_t *>(in(CGIC_ARENA_MF)), P.nb, s->h,
+                             s->w, s->mode, s->index, s->table, reinterpret_cast<int64_t *>(out(CGIC_ARENA_IDX)),
+                             (flags & 2) ? reinterpret_cast<float *>(out(CGIC_ARENA_ZQ)) : nullptr, reinterpret_cast<double *>(out(CGIC_ARENA_SQERR)),
+                             out(CGIC_ARENA_BYTES), reinterpret_cast<int32_t *>(out(CGIC_ARENA_SIZES)), s->ws_en + p * s->ws_en_bytes,
+                             s->ws_en_bytes, st);
         if (rc) return rc;
         rc = cgic_unpack(out(CGIC_ARENA_BYTES), reinterpret_cast<const int32_t *>(out(CGIC_ARENA_SIZES)), P.nb, s->h, s->w, s->mode, s->table,
                          s->codebook, reinterpret_cast<int64_t *>(out(CGIC_ARENA_DMC)), reinterpret_cast<int64_t *>(out(CGIC_ARENA_DMM)),
@@ -413,7 +417,9 @@ static int arena_enqueue(cgic_session *s, int flags)
                          reinterpret_cast<float *>(out(CGIC_ARENA_QUANT)), reinterpret_cast<int32_t *>(out(CGIC_ARENA_STATUS)),
                          s->ws_un + p * s->ws_un_bytes, s->ws_un_bytes, st);
         if (rc) return rc;
-        const size_t len = (flags & 2) ? P.out_all : ((flags & 1) ? P.out_idx : P.out_core);
+        // D2H: one copy of the block's head.  Bit 2 of flags: the decoded tensors (ind, quant, masks) stay in HBM for the
+        // decoder CNN, as model.py:391-399 hands them over -- only [bytes | sizes | status | sqerr] come back.
+        const size_t len = (flags & 4) ? P.o[CGIC_ARENA_IND] : ((flags & 2) ? P.out_all : ((flags & 1) ? P.out_idx : P.out_core));
         CGIC_CUDA_CHECK(cudaMemcpyAsync(s->h_out + P.out_off, dout, len, cudaMemcpyDeviceToHost, st));
         if (p) {
             CGIC_CUDA_CHECK(cudaEventRecord(s->join[p], st));
@@ -426,7 +432,8 @@ static int arena_enqueue(cgic_session *s, int flags)
 extern "C" int cgic_session_roundtrip_arena(cgic_session *s, int flags, double *sqerr_out)
 {
     CGIC_REQUIRE(s && s->a_parts > 0, CGIC_EINVAL, "cgic_session_roundtrip_arena: call cgic_session_arena first");
-    CGIC_REQUIRE(flags >= 0 && flags < 4, CGIC_EINVAL, "cgic_session_roundtrip_arena: flags %d", flags);
+    CGIC_REQUIRE(flags >= 0 && flags < 8 && (flags & 6) != 6 && (flags & 5) != 5, CGIC_EINVAL,
+                 "cgic_session_roundtrip_arena: flags %d (bit 2 excludes bits 0 and 1: idx / z_q lie behind the decoded tensors)", flags);
     cudaStream_t s0 = s->streams[0];
     static const bool no_graph = getenv("CGIC_SESSION_NO_GRAPH") != nullptr;  // diagnosis only
     if (!s->warmed[flags] || no_graph) {

@@ -111,6 +111,7 @@ PackLayout make_pack_layout(int max_len, int h, int w)
 struct cgic_table {
     int K = 0;
     int max_len = 0;
+    int min_len = 0;
     int lut_bits = 0;
     int root = 0;
     std::vector<uint16_t> len;
@@ -270,6 +271,7 @@ int cgic_huff_build(const int64_t *freq, const int32_t *order, int K, cgic_table
         const std::string &c = t->code[s];
         t->len[s] = (uint16_t)c.size();
         t->max_len = std::max<int>(t->max_len, (int)c.size());
+        t->min_len = s == 0 ? (int)c.size() : std::min<int>(t->min_len, (int)c.size());
         t->off[s] = (uint32_t)t->pool.size();
         const size_t nw = (c.size() + 31) / 32;
         for (size_t j = 0; j < nw; ++j) {
@@ -405,6 +407,7 @@ int cgic_huff_upload(cgic_table *t)
     cgic::DevTable v{};
     v.K = t->K;
     v.max_len = t->max_len;
+    v.min_len = t->min_len;
     v.lut_bits = t->lut_bits;
     v.root = t->root;
     v.len = reinterpret_cast<const uint16_t *>(base + o_len);

@@ -909,12 +909,12 @@ __device__ __forceinline__ int fine_cell(const UnpackArgs &a, const uint8_t *mc,
 
 // bitmap + exclusive popcount prefix of one level, by the whole CTA; wordfn(wi) = the 32 cells
 // wi*32 .. wi*32+31 (bit i = cell wi*32+i; bits past n are masked here)
-template <typename F>
+template <int NT = UP_THREADS, typename F>
 __device__ void build_level(int64_t n, int nw, uint32_t *bits, uint32_t *prefix, int32_t *pop_out, F wordfn)
 {
-    __shared__ int s_warp[UP_THREADS / 32];
+    __shared__ int s_warp[NT / 32];
     int run = 0;
-    for (int base = 0; base < nw; base += UP_THREADS) {
+    for (int base = 0; base < nw; base += NT) {
         const int wi = base + threadIdx.x;
         uint32_t word = 0;
         if (wi < nw) {
@@ -935,7 +935,7 @@ __device__ void build_level(int64_t n, int nw, uint32_t *bits, uint32_t *prefix,
         __syncthreads();
         int woff = 0, tot = 0;
 #pragma unroll
-        for (int i = 0; i < UP_THREADS / 32; ++i) {
+        for (int i = 0; i < NT / 32; ++i) {
             const int t = s_warp[i];
             if (i < wid) woff += t;
             tot += t;
@@ -994,6 +994,56 @@ __device__ __forceinline__ const uint8_t *stage_bytes(const uint8_t *src, int nb
     const int n16 = (nbytes + 15) >> 4;
     for (int i = threadIdx.x; i < n16; i += blockDim.x) reinterpret_cast<uint4 *>(dst)[i] = __ldg(reinterpret_cast<const uint4 *>(src) + i);
     return dst;
+}
+
+// bitmaps + exclusive popcount prefixes + populations of the coarse, medium and derived fine level of one image, by the
+// whole CTA (NT threads); mc / mm = the mask streams (header byte first), bits / prefix [nw16 + nw8 + nw4], pop [3]
+template <int NT>
+__device__ __forceinline__ void build_mask_levels(const UnpackArgs &a, const uint8_t *mc, const uint8_t *mm, int cap_c, int cap_m, bool need_c,
+                                                  bool need_m, uint32_t *bits, uint32_t *prefix, int32_t *pop)
+{
+    const Geo &g = a.g;
+    {
+        if (need_c)
+            build_level<NT>(g.n16, g.nw16, bits, prefix, pop + 0, [&](int wi) { return word_from_stream(mc, cap_c, wi); });
+        else
+            build_level<NT>(g.n16, g.nw16, bits, prefix, pop + 0, [&](int) { return a.mode == 4 ? 0xFFFFFFFFu : 0u; });
+    }
+    {
+        if (need_m)
+            build_level<NT>(g.n8, g.nw8, bits + g.nw16, prefix + g.nw16, pop + 1, [&](int wi) { return word_from_stream(mm, cap_m, wi); });
+        else if (a.mode == 3)
+            build_level<NT>(g.n8, g.nw8, bits + g.nw16, prefix + g.nw16, pop + 1, [&](int wi) {
+                return word_from_cells(wi, g.w8, g.n8, [&](int y, int x) { return medium_cell(a, mc, mm, y, x); });
+            });
+        else
+            build_level<NT>(g.n8, g.nw8, bits + g.nw16, prefix + g.nw16, pop + 1, [&](int) { return a.mode == 5 ? 0xFFFFFFFFu : 0u; });
+        uint32_t *fb = bits + g.nw16 + g.nw8, *fp = prefix + g.nw16 + g.nw8;
+        if (a.mode > 2) {
+            build_level<NT>(g.n4, g.nw4, fb, fp, pop + 2, [&](int) { return a.mode == 6 ? 0xFFFFFFFFu : 0u; });
+        } else if (g.w % 32 == 0) {
+            // a bitmap word = 32 cells of one row = 16 medium cells (2 stream bytes) and 8 coarse cells (1 byte)
+            build_level<NT>(g.n4, g.nw4, fb, fp, pop + 2, [&](int wi) {
+                const int64_t p0 = (int64_t)wi * 32;
+                const int y = (int)(p0 / g.w), x0 = (int)(p0 - (int64_t)y * g.w);
+                uint32_t m16 = 0, c8 = 0;
+                if (need_m) {
+                    const int64_t p8 = (int64_t)(y >> 1) * g.w8 + (x0 >> 1);
+                    const uint8_t *q = mm + 1 + (p8 >> 3);
+                    m16 = __brev(((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16));
+                }
+                if (need_c) {
+                    const int64_t p16 = (int64_t)(y >> 2) * g.w16 + (x0 >> 2);
+                    c8 = __brev((uint32_t)mc[1 + (p16 >> 3)] << 24);
+                }
+                return ~(spread2(m16) | spread2(spread2(c8)));
+            });
+        } else {
+            build_level<NT>(g.n4, g.nw4, fb, fp, pop + 2, [&](int wi) {
+                return word_from_cells(wi, g.w, g.n4, [&](int y, int x) { return fine_cell(a, mc, mm, y, x); });
+            });
+        }
+    }
 }
 
 // grid (4, B): CTAs 0..2 decode the index streams, CTA 3 builds the coarse, medium and fine mask levels
@@ -1076,79 +1126,21 @@ __device__ __forceinline__ void unpack_decode_cta(const UnpackArgs &a, unsigned 
         if (need_m && ok_m) mm = stage_bytes(mm, cap_m, dyn + off_m);
         __syncthreads();
     }
-    uint32_t *bits = a.ws.bits + (int64_t)b * nwt;
-    uint32_t *prefix = a.ws.prefix + (int64_t)b * nwt;
-    int32_t *pop = a.ws.pop + b * 3;
-    {
-        if (need_c)
-            build_level(g.n16, g.nw16, bits, prefix, pop + 0, [&](int wi) { return word_from_stream(mc, cap_c, wi); });
-        else
-            build_level(g.n16, g.nw16, bits, prefix, pop + 0, [&](int) { return a.mode == 4 ? 0xFFFFFFFFu : 0u; });
-    }
-    {
-        if (need_m)
-            build_level(g.n8, g.nw8, bits + g.nw16, prefix + g.nw16, pop + 1, [&](int wi) { return word_from_stream(mm, cap_m, wi); });
-        else if (a.mode == 3)
-            build_level(g.n8, g.nw8, bits + g.nw16, prefix + g.nw16, pop + 1, [&](int wi) {
-                return word_from_cells(wi, g.w8, g.n8, [&](int y, int x) { return medium_cell(a, mc, mm, y, x); });
-            });
-        else
-            build_level(g.n8, g.nw8, bits + g.nw16, prefix + g.nw16, pop + 1, [&](int) { return a.mode == 5 ? 0xFFFFFFFFu : 0u; });
-        uint32_t *fb = bits + g.nw16 + g.nw8, *fp = prefix + g.nw16 + g.nw8;
-        if (a.mode > 2) {
-            build_level(g.n4, g.nw4, fb, fp, pop + 2, [&](int) { return a.mode == 6 ? 0xFFFFFFFFu : 0u; });
-        } else if (g.w % 32 == 0) {
-            // a bitmap word = 32 cells of one row = 16 medium cells (2 stream bytes) and 8 coarse cells (1 byte)
-            build_level(g.n4, g.nw4, fb, fp, pop + 2, [&](int wi) {
-                const int64_t p0 = (int64_t)wi * 32;
-                const int y = (int)(p0 / g.w), x0 = (int)(p0 - (int64_t)y * g.w);
-                uint32_t m16 = 0, c8 = 0;
-                if (need_m) {
-                    const int64_t p8 = (int64_t)(y >> 1) * g.w8 + (x0 >> 1);
-                    const uint8_t *q = mm + 1 + (p8 >> 3);
-                    m16 = __brev(((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16));
-                }
-                if (need_c) {
-                    const int64_t p16 = (int64_t)(y >> 2) * g.w16 + (x0 >> 2);
-                    c8 = __brev((uint32_t)mc[1 + (p16 >> 3)] << 24);
-                }
-                return ~(spread2(m16) | spread2(spread2(c8)));
-            });
-        } else {
-            build_level(g.n4, g.nw4, fb, fp, pop + 2, [&](int wi) {
-                return word_from_cells(wi, g.w, g.n4, [&](int y, int x) { return fine_cell(a, mc, mm, y, x); });
-            });
-        }
-    }
+    build_mask_levels<UP_THREADS>(a, mc, mm, cap_c, cap_m, need_c, need_m, a.ws.bits + (int64_t)b * nwt, a.ws.prefix + (int64_t)b * nwt,
+                                  a.ws.pop + b * 3);
 }
 
 // Re-assembly of 4 consecutive fine tokens of a row (w is a multiple of 4): they share one coarse
-// cell, two medium cells and one bitmap word per level.  16-byte stores throughout.
-__device__ __forceinline__ void assemble_quad(const UnpackArgs &a, int b, int64_t quad)
+// cell, two medium cells and one bitmap word per level.  16-byte stores throughout.  bits / prefix / sym / cnt may live
+// in global memory (two-kernel path) or in shared memory (fused small-grid kernel).  Returns true when an index beyond
+// the table came up (sums of overlapping levels cannot occur with valid masks).
+__device__ __forceinline__ bool assemble_quad_core(const UnpackArgs &a, int b, int64_t quad, const uint32_t *bits, const uint32_t *prefix,
+                                                   const uint16_t *sym, int cnt0, int cnt1, int cnt2)
 {
     const Geo &g = a.g;
-    const int nwt = g.nw16 + g.nw8 + g.nw4;
-    const uint32_t *bits = a.ws.bits + (int64_t)b * nwt;
-    const uint32_t *prefix = a.ws.prefix + (int64_t)b * nwt;
-    const int32_t *cntp = a.ws.count + b * 3;
-    if (quad == 0) {
-        // the reference's masked assignment raises unless #symbols == #set cells (an empty
-        // coarse / medium stream stands for zeros, model.py:284-290)
-        const int32_t *pop = a.ws.pop + b * 3;
-        bool bad = false;
-        for (int s = 0; s < 5; ++s) bad |= a.ws.flag[b * 5 + s] != 0;
-        for (int s = 0; s < 3; ++s) {
-            if (!stream_present(a.mode, s)) continue;
-            const bool empty_ok = cntp[s] == -1 && (s < 2 || pop[s] == 0);
-            if (!empty_ok && cntp[s] != pop[s]) bad = true;
-        }
-        if (bad) atomicExch(&a.status[b], CGIC_EFORMAT);
-    }
     const int64_t p = quad * 4;
-    if (p >= g.n4) return;
+    if (p >= g.n4) return false;
     const int y = (int)(p / g.w), x = (int)(p - (int64_t)y * g.w);
-    const uint16_t *sym = a.ws.sym + (int64_t)b * (g.n16 + g.n8 + g.n4);
-    const int cnt0 = cntp[0], cnt1 = cntp[1], cnt2 = cntp[2];
     const int64_t p16 = (int64_t)(y >> 2) * g.w16 + (x >> 2);
     const int64_t p8 = (int64_t)(y >> 1) * g.w8 + (x >> 1);  // even: p8 and p8 + 1 share a word
     // bitmap words, popcount prefixes and counts are all independent loads: issued together, one round trip
@@ -1197,12 +1189,12 @@ __device__ __forceinline__ void assemble_quad(const UnpackArgs &a, int b, int64_
     mf_o[1] = make_longlong2(fbit[2], fbit[3]);
     if ((y & 1) == 0) *reinterpret_cast<longlong2 *>(a.mm_out + (int64_t)b * g.n8 + p8) = make_longlong2(mbit[0], mbit[1]);
     if ((y & 3) == 0) a.mc_out[(int64_t)b * g.n16 + p16] = cbit;
+    bool bad = false;
     if (a.quant_out) {
         float4 e[4];
-        bool bad = false;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            bad |= ind[i] >= a.T.K;  // sums of overlapping levels cannot occur with valid masks
+            bad |= ind[i] >= a.T.K;
             e[i] = __ldg(reinterpret_cast<const float4 *>(a.codebook) + (ind[i] < a.T.K ? ind[i] : 0));
         }
         float4 *q = reinterpret_cast<float4 *>(a.quant_out + (int64_t)b * 4 * g.n4 + p);
@@ -1211,8 +1203,36 @@ __device__ __forceinline__ void assemble_quad(const UnpackArgs &a, int b, int64_
         q[plane4] = make_float4(e[0].y, e[1].y, e[2].y, e[3].y);
         q[2 * plane4] = make_float4(e[0].z, e[1].z, e[2].z, e[3].z);
         q[3 * plane4] = make_float4(e[0].w, e[1].w, e[2].w, e[3].w);
+    }
+    return bad;
+}
+
+// the reference's masked assignment raises unless #symbols == #set cells (an empty coarse / medium stream stands for
+// zeros, model.py:284-290)
+__device__ __forceinline__ bool counts_mismatch(int mode, const int32_t *cnt, const int32_t *pop)
+{
+    bool bad = false;
+    for (int s = 0; s < 3; ++s) {
+        if (!stream_present(mode, s)) continue;
+        const bool empty_ok = cnt[s] == -1 && (s < 2 || pop[s] == 0);
+        if (!empty_ok && cnt[s] != pop[s]) bad = true;
+    }
+    return bad;
+}
+
+__device__ __forceinline__ void assemble_quad(const UnpackArgs &a, int b, int64_t quad)
+{
+    const Geo &g = a.g;
+    const int nwt = g.nw16 + g.nw8 + g.nw4;
+    const int32_t *cntp = a.ws.count + b * 3;
+    if (quad == 0) {
+        bool bad = counts_mismatch(a.mode, cntp, a.ws.pop + b * 3);
+        for (int s = 0; s < 5; ++s) bad |= a.ws.flag[b * 5 + s] != 0;
         if (bad) atomicExch(&a.status[b], CGIC_EFORMAT);
     }
+    if (assemble_quad_core(a, b, quad, a.ws.bits + (int64_t)b * nwt, a.ws.prefix + (int64_t)b * nwt,
+                           a.ws.sym + (int64_t)b * (g.n16 + g.n8 + g.n4), cntp[0], cntp[1], cntp[2]))
+        atomicExch(&a.status[b], CGIC_EFORMAT);
 }
 
 // grid (4, B): one CTA per index stream, then the mask CTA
@@ -1243,6 +1263,551 @@ __global__ void __launch_bounds__(256) unpack_assemble_kernel(const UnpackArgs a
     assemble_quad(a, blockIdx.y, (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
     CGIC_STAMP(assemble, 2);
 }
+
+// ======================================================================================================================
+// Small token grids (<= DS_MAX_N4 fine tokens) with codes of at most 32 bits: ONE CTA per image decodes the three index
+// streams, builds the mask levels and re-assembles the image -- symbols, bitmaps and prefixes never leave shared memory
+// and the step is one launch instead of two (decode -> hand-over -> re-assembly).
+//
+// Decoder: the same idea as the candidate decoder above (the first codeword of a subsequence can only start at one of
+// D = max_len offsets), without its D-fold redundant chain walks.  Subsequences are single 32-bit stream words; after the
+// pass that writes the code length at every bit position (len8[]),
+//   DP    one thread per word sweeps its 32 positions from the last to the first:
+//             fn[q] = (exit offset into the next word, codewords started) = q + len >= 32 ? (q + len - 32, 1) : fn[q + len] + (0, 1)
+//         -- one table look-up per bit position, chains that merge share their tail.  Positions are handled in groups of
+//         G = 4: a group's look-ups only reach positions >= q + min_len of EARLIER groups, so with min_len >= 4 they are
+//         independent of the group's own stores and their latencies overlap (G = 1 for tables with shorter codes);
+//   B     the true entry offset of every word by composing fn along the stream: blocks of 16 words for every
+//         candidate entry (one thread each), a serial walk over the <= 32 blocks, blocks replayed;
+//   C     every word decodes the codewords that start in it from its true entry offset and writes the symbols at its
+//         prefix count into the image's symbol list in shared memory.
+// The three streams of an image share every pass: a batch is up to 512 words cut into at most three segments (one per
+// stream, block aligned, one look-ahead word each); streams longer than a batch continue in the next one, carrying
+// (entry offset, symbols so far).  Greedy semantics of the reference (indices_coding.py:140-151) as everywhere: a position
+// whose codeword would run past the payload ends the decoding of that stream.
+#ifndef CGIC_DS_THREADS
+#define CGIC_DS_THREADS 512
+#endif
+constexpr int DS_THREADS = CGIC_DS_THREADS;
+constexpr int DS_WORDS = 512;              // stream words (= subsequences) per batch
+constexpr int DS_BS = 16;                  // words per composition block
+constexpr int DS_NBLK = DS_WORDS / DS_BS;  // 32
+constexpr int DS_WCAP = DS_WORDS + 4;      // + one look-ahead word per segment + one zero word
+constexpr int DS_MAX_D = 32;
+constexpr int DS_MAX_N4 = 4096;
+constexpr uint32_t DS_STOP = 0xFFu;
+
+// len8[]: 36 bytes per word, fn[]: 34 u16 (68 bytes) per word -- word strides of 9 / 17 banks, so that the threads of a
+// warp (one word each) never meet in a bank
+
+struct DsSeg {
+    int s, sub0, n, nb, w0, blk0;  // stream, first stream word, words, blocks, first batch word, first batch block
+};
+
+struct DsLayout {
+    size_t words, len, fn, sym, bits, prefix, masks, total;
+};
+__host__ __device__ inline DsLayout ds_layout(uint32_t dec_stage_words, const Geo &g)
+{
+    auto up = [](size_t v) { return (v + 15) / 16 * 16; };
+    DsLayout L;
+    size_t o = up((size_t)dec_stage_words * 4);
+    L.words = o;
+    o += up((size_t)(DS_WCAP + 1) * 4);
+    L.len = o;
+    o += up((size_t)DS_WCAP * 36);
+    L.fn = o;
+    o += up((size_t)DS_WCAP * 68);
+    L.sym = o;
+    o += up((size_t)(g.n16 + g.n8 + g.n4) * 2);
+    L.bits = o;
+    o += up((size_t)(g.nw16 + g.nw8 + g.nw4) * 4);
+    L.prefix = o;
+    o += up((size_t)(g.nw16 + g.nw8 + g.nw4) * 4);
+    L.masks = o;
+    o += up((size_t)(g.n16 / 8 + 2)) + up((size_t)(g.n8 / 8 + 2));
+    L.total = o;
+    return L;
+}
+
+// (sym << 8) | len of the codeword at the head of `win` (32 stream bits, MSB first); codes of at most 32 bits
+__device__ __forceinline__ uint32_t ds_decode_win(uint32_t win, const uint32_t *s_lut, const uint32_t *lut2, const DevTable &T, int L)
+{
+    const uint32_t e = s_lut[win >> (32 - L)];
+    const uint32_t f = e & 0xFFu;
+    if (!(f & 0x80u)) return e;
+    if (f != 0xFFu) {
+        const uint32_t hgt = f & 0x7Fu;
+        return lut2[(e >> 8) + ((win << L) >> (32 - hgt))] + (uint32_t)L;  // second-level entries hold the bits used beyond L
+    }
+    int node = (int)(e >> 8);
+    uint32_t used = (uint32_t)L;
+    while (node >= T.K && used < 32u) {
+        node = __ldg(&T.child[2 * node + (int)((win >> (31u - used)) & 1u)]);
+        ++used;
+    }
+    return node >= T.K ? 0u : (((uint32_t)node << 8) | used);  // (max_len <= 32: the walk always ends on a leaf)
+}
+
+// bitmap + exclusive popcount prefix + population of one level by ONE warp (the levels of a small grid have at most
+// 128 words); wordfn(wi) = the 32 cells wi*32 .. wi*32+31 (bits past n are masked here)
+template <typename F>
+__device__ __forceinline__ void build_level_warp(int n, int nw, uint32_t *bits, uint32_t *prefix, int32_t *pop_out, int lane, F wordfn)
+{
+    int run = 0;
+    for (int base = 0; base < nw; base += 32) {
+        const int wi = base + lane;
+        uint32_t word = 0;
+        if (wi < nw) {
+            word = wordfn(wi);
+            const int left = n - wi * 32;
+            if (left < 32) word &= (1u << left) - 1u;
+            bits[wi] = word;
+        }
+        const int v = __popc(word);
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (wi < nw) prefix[wi] = (uint32_t)(run + inc - v);
+        run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) *pop_out = run;
+}
+
+// Re-assembly of 4 consecutive fine tokens of a row for the fused kernel: 32-bit arithmetic (the grid has at most 4096
+// cells), tables in shared memory.  Same outputs as assemble_quad_core.
+__device__ __forceinline__ bool assemble_quad_small(const UnpackArgs &a, int b, int quad, const uint32_t *bits, const uint32_t *prefix,
+                                                    const uint16_t *sym, int cnt0, int cnt1, int cnt2)
+{
+    const Geo &g = a.g;
+    const int n4 = (int)g.n4, n8 = (int)g.n8, n16 = (int)g.n16;
+    const int p = quad * 4;
+    const int wq = g.w >> 2;
+    const int y = quad / wq, x = (quad - y * wq) * 4;
+    const int p16 = (y >> 2) * g.w16 + (x >> 2);
+    const int p8 = (y >> 1) * g.w8 + (x >> 1);  // even: p8 and p8 + 1 share a word
+    const uint32_t wc = bits[p16 >> 5], wm = bits[g.nw16 + (p8 >> 5)], wf = bits[g.nw16 + g.nw8 + (p >> 5)];
+    const uint32_t pre_c = prefix[p16 >> 5], pre_m = prefix[g.nw16 + (p8 >> 5)], pre_f = prefix[g.nw16 + g.nw8 + (p >> 5)];
+    const int sc = p16 & 31, sm = p8 & 31, sf = p & 31;
+    const int cbit = (wc >> sc) & 1;
+    int base = 0;
+    if (cbit && cnt0 > 0) {
+        const int r = pre_c + __popc(wc & ((1u << sc) - 1u));
+        if (r < cnt0) base = sym[r];
+    }
+    int mbit[2], mval[2] = {0, 0};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        mbit[j] = (wm >> (sm + j)) & 1;
+        if (mbit[j] && cnt1 > 0) {
+            const int r = pre_m + __popc(wm & ((1u << (sm + j)) - 1u));
+            if (r < cnt1) mval[j] = sym[n16 + r];
+        }
+    }
+    int fbit[4], ind[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        fbit[i] = (wf >> (sf + i)) & 1;
+        int v = base + mval[i >> 1];
+        if (fbit[i] && cnt2 > 0) {
+            const int r = pre_f + __popc(wf & ((1u << (sf + i)) - 1u));
+            if (r < cnt2) v += sym[n16 + n8 + r];
+        }
+        ind[i] = v;
+    }
+    const size_t o4 = (size_t)b * n4 + p;
+    longlong2 *ind_o = reinterpret_cast<longlong2 *>(a.ind_out + o4);
+    ind_o[0] = make_longlong2(ind[0], ind[1]);
+    ind_o[1] = make_longlong2(ind[2], ind[3]);
+    longlong2 *mf_o = reinterpret_cast<longlong2 *>(a.mf_out + o4);
+    mf_o[0] = make_longlong2(fbit[0], fbit[1]);
+    mf_o[1] = make_longlong2(fbit[2], fbit[3]);
+    if ((y & 1) == 0) *reinterpret_cast<longlong2 *>(a.mm_out + (size_t)b * n8 + p8) = make_longlong2(mbit[0], mbit[1]);
+    if ((y & 3) == 0) a.mc_out[(size_t)b * n16 + p16] = cbit;
+    bool bad = false;
+    if (a.quant_out) {
+        float4 e[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            bad |= ind[i] >= a.T.K;  // sums of overlapping levels cannot occur with valid masks
+            e[i] = __ldg(reinterpret_cast<const float4 *>(a.codebook) + (ind[i] < a.T.K ? ind[i] : 0));
+        }
+        float4 *q = reinterpret_cast<float4 *>(a.quant_out + (size_t)b * 4 * n4 + p);
+        const int plane4 = n4 >> 2;
+        q[0] = make_float4(e[0].x, e[1].x, e[2].x, e[3].x);
+        q[plane4] = make_float4(e[0].y, e[1].y, e[2].y, e[3].y);
+        q[2 * plane4] = make_float4(e[0].z, e[1].z, e[2].z, e[3].z);
+        q[3 * plane4] = make_float4(e[0].w, e[1].w, e[2].w, e[3].w);
+    }
+    return bad;
+}
+
+template <int G>
+__global__ void __launch_bounds__(DS_THREADS, DS_THREADS <= 512 ? 2 : 1) unpack_small_kernel(const UnpackArgs a)
+{
+    extern __shared__ __align__(128) unsigned char dyn[];
+    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ uint32_t s_blockfn[DS_NBLK * 32];   // (symbols << 8) | exit offset of a block, per candidate entry offset
+    __shared__ uint8_t s_blkstart[DS_NBLK];
+    __shared__ uint32_t s_blkbase[DS_NBLK];
+    __shared__ uint16_t s_blkw0[DS_NBLK];
+    __shared__ uint8_t s_blkseg[DS_NBLK];
+    __shared__ uint8_t s_substart[DS_WCAP];
+    __shared__ uint32_t s_subbase[DS_WCAP];
+    __shared__ int s_nbits[3], s_nwords[3], s_done[3], s_nsym[3], s_nbytes[3];
+    __shared__ uint32_t s_entry[3];
+    __shared__ int32_t s_pop[3], s_cnt[3];
+    __shared__ int s_nseg, s_wcur, s_nblk, s_bad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
+    const Geo &g = a.g;
+    const DsLayout SL = ds_layout(a.T.dec_stage_words, g);
+    uint32_t *s_dec = reinterpret_cast<uint32_t *>(dyn);
+    uint32_t *s_w = reinterpret_cast<uint32_t *>(dyn + SL.words);
+    uint8_t *s_len = dyn + SL.len;
+    uint16_t *s_fn = reinterpret_cast<uint16_t *>(dyn + SL.fn);
+    uint16_t *s_sym = reinterpret_cast<uint16_t *>(dyn + SL.sym);
+    uint32_t *s_bits = reinterpret_cast<uint32_t *>(dyn + SL.bits);
+    uint32_t *s_prefix = reinterpret_cast<uint32_t *>(dyn + SL.prefix);
+    unsigned char *s_masks = dyn + SL.masks;
+    const int D = a.T.max_len, L = a.T.lut_bits;
+    CGIC_STAMP(unpack, 0);
+    pdl_trigger_step<4>();
+    // the (immutable) decode tables are staged while the predecessor kernel may still be running
+    if (tid == 0) {
+        mbar_init(&mbar);
+        s_bad = 0;
+    }
+    __syncthreads();
+    if (tid == 0) tma_load_1d(s_dec, a.T.lut, a.T.dec_stage_words * 4u, &mbar);
+    const bool lut2_shared = a.T.dec_stage_words > a.T.lut_pad;
+    const uint32_t *lut2 = lut2_shared ? s_dec + a.T.lut_pad : a.T.lut2;
+    pdl_wait();
+    CGIC_STAMP(unpack, 1);
+    const uint8_t *img = a.bytes + (int64_t)b * a.image_stride;
+    const int32_t *sz = a.sizes + b * 5;
+    // ---- ONE round trip to global memory for everything that does not depend on the stream sizes: the sizes themselves, the
+    //      header bytes of the index streams, the mask streams (their length follows from the grid)
+    const bool need_c = a.mode == 0 || a.mode == 2 || a.mode == 3;
+    const bool need_m = a.mode == 0 || a.mode == 1;
+    const int cap_c = (int)(g.n16 / 8 + 2), cap_m = (int)(g.n8 / 8 + 2);
+    const int off_m = (cap_c + 15) & ~15;
+    {
+        const int nc16 = need_c ? (cap_c + 15) >> 4 : 0, nm16 = need_m ? (cap_m + 15) >> 4 : 0;
+        for (int i = tid; i < nc16 + nm16; i += DS_THREADS) {
+            const bool isc = i < nc16;
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(img + (isc ? a.slot_off[3] : a.slot_off[4])) + (isc ? i : i - nc16));
+            reinterpret_cast<uint4 *>(s_masks + (isc ? 0 : off_m))[isc ? i : i - nc16] = v;
+        }
+    }
+    if (tid < 3) {
+        const int s = tid;
+        int nbytes = stream_present(a.mode, s) ? __ldg(sz + s) : 0;
+        const int pad = __ldg(img + a.slot_off[s]);  // (read whether or not the stream exists: the slot does)
+        if (nbytes < 0 || nbytes > a.slot_cap[s]) {  // a size no packer can have produced: never read past the slot
+            nbytes = 0;
+            atomicOr(&s_bad, 1);
+        }
+        int nbits = 0;
+        if (nbytes > 0) {
+            nbits = (nbytes - 1) * 8 - pad;
+            if (pad == 0 || nbits < 0) nbits = 0;  // text[:-0] is empty in the reference
+        }
+        s_nbytes[s] = nbytes;
+        s_nbits[s] = nbits;
+        s_nwords[s] = (nbits + 31) >> 5;
+        s_done[s] = 0;
+        s_nsym[s] = 0;
+        s_entry[s] = 0;
+    }
+    if (tid == 32 && need_c && __ldg(sz + 3) != cap_c) atomicOr(&s_bad, 1);
+    if (tid == 33 && need_m && __ldg(sz + 4) != cap_m) atomicOr(&s_bad, 1);
+    __syncthreads();
+    // ---- mask levels: one warp per level (framing of the mask streams checked on the staged bytes); meanwhile the other warps
+    //      go on to the first batch, whose global loads thus overlap this
+    if (warp < 3) {
+        const uint8_t *mc = s_masks, *mm = s_masks + off_m;
+        if (warp == 0) {
+            if (need_c && lane == 0 && mc[0] != 8 - (int)(g.n16 & 7)) atomicOr(&s_bad, 1);
+            if (need_c) build_level_warp((int)g.n16, g.nw16, s_bits, s_prefix, s_pop + 0, lane, [&](int wi) { return word_from_stream(mc, cap_c, wi); });
+            else build_level_warp((int)g.n16, g.nw16, s_bits, s_prefix, s_pop + 0, lane, [&](int) { return a.mode == 4 ? 0xFFFFFFFFu : 0u; });
+        } else if (warp == 1) {
+            uint32_t *bm = s_bits + g.nw16, *pm = s_prefix + g.nw16;
+            if (need_m && lane == 0 && mm[0] != 8 - (int)(g.n8 & 7)) atomicOr(&s_bad, 1);
+            if (need_m) build_level_warp((int)g.n8, g.nw8, bm, pm, s_pop + 1, lane, [&](int wi) { return word_from_stream(mm, cap_m, wi); });
+            else if (a.mode == 3)
+                build_level_warp((int)g.n8, g.nw8, bm, pm, s_pop + 1, lane, [&](int wi) {
+                    return word_from_cells(wi, g.w8, g.n8, [&](int y, int x) { return medium_cell(a, mc, mm, y, x); });
+                });
+            else build_level_warp((int)g.n8, g.nw8, bm, pm, s_pop + 1, lane, [&](int) { return a.mode == 5 ? 0xFFFFFFFFu : 0u; });
+        } else {
+            uint32_t *fb = s_bits + g.nw16 + g.nw8, *fp = s_prefix + g.nw16 + g.nw8;
+            if (a.mode > 2) {
+                build_level_warp((int)g.n4, g.nw4, fb, fp, s_pop + 2, lane, [&](int) { return a.mode == 6 ? 0xFFFFFFFFu : 0u; });
+            } else if (g.w % 32 == 0) {
+                // a bitmap word = 32 cells of one row = 16 medium cells (2 stream bytes) and 8 coarse cells (1 byte)
+                build_level_warp((int)g.n4, g.nw4, fb, fp, s_pop + 2, lane, [&](int wi) {
+                    const int p0 = wi * 32;
+                    const int y = p0 / g.w, x0 = p0 - y * g.w;
+                    uint32_t m16 = 0, c8 = 0;
+                    if (need_m) {
+                        const int p8 = (y >> 1) * g.w8 + (x0 >> 1);
+                        const uint8_t *q = mm + 1 + (p8 >> 3);
+                        m16 = __brev(((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16));
+                    }
+                    if (need_c) {
+                        const int p16 = (y >> 2) * g.w16 + (x0 >> 2);
+                        c8 = __brev((uint32_t)mc[1 + (p16 >> 3)] << 24);
+                    }
+                    return ~(spread2(m16) | spread2(spread2(c8)));
+                });
+            } else {
+                build_level_warp((int)g.n4, g.nw4, fb, fp, s_pop + 2, lane, [&](int wi) {
+                    return word_from_cells(wi, g.w, g.n4, [&](int y, int x) { return fine_cell(a, mc, mm, y, x); });
+                });
+            }
+        }
+    }
+    bool tables_ready = false;
+    CGIC_STAMP(unpack, 2);
+
+    auto symoff = [&](int s) { return s == 0 ? 0 : (s == 1 ? (int)g.n16 : (int)(g.n16 + g.n8)); };
+    auto symcap = [&](int s) { return s == 0 ? (int)g.n16 : (s == 1 ? (int)g.n8 : (int)g.n4); };
+    for (;;) {
+        // ---- plan the batch: up to three segments, block aligned (every thread computes the same plan from the shared state;
+        //      scalars, not an array: a dynamically indexed array would live in local memory)
+        int nseg = 0, wcur = 0, nblk = 0;
+        int g_s[3] = {0, 0, 0}, g_sub0[3] = {0, 0, 0}, g_n[3] = {0, 0, 0}, g_nb[3] = {0, 0, 0}, g_w0[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff},
+            g_blk0[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
+        {
+            int free_blk = DS_NBLK;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const int rem = s_nwords[s] - s_done[s];
+                if (rem <= 0 || s_entry[s] == DS_STOP || free_blk == 0) continue;
+                const int n = min(rem, free_blk * DS_BS), nb = (n + DS_BS - 1) / DS_BS;
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (k == nseg) {
+                        g_s[k] = s;
+                        g_sub0[k] = s_done[s];
+                        g_n[k] = n;
+                        g_nb[k] = nb;
+                        g_w0[k] = wcur;
+                        g_blk0[k] = DS_NBLK - free_blk;
+                    }
+                wcur += nb * DS_BS + 1;
+                free_blk -= nb;
+                ++nseg;
+            }
+            nblk = DS_NBLK - free_blk;
+        }
+        if (nseg == 0) break;
+        // segment of a batch word: stream, first stream word of that batch word
+        auto seg_stream = [&](int wi) { return wi >= g_w0[2] ? g_s[2] : (wi >= g_w0[1] ? g_s[1] : g_s[0]); };
+        auto seg_word = [&](int wi) { return wi >= g_w0[2] ? g_sub0[2] + (wi - g_w0[2]) : (wi >= g_w0[1] ? g_sub0[1] + (wi - g_w0[1]) : g_sub0[0] + (wi - g_w0[0])); };
+        if (tid < nblk) {
+            const int k = tid >= g_blk0[2] ? 2 : (tid >= g_blk0[1] ? 1 : 0);
+            const int w0k = k == 2 ? g_w0[2] : (k == 1 ? g_w0[1] : g_w0[0]), b0k = k == 2 ? g_blk0[2] : (k == 1 ? g_blk0[1] : g_blk0[0]);
+            s_blkw0[tid] = (uint16_t)(w0k + (tid - b0k) * DS_BS);
+            s_blkseg[tid] = (uint8_t)(k == 2 ? g_s[2] : (k == 1 ? g_s[1] : g_s[0]));
+        }
+        // ---- stage the stream words: word i of a stream = bytes 1 + 4 i .. 4 + 4 i (the header byte is skipped), MSB first
+        for (int wi = tid; wi <= wcur; wi += DS_THREADS) {
+            uint32_t v = 0;
+            if (wi < wcur) {
+                const int ss = seg_stream(wi), sw = seg_word(wi);
+                const uint32_t *W = reinterpret_cast<const uint32_t *>(img + a.slot_off[ss]);
+                const int cap = (int)a.slot_cap[ss];
+                const uint32_t lo = 4 * sw + 4 <= cap ? __ldg(W + sw) : 0u, hi = 4 * sw + 8 <= cap ? __ldg(W + sw + 1) : 0u;
+                v = __byte_perm(lo, hi, 0x1234);
+            }
+            s_w[wi] = v;
+        }
+        if (!tables_ready) {
+            tables_ready = true;
+            mbar_wait(&mbar, 0);
+        }
+        __syncthreads();
+        CGIC_STAMP(unpack, 3);
+        // ---- A0: code length at every bit position (0 where the codeword would run past the payload).  One- and two-level codes
+        //      without a branch (the second look-up is always issued, on entry 0 when unused); only codes beyond the second
+        //      level walk the tree.
+        for (int it = tid; it < wcur * 4; it += DS_THREADS) {
+            const int wi = it >> 2, qtr = it & 3;
+            const int lim = s_nbits[seg_stream(wi)] - 32 * seg_word(wi) - qtr * 8;  // position k of this quarter is valid iff k + len <= lim
+            const uint32_t w0 = s_w[wi], w1 = s_w[wi + 1];
+            uint32_t *dst = reinterpret_cast<uint32_t *>(s_len + 36 * wi + qtr * 8);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                uint32_t packed = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int pos = j * 4 + k;
+                    const uint32_t win = __funnelshift_l(w1, w0, qtr * 8 + pos);
+                    const uint32_t e = s_dec[win >> (32 - L)];
+                    uint32_t f = e & 0xFFu;
+                    if (f & 0x80u) {
+                        if (lut2_shared && f != 0xFFu) {
+                            const uint32_t hgt = f & 0x7Fu;
+                            f = (lut2[(e >> 8) + ((win << L) >> (32 - hgt))] & 0xFFu) + (uint32_t)L;
+                        } else {
+                            f = ds_decode_win(win, s_dec, lut2, a.T, L) & 0xFFu;
+                        }
+                    }
+                    if (pos + (int)f > lim) f = 0;
+                    packed |= f << (8 * k);
+                }
+                dst[j] = packed;
+            }
+        }
+        __syncthreads();
+        CGIC_STAMP(unpack, 7);
+        // ---- DP: fn[q] = (exit offset << 8) | codewords, from the last position of a word to the first
+        for (int wi = tid; wi < wcur; wi += DS_THREADS) {
+            const uint32_t *lw = reinterpret_cast<const uint32_t *>(s_len + 36 * wi);
+            uint16_t *fw = s_fn + 34 * wi;
+            uint32_t l8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) l8[i] = lw[i];
+            if (G == 4) {
+#pragma unroll
+                for (int grp = 7; grp >= 0; --grp) {
+                    uint32_t r[4], t[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t len = (l8[grp] >> (8 * u)) & 0xFFu;
+                        t[u] = (uint32_t)(4 * grp + u) + len;
+                        r[u] = len == 0 ? (DS_STOP << 8) : (t[u] >= 32u ? (((t[u] - 32u) << 8) | 1u) : 0xFFFFFFFFu);
+                    }
+                    uint32_t ld[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) ld[u] = fw[r[u] == 0xFFFFFFFFu ? t[u] : 31u];  // (every look-up reaches an earlier group)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (r[u] == 0xFFFFFFFFu) r[u] = ld[u] + 1u;  // same exit, one more codeword (<= 32: no carry into the exit byte)
+                    uint32_t *dst = reinterpret_cast<uint32_t *>(fw + 4 * grp);
+                    dst[0] = r[0] | (r[1] << 16);
+                    dst[1] = r[2] | (r[3] << 16);
+                }
+            } else {
+                for (int k = 31; k >= 0; --k) {
+                    const uint32_t len = (l8[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+                    const uint32_t t = (uint32_t)k + len;
+                    uint32_t r;
+                    if (len == 0) r = DS_STOP << 8;
+                    else if (t >= 32u) r = ((t - 32u) << 8) | 1u;
+                    else r = (uint32_t)fw[t] + 1u;
+                    fw[k] = (uint16_t)r;
+                }
+            }
+        }
+        __syncthreads();
+        CGIC_STAMP(unpack, 4);
+        // ---- B1: what a block of 16 words does to every candidate entry offset (items = blocks x D, no idle lanes)
+        for (int it = tid; it < nblk * D; it += DS_THREADS) {
+            const int blk = it / D, c = it - blk * D;
+            const uint16_t *fb = s_fn + 34 * (int)s_blkw0[blk];
+            uint32_t x = (uint32_t)c, n = 0;
+#pragma unroll 4
+            for (int i = 0; i < DS_BS; ++i) {
+                if (x != DS_STOP) {
+                    const uint32_t f = fb[34 * i + x];
+                    n += f & 0xFFu;
+                    x = f >> 8;
+                }
+            }
+            s_blockfn[blk * 32 + c] = (n << 8) | x;
+        }
+        __syncthreads();
+        CGIC_STAMP(unpack, 10);
+        // ---- B2: one thread per segment chains its blocks (and carries the stream's state into the next batch)
+        if (tid < nseg) {
+            const int st = tid == 0 ? g_s[0] : (tid == 1 ? g_s[1] : g_s[2]), nb = tid == 0 ? g_nb[0] : (tid == 1 ? g_nb[1] : g_nb[2]);
+            const int blk0 = tid == 0 ? g_blk0[0] : (tid == 1 ? g_blk0[1] : g_blk0[2]);
+            const int done = tid == 0 ? g_sub0[0] + g_n[0] : (tid == 1 ? g_sub0[1] + g_n[1] : g_sub0[2] + g_n[2]);
+            uint32_t x = s_entry[st], base = (uint32_t)s_nsym[st];
+            for (int k = 0; k < nb; ++k) {
+                const int blk = blk0 + k;
+                s_blkstart[blk] = (uint8_t)x;
+                s_blkbase[blk] = base;
+                if (x != DS_STOP) {
+                    const uint32_t f = s_blockfn[blk * 32 + x];
+                    base += f >> 8;
+                    x = f & 0xFFu;
+                }
+            }
+            s_entry[st] = x;
+            s_nsym[st] = (int)min(base, 0x7FFFFFFFu);
+            s_done[st] = done;
+        }
+        __syncthreads();
+        CGIC_STAMP(unpack, 11);
+        // ---- B3: blocks replayed from their true entry offset
+        if (tid < nblk) {
+            const int bw0 = s_blkw0[tid];
+            uint32_t x = s_blkstart[tid], base = s_blkbase[tid];
+#pragma unroll 4
+            for (int i = 0; i < DS_BS; ++i) {
+                s_substart[bw0 + i] = (uint8_t)x;
+                s_subbase[bw0 + i] = base;
+                if (x != DS_STOP) {
+                    const uint32_t f = s_fn[34 * (bw0 + i) + x];
+                    base += f & 0xFFu;
+                    x = f >> 8;
+                }
+            }
+        }
+        __syncthreads();
+        CGIC_STAMP(unpack, 5);
+        // ---- C: every word writes the symbols of the codewords that start in it
+        for (int it = tid; it < nblk * DS_BS; it += DS_THREADS) {
+            const int blk = it >> 4;
+            const int wi = s_blkw0[blk] + (it & 15);
+            uint32_t q = s_substart[wi];
+            if (q >= 32u) continue;  // DS_STOP, or the codeword that straddles into this word ends beyond it
+            const int s = s_blkseg[blk];
+            uint16_t *out = s_sym + symoff(s);
+            const int ocap = symcap(s);
+            int o = (int)min(s_subbase[wi], 0x7FFFFFFFu);
+            const uint32_t w0 = s_w[wi], w1 = s_w[wi + 1];
+            const uint8_t *lp = s_len + 36 * wi;
+            while (q < 32u) {
+                const uint32_t len = lp[q];
+                if (!len) break;
+                const uint32_t e = ds_decode_win(__funnelshift_l(w1, w0, q), s_dec, lut2, a.T, L);
+                if (o < ocap) out[o] = (uint16_t)(e >> 8);
+                ++o;
+                q += len;
+            }
+        }
+        __syncthreads();
+        CGIC_STAMP(unpack, 8);
+    }
+    if (!tables_ready) mbar_wait(&mbar, 0);  // never leave with the bulk copy in flight
+    CGIC_STAMP(unpack, 6);
+    // ---- symbol counts, status
+    if (tid < 3) {
+        int c = s_nbytes[tid] > 0 ? s_nsym[tid] : -1;
+        if (c > symcap(tid)) {  // more symbols than the level has cells: only a corrupt stream can
+            c = -2;
+            atomicOr(&s_bad, 1);
+        }
+        s_cnt[tid] = c;
+    }
+    __syncthreads();
+    const int cnt0 = s_cnt[0], cnt1 = s_cnt[1], cnt2 = s_cnt[2];
+    bool bad = false;
+    const int nquads = (int)(g.n4 >> 2);
+    for (int quad = tid; quad < nquads; quad += DS_THREADS) bad |= assemble_quad_small(a, b, quad, s_bits, s_prefix, s_sym, cnt0, cnt1, cnt2);
+    const int any_bad = __syncthreads_or(bad);
+    CGIC_STAMP(unpack, 9);
+    if (tid == 0) a.status[b] = (any_bad || s_bad || counts_mismatch(a.mode, s_cnt, s_pop)) ? CGIC_EFORMAT : 0;
+}
+
+size_t unpack_small_smem(const DevTable &T, const Geo &g) { return ds_layout(T.dec_stage_words, g).total; }
 
 __global__ void __launch_bounds__(DEC_THREADS)
 huff_decode_single_kernel(const uint8_t *bytes, int64_t nbytes, DevTable T, int32_t *out, int64_t cap, int32_t *count_out, int ch)
@@ -1337,6 +1902,21 @@ extern "C" int cgic_unpack(const uint8_t *bytes, const int32_t *sizes, int B, in
     {
         const int64_t chunks = (a.g.n4 * 12 / DEC_SUB_BITS + a.ch - 1) / a.ch;
         a.nslots = a.g.n4 <= 4096 || a.T.max_len > DEC_MAX_D ? 1 : (int)std::min<int64_t>(8, std::max<int64_t>(1, chunks));
+    }
+    // small token grids, codes of at most 32 bits: decode + re-assembly fused, one CTA per image
+    static const bool no_small = getenv("CGIC_NO_SMALL_KERNELS") != nullptr;  // diagnosis / A-B only
+    if (!no_small && a.g.n4 <= DS_MAX_N4 && a.T.max_len <= DS_MAX_D) {
+        const size_t smem_small = unpack_small_smem(a.T, a.g);
+        const bool g4 = a.T.min_len >= 4;
+        rc = ensure_smem(g4 ? (const void *)unpack_small_kernel<4> : (const void *)unpack_small_kernel<1>, smem_small);
+        if (rc) return rc;
+        {
+            CGIC_PROF("unpack_small_kernel", stream);
+            if (g4) CGIC_CUDA_CHECK(launch_pdl(unpack_small_kernel<4>, dim3(B), dim3(DS_THREADS), smem_small, stream, a));
+            else CGIC_CUDA_CHECK(launch_pdl(unpack_small_kernel<1>, dim3(B), dim3(DS_THREADS), smem_small, stream, a));
+        }
+        CGIC_LAUNCH_CHECK();
+        return CGIC_OK;
     }
     const size_t dec_bytes = decode_smem_bytes(a.T, a.ch);
     const size_t mask_bytes = (size_t)(((a.g.n16 / 8 + 2 + 15) & ~15) + ((a.g.n8 / 8 + 2 + 15) & ~15));

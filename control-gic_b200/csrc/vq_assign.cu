@@ -26,7 +26,7 @@
 //     dot = fma(z3,e3, fma(z2,e2, fma(z1,e1, fl(z0*e0))))
 //     d   = fl(fl(z2 + e2) - 2*dot) = fma(-2, dot, fl(z2 + e2))
 //     argmin with the LOWEST index among equal minima (torch.argmin).
-#include "codebook.cuh"
+#include "vq_tile.cuh"
 
 namespace cgic {
 
@@ -98,36 +98,6 @@ __device__ __forceinline__ float min3(float a, float b, float c)
     float r;
     asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
     return r;
-}
-
-__device__ __forceinline__ float sumsq4(float a, float b, float c, float d) { return sumsq4f(a, b, c, d); }
-
-// exact reference distance of one code (rounding sequence of quantize.py:73-75, see the header)
-__device__ __forceinline__ void eval_cand(unsigned k, const float4 &zv, float z2, const float4 *__restrict__ cbs,
-                                          const float *__restrict__ e2s, float &best, int &bk)
-{
-    const float4 e = cbs[k];
-    float dot = __fmul_rn(zv.x, e.x);
-    dot = __fmaf_rn(zv.y, e.y, dot);
-    dot = __fmaf_rn(zv.z, e.z, dot);
-    dot = __fmaf_rn(zv.w, e.w, dot);
-    const float d = __fmaf_rn(dot, -2.f, __fadd_rn(z2, e2s[k]));
-    if (d < best) {  // candidate lists ascend, so the lowest index wins ties (torch.argmin)
-        best = d;
-        bk = (int)k;
-    }
-}
-__device__ __forceinline__ void eval_word(unsigned wd, const float4 &zv, float z2, const float4 *cbs, const float *e2s, float &best, int &bk)
-{
-    eval_cand(wd & 0xffffu, zv, z2, cbs, e2s, best, bk);
-    eval_cand(wd >> 16, zv, z2, cbs, e2s, best, bk);
-}
-__device__ __forceinline__ void eval_piece(const uint4 &q, const float4 &zv, float z2, const float4 *cbs, const float *e2s, float &best, int &bk)
-{
-    eval_word(q.x, zv, z2, cbs, e2s, best, bk);
-    eval_word(q.y, zv, z2, cbs, e2s, best, bk);
-    eval_word(q.z, zv, z2, cbs, e2s, best, bk);
-    eval_word(q.w, zv, z2, cbs, e2s, best, bk);
 }
 
 // monotone map float -> uint32 (a < b  <=>  key(a) < key(b)); d is never -0 nor NaN here
@@ -497,67 +467,7 @@ vq_fused_kernel(const float *__restrict__ z, int B, int h, int w, const VqTiles 
 //   finalize  idx / z_q row segments, sum((e - z)^2) per lane, reduced per CTA at the end.
 constexpr int VQW_THREADS = 256;
 constexpr int VQW_WARPS = VQW_THREADS / 32;
-constexpr int VQW_TILE = 128;  // tokens per warp tile
 __host__ __device__ inline size_t vqw_smem_bytes(int K) { return vq_stage_bytes(K) + (size_t)VQW_WARPS * VQW_TILE * (16 + 2 + 1 + 1); }
-
-// Leaders the index could not serve (bits of `todo` = positions in list[]): the WARP searches all K codes, up to four
-// leaders per sweep (every code row is loaded once for all of them; lane k, k + 32, ...; per-lane ascending order + an
-// index tie-break in the reduction = the lowest index among equal minima; no finite distance at all leaves index 0,
-// like vq_fused_kernel).  Out of line: its registers must not weigh on the indexed path.
-__device__ __noinline__ void vq_exhaustive_sweep(unsigned todo, const uint8_t *list, const float4 *zs, uint16_t *res, const float4 *cbs,
-                                          const float *e2s, int K, int lane)
-{
-    while (todo) {
-        // up to four leaders per sweep over the codebook: every code row is loaded once for all of them
-        int tq[4];
-        float4 vq[4];
-        float z2q[4], bdq[4];
-        int bkq[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            tq[i] = -1;
-            if (todo) {
-                tq[i] = list[__ffs(todo) - 1];
-                todo &= todo - 1;
-            }
-            vq[i] = zs[tq[i] >= 0 ? tq[i] : 0];
-            z2q[i] = sumsq4(vq[i].x, vq[i].y, vq[i].z, vq[i].w);
-            bdq[i] = __int_as_float(0x7f800000);
-            bkq[i] = 0x7fffffff;
-        }
-        for (int k = lane; k < K; k += 32) {
-            const float4 e = cbs[k];
-            const float e2 = e2s[k];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float dot = __fmul_rn(vq[i].x, e.x);
-                dot = __fmaf_rn(vq[i].y, e.y, dot);
-                dot = __fmaf_rn(vq[i].z, e.z, dot);
-                dot = __fmaf_rn(vq[i].w, e.w, dot);
-                const float d = __fmaf_rn(dot, -2.f, __fadd_rn(z2q[i], e2));
-                if (d < bdq[i]) {
-                    bdq[i] = d;
-                    bkq[i] = k;
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float bd = bdq[i];
-            int bk = bkq[i];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float od = __shfl_xor_sync(0xffffffffu, bd, o);
-                const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
-                if (od < bd || (od == bd && ok < bk)) {
-                    bd = od;
-                    bk = ok;
-                }
-            }
-            if (lane == 0 && tq[i] >= 0) res[tq[i]] = (uint16_t)(bk == 0x7fffffff ? 0 : bk);
-        }
-    }
-}
 
 __global__ void __launch_bounds__(VQW_THREADS, 2)
 vq_warp_kernel(const float *__restrict__ z, int h, int w, int tiles_x, int tiles_y, int64_t n_tiles, const unsigned char *__restrict__ blob,
@@ -598,148 +508,15 @@ vq_warp_kernel(const float *__restrict__ z, int h, int w, int tiles_x, int tiles
     for (int64_t tile = wid; tile < n_tiles; tile += nwarps) {
         const int b = (int)(tile / tpi), rt = (int)(tile - (int64_t)b * tpi);
         const int ty = rt / tiles_x, tx = rt - ty * tiles_x;
-        const int gx = tx * 32 + lane, gy0 = ty * 4;
-        const bool col_ok = gx < w;
-        const float *zb = z + (int64_t)b * 4 * plane;
-        // ---- load
-        float zt[4][4];  // [row][channel]
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const bool ok = col_ok && gy0 + r < h;
-            const int64_t p = (int64_t)(gy0 + r) * w + gx;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) zt[r][c] = ok ? __ldg(zb + c * plane + p) : 0.f;
-        }
-        __syncwarp();  // the previous tile's slice is no longer read
-#pragma unroll
-        for (int r = 0; r < 4; ++r) zs[r * 32 + lane] = make_float4(zt[r][0], zt[r][1], zt[r][2], zt[r][3]);
-        if (!staged) {
-            staged = true;
-            mbar_wait(&mbar, 0);
-        }
-        __syncwarp();
-        VQ_STAMP(2);
-        // ---- classify + compact
-        int nlead = 0;
-        unsigned lmask[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int t = r * 32 + lane;
-            int ld = t;
-            const bool ok = col_ok && gy0 + r < h;
-            if (ok) {
-                const uint4 v = reinterpret_cast<const uint4 *>(zs)[t];
-                const int t4 = lane & ~3;  // row 0 of the tile is the top row of every 4x4 block
-                if (t4 != t) {
-                    const uint4 u = reinterpret_cast<const uint4 *>(zs)[t4];
-                    if (u.x == v.x && u.y == v.y && u.z == v.z && u.w == v.w) ld = t4;
-                }
-                if (ld == t) {
-                    const int t2 = (r & ~1) * 32 + (lane & ~1);
-                    if (t2 != t) {
-                        const uint4 u = reinterpret_cast<const uint4 *>(zs)[t2];
-                        if (u.x == v.x && u.y == v.y && u.z == v.z && u.w == v.w) ld = t2;
-                    }
-                }
-            }
-            lead[t] = (uint8_t)ld;
-            lmask[r] = __ballot_sync(0xffffffffu, ok && ld == t);
-        }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            if ((lmask[r] >> lane) & 1u) list[nlead + __popc(lmask[r] & ((1u << lane) - 1u))] = (uint8_t)(r * 32 + lane);
-            nlead += __popc(lmask[r]);
-        }
-        __syncwarp();
-        VQ_STAMP(3);
-        // ---- search: one lane per leader.  Pass 1 finds every leader's grid cell and prefetches its record, so that
-        //      the memory latency of all rounds overlaps; pass 2 evaluates.
-        const bool usable = hdr->valid != 0;
-        for (int j = lane; j < nlead; j += 32) {
-            const int t = list[j];
-            const float4 v = zs[t];
-            int cell = 0xffff;
-            if (usable) {
-                const int b0 = cb_bin(v.x, hdr->lo[0], hdr->inv[0]), b1 = cb_bin(v.y, hdr->lo[1], hdr->inv[1]),
-                          b2 = cb_bin(v.z, hdr->lo[2], hdr->inv[2]), b3 = cb_bin(v.w, hdr->lo[3], hdr->inv[3]);
-                if ((b0 | b1 | b2 | b3) >= 0) {
-                    cell = (((int)lut[b0] * CB_G + (int)lut[CB_NB + b1]) * CB_G + (int)lut[2 * CB_NB + b2]) * CB_G + (int)lut[3 * CB_NB + b3];
-                    const uint4 *rp = recs + (size_t)cell * (CB_RW / 8);
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 2));
-                }
-            }
-            res[t] = (uint16_t)cell;  // parked here until pass 2 overwrites it with the code
-        }
-        __syncwarp();
-        for (int j = lane; j < nlead; j += 32) {
-            const int t = list[j];
-            const float4 v = zs[t];
-            const int cell = res[t] == 0xffffu ? -1 : (int)res[t];
-            unsigned count = 0xffffu;
-            uint4 q0, q1, q2, q3;
-            const uint4 *rp = recs + (size_t)max(cell, 0) * (CB_RW / 8);
-            if (cell >= 0) {
-                q0 = __ldg(rp);
-                q1 = __ldg(rp + 1);
-                q2 = __ldg(rp + 2);
-                q3 = __ldg(rp + 3);
-                count = q0.x & 0xffffu;
-            }
-            const float z2 = sumsq4(v.x, v.y, v.z, v.w);
-            float bd = __int_as_float(0x7f800000);
-            int bk = 0;
-            if (count != 0xffffu) {
-                // entries past `count` repeat the last candidate, so whole 16-byte pieces are evaluated
-                eval_cand(q0.x >> 16, v, z2, cbs, e2s, bd, bk);
-                eval_word(q0.y, v, z2, cbs, e2s, bd, bk);
-                eval_word(q0.z, v, z2, cbs, e2s, bd, bk);
-                eval_word(q0.w, v, z2, cbs, e2s, bd, bk);
-                if (count > 7) eval_piece(q1, v, z2, cbs, e2s, bd, bk);
-                if (count > 15) eval_piece(q2, v, z2, cbs, e2s, bd, bk);
-                if (count > 23) eval_piece(q3, v, z2, cbs, e2s, bd, bk);
-                for (unsigned pc = 4; pc * 8 < count + 1; ++pc) eval_piece(__ldg(rp + pc), v, z2, cbs, e2s, bd, bk);
-            } else {
-                bk = 0xffff;  // outside the grid / overflowing cell / no usable index: searched exhaustively by the whole warp below
-            }
-            res[t] = (uint16_t)bk;
-        }
-        __syncwarp();
-        // ---- leaders the index could not serve: the WARP searches all K codes for one leader at a time (lane k, k + 32, ...;
-        //      per-lane ascending order + an index tie-break in the reduction = the lowest index among equal minima; no finite
-        //      distance at all leaves index 0, like vq_fused_kernel)
-        for (int j0 = 0; j0 < nlead; j0 += 32) {
-            const int j = j0 + lane;
-            unsigned todo = __ballot_sync(0xffffffffu, j < nlead && res[list[j < nlead ? j : 0]] == 0xffffu);
-            if (todo) vq_exhaustive_sweep(todo, list + j0, zs, res, cbs, e2s, K, lane);  // rare: kept out of line
-        }
-        __syncwarp();
-        VQ_STAMP(4);
-        // ---- finalize
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            if (!(col_ok && gy0 + r < h)) continue;
-            const int k = res[lead[r * 32 + lane]];
-            const int64_t p = (int64_t)(gy0 + r) * w + gx;
-            idx_out[(int64_t)b * plane + p] = k;
-            if (zq_out || sqerr_out) {
-                const float4 e = cbs[k];
-                const float d0 = __fsub_rn(e.x, zt[r][0]), d1 = __fsub_rn(e.y, zt[r][1]), d2 = __fsub_rn(e.z, zt[r][2]),
-                            d3 = __fsub_rn(e.w, zt[r][3]);
-                if (zq_out) {
-                    float *q = zq_out + (int64_t)b * 4 * plane + p;
-                    q[0] = __fadd_rn(zt[r][0], d0);
-                    q[plane] = __fadd_rn(zt[r][1], d1);
-                    q[2 * plane] = __fadd_rn(zt[r][2], d2);
-                    q[3 * plane] = __fadd_rn(zt[r][3], d3);
-                }
-                float acc = __fmul_rn(d0, d0);
-                acc = __fmaf_rn(d1, d1, acc);
-                acc = __fmaf_rn(d2, d2, acc);
-                acc = __fmaf_rn(d3, d3, acc);
-                sq += (double)acc;
-            }
-        }
+        VqTileCtx ctx{hdr, lut, cbs, e2s, recs, K, zs, res, list, lead};
+        vq_process_tile(ctx, z + (int64_t)b * 4 * plane, h, w, ty * 4, tx * 32 + lane, lane, idx_out + (int64_t)b * plane,
+                        zq_out ? zq_out + (int64_t)b * 4 * plane : nullptr, sqerr_out != nullptr, sq, (uint16_t *)nullptr, counters + 2,
+                        [&]() {
+                            if (!staged) {
+                                staged = true;
+                                mbar_wait(&mbar, 0);
+                            }
+                        });
     }
     VQ_STAMP(5);
     if (!staged) mbar_wait(&mbar, 0);  // never leave with the bulk copy in flight

@@ -207,8 +207,11 @@ def tiled_hot_path(z_groups: Sequence[torch.Tensor], mask_groups: Sequence[Tuple
     outs = []
     for z, (mc, mm, mf), (th, tw) in zip(z_groups, mask_groups, tile_pixels):
         h, w = z.shape[-2:]
-        idx, zq, sq = ops.vq_assign(z, prepared if prepared is not None else codebook)
-        packed, sizes = ops.pack(idx, mc, mm, mf, mode, table, h, w)
+        if prepared is not None:
+            idx, zq, sq, packed, sizes = ops.encode(z, prepared, mc, mm, mf, mode, table)
+        else:
+            idx, zq, sq = ops.vq_assign(z, codebook)
+            packed, sizes = ops.pack(idx, mc, mm, mf, mode, table, h, w)
         dmc, dmm, dmf, ind, quant, status = ops.unpack(packed, sizes, mode, table, codebook, h, w)
         sz = sizes.cpu()
         bpp = [int(sz[b].sum()) * 8 / (th * tw) for b in range(z.shape[0])]

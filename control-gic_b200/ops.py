@@ -401,6 +401,39 @@ def pack(idx: torch.Tensor, m_c, m_m, m_f, mode: int, table: HuffTable, h: int, 
 
 
 @_on_tensor_device
+def encode(z: torch.Tensor, codebook: "Codebook", m_c, m_m, m_f, mode: int, table: HuffTable, want_zq: bool = True, want_sqerr: bool = True):
+    """The encoder half in one call (cgic_encode): quantize.py:69-98 + model.py:217-260 for B images ->
+    (idx int64 [B*h*w], z_q fp32 NCHW or None, sqerr float64[1] or None, bytes uint8 [B, image_stride], sizes int32 [B,5]);
+    identical to vq_assign(z, codebook) followed by pack(idx, ...).  One launch on token grids of at most 4096 cells."""
+    if not isinstance(codebook, Codebook):
+        raise TypeError("encode needs a prepared Codebook (ops.Codebook(weight))")
+    z = _cuda(z, torch.float32, "z")
+    m_c, m_m, m_f = (_cuda(t, torch.int32, n) for t, n in ((m_c, "m_c"), (m_m, "m_m"), (m_f, "m_f")))
+    if z.dim() != 4 or z.shape[1] != 4:
+        raise ValueError(f"encode supports e_dim == 4 (z {tuple(z.shape)})")
+    B, _, h, w = z.shape
+    table.upload()
+    _, _, stride = table.layout(h, w)
+    dev = z.device
+    idx = torch.empty(B * h * w, dtype=torch.int64, device=dev)
+    zq = torch.empty_like(z) if want_zq else None
+    sq = torch.empty(1, dtype=torch.float64, device=dev) if want_sqerr else None
+    out = torch.empty(B, stride, dtype=torch.uint8, device=dev)
+    sizes = torch.empty(B, 5, dtype=torch.int32, device=dev)
+    ws = _workspace("encode", lib().cgic_encode_workspace_bytes(B, h, w), dev)
+    check(lib().cgic_encode(z.data_ptr(), m_c.data_ptr(), m_m.data_ptr(), m_f.data_ptr(), B, h, w, mode, codebook.handle, table.handle,
+                            idx.data_ptr(), _p(zq), _p(sq), out.data_ptr(), sizes.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+          "cgic_encode")
+    return idx, zq, sq, out, sizes
+
+
+def exhaustive_count(tag: str = "encode") -> int:
+    """Running count (since the workspace was created) of latents the indexed search handed to its exhaustive path, summed
+    over this op's workspaces (synchronises).  tag: "encode" or "vq"."""
+    return int(sum(int(b[8:12].view(torch.int32).item()) for k, b in _ws_cache.items() if k[0] == tag))
+
+
+@_on_tensor_device
 def unpack(bytes_: torch.Tensor, sizes: torch.Tensor, mode: int, table: HuffTable, codebook: torch.Tensor, h: int, w: int):
     """model.py:269-392 for B images -> (mc, mm, mf int64, ind int64 [B,h,w], quant fp32 [B,4,h,w], status int32 [B])."""
     bytes_ = _cuda(bytes_, torch.uint8, "bytes")
@@ -596,12 +629,24 @@ class Session:
         self._arena_views = views
         return views
 
-    def roundtrip_arena(self, want_idx: bool = False, want_zq: bool = False) -> float:
-        """CGIC.compress on the arena contents; returns sum((e - z)^2) over the batch."""
+    def roundtrip_arena(self, want_idx: bool = False, want_zq: bool = False, decoded_on_device: bool = False) -> float:
+        """CGIC.compress on the arena contents; returns sum((e - z)^2) over the batch.  decoded_on_device: the decoded
+        tensors (ind, quant, mc, mm, mf) stay in HBM (fetch them with device_tensor); only bytes / sizes / status return."""
         sq = C.c_double()
-        check(lib().cgic_session_roundtrip_arena(self._s, int(want_idx) | (int(want_zq) << 1), C.byref(sq)),
-              "cgic_session_roundtrip_arena")
+        flags = 4 if decoded_on_device else int(want_idx) | (int(want_zq) << 1)
+        check(lib().cgic_session_roundtrip_arena(self._s, flags, C.byref(sq)), "cgic_session_roundtrip_arena")
         return sq.value
+
+    def device_tensor(self, name: str) -> torch.Tensor:
+        """Output tensor `name` (ind, quant, mc, mm, mf, bytes, sizes, status, idx, zq) of the last arena round trip for
+        the whole batch, gathered device-to-device into one CUDA tensor."""
+        what, dtype = self._ARENA[name]
+        B, h, w = self.B, self.h, self.w
+        shape = dict(bytes=(B, self.image_stride), sizes=(B, 5), status=(B,), ind=(B, h, w), quant=(B, 4, h, w), mc=(B, h // 4, w // 4),
+                     mm=(B, h // 2, w // 2), mf=(B, h, w), idx=(B * h * w,), zq=(B, 4, h, w))[name]
+        out = torch.empty(shape, dtype=dtype, device="cuda")
+        check(lib().cgic_session_arena_gather_device(self._s, what, out.data_ptr()), "cgic_session_arena_gather_device")
+        return out
 
     def roundtrip(self, z, m_c, m_m, m_f, want_idx: bool = False):
         """CGIC.compress in one call: host z + masks -> (bytes, sizes, mc, mm, mf, ind, quant, status[, idx]) (pinned host)."""

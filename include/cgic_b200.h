@@ -88,7 +88,8 @@ CGIC_API int cgic_huff_upload(cgic_table *t);
  *     sqerr_out double[1]      sum over all elements of (e - z)^2; loss = (1+beta)*sqerr/numel
  *                              (nullable)
  *     workspace: cgic_vq_workspace_bytes() bytes whose first 64 bytes are ZERO before the first call
- *     (the kernel leaves them zero); one workspace per concurrently running call.
+ *     (the kernel leaves them zero, except bytes 8..11: a running int32 count of the latents the indexed
+ *     search had to hand to its exhaustive path); one workspace per concurrently running call.
  *     Tokens whose latent is bit-identical to the top-left token of their 4x4 / 2x2 block (the
  *     structure the mask-mix of vqvae_blocks.py:364-366 creates) share that token's search.
  * ------------------------------------------------------------------------------------------ */
@@ -198,6 +199,21 @@ CGIC_API int cgic_pack_ws(const int64_t *idx, const int32_t *m_c, const int32_t 
                  size_t workspace_bytes, cgic_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * a1 + a7 + a9 + a11 + a12  the encoder half in one call: VectorQuantize2.forward (quantize.py:69-98) on a prepared
+ *     codebook, then selection + the five-stream pack (model.py:217-260) -- i.e. cgic_vq_assign_indexed followed by
+ *     cgic_pack_ws, with identical outputs (idx_out, zq_out (nullable), sqerr_out (nullable), bytes_out, sizes_out).
+ *     On token grids of at most 4096 cells with codes of at most 32 bits both steps run in ONE launch, one CTA per
+ *     image (the indices reach the packer through shared memory); larger grids take the two launches.
+ *     workspace: cgic_encode_workspace_bytes() bytes, ZERO-filled before the first use (bytes 8..11 hold a running
+ *     count of latents that took the exhaustive search, everything else is left zeroed).
+ * ------------------------------------------------------------------------------------------ */
+CGIC_API size_t cgic_encode_workspace_bytes(int B, int h, int w);
+CGIC_API int cgic_encode(const float *z, const int32_t *m_c, const int32_t *m_m, const int32_t *m_f, int B, int h, int w,
+                int mode, const cgic_codebook *cb, const cgic_table *t, int64_t *idx_out, float *zq_out,
+                double *sqerr_out, uint8_t *bytes_out, int32_t *sizes_out, void *workspace, size_t workspace_bytes,
+                cgic_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * a10 + a11 + a13 + a14  unpack + mask / index re-assembly + codebook gather
  *     CGIC/models/model.py:269-392, decompress_string indices_coding.py:153-168, mask_coding.py:81-96.
  *     bytes / sizes use the cgic_pack layout.  Outputs (all device, caller-allocated):
@@ -268,7 +284,11 @@ CGIC_API int cgic_session_roundtrip_host(cgic_session *s, const float *z, const 
  *   cgic_session_arena        fixes `parts` (<= 8) and (re)allocates the arenas (init time);
  *   cgic_session_arena_tensor host pointer of tensor `what` of range `part` (+ its image range);
  *                             inputs are written there by the caller before the call, outputs read after;
- *   cgic_session_roundtrip_arena  flags: bit 0 also return idx (VQ indices), bit 1 also z_q.
+ *   cgic_session_roundtrip_arena  flags: bit 0 also return idx (VQ indices), bit 1 also z_q; bit 2 (alone): the
+ *                             decoded tensors (IND, QUANT, DMC, DMM, DMF) stay in HBM for the decoder CNN, as
+ *                             model.py:391-399 hands them over -- only BYTES, SIZES, STATUS, SQERR come back to the host;
+ *   cgic_session_arena_gather_device  copies output tensor `what` of all ranges, in image order, into one contiguous
+ *                             DEVICE buffer of the caller (device to device, then synchronises).
  * Tensor shapes per range of nb images: Z/QUANT/ZQ fp32 [nb,4,h,w]; MC/MM/MF int32 [nb,1,.,.]; BYTES
  * uint8 [nb,image_stride]; SIZES int32 [nb,5]; STATUS int32 [nb]; SQERR double[1]; IND/IDX int64 [nb,h,w];
  * DMC/DMM/DMF int64 [nb,.,.]. */
@@ -282,6 +302,7 @@ CGIC_API int cgic_session_arena(cgic_session *s, int parts);
 CGIC_API int cgic_session_arena_tensor(const cgic_session *s, int what, int part, void **host_ptr, int *first_image,
                               int *n_images);
 CGIC_API int cgic_session_roundtrip_arena(cgic_session *s, int flags, double *sqerr_out);
+CGIC_API int cgic_session_arena_gather_device(cgic_session *s, int what, void *dst_device);
 
 #ifdef __cplusplus
 }

@@ -655,3 +655,135 @@ def test_vq_training_counters_stay_views(cg):
     total += torch.bincount(idx.cpu(), minlength=1024).float()
     assert torch.equal(vq2.counters_flat().cpu(), total)
     assert list(vq2.embedding_counter.keys())[:4] == ["0", "1", "10", "100"]
+
+
+# ------------------------------------------------- small token grids: decode + re-assembly fused in one CTA per image
+def _skew_counts(kind):
+    if kind == "short":     # 1- to 3-bit codes for the frequent symbols: the decoder's group-of-one path (min_len < 4)
+        return np.asarray([900000, 400000, 200000, 100000, 50000] + [100] * 1019, np.int64)
+    if kind == "flat":      # all 1024 codes 10 bits long
+        return np.ones(1024, np.int64)
+    g = torch.Generator().manual_seed(1234)
+    return (-torch.log(torch.rand(1024, generator=g)) * 1000).floor().long().numpy()
+
+
+@pytest.mark.parametrize("kind", ["kat5", "short", "flat"])
+@pytest.mark.parametrize("H,W,c,m", [(256, 256, 0.0, 0.0), (256, 256, 0.05, 0.05), (256, 256, 0.1, 0.8), (192, 208, 0.3, 0.6),
+                                     (64, 48, 0.0, 0.5), (16, 16, 0.1, 0.8), (256, 256, 1.0, 0.0)])
+def test_small_grid_fused_decoder(cg, orc, kind, H, W, c, m):
+    """unpack_small_kernel: streams of several batches (an all-fine 256x256 image carries ~44 kbit in its fine stream, a
+    batch holds 16 kbit), tables with codes shorter than the look-up group, ragged grids, every mode -- indices, masks and
+    latents against the oracle's unpack of the same bytes; the bytes themselves against the oracle's pack."""
+    counts = _skew_counts(kind)
+    order = orc.lexicographic_order(1024)
+    t = cg.ops.HuffTable(counts, order)
+    ot = orc.huff_build(counts, order)
+    B, h, w = 3, H // 4, W // 4
+    g = torch.Generator().manual_seed(H * 7 + W + int(100 * c))
+    e16, e8 = torch.rand(B, H // 16, W // 16, generator=g), torch.rand(B, H // 8, W // 8, generator=g)
+    masks = cg.ops.router(e16.cuda(), e8.cuda(), c, m, per_image=True)
+    mode = masks[4]
+    p = torch.from_numpy(counts / counts.sum())
+    idx = torch.multinomial(p, B * h * w, replacement=True, generator=g).cuda()   # symbols drawn from the table's own statistics
+    cb = torch.randn(1024, 4, generator=g).cuda()
+    packed, sizes = cg.ops.pack(idx, *masks[:3], mode, t, h, w)
+    mc, mm, mf, ind, quant, status = cg.ops.unpack(packed, sizes, mode, t, cb, h, w)
+    torch.cuda.synchronize()
+    assert int(status.abs().sum()) == 0
+    offs, _, _ = t.layout(h, w)
+    for b in range(B):
+        omask = [mk[b, 0].cpu().numpy() for mk in masks[:3]]
+        streams = orc.pack_image(ot, idx.view(B, h, w)[b].cpu().numpy(), *omask, mode)
+        blob, sz = packed[b].cpu().numpy(), sizes[b].cpu().numpy()
+        for s in range(5):
+            assert blob[offs[s]: offs[s] + sz[s]].tobytes() == streams[s], (b, s)
+        umc, umm, umf, uind, uq = orc.unpack_image(ot, streams, h, w, mode, cb.cpu().numpy())
+        assert np.array_equal(ind[b].cpu().numpy(), uind) and np.array_equal(quant[b].cpu().numpy(), uq)
+        for got, want in zip((mc, mm, mf), (umc, umm, umf)):
+            assert np.array_equal(got[b].cpu().numpy(), want)
+
+
+def test_small_grid_fused_decoder_truncated_and_corrupt(cg, orc):
+    """Greedy semantics on damaged input: a stream cut short decodes to a prefix (status raised: the symbol count no
+    longer matches the mask population), flipped payload bits still decode to SOMETHING without faulting."""
+    counts = _skew_counts("kat5")
+    order = orc.lexicographic_order(1024)
+    t = cg.ops.HuffTable(counts, order)
+    B, H, W = 2, 256, 256
+    h, w = H // 4, W // 4
+    cb, _, z, masks, mode = _synthetic(cg, B, H, W, 0.1, 0.8, seed=91)
+    idx, _, _ = cg.ops.vq_assign(z, cb)
+    packed, sizes = cg.ops.pack(idx, *masks, mode, t, h, w)
+    offs, caps, _ = t.layout(h, w)
+    short = sizes.clone()
+    short[0, 1] = int(sizes[0, 1]) // 2
+    *_, ind, quant, status = cg.ops.unpack(packed, short, mode, t, cb, h, w)
+    torch.cuda.synchronize()
+    assert int(status[0]) == -5 and int(status[1]) == 0
+    assert torch.equal(ind[1].view(-1), idx.view(B, -1)[1])
+    g = torch.Generator().manual_seed(5)
+    noisy = packed.clone()
+    pos = torch.randint(int(offs[1]) + 1, int(offs[1]) + int(sizes[0, 1]), (64,), generator=g)
+    noisy[0, pos] ^= 0x5A
+    *_, status = cg.ops.unpack(noisy, sizes, mode, t, cb, h, w)
+    torch.cuda.synchronize()
+    assert int(status[1]) == 0          # (image 0 may or may not decode to the right count; it must not fault)
+
+
+# ------------------------------------------------- small token grids: VQ + select + pack fused in one CTA per image
+@pytest.mark.parametrize("H,W,c,m", [(256, 256, 0.1, 0.8), (256, 256, 0.0, 0.0), (256, 256, 0.05, 0.05), (192, 208, 0.3, 0.6), (64, 48, 0.0, 0.5),
+                                     (16, 16, 0.1, 0.8), (256, 256, 1.0, 0.0), (128, 256, 0.2, 0.8), (256, 128, 0.5, 0.0), (512, 768, 0.1, 0.8)])
+def test_encode_fused_matches_two_launch_path(cg, orc, H, W, c, m):
+    """cgic_encode == cgic_vq_assign_indexed + cgic_pack_ws: indices, z_q bits, every stream byte, sizes; sum((e-z)^2) to
+    1e-12 (another summation order).  512x768 takes the two launches inside cgic_encode."""
+    B = 5
+    cb, t, z, masks, mode = _synthetic(cg, B, H, W, c, m, seed=H + W)
+    h, w = H // 4, W // 4
+    pc = cg.ops.Codebook(cb)
+    idx0, zq0, sq0 = cg.ops.vq_assign(z, pc)
+    packed0, sizes0 = cg.ops.pack(idx0, *masks, mode, t, h, w)
+    idx1, zq1, sq1, packed1, sizes1 = cg.ops.encode(z, pc, *masks, mode, t)
+    torch.cuda.synchronize()
+    assert torch.equal(idx0, idx1) and torch.equal(zq0.view(torch.int32), zq1.view(torch.int32))
+    assert np.isclose(float(sq0), float(sq1), rtol=1e-12)
+    assert torch.equal(sizes0, sizes1)
+    offs, _, _ = t.layout(h, w)
+    sz = sizes0.cpu().numpy()
+    p0, p1 = packed0.cpu().numpy(), packed1.cpu().numpy()
+    for b in range(B):
+        for s in range(5):
+            assert p0[b, offs[s]: offs[s] + sz[b, s]].tobytes() == p1[b, offs[s]: offs[s] + sz[b, s]].tobytes(), (b, s)
+    # and against the oracle end to end on one image
+    import workload
+    ot = orc.huff_build(workload.codebook_and_counts()[1].numpy(), orc.lexicographic_order(1024))
+    b = B - 1
+    _, _, oidx = orc.vq_assign(z[b:b + 1].cpu().numpy(), cb.cpu().numpy())
+    streams = orc.pack_image(ot, oidx.reshape(h, w), *(mk[b, 0].cpu().numpy() for mk in masks), mode)
+    for s in range(5):
+        assert p1[b, offs[s]: offs[s] + sz[b, s]].tobytes() == streams[s], s
+    want_zq_none = cg.ops.encode(z, pc, *masks, mode, t, want_zq=False, want_sqerr=False)
+    assert want_zq_none[1] is None and want_zq_none[2] is None and torch.equal(want_zq_none[0], idx0) and torch.equal(want_zq_none[4], sizes0)
+
+
+@pytest.mark.parametrize("tag", ["c1_256"] + [n for n in e2e_case_names() if "long" not in n])
+def test_encode_fused_golden(cg, tag):
+    """The fused encoder on the reference's own runs: z -> indices, z_q, the five files, bpp."""
+    g = load_npz(f"big_{tag}.npz" if tag.startswith("c") else f"e2e_{tag}.npz")
+    H, W = (map(int, g["shape"]) if "shape" in g else g["x"].shape[-2:])
+    h, w = H // 4, W // 4
+    mode = int(g["mode"])
+    c_ratio, m_ratio = map(float, g["ratios"])
+    masks, _, _, _ = cg.TripleGrainFixedEntropyRouter(c_ratio, m_ratio)(dev(g["e16"]), dev(g["e8"]))
+    t = cg.ops.HuffTable(g["counts"], g["order"])
+    idx, zq, sq, packed, sizes = cg.ops.encode(dev(g["z"]), cg.ops.Codebook(dev(g["codebook"])), *masks, mode, t)
+    assert np.array_equal(idx.cpu().numpy(), g["ind"].astype(np.int64))
+    if "zq" in g:
+        assert np.array_equal(zq.cpu().numpy().view(np.uint32), g["zq"].view(np.uint32))
+    else:
+        assert hashlib.sha256(zq.cpu().numpy().tobytes()).digest() == g["zq_sha"].tobytes()
+    assert np.isclose(1.25 * float(sq.item()) / g["z"].size, g["loss"], rtol=LOSS_RTOL)
+    offs, _, _ = t.layout(h, w)
+    blob, sz = packed.cpu().numpy()[0], sizes.cpu().numpy()[0]
+    for s, n in enumerate(STREAMS):
+        assert blob[offs[s]: offs[s] + sz[s]].tobytes() == g["file_" + n].tobytes(), n
+    assert int(sz.sum()) * 8 / (H * W) == float(g["bpp"])
