@@ -20,6 +20,7 @@ c_void_p, c_int, c_int64, c_size_t = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
 _SIGNATURES = {
     "cgic_abi_version": (c_int, []),
     "cgic_last_error": (C.c_char_p, []),
+    "cgic_tune": (c_int, [C.c_char_p, c_int]),
     "cgic_prof_enable": (c_int, [c_int]),
     "cgic_prof_report": (c_int, [C.c_char_p, c_int]),
     "cgic_huff_build": (c_int, [c_void_p, c_void_p, c_int, C.POINTER(c_void_p)]),

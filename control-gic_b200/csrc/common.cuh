@@ -168,6 +168,11 @@ static inline cudaStream_t as_stream(cgic_stream_t s) { return reinterpret_cast<
 int ensure_smem(const void *fn, size_t bytes);
 int device_sm_count(int *n_sm);
 
+// Dispatch knobs (cgic_tune): which kernel variant serves a call.  Defaults come from the environment once
+// (CGIC_DS_CLUSTER, CGIC_FUSED_ENCODE, CGIC_NO_SMALL_KERNELS), cgic_tune() changes them at run time (tests, A-B runs).
+int tune_fused_decode_ctas();  // 0 = automatic (by batch size), 1 / 2 / 4 = fused small-grid decoder with that many CTAs per image, -1 = never
+int tune_fused_encode();       // 0 = two launches (default), 1 = one-CTA-per-image encoder on small grids
+
 // Per-kernel device timing (cgic_prof_*): while enabled, every kernel launch of the library is
 // bracketed by two CUDA events recorded on the launching stream.  Off by default; costs one
 // relaxed load per launch when off.

@@ -942,9 +942,12 @@ extern "C" int cgic_encode(const float *z, const int32_t *m_c, const int32_t *m_
     const int K = codebook_size(cb);
     const size_t vq_ws = ((std::max(cgic_vq_workspace_bytes((int64_t)B * h * w), (size_t)256 + 8 * (size_t)B)) + 255) / 256 * 256;
     cudaStream_t stream = as_stream(stream_);
-    static const bool no_small = getenv("CGIC_NO_SMALL_KERNELS") != nullptr;  // diagnosis / A-B only
+    // The one-CTA-per-image encoder is opt-in (cgic_tune("fused_encode", 1) or CGIC_FUSED_ENCODE=1): measured on B200 it loses to the two launches at every
+    // batch size tried (64 images: 26.6 us against 17.9 us; 2048 images: 382 us against 324 us) -- the warp-tile search is
+    // instruction-issue bound, and one SM per image serialises what the two-launch path spreads over the whole machine.
+    const bool fused = tune_fused_encode() == 1;
     const PackLayout L = make_pack_layout(a.T.max_len, h, w);
-    bool small = !no_small && (int64_t)h * w <= ES_MAX_N4 && a.T.enc != nullptr && a.T.K == K;
+    bool small = fused && (int64_t)h * w <= ES_MAX_N4 && a.T.enc != nullptr && a.T.K == K;
     size_t smem = 0;
     if (small) {
         smem = es_layout(K, h, w, L.cap).total;

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <atomic>
 #include <map>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -89,6 +90,33 @@ int device_sm_count(int *n_sm)
     if (!c) CGIC_CUDA_CHECK(cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev));
     *n_sm = c;
     return CGIC_OK;
+}
+
+namespace {
+std::atomic<int> g_tune_decode{-100}, g_tune_encode{-100};
+}
+int tune_fused_decode_ctas()
+{
+    int v = g_tune_decode.load(std::memory_order_relaxed);
+    if (v == -100) {
+        v = 0;
+        if (getenv("CGIC_NO_SMALL_KERNELS")) v = -1;
+        else if (const char *e = getenv("CGIC_DS_CLUSTER")) {
+            const int c = atoi(e);
+            if (c == 1 || c == 2 || c == 4) v = c;
+        }
+        g_tune_decode.store(v);
+    }
+    return v;
+}
+int tune_fused_encode()
+{
+    int v = g_tune_encode.load(std::memory_order_relaxed);
+    if (v == -100) {
+        v = getenv("CGIC_FUSED_ENCODE") && !getenv("CGIC_NO_SMALL_KERNELS") ? 1 : 0;
+        g_tune_encode.store(v);
+    }
+    return v;
 }
 
 PackLayout make_pack_layout(int max_len, int h, int w)
@@ -180,6 +208,23 @@ struct FreqHeap {
 extern "C" {
 
 int cgic_abi_version(void) { return CGIC_ABI_VERSION; }
+
+int cgic_tune(const char *key, int value)
+{
+    CGIC_REQUIRE(key, CGIC_EINVAL, "cgic_tune: null key");
+    if (!strcmp(key, "fused_decode_ctas")) {
+        CGIC_REQUIRE(value == -1 || value == 0 || value == 1 || value == 2 || value == 4, CGIC_EINVAL, "cgic_tune: fused_decode_ctas must be -1, 0, 1, 2 or 4");
+        cgic::g_tune_decode.store(value);
+        return CGIC_OK;
+    }
+    if (!strcmp(key, "fused_encode")) {
+        CGIC_REQUIRE(value == 0 || value == 1, CGIC_EINVAL, "cgic_tune: fused_encode must be 0 or 1");
+        cgic::g_tune_encode.store(value);
+        return CGIC_OK;
+    }
+    cgic::set_error("cgic_tune: unknown key '%s'", key);
+    return CGIC_EINVAL;
+}
 
 const char *cgic_last_error(void) { return cgic::g_err; }
 

@@ -18,6 +18,8 @@
 //   up4(coarse); quant = codebook[ind] written NCHW; masks written as int64 like the reference.
 #include <algorithm>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 CGIC_TRACE_DECL(unpack)
@@ -1292,7 +1294,7 @@ constexpr int DS_THREADS = CGIC_DS_THREADS;
 constexpr int DS_WORDS = 512;              // stream words (= subsequences) per batch
 constexpr int DS_BS = 16;                  // words per composition block
 constexpr int DS_NBLK = DS_WORDS / DS_BS;  // 32
-constexpr int DS_WCAP = DS_WORDS + 4;      // + one look-ahead word per segment + one zero word
+constexpr int DS_WCAP = DS_NBLK * 17 + 1;   // a CTA's blocks as 16 words + the word after them
 constexpr int DS_MAX_D = 32;
 constexpr int DS_MAX_N4 = 4096;
 constexpr uint32_t DS_STOP = 0xFFu;
@@ -1445,23 +1447,29 @@ __device__ __forceinline__ bool assemble_quad_small(const UnpackArgs &a, int b, 
     return bad;
 }
 
-template <int G>
+// CL = CTAs per image (a thread-block cluster when > 1).  All CTAs of an image plan the same batches; the 16-word blocks of
+// a batch are dealt round-robin over them (block k -> CTA k % CL): staging, len8[], DP, the block functions (B1), the replay
+// (B3) and the symbol write-out (C) touch a CTA's own blocks only.  What every CTA needs from the others travels through
+// distributed shared memory: the block functions (written into every CTA's table before the serial walk B2, which each CTA
+// then does for itself) and the decoded symbols (written into every CTA's symbol list); the re-assembly is split by quads.
+// Small batches thus spread one image over 2 or 4 SMs instead of leaving most of the machine idle.
+template <int G, int CL>
 __global__ void __launch_bounds__(DS_THREADS, DS_THREADS <= 512 ? 2 : 1) unpack_small_kernel(const UnpackArgs a)
 {
+    namespace cgs = cooperative_groups;
     extern __shared__ __align__(128) unsigned char dyn[];
     __shared__ __align__(8) unsigned long long mbar;
     __shared__ uint32_t s_blockfn[DS_NBLK * 32];   // (symbols << 8) | exit offset of a block, per candidate entry offset
     __shared__ uint8_t s_blkstart[DS_NBLK];
     __shared__ uint32_t s_blkbase[DS_NBLK];
-    __shared__ uint16_t s_blkw0[DS_NBLK];
-    __shared__ uint8_t s_blkseg[DS_NBLK];
     __shared__ uint8_t s_substart[DS_WCAP];
     __shared__ uint32_t s_subbase[DS_WCAP];
     __shared__ int s_nbits[3], s_nwords[3], s_done[3], s_nsym[3], s_nbytes[3];
     __shared__ uint32_t s_entry[3];
     __shared__ int32_t s_pop[3], s_cnt[3];
-    __shared__ int s_nseg, s_wcur, s_nblk, s_bad;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
+    __shared__ int s_bad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = CL == 1 ? (int)blockIdx.x : (int)blockIdx.x / CL, rank = CL == 1 ? 0 : (int)blockIdx.x % CL;
     const Geo &g = a.g;
     const DsLayout SL = ds_layout(a.T.dec_stage_words, g);
     uint32_t *s_dec = reinterpret_cast<uint32_t *>(dyn);
@@ -1473,6 +1481,12 @@ __global__ void __launch_bounds__(DS_THREADS, DS_THREADS <= 512 ? 2 : 1) unpack_
     uint32_t *s_prefix = reinterpret_cast<uint32_t *>(dyn + SL.prefix);
     unsigned char *s_masks = dyn + SL.masks;
     const int D = a.T.max_len, L = a.T.lut_bits;
+    auto cluster_sync = [&]() {
+        if (CL == 1) __syncthreads();
+        else cgs::this_cluster().sync();
+    };
+    // the same object in the shared memory of cluster rank rr
+    auto remote = [&](auto *ptr, int rr) { return CL == 1 ? ptr : cgs::this_cluster().map_shared_rank(ptr, rr); };
     CGIC_STAMP(unpack, 0);
     pdl_trigger_step<4>();
     // the (immutable) decode tables are staged while the predecessor kernel may still be running
@@ -1526,7 +1540,7 @@ __global__ void __launch_bounds__(DS_THREADS, DS_THREADS <= 512 ? 2 : 1) unpack_
     if (tid == 33 && need_m && __ldg(sz + 4) != cap_m) atomicOr(&s_bad, 1);
     __syncthreads();
     // ---- mask levels: one warp per level (framing of the mask streams checked on the staged bytes); meanwhile the other warps
-    //      go on to the first batch, whose global loads thus overlap this
+    //      go on to the first batch, whose global loads thus overlap this.  Every CTA of a cluster builds its own copy.
     if (warp < 3) {
         const uint8_t *mc = s_masks, *mm = s_masks + off_m;
         if (warp == 0) {
@@ -1576,11 +1590,10 @@ __global__ void __launch_bounds__(DS_THREADS, DS_THREADS <= 512 ? 2 : 1) unpack_
     auto symoff = [&](int s) { return s == 0 ? 0 : (s == 1 ? (int)g.n16 : (int)(g.n16 + g.n8)); };
     auto symcap = [&](int s) { return s == 0 ? (int)g.n16 : (s == 1 ? (int)g.n8 : (int)g.n4); };
     for (;;) {
-        // ---- plan the batch: up to three segments, block aligned (every thread computes the same plan from the shared state;
-        //      scalars, not an array: a dynamically indexed array would live in local memory)
-        int nseg = 0, wcur = 0, nblk = 0;
-        int g_s[3] = {0, 0, 0}, g_sub0[3] = {0, 0, 0}, g_n[3] = {0, 0, 0}, g_nb[3] = {0, 0, 0}, g_w0[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff},
-            g_blk0[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
+        // ---- plan the batch: up to three segments, block aligned (every thread of every CTA computes the same plan from its
+        //      copy of the stream state; scalars, not an array: a dynamically indexed array would live in local memory)
+        int nseg = 0, nblk = 0;
+        int g_s[3] = {0, 0, 0}, g_sub0[3] = {0, 0, 0}, g_n[3] = {0, 0, 0}, g_nb[3] = {0, 0, 0}, g_blk0[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
         {
             int free_blk = DS_NBLK;
 #pragma unroll
@@ -1595,36 +1608,29 @@ __global__ void __launch_bounds__(DS_THREADS, DS_THREADS <= 512 ? 2 : 1) unpack_
                         g_sub0[k] = s_done[s];
                         g_n[k] = n;
                         g_nb[k] = nb;
-                        g_w0[k] = wcur;
                         g_blk0[k] = DS_NBLK - free_blk;
                     }
-                wcur += nb * DS_BS + 1;
                 free_blk -= nb;
                 ++nseg;
             }
             nblk = DS_NBLK - free_blk;
         }
         if (nseg == 0) break;
-        // segment of a batch word: stream, first stream word of that batch word
-        auto seg_stream = [&](int wi) { return wi >= g_w0[2] ? g_s[2] : (wi >= g_w0[1] ? g_s[1] : g_s[0]); };
-        auto seg_word = [&](int wi) { return wi >= g_w0[2] ? g_sub0[2] + (wi - g_w0[2]) : (wi >= g_w0[1] ? g_sub0[1] + (wi - g_w0[1]) : g_sub0[0] + (wi - g_w0[0])); };
-        if (tid < nblk) {
-            const int k = tid >= g_blk0[2] ? 2 : (tid >= g_blk0[1] ? 1 : 0);
-            const int w0k = k == 2 ? g_w0[2] : (k == 1 ? g_w0[1] : g_w0[0]), b0k = k == 2 ? g_blk0[2] : (k == 1 ? g_blk0[1] : g_blk0[0]);
-            s_blkw0[tid] = (uint16_t)(w0k + (tid - b0k) * DS_BS);
-            s_blkseg[tid] = (uint8_t)(k == 2 ? g_s[2] : (k == 1 ? g_s[1] : g_s[0]));
-        }
-        // ---- stage the stream words: word i of a stream = bytes 1 + 4 i .. 4 + 4 i (the header byte is skipped), MSB first
-        for (int wi = tid; wi <= wcur; wi += DS_THREADS) {
-            uint32_t v = 0;
-            if (wi < wcur) {
-                const int ss = seg_stream(wi), sw = seg_word(wi);
-                const uint32_t *W = reinterpret_cast<const uint32_t *>(img + a.slot_off[ss]);
-                const int cap = (int)a.slot_cap[ss];
-                const uint32_t lo = 4 * sw + 4 <= cap ? __ldg(W + sw) : 0u, hi = 4 * sw + 8 <= cap ? __ldg(W + sw + 1) : 0u;
-                v = __byte_perm(lo, hi, 0x1234);
-            }
-            s_w[wi] = v;
+        // this CTA's blocks: k = rank, rank + CL, ...; local block j lives in words [17 j, 17 j + 17) of the CTA's buffers
+        // (16 words + the word after them, which the last word's windows reach into)
+        const int nown = nblk > rank ? (nblk - rank + CL - 1) / CL : 0;
+        auto blk_stream = [&](int k) { return k >= g_blk0[2] ? g_s[2] : (k >= g_blk0[1] ? g_s[1] : g_s[0]); };
+        auto blk_word0 = [&](int k) {  // first STREAM word of block k
+            return k >= g_blk0[2] ? g_sub0[2] + (k - g_blk0[2]) * DS_BS : (k >= g_blk0[1] ? g_sub0[1] + (k - g_blk0[1]) * DS_BS : g_sub0[0] + (k - g_blk0[0]) * DS_BS);
+        };
+        // ---- stage the stream words of the own blocks: word i of a stream = bytes 1 + 4 i .. 4 + 4 i (header byte skipped), MSB first
+        for (int it = tid; it < nown * 17; it += DS_THREADS) {
+            const int j = it / 17, i = it - j * 17, k = rank + j * CL;
+            const int ss = blk_stream(k), sw = blk_word0(k) + i;
+            const uint32_t *W = reinterpret_cast<const uint32_t *>(img + a.slot_off[ss]);
+            const int cap = (int)a.slot_cap[ss];
+            const uint32_t lo = 4 * sw + 4 <= cap ? __ldg(W + sw) : 0u, hi = 4 * sw + 8 <= cap ? __ldg(W + sw + 1) : 0u;
+            s_w[it] = __byte_perm(lo, hi, 0x1234);
         }
         if (!tables_ready) {
             tables_ready = true;
@@ -1632,43 +1638,41 @@ __global__ void __launch_bounds__(DS_THREADS, DS_THREADS <= 512 ? 2 : 1) unpack_
         }
         __syncthreads();
         CGIC_STAMP(unpack, 3);
-        // ---- A0: code length at every bit position (0 where the codeword would run past the payload).  One- and two-level codes
-        //      without a branch (the second look-up is always issued, on entry 0 when unused); only codes beyond the second
-        //      level walk the tree.
-        for (int it = tid; it < wcur * 4; it += DS_THREADS) {
-            const int wi = it >> 2, qtr = it & 3;
-            const int lim = s_nbits[seg_stream(wi)] - 32 * seg_word(wi) - qtr * 8;  // position k of this quarter is valid iff k + len <= lim
-            const uint32_t w0 = s_w[wi], w1 = s_w[wi + 1];
-            uint32_t *dst = reinterpret_cast<uint32_t *>(s_len + 36 * wi + qtr * 8);
+        // ---- A0: code length at every bit position (0 where the codeword would run past the payload).  The eight look-ups of an
+        //      item are issued together; entries that need the second level (or the tree) are resolved afterwards.
+        for (int it = tid; it < nown * 64; it += DS_THREADS) {
+            const int j = it >> 6, i = (it >> 2) & 15, qtr = it & 3, k = rank + j * CL;
+            const int wl = 17 * j + i;                                                  // local word
+            const int lim = s_nbits[blk_stream(k)] - 32 * (blk_word0(k) + i) - qtr * 8;  // position p of this quarter is valid iff p + len <= lim
+            const uint32_t w0 = s_w[wl], w1 = s_w[wl + 1];
+            uint32_t e[8];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                uint32_t packed = 0;
+            for (int p8 = 0; p8 < 8; ++p8) e[p8] = s_dec[__funnelshift_l(w1, w0, qtr * 8 + p8) >> (32 - L)];
+            uint32_t any = 0;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int pos = j * 4 + k;
-                    const uint32_t win = __funnelshift_l(w1, w0, qtr * 8 + pos);
-                    const uint32_t e = s_dec[win >> (32 - L)];
-                    uint32_t f = e & 0xFFu;
-                    if (f & 0x80u) {
-                        if (lut2_shared && f != 0xFFu) {
-                            const uint32_t hgt = f & 0x7Fu;
-                            f = (lut2[(e >> 8) + ((win << L) >> (32 - hgt))] & 0xFFu) + (uint32_t)L;
-                        } else {
-                            f = ds_decode_win(win, s_dec, lut2, a.T, L) & 0xFFu;
-                        }
-                    }
-                    if (pos + (int)f > lim) f = 0;
-                    packed |= f << (8 * k);
-                }
-                dst[j] = packed;
+            for (int p8 = 0; p8 < 8; ++p8) {
+                any |= e[p8];
+                e[p8] &= 0xFFu;
             }
+            if (any & 0x80u) {  // uncommon: second-level table, rare: tree walk
+#pragma unroll
+                for (int p8 = 0; p8 < 8; ++p8)
+                    if (e[p8] & 0x80u) e[p8] = ds_decode_win(__funnelshift_l(w1, w0, qtr * 8 + p8), s_dec, lut2, a.T, L) & 0xFFu;
+            }
+#pragma unroll
+            for (int p8 = 0; p8 < 8; ++p8)
+                if (p8 + (int)e[p8] > lim) e[p8] = 0;
+            uint32_t *dst = reinterpret_cast<uint32_t *>(s_len + 36 * wl + qtr * 8);
+            dst[0] = e[0] | (e[1] << 8) | (e[2] << 16) | (e[3] << 24);
+            dst[1] = e[4] | (e[5] << 8) | (e[6] << 16) | (e[7] << 24);
         }
         __syncthreads();
         CGIC_STAMP(unpack, 7);
         // ---- DP: fn[q] = (exit offset << 8) | codewords, from the last position of a word to the first
-        for (int wi = tid; wi < wcur; wi += DS_THREADS) {
-            const uint32_t *lw = reinterpret_cast<const uint32_t *>(s_len + 36 * wi);
-            uint16_t *fw = s_fn + 34 * wi;
+        for (int it = tid; it < nown * DS_BS; it += DS_THREADS) {
+            const int wl = 17 * (it >> 4) + (it & 15);
+            const uint32_t *lw = reinterpret_cast<const uint32_t *>(s_len + 36 * wl);
+            uint16_t *fw = s_fn + 34 * wl;
             uint32_t l8[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) l8[i] = lw[i];
@@ -1706,10 +1710,11 @@ __global__ void __launch_bounds__(DS_THREADS, DS_THREADS <= 512 ? 2 : 1) unpack_
         }
         __syncthreads();
         CGIC_STAMP(unpack, 4);
-        // ---- B1: what a block of 16 words does to every candidate entry offset (items = blocks x D, no idle lanes)
-        for (int it = tid; it < nblk * D; it += DS_THREADS) {
-            const int blk = it / D, c = it - blk * D;
-            const uint16_t *fb = s_fn + 34 * (int)s_blkw0[blk];
+        // ---- B1: what an own block does to every candidate entry offset (items = blocks x D, no idle lanes); the result goes
+        //      into the table of EVERY CTA of the cluster
+        for (int it = tid; it < nown * D; it += DS_THREADS) {
+            const int j = it / D, c = it - j * D;
+            const uint16_t *fb = s_fn + 34 * 17 * j;
             uint32_t x = (uint32_t)c, n = 0;
 #pragma unroll 4
             for (int i = 0; i < DS_BS; ++i) {
@@ -1719,11 +1724,14 @@ __global__ void __launch_bounds__(DS_THREADS, DS_THREADS <= 512 ? 2 : 1) unpack_
                     x = f >> 8;
                 }
             }
-            s_blockfn[blk * 32 + c] = (n << 8) | x;
+            const uint32_t v = (n << 8) | x;
+            uint32_t *dst = &s_blockfn[(rank + j * CL) * 32 + c];
+#pragma unroll
+            for (int rr = 0; rr < CL; ++rr) *remote(dst, rr) = v;
         }
-        __syncthreads();
+        cluster_sync();
         CGIC_STAMP(unpack, 10);
-        // ---- B2: one thread per segment chains its blocks (and carries the stream's state into the next batch)
+        // ---- B2: one thread per segment chains the blocks (every CTA for itself) and carries the stream's state into the next batch
         if (tid < nseg) {
             const int st = tid == 0 ? g_s[0] : (tid == 1 ? g_s[1] : g_s[2]), nb = tid == 0 ? g_nb[0] : (tid == 1 ? g_nb[1] : g_nb[2]);
             const int blk0 = tid == 0 ? g_blk0[0] : (tid == 1 ? g_blk0[1] : g_blk0[2]);
@@ -1745,16 +1753,17 @@ __global__ void __launch_bounds__(DS_THREADS, DS_THREADS <= 512 ? 2 : 1) unpack_
         }
         __syncthreads();
         CGIC_STAMP(unpack, 11);
-        // ---- B3: blocks replayed from their true entry offset
-        if (tid < nblk) {
-            const int bw0 = s_blkw0[tid];
-            uint32_t x = s_blkstart[tid], base = s_blkbase[tid];
+        // ---- B3: own blocks replayed from their true entry offset
+        if (tid < nown) {
+            const int k = rank + tid * CL;
+            uint32_t x = s_blkstart[k], base = s_blkbase[k];
+            const uint16_t *fb = s_fn + 34 * 17 * tid;
 #pragma unroll 4
             for (int i = 0; i < DS_BS; ++i) {
-                s_substart[bw0 + i] = (uint8_t)x;
-                s_subbase[bw0 + i] = base;
+                s_substart[17 * tid + i] = (uint8_t)x;
+                s_subbase[17 * tid + i] = base;
                 if (x != DS_STOP) {
-                    const uint32_t f = s_fn[34 * (bw0 + i) + x];
+                    const uint32_t f = fb[34 * i + x];
                     base += f & 0xFFu;
                     x = f >> 8;
                 }
@@ -1762,28 +1771,30 @@ __global__ void __launch_bounds__(DS_THREADS, DS_THREADS <= 512 ? 2 : 1) unpack_
         }
         __syncthreads();
         CGIC_STAMP(unpack, 5);
-        // ---- C: every word writes the symbols of the codewords that start in it
-        for (int it = tid; it < nblk * DS_BS; it += DS_THREADS) {
-            const int blk = it >> 4;
-            const int wi = s_blkw0[blk] + (it & 15);
-            uint32_t q = s_substart[wi];
+        // ---- C: every own word writes the symbols of the codewords that start in it -- into the symbol list of every CTA
+        for (int it = tid; it < nown * DS_BS; it += DS_THREADS) {
+            const int j = it >> 4, wl = 17 * j + (it & 15);
+            uint32_t q = s_substart[wl];
             if (q >= 32u) continue;  // DS_STOP, or the codeword that straddles into this word ends beyond it
-            const int s = s_blkseg[blk];
+            const int s = blk_stream(rank + j * CL);
             uint16_t *out = s_sym + symoff(s);
             const int ocap = symcap(s);
-            int o = (int)min(s_subbase[wi], 0x7FFFFFFFu);
-            const uint32_t w0 = s_w[wi], w1 = s_w[wi + 1];
-            const uint8_t *lp = s_len + 36 * wi;
+            int o = (int)min(s_subbase[wl], 0x7FFFFFFFu);
+            const uint32_t w0 = s_w[wl], w1 = s_w[wl + 1];
+            const uint8_t *lp = s_len + 36 * wl;
             while (q < 32u) {
                 const uint32_t len = lp[q];
                 if (!len) break;
                 const uint32_t e = ds_decode_win(__funnelshift_l(w1, w0, q), s_dec, lut2, a.T, L);
-                if (o < ocap) out[o] = (uint16_t)(e >> 8);
+                if (o < ocap) {
+#pragma unroll
+                    for (int rr = 0; rr < CL; ++rr) remote(out, rr)[o] = (uint16_t)(e >> 8);
+                }
                 ++o;
                 q += len;
             }
         }
-        __syncthreads();
+        cluster_sync();  // symbols of the batch are in place everywhere; nobody reads the block functions any more
         CGIC_STAMP(unpack, 8);
     }
     if (!tables_ready) mbar_wait(&mbar, 0);  // never leave with the bulk copy in flight
@@ -1801,10 +1812,16 @@ __global__ void __launch_bounds__(DS_THREADS, DS_THREADS <= 512 ? 2 : 1) unpack_
     const int cnt0 = s_cnt[0], cnt1 = s_cnt[1], cnt2 = s_cnt[2];
     bool bad = false;
     const int nquads = (int)(g.n4 >> 2);
-    for (int quad = tid; quad < nquads; quad += DS_THREADS) bad |= assemble_quad_small(a, b, quad, s_bits, s_prefix, s_sym, cnt0, cnt1, cnt2);
+    for (int quad = rank * DS_THREADS + tid; quad < nquads; quad += CL * DS_THREADS)
+        bad |= assemble_quad_small(a, b, quad, s_bits, s_prefix, s_sym, cnt0, cnt1, cnt2);
     const int any_bad = __syncthreads_or(bad);
     CGIC_STAMP(unpack, 9);
-    if (tid == 0) a.status[b] = (any_bad || s_bad || counts_mismatch(a.mode, s_cnt, s_pop)) ? CGIC_EFORMAT : 0;
+    if (CL > 1) {
+        // rank 0 reports for the image; nobody may leave while its shared memory can still be written from outside
+        if (tid == 0 && rank != 0 && (any_bad || s_bad)) atomicOr(remote(&s_bad, 0), 1);
+        cluster_sync();
+    }
+    if (tid == 0 && rank == 0) a.status[b] = (any_bad || s_bad || counts_mismatch(a.mode, s_cnt, s_pop)) ? CGIC_EFORMAT : 0;
 }
 
 size_t unpack_small_smem(const DevTable &T, const Geo &g) { return ds_layout(T.dec_stage_words, g).total; }
@@ -1903,17 +1920,51 @@ extern "C" int cgic_unpack(const uint8_t *bytes, const int32_t *sizes, int B, in
         const int64_t chunks = (a.g.n4 * 12 / DEC_SUB_BITS + a.ch - 1) / a.ch;
         a.nslots = a.g.n4 <= 4096 || a.T.max_len > DEC_MAX_D ? 1 : (int)std::min<int64_t>(8, std::max<int64_t>(1, chunks));
     }
-    // small token grids, codes of at most 32 bits: decode + re-assembly fused, one CTA per image
-    static const bool no_small = getenv("CGIC_NO_SMALL_KERNELS") != nullptr;  // diagnosis / A-B only
-    if (!no_small && a.g.n4 <= DS_MAX_N4 && a.T.max_len <= DS_MAX_D) {
+    // Small token grids, codes of at most 32 bits: decode + re-assembly fused, one CTA per image (unpack_small_kernel) -- once
+    // the batch fills the machine.  Measured on B200 (256x256 images, decode + re-assembly per step): 2048 images 175 us
+    // against 245 us for the two launches below, 512 images 58 us against 77 us; at 64 images the two launches, which put
+    // four CTAs on every image, are the faster ones (15.8 us in the graph against 18.2 us for the fused kernel as clusters
+    // of two CTAs per image, 20.2 us as one CTA per image), so batches that leave SMs idle keep them.
+    // cgic_tune("fused_decode_ctas", 1 | 2 | 4) (or CGIC_DS_CLUSTER in the environment) forces the fused kernel with that many
+    // CTAs per image -- a thread-block cluster when > 1 -- for A-B runs and the tests; -1 switches it off.
+    const int force_cl = tune_fused_decode_ctas();
+    const bool no_small = force_cl < 0;
+    int n_sm = 0;
+    rc = device_sm_count(&n_sm);
+    if (rc) return rc;
+    const bool forced = force_cl == 1 || force_cl == 2 || force_cl == 4;
+    if (!no_small && a.g.n4 <= DS_MAX_N4 && a.T.max_len <= DS_MAX_D && (forced || B > n_sm)) {
         const size_t smem_small = unpack_small_smem(a.T, a.g);
         const bool g4 = a.T.min_len >= 4;
-        rc = ensure_smem(g4 ? (const void *)unpack_small_kernel<4> : (const void *)unpack_small_kernel<1>, smem_small);
+        const int cl = forced && g4 ? force_cl : 1;
+        void (*kern)(const UnpackArgs) = !g4 ? unpack_small_kernel<1, 1> : (cl == 4 ? unpack_small_kernel<4, 4> : (cl == 2 ? unpack_small_kernel<4, 2> : unpack_small_kernel<4, 1>));
+        rc = ensure_smem((const void *)kern, smem_small);
         if (rc) return rc;
         {
             CGIC_PROF("unpack_small_kernel", stream);
-            if (g4) CGIC_CUDA_CHECK(launch_pdl(unpack_small_kernel<4>, dim3(B), dim3(DS_THREADS), smem_small, stream, a));
-            else CGIC_CUDA_CHECK(launch_pdl(unpack_small_kernel<1>, dim3(B), dim3(DS_THREADS), smem_small, stream, a));
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)(B * cl));
+            cfg.blockDim = dim3(DS_THREADS);
+            cfg.dynamicSmemBytes = smem_small;
+            cfg.stream = stream;
+            static const bool no_pdl = getenv("CGIC_NO_PDL") != nullptr;
+            cudaLaunchAttribute attr[2];
+            int na = 0;
+            if (!no_pdl) {
+                attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[na].val.programmaticStreamSerializationAllowed = 1;
+                ++na;
+            }
+            if (cl > 1) {
+                attr[na].id = cudaLaunchAttributeClusterDimension;
+                attr[na].val.clusterDim.x = (unsigned)cl;
+                attr[na].val.clusterDim.y = 1;
+                attr[na].val.clusterDim.z = 1;
+                ++na;
+            }
+            cfg.attrs = attr;
+            cfg.numAttrs = na;
+            CGIC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a));
         }
         CGIC_LAUNCH_CHECK();
         return CGIC_OK;

@@ -37,6 +37,12 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def tune(key: str, value: int) -> None:
+    """Dispatch knobs (cgic_tune): "fused_decode_ctas" in (-1, 0, 1, 2, 4), "fused_encode" in (0, 1).  Which kernels serve a
+    call changes, the results do not."""
+    check(lib().cgic_tune(key.encode(), int(value)), "cgic_tune")
+
+
 def _on_tensor_device(fn):
     """Runs `fn` with the device of its first CUDA tensor argument current, so that the launch, torch's current stream
     and the per-device set-up inside the library (shared-memory opt-ins, uploaded tables) all refer to the device the

@@ -52,6 +52,12 @@ typedef struct cgic_session cgic_session;
 typedef struct cgic_codebook cgic_codebook; /* prepared codebook: device copy + e^2 + cell index */
 
 CGIC_API int cgic_abi_version(void);
+/* Dispatch knobs for A-B runs and tests (process-wide; defaults: environment CGIC_DS_CLUSTER / CGIC_FUSED_ENCODE /
+ * CGIC_NO_SMALL_KERNELS, else automatic).  Results never depend on them, only which kernels produce them:
+ *   "fused_decode_ctas"  0 automatic (the fused small-grid decoder serves batches larger than the SM count), 1 | 2 | 4 always,
+ *                        with that many CTAs per image (a thread-block cluster when > 1), -1 never;
+ *   "fused_encode"       0 (default) cgic_encode = two launches, 1 = one CTA per image on grids of at most 4096 cells. */
+CGIC_API int cgic_tune(const char *key, int value);
 CGIC_API const char *cgic_last_error(void);
 
 /* Per-kernel device timing for bench.py's roofline: while enabled, every kernel the library

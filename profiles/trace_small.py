@@ -18,7 +18,9 @@ runner, graph, _ = bench.capture(torch, step, "--eager" in sys.argv)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 for _ in range(5):
-    flush.zero_(); ev[0].record(); runner(); ev[1].record()
+    if "--no-flush" not in sys.argv:
+        flush.zero_()
+    ev[0].record(); runner(); ev[1].record()
 torch.cuda.synchronize()
 print("step (events):", round(1e3 * ev[0].elapsed_time(ev[1]), 2), "us")
 SL = 16

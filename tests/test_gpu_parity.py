@@ -658,6 +658,15 @@ def test_vq_training_counters_stay_views(cg):
 
 
 # ------------------------------------------------- small token grids: decode + re-assembly fused in one CTA per image
+@pytest.fixture(params=[1, 2, 4], ids=lambda c: f"ctas{c}")
+def fused_decode(request, cg):
+    """Forces unpack_small_kernel with 1, 2 or 4 CTAs per image (clusters over distributed shared memory when > 1); by
+    default it only serves batches larger than the SM count."""
+    cg.ops.tune("fused_decode_ctas", request.param)
+    yield request.param
+    cg.ops.tune("fused_decode_ctas", 0)
+
+
 def _skew_counts(kind):
     if kind == "short":     # 1- to 3-bit codes for the frequent symbols: the decoder's group-of-one path (min_len < 4)
         return np.asarray([900000, 400000, 200000, 100000, 50000] + [100] * 1019, np.int64)
@@ -670,7 +679,7 @@ def _skew_counts(kind):
 @pytest.mark.parametrize("kind", ["kat5", "short", "flat"])
 @pytest.mark.parametrize("H,W,c,m", [(256, 256, 0.0, 0.0), (256, 256, 0.05, 0.05), (256, 256, 0.1, 0.8), (192, 208, 0.3, 0.6),
                                      (64, 48, 0.0, 0.5), (16, 16, 0.1, 0.8), (256, 256, 1.0, 0.0)])
-def test_small_grid_fused_decoder(cg, orc, kind, H, W, c, m):
+def test_small_grid_fused_decoder(cg, orc, fused_decode, kind, H, W, c, m):
     """unpack_small_kernel: streams of several batches (an all-fine 256x256 image carries ~44 kbit in its fine stream, a
     batch holds 16 kbit), tables with codes shorter than the look-up group, ragged grids, every mode -- indices, masks and
     latents against the oracle's unpack of the same bytes; the bytes themselves against the oracle's pack."""
@@ -703,7 +712,7 @@ def test_small_grid_fused_decoder(cg, orc, kind, H, W, c, m):
             assert np.array_equal(got[b].cpu().numpy(), want)
 
 
-def test_small_grid_fused_decoder_truncated_and_corrupt(cg, orc):
+def test_small_grid_fused_decoder_truncated_and_corrupt(cg, orc, fused_decode):
     """Greedy semantics on damaged input: a stream cut short decodes to a prefix (status raised: the symbol count no
     longer matches the mask population), flipped payload bits still decode to SOMETHING without faulting."""
     counts = _skew_counts("kat5")
@@ -731,9 +740,16 @@ def test_small_grid_fused_decoder_truncated_and_corrupt(cg, orc):
 
 
 # ------------------------------------------------- small token grids: VQ + select + pack fused in one CTA per image
+@pytest.fixture(params=[0, 1], ids=["two_launches", "fused"])
+def fused_encode(request, cg):
+    cg.ops.tune("fused_encode", request.param)
+    yield request.param
+    cg.ops.tune("fused_encode", 0)
+
+
 @pytest.mark.parametrize("H,W,c,m", [(256, 256, 0.1, 0.8), (256, 256, 0.0, 0.0), (256, 256, 0.05, 0.05), (192, 208, 0.3, 0.6), (64, 48, 0.0, 0.5),
                                      (16, 16, 0.1, 0.8), (256, 256, 1.0, 0.0), (128, 256, 0.2, 0.8), (256, 128, 0.5, 0.0), (512, 768, 0.1, 0.8)])
-def test_encode_fused_matches_two_launch_path(cg, orc, H, W, c, m):
+def test_encode_fused_matches_two_launch_path(cg, orc, fused_encode, H, W, c, m):
     """cgic_encode == cgic_vq_assign_indexed + cgic_pack_ws: indices, z_q bits, every stream byte, sizes; sum((e-z)^2) to
     1e-12 (another summation order).  512x768 takes the two launches inside cgic_encode."""
     B = 5
@@ -766,7 +782,7 @@ def test_encode_fused_matches_two_launch_path(cg, orc, H, W, c, m):
 
 
 @pytest.mark.parametrize("tag", ["c1_256"] + [n for n in e2e_case_names() if "long" not in n])
-def test_encode_fused_golden(cg, tag):
+def test_encode_fused_golden(cg, fused_encode, tag):
     """The fused encoder on the reference's own runs: z -> indices, z_q, the five files, bpp."""
     g = load_npz(f"big_{tag}.npz" if tag.startswith("c") else f"e2e_{tag}.npz")
     H, W = (map(int, g["shape"]) if "shape" in g else g["x"].shape[-2:])
@@ -787,3 +803,33 @@ def test_encode_fused_golden(cg, tag):
     for s, n in enumerate(STREAMS):
         assert blob[offs[s]: offs[s] + sz[s]].tobytes() == g["file_" + n].tobytes(), n
     assert int(sz.sum()) * 8 / (H * W) == float(g["bpp"])
+
+
+@pytest.mark.parametrize("tag", ["c1_256"] + [n for n in e2e_case_names() if "long" not in n])
+def test_fused_decoder_golden(cg, fused_decode, tag):
+    """The fused decoder (every cluster size) on the reference's own files: decoded indices, masks, latents."""
+    g = load_npz(f"big_{tag}.npz" if tag.startswith("c") else f"e2e_{tag}.npz")
+    H, W = (map(int, g["shape"]) if "shape" in g else g["x"].shape[-2:])
+    h, w = H // 4, W // 4
+    mode = int(g["mode"])
+    t = cg.ops.HuffTable(g["counts"], g["order"])
+    offs, caps, stride = t.layout(h, w)
+    blob = torch.zeros(1, stride, dtype=torch.uint8)
+    sizes = torch.zeros(1, 5, dtype=torch.int32)
+    for s, n in enumerate(STREAMS):
+        data = g["file_" + n]
+        blob[0, offs[s]: offs[s] + len(data)] = torch.from_numpy(data.copy())
+        sizes[0, s] = len(data)
+    cb = dev(g["codebook"])
+    mc, mm, mf, ind, quant, status = cg.ops.unpack(blob.cuda(), sizes.cuda(), mode, t, cb, h, w)
+    torch.cuda.synchronize()
+    assert int(status.abs().sum()) == 0
+    assert np.array_equal(ind.cpu().numpy(), g["ind_dec"].astype(np.int64))
+    if "quant_dec" in g:
+        assert np.array_equal(quant.cpu().numpy(), g["quant_dec"])
+        for lvl, arr in enumerate((mc, mm, mf)):
+            assert np.array_equal(arr.cpu().numpy().astype(np.uint8), g[f"mask_dec{lvl}"][0])
+    else:
+        assert hashlib.sha256(quant.cpu().numpy().tobytes()).digest() == g["quant_dec_sha"].tobytes()
+        for lvl, arr in enumerate((mc, mm, mf)):
+            assert np.array_equal(np.packbits(arr.cpu().numpy().astype(np.uint8).ravel()), g[f"mask_dec{lvl}_bits"]), lvl
