@@ -269,16 +269,32 @@ class HotPath:
         return z, (mc, mm, mf), mode
 
     def step_fn(self, groups):
-        """groups: list of (z, masks, mode).  One step = for every group: cgic_encode, then cgic_unpack."""
+        """groups: list of (z, masks, mode).  One step = for every group: cgic_encode, then cgic_unpack.  Several groups (the
+        tile shapes of one tiled image) are independent: each runs on a stream of its own, forked from and joined to the
+        launching stream, so under graph capture they become parallel branches."""
+        import torch
         ops = self.cg.ops
+        side = [torch.cuda.Stream() for _ in groups[1:]]
+
+        def one(z, masks, mode):
+            mc, mm, mf = masks
+            h, w = z.shape[-2:]
+            idx, zq, sq, packed, sizes = ops.encode(z, self.prepared, mc, mm, mf, mode, self.table)
+            dmc, dmm, dmf, ind, quant, status = ops.unpack(packed, sizes, mode, self.table, self.cb, h, w)
+            return idx, sq, packed, sizes, ind, quant, status
 
         def step():
-            outs = []
-            for z, (mc, mm, mf), mode in groups:
-                h, w = z.shape[-2:]
-                idx, zq, sq, packed, sizes = ops.encode(z, self.prepared, mc, mm, mf, mode, self.table)
-                dmc, dmm, dmf, ind, quant, status = ops.unpack(packed, sizes, mode, self.table, self.cb, h, w)
-                outs.append((idx, sq, packed, sizes, ind, quant, status))
+            if len(groups) <= 1:
+                return [one(*g) for g in groups]
+            main = torch.cuda.current_stream()
+            outs = [None] * len(groups)
+            for k, st in enumerate(side):
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    outs[k + 1] = one(*groups[k + 1])
+            outs[0] = one(*groups[0])
+            for st in side:
+                main.wait_stream(st)
             return outs
         return step
 
@@ -472,15 +488,16 @@ def run_b200(args):
     hc2, hm2, hf2 = (t_.to(dev) for t_ in workload.heads(B, H, W, cbk, SEED, first))
 
     def step_image_in():
-        e8_, e16_ = cg.ops.entropy_maps(x_img)
-        mc_, mm_, mf_, _, mode_ = cg.ops.router(e16_, e8_, c, m, per_image=True)
-        z_ = cg.ops.mask_mix(hc2, hm2, hf2, mc_, mm_, mf_)
+        # two launches that read the image once (entropy maps + per-image routing; fine mask + mask-mix)
+        e8_, e16_, mc_, mm_, near_, mode_ = cg.ops.entropy_route(x_img, c, m)
+        mf_, _, z_ = cg.ops.route_mix(hc2, hm2, hf2, mc_, mm_, mode_)
         idx_, zq_, sq_, packed_, sizes_ = cg.ops.encode(z_, prepared, mc_, mm_, mf_, mode_, table)
         out_ = cg.ops.unpack(packed_, sizes_, mode_, table, cb, h, w)
-        return idx_, out_[3], out_[5]
-    i_idx, i_ind, i_status = step_image_in()
+        return idx_, out_[3], out_[5], near_
+    i_idx, i_ind, i_status, i_near = step_image_in()
     torch.cuda.synchronize()
     assert int(i_status.abs().sum()) == 0 and torch.equal(i_ind.view(-1), i_idx)
+    near_total = [int(v) for v in i_near.sum(0).tolist()]
     img_launches = launches_per_step(lib, step_image_in, flush, reps=2)
     img_runner, _, _ = capture(torch, step_image_in, args.no_graph)
     n_img = max(10, args.steps // 2)
@@ -579,7 +596,10 @@ def run_b200(args):
             "gpu_launches": kernels_per_step * args.steps, "kernels_per_step": kernels_per_step, "cuda_graph": graph is not None,
             "image_in": {"value": world * pixels / 1e6 / (img_ms * 1e-3), "unit": UNIT, "ms_per_step": img_ms, "steps": n_img,
                          "kernels_per_step": img_launches,
-                         "adds": "a4 entropy maps (12 B/pixel image read) + a5 router + a6 mask-mix in front of the step"},
+                         "adds": "a4 entropy maps (12 B/pixel image read) + a5 router + a6 mask-mix in front of the step, as the two launches "
+                                 "cgic_entropy_route + cgic_route_mix",
+                         "threshold_adjacent_cells": {"coarse": near_total[0], "medium": near_total[1],
+                                                      "of": [B * (H // 16) * (W // 16), B * (H // 8) * (W // 8)]}},
             "job": {"value": world * pixels * args.steps / 1e6 / ((dev_ms + reduce_ms) * 1e-3), "unit": UNIT, "reduce_ms": reduce_ms,
                     "includes": f"the {args.steps} timed steps + the final all-reduce of {{bytes, pixels, sqerr}} (the path's only collective)"},
             "vq_exhaustive_leader_frac": exhaustive_frac,

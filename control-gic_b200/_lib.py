@@ -43,6 +43,11 @@ _SIGNATURES = {
                                        c_size_t, c_void_p]),
     "cgic_vq_count": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     "cgic_entropy_maps": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cgic_entropy_route_workspace_bytes": (c_size_t, [c_int]),
+    "cgic_entropy_route": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, C.c_float, C.c_float,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cgic_route_mix": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                               c_void_p, c_void_p]),
     "cgic_router_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "cgic_router": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p,
                             c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -16,7 +16,7 @@
 // fp32 throughout, denormals kept (eps = 1e-40 is a denormal; flush-to-zero would turn every entropy into
 // NaN).  Float-tolerance parity (rtol 2e-5 in the tests): the summation order is ours, and
 // exp(-0.5 ((v - bin) / 0.01)^2) is evaluated as ex2.approx(-((v - bin) * c)^2), c = 100 sqrt(log2(e) / 2).
-#include "common.cuh"
+#include "router_select.cuh"
 
 namespace cgic {
 namespace {
@@ -36,22 +36,35 @@ __device__ __forceinline__ float ex2_approx(float x)  // no flush-to-zero: denor
     return y;
 }
 
+// Routing request of the fused kernel (f1, first half): when m_c is set, the LAST CTA of an image to finish its entropy maps
+// also runs TripleGrainFixedEntropyRouter.forward for that image (per-image thresholds; route_image, router_select.cuh).
+struct RouteReq {
+    int32_t *m_c, *m_m;   // [B, n16], [B, 4 n16]; m_c == nullptr: entropy maps only
+    int32_t *near;        // [B, 2] entropies within tolerance of the coarse / medium threshold (nullable)
+    int32_t *tickets;     // [B] zero before the launch, left zero
+    int mode;
+    int64_t k_c, k_m;
+    float rtol, atol;
+};
+
+// grid (CTAs per image, B): the regions of an image are dealt to its own CTAs, so that an image's last CTA is well defined
 __global__ void __launch_bounds__(EN_WARPS * 32, 8)
-entropy_kernel(const float *__restrict__ x, int H, int W, int regions_x, int64_t n_regions, const Bins bins, float *__restrict__ e8,
-               float *__restrict__ e16)
+entropy_kernel(const float *__restrict__ x, int H, int W, int regions_x, int regions_img, const Bins bins, float *__restrict__ e8,
+               float *__restrict__ e16, const RouteReq rq)
 {
     __shared__ __align__(16) float s_rows[EN_WARPS][32 * EN_STRIDE + 4];  // per warp: 32 histogram rows (slice a multiple of 16 bytes)
     __shared__ float s_bins[32];
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_state[4];
+    __shared__ int s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     pdl_launch_dependents();
     if (threadIdx.x < 32) s_bins[threadIdx.x] = bins.v[threadIdx.x];
     __syncthreads();
     pdl_wait();  // the image may come straight from a preceding kernel
-    const int64_t region = (int64_t)blockIdx.x * EN_WARPS + warp;
-    if (region >= n_regions) return;
-    const int regions_y = H / 16;
-    const int b = (int)(region / ((int64_t)regions_x * regions_y));
-    const int rr = (int)(region - (int64_t)b * regions_x * regions_y);
+    const int b = blockIdx.y;
+    const int rr = (int)blockIdx.x * EN_WARPS + warp;
+    if (rr < regions_img) {
     const int ry = rr / regions_x, rx = rr - ry * regions_x;
     const int gx = rx * 32 + lane;
     const bool col_ok = gx < W;
@@ -154,6 +167,22 @@ entropy_kernel(const float *__restrict__ x, int H, int W, int regions_x, int64_t
             if (e16 && 2 * kx < valid_pq) e16[((int64_t)b * (H / 16) + ry) * (W / 16) + rx * 2 + kx] = ent;
         }
     }
+    }  // rr < regions_img
+    if (!rq.m_c) return;
+    // ---- routing by the last CTA of the image (all its entropies are then in global memory)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(&rq.tickets[b], 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int h16 = H / 16, w16 = W / 16, n16 = h16 * w16;
+    uint32_t *s_keys = 4 * n16 <= (int)(sizeof(s_rows) / 4) ? reinterpret_cast<uint32_t *>(&s_rows[0][0]) : nullptr;  // the histogram rows are dead
+    route_image(e16 + (int64_t)b * n16, e8 + (int64_t)b * 4 * n16, h16, w16, rq.mode, rq.k_c, rq.k_m, rq.m_c + (int64_t)b * n16,
+                rq.m_m + (int64_t)b * 4 * n16, rq.near ? rq.near + 2 * b : nullptr, rq.rtol, rq.atol, s_hist, s_state, s_keys);
+    if (threadIdx.x == 0) rq.tickets[b] = 0;  // (workspace contract: zero between launches)
 }
 
 }  // namespace
@@ -161,23 +190,52 @@ entropy_kernel(const float *__restrict__ x, int H, int W, int regions_x, int64_t
 
 using namespace cgic;
 
+static int entropy_launch(const char *who, const float *x, int B, int H, int W, const float *bins32_host, float *e8_out, float *e16_out,
+                          const RouteReq &rq, cudaStream_t stream)
+{
+    CGIC_REQUIRE(B >= 0 && H > 0 && W > 0 && H % 16 == 0 && W % 16 == 0, CGIC_EINVAL, "%s: image %dx%d must be multiples of 16", who, H, W);
+    if (B == 0) return CGIC_OK;
+    const int regions_x = (W + 31) / 32;
+    const int64_t regions_img = (int64_t)(H / 16) * regions_x;
+    CGIC_REQUIRE(regions_img < ((int64_t)1 << 30) && B <= 65535, CGIC_EINVAL, "%s: grid too large (B <= 65535)", who);
+    Bins bins;
+    for (int i = 0; i < 32; ++i) bins.v[i] = bins32_host[i];
+    {
+        CGIC_PROF("entropy_kernel", stream);
+        CGIC_CUDA_CHECK(launch_pdl(entropy_kernel, dim3((unsigned)((regions_img + EN_WARPS - 1) / EN_WARPS), (unsigned)B), dim3(EN_WARPS * 32), 0, stream, x,
+                                   H, W, regions_x, (int)regions_img, bins, e8_out, e16_out, rq));
+    }
+    CGIC_LAUNCH_CHECK();
+    return CGIC_OK;
+}
+
 extern "C" int cgic_entropy_maps(const float *x, int B, int H, int W, const float *bins32_host, float *e8_out, float *e16_out,
                                  cgic_stream_t stream)
 {
     CGIC_REQUIRE(x && bins32_host && (e8_out || e16_out), CGIC_EINVAL, "cgic_entropy_maps: null argument");
-    CGIC_REQUIRE(B >= 0 && H > 0 && W > 0 && H % 16 == 0 && W % 16 == 0, CGIC_EINVAL,
-                 "cgic_entropy_maps: image %dx%d must be multiples of 16", H, W);
-    if (B == 0) return CGIC_OK;
-    const int regions_x = (W + 31) / 32;
-    const int64_t n_regions = (int64_t)B * (H / 16) * regions_x;
-    CGIC_REQUIRE((n_regions + EN_WARPS - 1) / EN_WARPS < ((int64_t)1 << 31), CGIC_EINVAL, "cgic_entropy_maps: grid too large");
-    Bins bins;
-    for (int i = 0; i < 32; ++i) bins.v[i] = bins32_host[i];
-    {
-        CGIC_PROF("entropy_kernel", as_stream(stream));
-        CGIC_CUDA_CHECK(launch_pdl(entropy_kernel, dim3((unsigned)((n_regions + EN_WARPS - 1) / EN_WARPS)), dim3(EN_WARPS * 32), 0, as_stream(stream), x,
-                                   H, W, regions_x, n_regions, bins, e8_out, e16_out));
+    if (B > 65535) {  // (grid y limit) -- slices of the batch
+        for (int b0 = 0; b0 < B; b0 += 65535) {
+            const int nb = B - b0 < 65535 ? B - b0 : 65535;
+            const int rc = cgic_entropy_maps(x + (int64_t)b0 * 3 * H * W, nb, H, W, bins32_host, e8_out ? e8_out + (int64_t)b0 * (H / 8) * (W / 8) : nullptr,
+                                             e16_out ? e16_out + (int64_t)b0 * (H / 16) * (W / 16) : nullptr, stream);
+            if (rc) return rc;
+        }
+        return CGIC_OK;
     }
-    CGIC_LAUNCH_CHECK();
-    return CGIC_OK;
+    return entropy_launch("cgic_entropy_maps", x, B, H, W, bins32_host, e8_out, e16_out, RouteReq{}, as_stream(stream));
+}
+
+extern "C" size_t cgic_entropy_route_workspace_bytes(int B) { return ((size_t)(B > 0 ? B : 0) * 4 + 255) / 256 * 256 + 256; }
+
+extern "C" int cgic_entropy_route(const float *x, int B, int H, int W, const float *bins32_host, float *e8_out, float *e16_out, int mode, int64_t k_c,
+                                  int64_t k_m, float rtol, float atol, int32_t *m_c, int32_t *m_m, int32_t *near_out, void *workspace,
+                                  size_t workspace_bytes, cgic_stream_t stream)
+{
+    CGIC_REQUIRE(x && bins32_host && e8_out && e16_out && m_c && m_m && workspace, CGIC_EINVAL, "cgic_entropy_route: null argument");
+    CGIC_REQUIRE(mode >= 0 && mode <= 6 && k_c >= 0 && k_m >= 0, CGIC_EINVAL, "cgic_entropy_route: bad mode / ranks");
+    CGIC_REQUIRE(workspace_bytes >= cgic_entropy_route_workspace_bytes(B), CGIC_ESPACE, "cgic_entropy_route: workspace %zu < %zu bytes", workspace_bytes,
+                 cgic_entropy_route_workspace_bytes(B));
+    if (near_out && B > 0) CGIC_CUDA_CHECK(cudaMemsetAsync(near_out, 0, (size_t)B * 2 * sizeof(int32_t), as_stream(stream)));
+    RouteReq rq{m_c, m_m, near_out, static_cast<int32_t *>(workspace), mode, k_c, k_m, rtol, atol};
+    return entropy_launch("cgic_entropy_route", x, B, H, W, bins32_host, e8_out, e16_out, rq, as_stream(stream));
 }

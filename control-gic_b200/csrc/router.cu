@@ -8,97 +8,12 @@
 // the mode come from the host (Python round() on doubles, banker's rounding).
 //   per_image = 1 : one CTA per image, thresholds per image (B independent B == 1 calls)
 //   per_image = 0 : one CTA, thresholds over the whole batch (reference behaviour for B > 1)
-#include "common.cuh"
+#include "router_select.cuh"
 
 namespace cgic {
 namespace {
 
 constexpr int RT_THREADS = 512;
-
-__device__ __forceinline__ uint32_t float_key(float v)
-{
-    if (v != v) return 0xFFFFFFFFu;  // torch.sort places NaN last
-    const uint32_t u = __float_as_uint(v);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float key_float(uint32_t k)
-{
-    if (k == 0xFFFFFFFFu) return __int_as_float(0x7fc00000);
-    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
-}
-
-// value of rank `rank` (0-based) among fetch(0..n-1); whole CTA must call.  s_keys (nullable): room for n keys in
-// shared memory -- the values are fetched and converted once instead of once per pass.
-template <typename Fetch>
-__device__ float select_rank(Fetch fetch, int64_t n, int64_t rank, uint32_t *s_hist, uint32_t *s_state, uint32_t *s_keys)
-{
-    uint32_t prefix = 0, mask = 0;
-    if (rank > n - 1) rank = n - 1;
-    if (rank < 0) rank = 0;
-    if (threadIdx.x == 0) {
-        s_state[0] = 0;
-        s_state[1] = (uint32_t)rank;
-        s_state[2] = (uint32_t)((uint64_t)rank >> 32);
-    }
-    if (s_keys)
-        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = float_key(fetch(i));
-    for (int pass = 0; pass < 4; ++pass) {
-        const int shift = 24 - 8 * pass;
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
-        __syncthreads();
-        for (int64_t i0 = 0; i0 < n; i0 += blockDim.x) {  // uniform trip count: the warp votes below need every lane
-            const int64_t i = i0 + threadIdx.x;
-            uint32_t digit = 0xFFFFFFFFu;
-            if (i < n) {
-                const uint32_t k = s_keys ? s_keys[i] : float_key(fetch(i));
-                if ((k & mask) == prefix) digit = (k >> shift) & 255u;
-            }
-            // one atomic per distinct digit and warp (entropies share their exponent: the first pass would otherwise
-            // serialise hundreds of increments on one or two counters)
-            const unsigned same = __match_any_sync(0xffffffffu, digit);
-            if (digit != 0xFFFFFFFFu && (threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&s_hist[digit], (uint32_t)__popc(same));
-        }
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            // the bucket holding the wanted rank: lane l owns buckets 8l .. 8l+7; inclusive scan of the lane totals by
-            // shuffles, then the owning lane walks its 8 buckets (a serial walk over 256 buckets cost 4 us per pass)
-            const int lane = threadIdx.x;
-            uint64_t rk = ((uint64_t)s_state[2] << 32) | s_state[1];
-            uint32_t cnt[8], tot = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                cnt[i] = s_hist[lane * 8 + i];
-                tot += cnt[i];
-            }
-            uint32_t inc = tot;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += v;
-            }
-            const uint32_t exc = inc - tot;
-            // rank < n always, so exactly one lane has exc <= rk < inc (the last lane takes everything beyond: d <= 255)
-            const bool mine = (rk >= exc && rk < inc) || (lane == 31 && rk >= inc);
-            __syncwarp();  // every lane has read the rank before the owning lane replaces it
-            if (mine) {
-                uint64_t rem = rk - exc;
-                uint32_t d = 0;
-                for (; d < 7; ++d) {
-                    if (rem < cnt[d]) break;
-                    rem -= cnt[d];
-                }
-                s_state[0] = prefix | ((uint32_t)(lane * 8 + d) << shift);
-                s_state[1] = (uint32_t)rem;
-                s_state[2] = (uint32_t)(rem >> 32);
-            }
-        }
-        __syncthreads();
-        prefix = s_state[0];
-        mask |= 0xFFu << shift;
-        __syncthreads();
-    }
-    return key_float(prefix);
-}
 
 // grid = B (per_image) or 1; writes m_c and m_m.
 __global__ void __launch_bounds__(RT_THREADS)
@@ -233,6 +148,62 @@ mask_mix_kernel(const float *__restrict__ h_c, const float *__restrict__ h_m, co
     *reinterpret_cast<float4 *>(&out[rowi * w + 4 * xq]) = o;
 }
 
+// f1, second half: fine mask (+ gate) + mask-mix in one launch.  One thread per 4 consecutive fine tokens of a row and
+// channel; the fine mask follows from the coarse / medium cells (RouterTriple.py:34), so it is computed, not loaded; the
+// threads of channel 0 also write m_f and the gate tensor.
+__global__ void __launch_bounds__(256)
+route_mix_kernel(const float *__restrict__ h_c, const float *__restrict__ h_m, const float *__restrict__ h_f, const int32_t *__restrict__ m_c,
+                 const int32_t *__restrict__ m_m, int mode, int64_t n_quads, int C, int h, int w, int32_t *__restrict__ m_f_out,
+                 float *__restrict__ gate, float *__restrict__ out)
+{
+    const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
+    if (qi >= n_quads) return;
+    const unsigned wq = (unsigned)w / 4u;
+    const int64_t rowi = qi / wq;              // (b*C + c) * h + y
+    const int xq = (int)(qi - rowi * wq);      // = x / 4
+    const int64_t bc = rowi / h;
+    const int y = (int)(rowi - bc * h);
+    const int64_t b = bc / C;
+    const int ch = (int)(bc - b * C);
+    const int h8 = h / 2, w8 = w / 2, h16 = h / 4, w16 = w / 4;
+    const float hc = __ldg(&h_c[(bc * h16 + (y >> 2)) * w16 + xq]);
+    const int cc = __ldg(&m_c[(b * h16 + (y >> 2)) * w16 + xq]);
+    const float2 hm = __ldg(reinterpret_cast<const float2 *>(&h_m[(bc * h8 + (y >> 1)) * w8 + 2 * xq]));
+    const int2 mm = __ldg(reinterpret_cast<const int2 *>(&m_m[(b * h8 + (y >> 1)) * w8 + 2 * xq]));
+    const float4 hf = __ldg(reinterpret_cast<const float4 *>(&h_f[rowi * w + 4 * xq]));
+    int4 mf;
+    float4 gf;  // the gate's fine third: 1 - up4(c) - up2(m) as a FLOAT in modes 0..2 (RouterTriple.py:34), the mask itself otherwise
+    if (mode <= 2) {
+        const int f0 = 1 - cc - mm.x, f1 = 1 - cc - mm.y;
+        mf = make_int4(f0 != 0, f0 != 0, f1 != 0, f1 != 0);
+        gf = make_float4((float)f0, (float)f0, (float)f1, (float)f1);
+    } else {
+        const int f = mode == 6;
+        mf = make_int4(f, f, f, f);
+        gf = make_float4((float)f, (float)f, (float)f, (float)f);
+    }
+    const float a = __fmul_rn(hc, (float)cc);
+    const float m0 = __fmul_rn(hm.x, (float)mm.x), m1 = __fmul_rn(hm.y, (float)mm.y);
+    float4 o;
+    o.x = __fadd_rn(__fadd_rn(a, m0), __fmul_rn(hf.x, (float)mf.x));
+    o.y = __fadd_rn(__fadd_rn(a, m0), __fmul_rn(hf.y, (float)mf.y));
+    o.z = __fadd_rn(__fadd_rn(a, m1), __fmul_rn(hf.z, (float)mf.z));
+    o.w = __fadd_rn(__fadd_rn(a, m1), __fmul_rn(hf.w, (float)mf.w));
+    *reinterpret_cast<float4 *>(&out[rowi * w + 4 * xq]) = o;
+    if (ch == 0) {
+        *reinterpret_cast<int4 *>(&m_f_out[(b * h + y) * (int64_t)w + 4 * xq]) = mf;
+        if (gate) {
+            float *row = gate + (b * h + y) * (int64_t)(3 * w);
+            const float fc = (float)cc;
+            *reinterpret_cast<float4 *>(&row[4 * xq]) = make_float4(fc, fc, fc, fc);
+            *reinterpret_cast<float4 *>(&row[w + 4 * xq]) = make_float4((float)mm.x, (float)mm.x, (float)mm.y, (float)mm.y);
+            *reinterpret_cast<float4 *>(&row[2 * w + 4 * xq]) = gf;
+        }
+    }
+}
+
 // f4  decoder entry (CGIC/modules/vqvae/decoder.py:373-382): mask-gated merge of the decoder's branches, two elements per thread.
 //   LEVEL 2: out = h * up2(m_c) + other * m_m                       tensors [B,C,hh,ww], m_c [B,1,hh/2,ww/2], m_m [B,1,hh,ww]
 //   LEVEL 3: out = (h * up4(m_c) + h * up2(m_m)) + other * m_f      tensors [B,C,hh,ww], m_c [B,1,hh/4,ww/4], m_m [B,1,hh/2,ww/2], m_f [B,1,hh,ww]
@@ -357,6 +328,24 @@ extern "C" int cgic_mask_mix(const float *h_c, const float *h_m, const float *h_
         CGIC_PROF("mask_mix_kernel", as_stream(stream));
         CGIC_CUDA_CHECK(launch_pdl(mask_mix_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, as_stream(stream), h_c, h_m, h_f, m_c, m_m, m_f, n, C, h,
                                    w, out));
+    }
+    CGIC_LAUNCH_CHECK();
+    return CGIC_OK;
+}
+
+extern "C" int cgic_route_mix(const float *h_c, const float *h_m, const float *h_f, const int32_t *m_c, const int32_t *m_m, int mode, int B, int C,
+                              int h, int w, int32_t *m_f_out, float *gate_out, float *out, cgic_stream_t stream)
+{
+    CGIC_REQUIRE(h_c && h_m && h_f && m_c && m_m && m_f_out && out, CGIC_EINVAL, "cgic_route_mix: null argument");
+    CGIC_REQUIRE(B >= 0 && C > 0 && h > 0 && w > 0 && h % 4 == 0 && w % 4 == 0 && mode >= 0 && mode <= 6, CGIC_EINVAL, "cgic_route_mix: bad shape / mode");
+    const int64_t n = (int64_t)B * C * h * w / 4;
+    if (n == 0) return CGIC_OK;
+    for (const void *ptr : {(const void *)h_m, (const void *)h_f, (const void *)m_m, (const void *)m_f_out, (const void *)out, (const void *)gate_out})
+        CGIC_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, CGIC_EINVAL, "cgic_route_mix: buffers must be 16-byte aligned");
+    {
+        CGIC_PROF("route_mix_kernel", as_stream(stream));
+        CGIC_CUDA_CHECK(launch_pdl(route_mix_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, as_stream(stream), h_c, h_m, h_f, m_c, m_m, mode, n, C,
+                                   h, w, m_f_out, gate_out, out));
     }
     CGIC_LAUNCH_CHECK();
     return CGIC_OK;

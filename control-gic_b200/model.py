@@ -109,20 +109,36 @@ class CGIC(nn.Module):
         self.load_state_dict(sd, strict=False)
 
     # ---------------------------------------------------------------- model.py:99-112
+    def _heads(self, x, e16, e8):
+        if self._heads_arity == 3:
+            return self.encoder.forward_heads(x, e16, e8)
+        return self.encoder.forward_heads(x)
+
     def _router(self, per_image=False):
         p = self.router_config["params"]
         return TripleGrainFixedEntropyRouter(p["coarse_grain_ratio"], p["medium_grain_ratio"], per_image=per_image)
 
     def encode(self, x, per_image: bool = False):
-        x_entropy_p8, x_entropy_p16 = entropy_pair(x)
-        if self._heads_arity == 3:
-            h_coarse, h_medium, h_fine = self.encoder.forward_heads(x, x_entropy_p16, x_entropy_p8)
+        """model.py:99-112.  With per-image thresholds (per_image=True, or a single image, where the reference's batch-wide
+        thresholds ARE per-image) the tail runs as the two launches of SURVEY 8f f1: entropy maps + routing, then fine mask +
+        gate + mask-mix; `self.threshold_adjacent` [B,2] then counts the coarse / medium entropies within the Entropy kernel's
+        float tolerance of a threshold (all zero = masks provably those of the reference)."""
+        router = self._router(per_image)
+        if per_image or x.shape[0] == 1:
+            x_entropy_p8, x_entropy_p16, m_c, m_m, near, mode = ops.entropy_route(x, router.coarse_grain_ratio, router.medium_grain_ratio)
+            self.threshold_adjacent = near
+            h_coarse, h_medium, h_fine = self._heads(x, x_entropy_p16, x_entropy_p8)
+            m_f, gate, h = ops.route_mix(h_coarse, h_medium, h_fine, m_c, m_m, mode, want_gate=True)
+            grain_mask = [m_c, m_m, m_f]
+            ratios = [router.coarse_grain_ratio, router.medium_grain_ratio, router.fine_grain_ratio]
         else:
-            h_coarse, h_medium, h_fine = self.encoder.forward_heads(x)
-        grain_mask, gate, ratios, mode = self._router(per_image)(x_entropy_p16, x_entropy_p8)
+            x_entropy_p8, x_entropy_p16 = entropy_pair(x)
+            self.threshold_adjacent = None
+            h_coarse, h_medium, h_fine = self._heads(x, x_entropy_p16, x_entropy_p8)
+            grain_mask, gate, ratios, mode = router(x_entropy_p16, x_entropy_p8)
+            h = ops.mask_mix(h_coarse, h_medium, h_fine, *grain_mask)
         # vqvae_blocks.py:357-359 (quirk Q6: argmax over the width-concatenated axis; kept as is)
         grain_indices = gate.permute(0, 3, 1, 2).argmax(dim=1)
-        h = ops.mask_mix(h_coarse, h_medium, h_fine, *grain_mask)
         h = self.quant_conv(h)
         quant, emb_loss, ind = self.quantize(h)
         return quant, emb_loss, grain_indices, grain_mask, ind, ratios, mode

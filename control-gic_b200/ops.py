@@ -324,6 +324,50 @@ def router(e16: torch.Tensor, e8: torch.Tensor, coarse_ratio: float, medium_rati
     return m_c, m_m, m_f, gate, mode
 
 
+ENTROPY_RTOL, ENTROPY_ATOL = 2e-5, 1e-6   # float tolerance of Entropy against the reference (tests)
+
+
+@_on_tensor_device
+def entropy_route(x: torch.Tensor, coarse_ratio: float, medium_ratio: float, rtol: float = ENTROPY_RTOL, atol: float = ENTROPY_ATOL):
+    """f1, first launch: model.py:440-483 for both patch sizes AND RouterTriple.py:15-96 with per-image thresholds, the image
+    read once -> (e8 [B,H/8,W/8], e16 [B,H/16,W/16], m_c, m_m int32 [B,1,.,.], near int32 [B,2], mode).  near[b] = how many
+    coarse / medium entropies of image b lie within rtol*|thr| + atol of their threshold."""
+    x = _cuda(x, torch.float32, "x")
+    if x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError("entropy_route expects [B,3,H,W]")
+    B, _, H, W = x.shape
+    dev = x.device
+    h16, w16 = H // 16, W // 16
+    mode = router_mode(coarse_ratio, medium_ratio)
+    k_c, k_m = router_ranks(coarse_ratio, medium_ratio, h16 * w16, 4 * h16 * w16, mode)
+    e8 = torch.empty(B, H // 8, W // 8, dtype=torch.float32, device=dev)
+    e16 = torch.empty(B, h16, w16, dtype=torch.float32, device=dev)
+    m_c = torch.empty(B, 1, h16, w16, dtype=torch.int32, device=dev)
+    m_m = torch.empty(B, 1, 2 * h16, 2 * w16, dtype=torch.int32, device=dev)
+    near = torch.empty(B, 2, dtype=torch.int32, device=dev)
+    ws = _workspace("entropy_route", lib().cgic_entropy_route_workspace_bytes(B), dev)
+    check(lib().cgic_entropy_route(x.data_ptr(), B, H, W, linspace_bins().ctypes.data, e8.data_ptr(), e16.data_ptr(), mode, k_c, k_m,
+                                   float(rtol), float(atol), m_c.data_ptr(), m_m.data_ptr(), near.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+          "cgic_entropy_route")
+    return e8, e16, m_c, m_m, near, mode
+
+
+@_on_tensor_device
+def route_mix(h_c, h_m, h_f, m_c, m_m, mode: int, want_gate: bool = False):
+    """f1, second launch: fine mask (RouterTriple.py:34) + gate + mask-mix (vqvae_blocks.py:361-366) -> (m_f int32 [B,1,h,w],
+    gate fp32 [B,1,h,3w] or None, h fp32 [B,C,h,w])."""
+    h_c, h_m, h_f = (_cuda(t, torch.float32, n) for t, n in ((h_c, "h_c"), (h_m, "h_m"), (h_f, "h_f")))
+    m_c, m_m = (_cuda(t, torch.int32, n) for t, n in ((m_c, "m_c"), (m_m, "m_m")))
+    B, Cc, h, w = h_f.shape
+    dev = h_f.device
+    m_f = torch.empty(B, 1, h, w, dtype=torch.int32, device=dev)
+    gate = torch.empty(B, 1, h, 3 * w, dtype=torch.float32, device=dev) if want_gate else None
+    out = torch.empty_like(h_f)
+    check(lib().cgic_route_mix(h_c.data_ptr(), h_m.data_ptr(), h_f.data_ptr(), m_c.data_ptr(), m_m.data_ptr(), mode, B, Cc, h, w,
+                               m_f.data_ptr(), _p(gate), out.data_ptr(), _stream()), "cgic_route_mix")
+    return m_f, gate, out
+
+
 @_on_tensor_device
 def mask_mix(h_c, h_m, h_f, m_c, m_m, m_f) -> torch.Tensor:
     """vqvae_blocks.py:361-366: up4(h_c)*up4(m_c) + up2(h_m)*up2(m_m) + h_f*m_f."""

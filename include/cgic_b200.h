@@ -144,6 +144,25 @@ CGIC_API int cgic_entropy_maps(const float *x, int B, int H, int W, const float 
                       float *e16_out, cgic_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * f1  The encode tail in two launches that read the image once:
+ *   cgic_entropy_route = Entropy(8) + Entropy(16) (model.py:433-483) AND TripleGrainFixedEntropyRouter.forward
+ *     (RouterTriple.py:15-96) with per-image thresholds (the reference's B == 1 call for every image): the last CTA of an
+ *     image to finish its entropy maps selects the thresholds and writes m_c int32 [B,1,H/16,W/16], m_m int32 [B,1,H/8,W/8].
+ *     mode / k_c / k_m as for cgic_router (host doubles, banker's rounding; k for ONE image).  near_out int32 [B,2]
+ *     (nullable): how many coarse / medium entropies lie within rtol*|thr| + atol of their threshold -- the cells a
+ *     float-tolerance difference between this Entropy and the reference's could flip (0 = masks provably identical).
+ *     workspace: cgic_entropy_route_workspace_bytes(B) bytes, ZERO before the first use (left zero).
+ *   cgic_route_mix = fine mask (RouterTriple.py:34) + gate (nullable, fp32 [B,1,h,3w]) + mask-mix (vqvae_blocks.py:361-366)
+ *     of the three encoder heads: m_f_out int32 [B,1,h,w], out fp32 [B,C,h,w].  The CNN encoder runs between the two.
+ * ------------------------------------------------------------------------------------------ */
+CGIC_API size_t cgic_entropy_route_workspace_bytes(int B);
+CGIC_API int cgic_entropy_route(const float *x, int B, int H, int W, const float *bins32_host, float *e8_out, float *e16_out,
+                       int mode, int64_t k_c, int64_t k_m, float rtol, float atol, int32_t *m_c, int32_t *m_m,
+                       int32_t *near_out, void *workspace, size_t workspace_bytes, cgic_stream_t stream);
+CGIC_API int cgic_route_mix(const float *h_c, const float *h_m, const float *h_f, const int32_t *m_c, const int32_t *m_m, int mode,
+                   int B, int C, int h, int w, int32_t *m_f_out, float *gate_out, float *out, cgic_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * a5  TripleGrainFixedEntropyRouter.forward   CGIC/modules/vqvae/RouterTriple.py:15-96
  *     e16 [B,h16,w16], e8 [B,2*h16,2*w16] fp32.  mode 0..6 and the ranks k_c, k_m are computed
  *     by the caller in Python doubles with round() exactly as RouterTriple.py:19-30,36-90 does.

@@ -833,3 +833,86 @@ def test_fused_decoder_golden(cg, fused_decode, tag):
         assert hashlib.sha256(quant.cpu().numpy().tobytes()).digest() == g["quant_dec_sha"].tobytes()
         for lvl, arr in enumerate((mc, mm, mf)):
             assert np.array_equal(np.packbits(arr.cpu().numpy().astype(np.uint8).ravel()), g[f"mask_dec{lvl}_bits"]), lvl
+
+
+# ------------------------------------------------- f1: the encode tail in two launches (entropy + routing, fine mask + gate + mix)
+def _near_counts(e16, e8, masks_c, c_ratio, m_ratio, rtol=2e-5, atol=1e-6):
+    """numpy restatement of the near-threshold counter for ONE image in mode 0 / 1 / 2 / 3."""
+    from oracle import oracle as orc
+    mode = orc.router_mode(c_ratio, m_ratio)
+    k_c, k_m = orc.router_ranks(c_ratio, m_ratio, e16.size, e8.size, mode)
+    out = [0, 0]
+    if mode in (0, 2, 3):
+        thr = np.sort(e16.ravel())[max(k_c - 1, 0)]
+        out[0] = int((np.abs(e16 - thr) <= np.float32(rtol) * np.abs(thr) + np.float32(atol)).sum())
+    if mode in (0, 1):
+        under = np.repeat(np.repeat(masks_c, 2, -1), 2, -2).astype(bool) if mode == 0 else np.zeros_like(e8, bool)
+        key = np.where(under, np.float32(0), e8)
+        thr = np.sort(key.ravel())[max(k_m - 1, 0)]
+        out[1] = int(((np.abs(e8 - thr) <= np.float32(rtol) * np.abs(thr) + np.float32(atol)) & ~under).sum())
+    return out
+
+
+@pytest.mark.parametrize("tag", [n for n in e2e_case_names()] + ["big:c1_256"])
+def test_f1_two_launch_tail_golden(cg, tag):
+    """cgic_entropy_route + cgic_route_mix on the reference's own runs: entropy maps within tolerance; masks, gate and the
+    mixed latent bit-exact (asserted whenever no entropy sits within tolerance of a threshold, else at most that many cells
+    may differ); the near-threshold counter against a numpy restatement on OUR entropy maps."""
+    g = load_npz(f"big_{tag[4:]}.npz" if tag.startswith("big:") else f"e2e_{tag}.npz")
+    c_ratio, m_ratio = map(float, g["ratios"])
+    mode = int(g["mode"])
+    x = dev(g["x"])
+    e8, e16, m_c, m_m, near, rmode = cg.ops.entropy_route(x, c_ratio, m_ratio)
+    torch.cuda.synchronize()
+    assert rmode == mode
+    assert np.allclose(e8.cpu().numpy(), g["e8"], rtol=ENTROPY_RTOL, atol=1e-6) and np.allclose(e16.cpu().numpy(), g["e16"], rtol=ENTROPY_RTOL, atol=1e-6)
+    # the same masks as the stand-alone router on the same (our) entropy maps -- bit for bit
+    r_c, r_m, r_f, r_gate, _ = cg.ops.router(e16, e8, c_ratio, m_ratio, per_image=True, want_gate=True)
+    assert torch.equal(m_c, r_c) and torch.equal(m_m, r_m)
+    want = _near_counts(e16.cpu().numpy()[0], e8.cpu().numpy()[0], m_c.cpu().numpy()[0, 0], c_ratio, m_ratio)
+    assert near.cpu().numpy()[0].tolist() == want, (near.cpu().numpy(), want)
+    golden = [g["mask0"], g["mask1"], g["mask2"]] if "mask0" in g else None
+    if golden is None:
+        H, W = map(int, g["shape"])
+        golden = [np.unpackbits(g[f"mask{l}_bits"])[: (H // (16 >> l)) * (W // (16 >> l))].reshape(1, 1, H // (16 >> l), W // (16 >> l)) for l in range(3)]
+    diff_c = int((m_c.cpu().numpy().astype(np.uint8) != golden[0]).sum())
+    diff_m = int((m_m.cpu().numpy().astype(np.uint8) != golden[1]).sum())
+    n = near.cpu().numpy()[0]
+    assert diff_c <= n[0] and diff_m <= n[1] + 4 * diff_c, (diff_c, diff_m, n)
+    # second launch on the reference's heads and the reference's masks: fine mask, gate, mixed latent
+    m_f, gate, h = cg.ops.route_mix(dev(g["hc"]), dev(g["hm"]), dev(g["hf"]), dev(golden[0].astype(np.int32)), dev(golden[1].astype(np.int32)), mode,
+                                    want_gate=True)
+    assert np.array_equal(m_f.cpu().numpy().astype(np.uint8), golden[2])
+    if "h" in g:
+        assert np.array_equal(h.cpu().numpy().view(np.uint32), g["h"].view(np.uint32))
+    else:
+        assert hashlib.sha256(h.cpu().numpy().tobytes()).digest() == g["h_sha"].tobytes()
+    if diff_c == 0 and diff_m == 0:
+        assert torch.equal(gate, r_gate) and torch.equal(m_f, r_f)
+
+
+@pytest.mark.parametrize("B,H,W,c,m", [(3, 256, 256, 0.1, 0.8), (2, 512, 768, 0.3, 0.6), (5, 16, 16, 0.1, 0.8), (2, 64, 48, 0.0, 0.5), (2, 96, 64, 0.5, 0.0),
+                                        (2, 64, 64, 0.2, 0.8), (2, 32, 64, 1.0, 0.0), (1, 768, 768, 0.05, 0.05)])
+def test_f1_entropy_route_per_image_batches(cg, orc, B, H, W, c, m):
+    """Per-image thresholds for every image of a batch == B separate B = 1 calls of the stand-alone kernels; with and
+    without the shared-memory key cache (a 512x768 image has 6144 medium cells, the cache holds 4224); all modes."""
+    g = torch.Generator().manual_seed(B * H + W)
+    x = torch.rand(B, 3, H, W, generator=g).cuda()
+    x[0, :, : H // 2] = 0.25          # ties: large constant area
+    e8, e16, m_c, m_m, near, mode = cg.ops.entropy_route(x, c, m)
+    e8_s, e16_s = cg.ops.entropy_maps(x)
+    assert torch.equal(e8, e8_s) and torch.equal(e16, e16_s)
+    for b in range(B):
+        r_c, r_m, r_f, _, rmode = cg.ops.router(e16[b:b + 1], e8[b:b + 1], c, m)
+        assert rmode == mode and torch.equal(m_c[b:b + 1], r_c) and torch.equal(m_m[b:b + 1], r_m), b
+        omc, omm, omf, _ = orc.router(e16[b:b + 1].cpu().numpy(), e8[b:b + 1].cpu().numpy(), c, m)
+        assert np.array_equal(m_c[b:b + 1].cpu().numpy(), omc) and np.array_equal(m_m[b:b + 1].cpu().numpy(), omm)
+        assert near[b].cpu().numpy().tolist() == _near_counts(e16[b].cpu().numpy(), e8[b].cpu().numpy(), m_c[b, 0].cpu().numpy(), c, m), b
+    hc, hm, hf = (torch.randn(B, 4, H // d, W // d, generator=g).cuda() for d in (16, 8, 4))
+    m_f, gate, h = cg.ops.route_mix(hc, hm, hf, m_c, m_m, mode, want_gate=True)
+    _, _, r_f, r_gate, _ = cg.ops.router(e16, e8, c, m, per_image=True, want_gate=True)
+    assert torch.equal(m_f, r_f) and torch.equal(gate, r_gate)
+    assert torch.equal(h.view(torch.int32), cg.ops.mask_mix(hc, hm, hf, m_c, m_m, m_f).view(torch.int32))
+    # twice in a row: the tickets were left zero
+    again = cg.ops.entropy_route(x, c, m)
+    assert torch.equal(again[2], m_c) and torch.equal(again[3], m_m) and torch.equal(again[4], near)
