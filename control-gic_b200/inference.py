@@ -74,8 +74,8 @@ def load_config(config_path, display: bool = False):
 
 
 def load_model(config, ckpt_path=None, encoder=None, decoder=None):
-    """inference.py:87-93.  The CNNs are not rebuilt here: pass `encoder` / `decoder` modules (e.g. the
-    reference's own `Encoder(**ddconfig)` / `Decoder(zq_ch=embed_dim, **ddconfig)`)."""
+    """inference.py:87-93.  The CNNs are out of scope: they are built from `ddconfig` with the reference's own classes when
+    that package is importable (CGIC.__init__ / model.reference_cnns), or passed in as `encoder` / `decoder`."""
     from .model import CGIC
     params = dict(config["model"]["params"])
     params.pop("ckpt_path", None)
@@ -86,6 +86,58 @@ def load_model(config, ckpt_path=None, encoder=None, decoder=None):
         model.load_state_dict(sd, strict=False)
         print(f"Restored from {ckpt_path}")
     return model.eval()
+
+
+# ------------------------------------------------------------------------------------ data in / images out
+class ImageDataset(torch.utils.data.Dataset):
+    """inference.py:34-79: every .jpg / .jpeg / .png below a directory (sorted), optionally the slice `images_range`,
+    centre-cropped to multiples of 16 and turned into a [3,H,W] float tensor in [0, 1] (`ToTensor`)."""
+
+    def __init__(self, imagenet_images_dir, target_size: int = 512, images_range: Tuple[int, int] = (0, -1)) -> None:
+        super().__init__()
+        from pathlib import Path
+        self.target_size = target_size
+        root = Path(imagenet_images_dir)
+        self.image_paths = sorted(p for p in root.glob("**/*") if self._is_image_path(p))
+        if images_range[1] > 0:
+            self.image_paths = self.image_paths[images_range[0]:images_range[1]]
+        print(f"Found {len(self.image_paths)} images to reconstruct")
+
+    def __getitem__(self, index: int) -> torch.Tensor:
+        from PIL import Image
+        image = self._resize_and_crop(Image.open(self.image_paths[index]))
+        a = np.asarray(image)
+        if a.ndim == 2:
+            a = a[:, :, None]
+        # torchvision's ToTensor: HWC uint8 -> CHW float32 / 255
+        return torch.from_numpy(np.ascontiguousarray(a.transpose(2, 0, 1))).to(torch.float32).div(255)
+
+    @staticmethod
+    def _resize_and_crop(img):
+        """centre crop to (16 * (h // 16), 16 * (w // 16)) with torchvision's rounding of the offsets (inference.py:62-67)"""
+        w, h = img.size
+        ch, cw = 16 * (h // 16), 16 * (w // 16)
+        top, left = int(round((h - ch) / 2.0)), int(round((w - cw) / 2.0))
+        return img.crop((left, top, left + cw, top + ch))
+
+    def __len__(self) -> int:
+        return len(self.image_paths)
+
+    @staticmethod
+    def _is_image_path(path) -> bool:
+        ext = path.name[path.name.rfind(".") + 1:]
+        return not (path.is_dir() or path.name.startswith(".") or len(ext) == 0 or ext.lower() not in ("jpg", "jpeg", "png"))
+
+
+def write_images(images: torch.Tensor, output_dir, i: int, batch_size: int, start_offset: int, bpp=None) -> None:
+    """inference.py:95-110: `{k:03d}_{bpp:05f}.png` (or `{k:03d}.png`), k = i * batch_size + j + start_offset."""
+    from pathlib import Path
+    from PIL import Image
+    images = (255 * images.permute(0, 2, 3, 1).detach().cpu().numpy()).astype(np.uint8)
+    for j, img in enumerate(images):
+        k = i * batch_size + j + start_offset
+        name = f"{k:03d}_{bpp:05f}.png" if bpp is not None else f"{k:03d}.png"
+        Image.fromarray(img).save(Path(output_dir) / name)
 
 
 # ------------------------------------------------------------------------------------ tiling geometry
@@ -244,3 +296,31 @@ def run(model, dataloader, output_dir, h_indices: HuffmanCoding, h_mask: BinaryC
         f.write(f"Bpp Average: {bpp_sum / max(total, 1)}")
     print(f"Bpp Average: {bpp_sum / max(total, 1)}")
     return bpp_sum / max(total, 1)
+
+
+def main(argv=None, high_resolution: bool = False, config_path: str = "./configs/config_inference.yaml", encoder=None, decoder=None):
+    """inference.py:127-171 / inference_high_resolution.py:197-262: parse the reference's flags, load the images, build the
+    model from the reference's YAML, `HuffmanCoding(model.quantize.embedding_counter)`, compress every image (tiled at 768
+    pixels when high_resolution), write `reconstructed/{k:03d}_{bpp:05f}.png` and `bpp.txt`.  Returns the average bpp."""
+    from pathlib import Path
+    from torch.utils.data import DataLoader
+    opt, _ = get_parser(high_resolution).parse_known_args(argv)
+    dataset = ImageDataset(opt.images_dir, opt.image_size, tuple(opt.images_range))
+    dataloader = DataLoader(dataset, opt.batch_size, num_workers=opt.num_workers)
+    config = load_config(config_path, display=True)
+    ckpt = config["model"]["params"].get("ckpt_path")
+    model = load_model(config, ckpt if ckpt and os.path.exists(ckpt) else None, encoder=encoder, decoder=decoder).to("cuda")
+    h_string = HuffmanCoding(model.quantize.embedding_counter)
+    h_mask = BinaryCoding()
+    print("number of params (M): %.2f" % (sum(p.numel() for p in model.parameters() if p.requires_grad) / 1.e6))
+    Path(opt.output_dir).mkdir(parents=True, exist_ok=True)
+    rec_output_dir = Path(opt.output_dir) / "reconstructed"
+    rec_output_dir.mkdir(parents=True, exist_ok=True)
+    start = opt.images_range[0]
+    return run(model, dataloader, opt.output_dir, h_string, h_mask, high_resolution=high_resolution,
+               write_image=lambda x_rec, i, bpp: write_images(x_rec, rec_output_dir, i, opt.batch_size, start, bpp=bpp), n_images=len(dataset))
+
+
+if __name__ == "__main__":
+    import sys
+    main(high_resolution="--high-resolution" in sys.argv)

@@ -54,6 +54,32 @@ class ReferenceEncoderHeads(nn.Module):
         return taps["c"], taps["m"], taps["f"]
 
 
+def reference_cnns(ddconfig, embed_dim):
+    """The out-of-scope CNNs built from the reference package itself -- `Encoder(**ddconfig)`, `Decoder(zq_ch=embed_dim,
+    **ddconfig)` exactly as CGIC/models/model.py:42-43 does -- when that package can be imported: already on sys.path, or
+    under $CGIC_REFERENCE, or in this repository's git-ignored baseline/_ref copy.  Returns (encoder, decoder) or None.
+    `import pytorch_lightning` (which the reference's blocks do not need, only its model.py) is never touched."""
+    import importlib
+    import sys
+    roots = [None, os.environ.get("CGIC_REFERENCE"),
+             os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")]
+    for root in roots:
+        if root is not None and not os.path.isdir(os.path.join(root, "CGIC", "modules", "vqvae")):
+            continue
+        if root is not None:
+            sys.path.insert(0, root)
+        try:
+            blocks = importlib.import_module("CGIC.modules.vqvae.vqvae_blocks")
+            dec = importlib.import_module("CGIC.modules.vqvae.decoder")
+            return blocks.Encoder(**ddconfig), dec.Decoder(zq_ch=embed_dim, **ddconfig)
+        except ImportError:
+            continue
+        finally:
+            if root is not None and sys.path and sys.path[0] == root:
+                sys.path.pop(0)
+    return None
+
+
 def _heads_arity(encoder) -> int:
     """How many positional arguments `encoder.forward_heads` takes: 3 = (x, e16, e8) like the reference Encoder's
     forward, 1 = (x).  Decided once from the signature (no try / except around the CNN: an error raised inside it
@@ -78,8 +104,15 @@ class CGIC(nn.Module):
         ddconfig = dict(ddconfig or {})
         self.image_key = image_key
         if encoder is None or decoder is None:
-            raise ValueError("pass the (out-of-scope, stock PyTorch) CNN `encoder` and `decoder` modules; e.g. "
-                             "ReferenceEncoderHeads(Encoder(**ddconfig)) and Decoder(zq_ch=embed_dim, **ddconfig)")
+            # like the reference (model.py:42-43): build the CNNs from ddconfig -- with the reference's own classes, which stay
+            # out of scope here (stock PyTorch); explicit `encoder=` / `decoder=` arguments take precedence
+            built = reference_cnns(ddconfig, embed_dim) if ddconfig else None
+            if built is None:
+                raise ValueError("the reference package (CGIC.modules.vqvae) is not importable, so the out-of-scope CNNs cannot be built "
+                                 "from ddconfig: pass `encoder` and `decoder` modules, e.g. ReferenceEncoderHeads(Encoder(**ddconfig)) and "
+                                 "Decoder(zq_ch=embed_dim, **ddconfig), or put the reference on sys.path / $CGIC_REFERENCE")
+            encoder = encoder if encoder is not None else built[0]
+            decoder = decoder if decoder is not None else built[1]
         self.encoder = encoder if hasattr(encoder, "forward_heads") else ReferenceEncoderHeads(encoder)
         self.decoder = decoder
         self._heads_arity = _heads_arity(self.encoder)
@@ -168,8 +201,7 @@ class CGIC(nn.Module):
         assert len(input.shape) == 4
         if input.shape[0] != 1:
             raise ValueError("compress() follows the reference and handles one image per call; use compress_batch()")
-        if not hasattr(h_indices, "table"):
-            raise TypeError("h_indices must be the cgic_b200 HuffmanCoding (it owns the native code table)")
+        h_indices = self._native_coder(h_indices)
         out = self.compress_batch(input, h_indices, per_image=False)
         sizes = out["sizes_host"][0].tolist()
         blob = out["bytes"][0].cpu().numpy()
@@ -181,6 +213,23 @@ class CGIC(nn.Module):
         partition_map = None  # drawing (CGIC/modules/draw.py) is out of scope; save_img is accepted and ignored
         return out["dec"], out["bpp"][0], partition_map
 
+    def _native_coder(self, h_indices):
+        """A caller that built the REFERENCE's HuffmanCoding (inference.py:137-139 does, from `model.quantize.embedding_counter`)
+        gets the native table for the same counters; its codes are checked against the object passed in, so a coder built
+        from other frequencies is refused rather than silently replaced."""
+        if hasattr(h_indices, "table"):
+            return h_indices
+        own = getattr(self, "_own_coder", None)
+        if own is None or own[0] is not h_indices:
+            native = HuffmanCoding(self.quantize.embedding_counter)
+            theirs = getattr(h_indices, "codes", None)
+            if not isinstance(theirs, dict) or {int(k): v for k, v in theirs.items()} != native.codes:
+                raise TypeError("h_indices is neither a cgic_b200 HuffmanCoding nor a coder whose codes are those of this model's "
+                                "embedding_counter")
+            own = (h_indices, native)
+            self._own_coder = own
+        return own[1]
+
     def compress_batch(self, input, h_indices: HuffmanCoding, per_image: bool = True, decode: bool = True):
         """B independent images in one pass (per-image router thresholds when per_image=True):
         returns dict(bytes [B,stride] uint8 cuda, sizes [B,5], sizes_host, bpp list, mode, grid,
@@ -188,6 +237,7 @@ class CGIC(nn.Module):
         quant, diff, grain_indices, grain_mask, ind, _, mode = self.encode(input, per_image=per_image)
         B, _, H, W = input.shape
         h, w = quant.shape[-2:]
+        h_indices = self._native_coder(h_indices)
         table = h_indices.table
         packed, sizes = ops.pack(ind, *grain_mask, mode, table, h, w)
         out = dict(bytes=packed, sizes=sizes, mode=mode, grid=(h, w), ind=ind, quant=quant, masks=grain_mask, emb_loss=diff)

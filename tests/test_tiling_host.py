@@ -55,3 +55,32 @@ def test_parsers_and_config_keys():
             list(args.images_range)) == ("d", 2, 3, 256, "o", True, [4, 9])
     cfg = cg.inference._Cfg({"model": {"params": {"ddconfig": {"router_config": {"params": {"coarse_grain_ratio": 0.1}}}}}})
     assert cfg.model.params.ddconfig.router_config.params.coarse_grain_ratio == 0.1
+
+
+def test_image_dataset_and_writer(tmp_path):
+    """inference.py:34-79, 95-110: image discovery, centre crop to multiples of 16 (== torchvision's center_crop + ToTensor),
+    `images_range`, and the `{k:03d}_{bpp:05f}.png` naming."""
+    import numpy as np
+    import torch
+    import torchvision.transforms as T
+    import torchvision.transforms.functional as TF
+    from PIL import Image
+    import cgic_b200 as cg
+    rng = np.random.default_rng(0)
+    for name, (h, w) in {"a.png": (70, 53), "b.jpg": (64, 64), "sub/c.PNG": (33, 47), ".hidden.png": (32, 32)}.items():
+        path = tmp_path / name
+        path.parent.mkdir(exist_ok=True)
+        Image.fromarray(rng.integers(0, 255, (h, w, 3), dtype=np.uint8)).save(path)
+    (tmp_path / "notes.txt").write_text("x")
+    ds = cg.inference.ImageDataset(tmp_path)
+    assert [p.name for p in ds.image_paths] == ["a.png", "b.jpg", "c.PNG"]
+    for i, p in enumerate(ds.image_paths):
+        img = Image.open(p)
+        w, h = img.size
+        assert torch.equal(ds[i], T.ToTensor()(TF.center_crop(img, [16 * (h // 16), 16 * (w // 16)])))
+    assert len(cg.inference.ImageDataset(tmp_path, images_range=(1, 3))) == 2
+    out = tmp_path / "out"
+    out.mkdir()
+    cg.inference.write_images(torch.rand(2, 3, 16, 16), out, 3, 2, 10, bpp=0.22961)
+    cg.inference.write_images(torch.rand(1, 3, 16, 16), out, 0, 1, 0)
+    assert sorted(p.name for p in out.iterdir()) == ["000.png", "016_0.229610.png", "017_0.229610.png"]
