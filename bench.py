@@ -516,16 +516,18 @@ def run_b200(args):
         rt = sess.roundtrip(zh, *mh)
     assert torch.equal(rt[1], sizes_first) and torch.equal(rt[5].view(-1), idx.cpu()) and int(rt[7].abs().sum()) == 0
     # the same call on the session's pinned arenas: one copy per direction and image range, ranges pipelined, CUDA graph
-    views = sess.arena(args.e2e_parts or 8)
-    for v in views:
-        r = v["images"]
-        v["z"].copy_(zh[r.start:r.stop])
-        for name, src in zip(("m_c", "m_m", "m_f"), mh):
-            v[name].copy_(src[r.start:r.stop])
     n_e2e = max(10, args.steps)
-    e2e = {}
-    for key, on_device in (("full", False), ("decoded_on_device", True)):
+    e2e, e2e_parts = {}, {}
+    # image ranges: 8 pipeline the 15 MB of the full copy best; with the decoded tensors left on the device the D2H side is
+    # small and per-copy latency dominates: 2 ranges (profiles/e2e_probe.py)
+    for key, on_device, parts in (("full", False, args.e2e_parts or 8), ("decoded_on_device", True, 2)):
+        views = sess.arena(parts)
+        e2e_parts[key] = len(views)
         for v in views:
+            r = v["images"]
+            v["z"].copy_(zh[r.start:r.stop])
+            for name, src in zip(("m_c", "m_m", "m_f"), mh):
+                v[name].copy_(src[r.start:r.stop])
             v["sizes"].zero_()
             v["ind"].zero_()
         for _ in range(5):
@@ -588,9 +590,9 @@ def run_b200(args):
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config_of(args, world),
             "e2e": {"value": world * pixels * n_e2e / 1e6 / e2e["full"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": n_e2e, "ms_per_step": 1e3 * e2e["full"] / n_e2e, "call": "cgic_session_roundtrip_arena", "image_ranges": len(views)},
+                    "steps": n_e2e, "ms_per_step": 1e3 * e2e["full"] / n_e2e, "call": "cgic_session_roundtrip_arena", "image_ranges": e2e_parts["full"]},
             "e2e_decoded_on_device": {"value": world * pixels * n_e2e / 1e6 / e2e["decoded_on_device"], "unit": UNIT, "h2d_bytes_per_step": h2d,
-                                      "d2h_bytes_per_step": d2h_wire, "ms_per_step": 1e3 * e2e["decoded_on_device"] / n_e2e,
+                                      "d2h_bytes_per_step": d2h_wire, "ms_per_step": 1e3 * e2e["decoded_on_device"] / n_e2e, "image_ranges": e2e_parts["decoded_on_device"],
                                       "call": "cgic_session_roundtrip_arena(flags | 4): streams, sizes, status come back; ind / quant / masks stay "
                                               "in HBM for the decoder CNN, as in model.py:391-399"},
             "gpu_launches": kernels_per_step * args.steps, "kernels_per_step": kernels_per_step, "cuda_graph": graph is not None,

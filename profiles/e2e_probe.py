@@ -30,7 +30,8 @@ for parts in parts_list:
     for v in views:
         r = v["images"]; v["z"].copy_(zh[r.start:r.stop])
         for name, src in zip(("m_c", "m_m", "m_f"), mh): v[name].copy_(src[r.start:r.stop])
-    print("arena parts", parts, "graph" if not os.environ.get("CGIC_SESSION_NO_GRAPH") else "eager", "us:", round(timeit(sess.roundtrip_arena), 1))
+    print("arena parts", parts, "graph" if not os.environ.get("CGIC_SESSION_NO_GRAPH") else "eager", "us:", round(timeit(sess.roundtrip_arena), 1),
+          "| decoded tensors left on the device us:", round(timeit(lambda: sess.roundtrip_arena(decoded_on_device=True)), 1))
 # raw copies of the arena-sized buffers through torch for reference
 a = torch.empty(5570560, dtype=torch.uint8).pin_memory(); d = torch.empty(9878016, dtype=torch.uint8, device=dev); b = torch.empty(9878016, dtype=torch.uint8).pin_memory(); da = torch.empty_like(a, device=dev)
 def cp():
