@@ -1538,7 +1538,7 @@ __global__ void __launch_bounds__(DS_THREADS, DS_THREADS <= 512 ? 2 : 1) unpack_
     }
     if (tid == 32 && need_c && __ldg(sz + 3) != cap_c) atomicOr(&s_bad, 1);
     if (tid == 33 && need_m && __ldg(sz + 4) != cap_m) atomicOr(&s_bad, 1);
-    __syncthreads();
+    cluster_sync();  // (also: every CTA of the cluster has started -- a precondition for writing into its shared memory)
     // ---- mask levels: one warp per level (framing of the mask streams checked on the staged bytes); meanwhile the other warps
     //      go on to the first batch, whose global loads thus overlap this.  Every CTA of a cluster builds its own copy.
     if (warp < 3) {
