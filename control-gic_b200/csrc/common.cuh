@@ -172,6 +172,7 @@ int device_sm_count(int *n_sm);
 // (CGIC_DS_CLUSTER, CGIC_FUSED_ENCODE, CGIC_NO_SMALL_KERNELS), cgic_tune() changes them at run time (tests, A-B runs).
 int tune_fused_decode_ctas();  // 0 = automatic (by batch size), 1 / 2 / 4 = fused small-grid decoder with that many CTAs per image, -1 = never
 int tune_fused_encode();       // 0 = two launches (default), 1 = one-CTA-per-image encoder on small grids
+int tune_pack_image();         // 0 = automatic (one CTA per image on small grids once the batch exceeds the SM count), 1 = always, -1 = never
 
 // Per-kernel device timing (cgic_prof_*): while enabled, every kernel launch of the library is
 // bracketed by two CUDA events recorded on the launching stream.  Off by default; costs one

@@ -39,7 +39,29 @@ struct PackArgs {
     // 64-bit records per tile in the workspace (bit position / carry word), see pack_index_stream_chained
     unsigned long long *chain;  // [B][3][2][max_tiles]
     int max_tiles, nslots;
+    // cgic_encode: the per-CTA partial sums of (e - z)^2 the search kernel left behind (its deferred reduction); the mask CTA of
+    // image 0 adds them in CTA order and writes *sq_out
+    const double *sq_partials;
+    int sq_n;
+    double *sq_out;
 };
+
+// deterministic sum of n doubles by the whole CTA (thread t takes t, t + T, ...; lanes by xor shuffles; warps in order)
+__device__ void reduce_partials(const double *partials, int n, double *out)
+{
+    __shared__ double s_part[PK_THREADS / 32];
+    double tot = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) tot += __ldcg(&partials[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = tot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double all = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) all += s_part[i];
+        *out = all;
+    }
+}
 
 __device__ __forceinline__ uint32_t to_big_endian(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
 
@@ -65,6 +87,74 @@ __device__ __forceinline__ int block_exscan(int v, int *s_warp, int *total)
     *total = tot;
     __syncthreads();
     return woff + inc - v;
+}
+
+// Codes of one thread's 8 consecutive positions of a level grid (lean path: 32-bit arithmetic, shifts for the level's step,
+// vector loads).  Requires (grid width of the level) % 8 == 0 -- a thread's positions then lie in one grid row, 16-byte aligned --
+// and the (code, length) table in shared memory.  pos0 >= n_pos: nothing.  Returns the bits; *bad |= symbol outside the table.
+struct LevelGrid {
+    int sh, gw, n_pos;             // log2(step), level grid width, level grid cells
+    const int32_t *mask;           // [n_pos] of this image
+    const int64_t *src;            // [h * w] of this image
+    int w;                         // fine grid width
+};
+__device__ __forceinline__ LevelGrid level_grid(const PackArgs &a, int s, int b)
+{
+    LevelGrid g;
+    g.sh = 2 - s;
+    g.gw = a.w >> g.sh;
+    g.n_pos = (a.h >> g.sh) * g.gw;
+    g.mask = a.mask[s] + (size_t)b * g.n_pos;
+    g.src = a.idx + (size_t)b * a.h * a.w;
+    g.w = a.w;
+    return g;
+}
+__device__ __forceinline__ bool level_grid_fast(const PackArgs &a, int s) { return a.n_direct < 0 && a.T.enc != nullptr && ((a.w >> (2 - s)) & 7) == 0; }
+
+__device__ __forceinline__ void load_tile_inputs(const LevelGrid &g, int pos0, int4 &m0, int4 &m1, long long (&v)[8])
+{
+    m0 = make_int4(0, 0, 0, 0);
+    m1 = m0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0;
+    if (pos0 >= g.n_pos) return;
+    m0 = __ldg(reinterpret_cast<const int4 *>(g.mask + pos0));
+    m1 = __ldg(reinterpret_cast<const int4 *>(g.mask + pos0) + 1);
+    const int y = pos0 / g.gw, x = pos0 - y * g.gw;
+    const long long *p = reinterpret_cast<const long long *>(g.src) + (size_t)(y << g.sh) * g.w + (x << g.sh);
+    if (g.sh == 0) {  // fine level: the symbols are the 8 consecutive tokens themselves
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const longlong2 t = __ldg(reinterpret_cast<const longlong2 *>(p) + i);
+            v[2 * i] = t.x;
+            v[2 * i + 1] = t.y;
+        }
+    } else {          // the block's top-left token (model.py:219-221)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __ldg(p + (i << g.sh));
+    }
+}
+__device__ __forceinline__ int tile_codes(const int4 &m0, const int4 &m1, const long long (&v)[8], const uint2 *s_enc, int K, uint32_t (&code)[8],
+                                          uint32_t (&len)[8], int *bad)
+{
+    const int on[8] = {m0.x == 1, m0.y == 1, m0.z == 1, m0.w == 1, m1.x == 1, m1.y == 1, m1.z == 1, m1.w == 1};
+    int tsum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        code[i] = 0;
+        len[i] = 0;
+        if (on[i]) {
+            if ((unsigned long long)v[i] >= (unsigned long long)K) {
+                *bad = 1;
+            } else {
+                const uint2 e = s_enc[(int)v[i]];
+                code[i] = e.x;
+                len[i] = e.y;
+            }
+        }
+        tsum += (int)len[i];
+    }
+    return tsum;
 }
 
 // One index stream by the whole CTA.  ITEMS consecutive grid positions per thread and tile; the
@@ -110,10 +200,25 @@ __device__ void pack_index_stream(const PackArgs &a, int s, int b, uint32_t *sta
     }
     __syncthreads();
     int64_t P = 8;  // stream bit position (header byte first)
+    const bool fast = ITEMS == 8 && level_grid_fast(a, s);
+    const LevelGrid lg = fast ? level_grid(a, s, b) : LevelGrid{};
     for (int64_t tile = 0; tile < n_pos; tile += TILE) {
         int sym[ITEMS];
         uint32_t len[ITEMS], code[ITEMS];
         const int64_t pos0 = tile + (int64_t)tid * ITEMS;
+        int tsum = 0;
+        if (ITEMS == 8 && fast) {
+            int4 m0, m1;
+            long long v[8];
+            load_tile_inputs(lg, (int)pos0, m0, m1, v);
+            if (mbar) {  // the code table's bulk copy was started before the loads above; first use is below
+                mbar_wait(mbar, 0);
+                mbar = nullptr;
+            }
+            int bad = 0;
+            tsum = tile_codes(m0, m1, v, s_enc, a.T.K, reinterpret_cast<uint32_t (&)[8]>(code), reinterpret_cast<uint32_t (&)[8]>(len), &bad);
+            if (bad) s_bad = 1;
+        } else {
         // ---- which positions emit a symbol (vector loads of the mask where possible)
         bool on[ITEMS];
         if (!mask) {
@@ -164,7 +269,6 @@ __device__ void pack_index_stream(const PackArgs &a, int s, int b, uint32_t *sta
             mbar_wait(mbar, 0);
             mbar = nullptr;
         }
-        int tsum = 0;
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             len[i] = 0;
@@ -180,6 +284,7 @@ __device__ void pack_index_stream(const PackArgs &a, int s, int b, uint32_t *sta
             }
             tsum += (int)len[i];
         }
+        }  // generic path
         int tot;
         int o = block_exscan(tsum, s_warp, &tot);
         const int r0 = (int)(P & 31);
@@ -291,11 +396,26 @@ __device__ void pack_index_stream_chained(const PackArgs &a, int s, int b, int s
     }
     __syncthreads();
     int64_t P_end = 8;
+    const bool fast = ITEMS == 8 && level_grid_fast(a, s);
+    const LevelGrid lg = fast ? level_grid(a, s, b) : LevelGrid{};
     for (int t = slot; t < n_tiles; t += a.nslots) {
         const int64_t tile = (int64_t)t * TILE;
-        int sym[ITEMS];
         uint32_t len[ITEMS], code[ITEMS];
         const int64_t pos0 = tile + (int64_t)tid * ITEMS;
+        int tsum = 0;
+        if (ITEMS == 8 && fast) {
+            int4 m0, m1;
+            long long v[8];
+            load_tile_inputs(lg, (int)pos0, m0, m1, v);
+            if (mbar) {
+                mbar_wait(mbar, 0);
+                mbar = nullptr;
+            }
+            int bad = 0;
+            tsum = tile_codes(m0, m1, v, s_enc, a.T.K, reinterpret_cast<uint32_t (&)[8]>(code), reinterpret_cast<uint32_t (&)[8]>(len), &bad);
+            if (bad) s_bad = 1;
+        } else {
+        int sym[ITEMS];
         bool on[ITEMS];
         if (ITEMS % 4 == 0 && pos0 + ITEMS <= n_pos && (reinterpret_cast<uintptr_t>(mask + pos0) & 15) == 0) {
 #pragma unroll
@@ -333,7 +453,6 @@ __device__ void pack_index_stream_chained(const PackArgs &a, int s, int b, int s
             mbar_wait(mbar, 0);
             mbar = nullptr;
         }
-        int tsum = 0;
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             len[i] = 0;
@@ -345,6 +464,7 @@ __device__ void pack_index_stream_chained(const PackArgs &a, int s, int b, int s
             }
             tsum += (int)len[i];
         }
+        }  // generic path
         int tot;
         int o = block_exscan(tsum, s_warp, &tot);  // (its barriers also order the s_bad writes above before the read below)
         if (tid == 0) {
@@ -501,6 +621,7 @@ __global__ void __launch_bounds__(PK_THREADS) pack_kernel(const PackArgs a)
     }
     pdl_wait();
     CGIC_STAMP(pack, 2);
+    if (a.sq_out && b == 0) reduce_partials(a.sq_partials, a.sq_n, a.sq_out);
     for (int ms = 3; ms < 5; ++ms) {
         if (!stream_present(a.mode, ms)) {
             if (threadIdx.x == 0) a.sizes[b * 5 + ms] = 0;
@@ -535,6 +656,7 @@ __global__ void __launch_bounds__(PK_THREADS) pack_chained_kernel(const PackArgs
         if (threadIdx.x == 0 && slot == 0) a.sizes[b * 5 + s] = 0;
     }
     if (blockIdx.x != 0) return;
+    if (a.sq_out && b == 0) reduce_partials(a.sq_partials, a.sq_n, a.sq_out);
     for (int ms = 3; ms < 5; ++ms) {
         if (!stream_present(a.mode, ms)) {
             if (threadIdx.x == 0) a.sizes[b * 5 + ms] = 0;
@@ -827,6 +949,166 @@ __global__ void __launch_bounds__(ES_THREADS, 1) encode_small_kernel(const Encod
     }
 }
 
+// ======================================================================================================================
+// One CTA per IMAGE packs all five streams (token grids of at most PI_MAX_GROUPS * 8 level cells, codes of at most 32 bits,
+// level grid widths multiples of 8).  pack_kernel gives every stream a CTA of its own -- four CTAs per image that each pay
+// the whole fixed cost (table staging, scan, barriers) whatever their stream's length: 41 k warp instructions per 256x256
+// image, most of them in the nearly empty coarse and mask CTAs.  Here the work items are groups of 8 consecutive cells of the
+// concatenated level grids [coarse | medium | fine] (= stream order), two consecutive groups per thread; ONE exclusive scan
+// of the code lengths serves the three streams (a stream's bit offsets are relative to the scan value at its first group),
+// codes are OR-ed into per-stream staging windows and leave as coalesced big-endian words with header byte and padding.
+constexpr int PI_THREADS = 512;
+constexpr int PI_GPT = 2;                                  // groups per thread
+constexpr int PI_MAX_GROUPS = PI_THREADS * PI_GPT;         // 1024 groups = 8192 level cells (a 256x256 image has 5376)
+
+struct PiLayout {
+    size_t stage[3], total;
+};
+__host__ __device__ inline PiLayout pi_layout(int K, const int64_t cap[5])
+{
+    auto up = [](size_t v) { return (v + 127) / 128 * 128; };
+    PiLayout L;
+    size_t o = up((size_t)((K + 1) / 2 * 2) * 8);
+    for (int s = 0; s < 3; ++s) {
+        L.stage[s] = o;
+        o += up((size_t)cap[s] + 8);
+    }
+    L.total = o;
+    return L;
+}
+
+__global__ void __launch_bounds__(PI_THREADS, 2) pack_image_kernel(const PackArgs a)
+{
+    extern __shared__ __align__(128) unsigned char dyn[];
+    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ int s_wsum[PI_THREADS / 32];
+    __shared__ int s_base[4];
+    __shared__ int s_badv[3];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
+    const PiLayout SL = pi_layout(a.T.K, a.slot_cap);
+    const uint2 *s_enc = reinterpret_cast<const uint2 *>(dyn);
+    uint32_t *const stage0 = reinterpret_cast<uint32_t *>(dyn + SL.stage[0]), *const stage1 = reinterpret_cast<uint32_t *>(dyn + SL.stage[1]),
+                    *const stage2 = reinterpret_cast<uint32_t *>(dyn + SL.stage[2]);
+    auto stage_of = [&](int s) { return s == 0 ? stage0 : (s == 1 ? stage1 : stage2); };
+    CGIC_STAMP(pack, 0);
+    pdl_trigger_step<2>();
+    if (tid == 0) mbar_init(&mbar);
+    if (tid < 3) s_badv[tid] = 0;
+    __syncthreads();
+    if (tid == 0) tma_load_1d(dyn, a.T.enc, (uint32_t)((a.T.K + 1) / 2 * 2) * 8u, &mbar);  // the code table is immutable: staged before the wait
+    // zero the staging windows while the table travels
+    {
+        const int nz = (int)((SL.total - SL.stage[0]) / 16);
+        uint4 *zp = reinterpret_cast<uint4 *>(dyn + SL.stage[0]);
+        for (int i = tid; i < nz; i += PI_THREADS) zp[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    pdl_wait();  // indices and masks come from the predecessor
+    CGIC_STAMP(pack, 2);
+    const int n4 = a.h * a.w, n8 = n4 >> 2, n16 = n4 >> 4;
+    const int g16 = n16 >> 3, g8 = n8 >> 3, g4 = n4 >> 3, n_groups = g16 + g8 + g4;
+    // ---- loads of both groups first, then the table
+    int4 m0[PI_GPT], m1[PI_GPT];
+    long long v[PI_GPT][8];
+    int lvl[PI_GPT];
+#pragma unroll
+    for (int g = 0; g < PI_GPT; ++g) {
+        const int item = PI_GPT * tid + g;
+        lvl[g] = item < g16 ? 0 : (item < g16 + g8 ? 1 : 2);
+        const int pos0 = (item - (lvl[g] == 0 ? 0 : (lvl[g] == 1 ? g16 : g16 + g8))) * 8;
+        if (item < n_groups && stream_present(a.mode, lvl[g])) {
+            const LevelGrid lg = level_grid(a, lvl[g], b);
+            load_tile_inputs(lg, pos0, m0[g], m1[g], v[g]);
+        } else {
+            m0[g] = make_int4(0, 0, 0, 0);
+            m1[g] = m0[g];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[g][i] = 0;
+        }
+    }
+    if (a.sq_out && b == 0) reduce_partials(a.sq_partials, a.sq_n, a.sq_out);  // (cgic_encode: the search kernel's deferred reduction)
+    mbar_wait(&mbar, 0);
+    uint32_t code[PI_GPT][8], len[PI_GPT][8];
+    int gsum[PI_GPT], tsum = 0;
+#pragma unroll
+    for (int g = 0; g < PI_GPT; ++g) {
+        int bad = 0;
+        gsum[g] = tile_codes(m0[g], m1[g], v[g], s_enc, a.T.K, code[g], len[g], &bad);
+        if (bad) s_badv[lvl[g]] = 1;
+        tsum += gsum[g];
+    }
+    // ---- one exclusive scan over all groups
+    int inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();
+    int woff = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < PI_THREADS / 32; ++i) {
+        const int t = s_wsum[i];
+        if (i < warp) woff += t;
+        total += t;
+    }
+    const int o0 = woff + inc - tsum;
+    // the scan value at a level's first group = the bits of the streams before it
+#pragma unroll
+    for (int g = 0; g < PI_GPT; ++g) {
+        const int item = PI_GPT * tid + g, og = g == 0 ? o0 : o0 + gsum[0];
+        if (item == 0) s_base[0] = og;
+        if (item == g16) s_base[1] = og;
+        if (item == g16 + g8) s_base[2] = og;
+    }
+    if (tid == 0) s_base[3] = total;
+    __syncthreads();
+    CGIC_STAMP(pack, 4);
+#pragma unroll
+    for (int g = 0; g < PI_GPT; ++g) {
+        int o = (g == 0 ? o0 : o0 + gsum[0]) - s_base[lvl[g]] + 8;  // the header byte is bits 0..7
+        uint32_t *st = stage_of(lvl[g]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (len[g][i]) {
+                const int sh = o & 31, wi = o >> 5;
+                atomicOr(&st[wi], code[g][i] >> sh);
+                if (sh + (int)len[g][i] > 32) atomicOr(&st[wi + 1], code[g][i] << (32 - sh));
+                o += (int)len[g][i];
+            }
+        }
+    }
+    // header byte (pad count, 1..8) of the non-empty streams
+    if (tid < 3) {
+        const int nbits = s_base[tid + 1] - s_base[tid];
+        if (nbits > 0) atomicOr(stage_of(tid), (uint32_t)(8 - (nbits & 7)) << 24);
+    }
+    __syncthreads();
+    CGIC_STAMP(pack, 5);
+    uint8_t *img = a.out + (int64_t)b * a.image_stride;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        const int nbits = s_base[s + 1] - s_base[s];
+        const int total_bytes = nbits > 0 ? nbits / 8 + 2 : 0;  // empty symbol list -> 0 bytes (the reference's empty file)
+        const bool bad = s_badv[s] != 0;
+        uint32_t *out32 = reinterpret_cast<uint32_t *>(img + a.slot_off[s]);
+        const uint32_t *st = stage_of(s);
+        if (!bad)
+            for (int j = tid; j < (total_bytes + 3) / 4; j += PI_THREADS) out32[j] = to_big_endian(st[j]);
+        if (tid == 0) a.sizes[b * 5 + s] = bad ? -1 : total_bytes;
+    }
+    CGIC_STAMP(pack, 6);
+    for (int ms = 3; ms < 5; ++ms) {
+        if (!stream_present(a.mode, ms)) {
+            if (tid == 0) a.sizes[b * 5 + ms] = 0;
+            continue;
+        }
+        const int64_t n = ms == 3 ? n16 : n8;
+        pack_bit_stream(a.mask[ms - 3] + (int64_t)b * n, n, img + a.slot_off[ms], a.slot_cap[ms], a.sizes + b * 5 + ms);
+    }
+    CGIC_STAMP(pack, 1);
+}
+
 // tile of PK_THREADS * items positions: output bits + 2 words, plus the staged code table
 size_t pack_smem_bytes(const DevTable &T, int items)
 {
@@ -854,9 +1136,20 @@ extern "C" int cgic_pack(const int64_t *idx, const int32_t *m_c, const int32_t *
     return cgic_pack_ws(idx, m_c, m_m, m_f, B, h, w, mode, t, bytes_out, sizes_out, nullptr, 0, stream);
 }
 
+static int pack_launch(const int64_t *idx, const int32_t *m_c, const int32_t *m_m, const int32_t *m_f, int B, int h, int w, int mode,
+                       const cgic_table *t, uint8_t *bytes_out, int32_t *sizes_out, void *workspace, size_t workspace_bytes, cgic_stream_t stream,
+                       const double *sq_partials, int sq_n, double *sq_out);
+
 extern "C" int cgic_pack_ws(const int64_t *idx, const int32_t *m_c, const int32_t *m_m, const int32_t *m_f, int B, int h, int w,
                             int mode, const cgic_table *t, uint8_t *bytes_out, int32_t *sizes_out, void *workspace,
                             size_t workspace_bytes, cgic_stream_t stream)
+{
+    return pack_launch(idx, m_c, m_m, m_f, B, h, w, mode, t, bytes_out, sizes_out, workspace, workspace_bytes, stream, nullptr, 0, nullptr);
+}
+
+static int pack_launch(const int64_t *idx, const int32_t *m_c, const int32_t *m_m, const int32_t *m_f, int B, int h, int w, int mode,
+                       const cgic_table *t, uint8_t *bytes_out, int32_t *sizes_out, void *workspace, size_t workspace_bytes, cgic_stream_t stream,
+                       const double *sq_partials, int sq_n, double *sq_out)
 {
     CGIC_REQUIRE(idx && m_c && m_m && m_f && bytes_out && sizes_out, CGIC_EINVAL, "cgic_pack: null argument");
     CGIC_REQUIRE(B >= 0 && h > 0 && w > 0 && h % 4 == 0 && w % 4 == 0, CGIC_EINVAL, "cgic_pack: token grid %dx%d must be multiples of 4", h, w);
@@ -884,11 +1177,39 @@ extern "C" int cgic_pack_ws(const int64_t *idx, const int32_t *m_c, const int32_
         a.slot_cap[s] = L.cap[s];
     }
     a.sizes = sizes_out;
+    a.sq_partials = sq_partials;
+    a.sq_n = sq_n;
+    a.sq_out = sq_out;
     const int items = a.T.enc ? 8 : 1;
     const size_t smem = pack_smem_bytes(a.T, items);
     CGIC_REQUIRE(smem <= 200 * 1024, CGIC_EINVAL, "cgic_pack: code length %d needs %zu bytes of staging", a.T.max_len, smem);
     rc = ensure_smem(items == 8 ? (const void *)pack_kernel<8> : (const void *)pack_kernel<1>, smem);
     if (rc) return rc;
+    // small token grids: one CTA per image packs all five streams (pack_image_kernel) -- every level's grid width a multiple of 8
+    // (so is then its cell count), all groups within one pass
+    {
+        const int64_t n4 = (int64_t)h * w;
+        // Measured on B200 (256x256 images): 2048 images 70 us against 123 us for one CTA per stream, 512 images 26 against 35 us;
+        // 64 images 12.7 against 11.2 us -- a batch that leaves SMs idle is better served by four CTAs per image.
+        int n_sm = 0;
+        rc = device_sm_count(&n_sm);
+        if (rc) return rc;
+        const int mode_pi = tune_pack_image();
+        const bool eligible = items == 8 && (w & 31) == 0 && (n4 + n4 / 4 + n4 / 16) / 8 <= PI_MAX_GROUPS && (mode_pi == 1 || (mode_pi == 0 && B > n_sm));
+        if (eligible) {
+            const size_t smem_pi = pi_layout(a.T.K, a.slot_cap).total;
+            if (smem_pi <= 100 * 1024) {
+                rc = ensure_smem((const void *)pack_image_kernel, smem_pi);
+                if (rc) return rc;
+                {
+                    CGIC_PROF("pack_image_kernel", as_stream(stream));
+                    CGIC_CUDA_CHECK(launch_pdl(pack_image_kernel, dim3(B), dim3(PI_THREADS), smem_pi, as_stream(stream), a));
+                }
+                CGIC_LAUNCH_CHECK();
+                return CGIC_OK;
+            }
+        }
+    }
     // large token grids (more than one tile per fine stream) with a workspace: tiles chained over several CTAs per stream
     const int fine_tiles = (int)(((int64_t)h * w + PK_THREADS * 8 - 1) / (PK_THREADS * 8));
     if (items == 8 && fine_tiles > 1 && workspace && workspace_bytes >= cgic_pack_workspace_bytes(B, h, w)) {
@@ -916,6 +1237,8 @@ extern "C" int cgic_pack_ws(const int64_t *idx, const int32_t *m_c, const int32_
 namespace cgic {
 const unsigned char *codebook_blob(const cgic_codebook *cb);  // codebook.cu
 int codebook_size(const cgic_codebook *cb);
+int vq_assign_indexed_launch(const float *z, int B, int h, int w, const cgic_codebook *cb, int64_t *idx_out, float *zq_out, double *sqerr_out,
+                             void *workspace, size_t workspace_bytes, cgic_stream_t stream_, bool defer_reduce, int *grid_out);  // vq_assign.cu
 }  // namespace cgic
 
 extern "C" size_t cgic_encode_workspace_bytes(int B, int h, int w)
@@ -955,10 +1278,14 @@ extern "C" int cgic_encode(const float *z, const int32_t *m_c, const int32_t *m_
     }
     if (!small) {
         // large token grids / long codes: the two launches (warp-tile search, then the chained packer)
-        rc = cgic_vq_assign_indexed(z, B, h, w, cb, idx_out, zq_out, sqerr_out, workspace, vq_ws, stream_);
+        // the sum of (e - z)^2 over the batch is finished by the packer (its mask CTA of image 0) from the search kernel's per-CTA
+        // partials: the search kernel's own last-CTA reduction would add ~2 us to the step's critical path
+        int vq_grid = 0;
+        rc = vq_assign_indexed_launch(z, B, h, w, cb, idx_out, zq_out, sqerr_out, workspace, vq_ws, stream_, true, &vq_grid);
         if (rc) return rc;
-        return cgic_pack_ws(idx_out, m_c, m_m, m_f, B, h, w, mode, t, bytes_out, sizes_out, static_cast<unsigned char *>(workspace) + vq_ws,
-                            workspace_bytes - vq_ws, stream_);
+        return pack_launch(idx_out, m_c, m_m, m_f, B, h, w, mode, t, bytes_out, sizes_out, static_cast<unsigned char *>(workspace) + vq_ws,
+                           workspace_bytes - vq_ws, stream_, reinterpret_cast<const double *>(static_cast<unsigned char *>(workspace) + 256),
+                           sqerr_out ? vq_grid : 0, sqerr_out);
     }
     for (const void *ptr : {(const void *)bytes_out, (const void *)m_c, (const void *)m_m, (const void *)m_f})
         CGIC_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, CGIC_EINVAL, "cgic_encode: bytes_out and masks must be 16-byte aligned");

@@ -93,7 +93,16 @@ int device_sm_count(int *n_sm)
 }
 
 namespace {
-std::atomic<int> g_tune_decode{-100}, g_tune_encode{-100};
+std::atomic<int> g_tune_decode{-100}, g_tune_encode{-100}, g_tune_pack{-100};
+}
+int tune_pack_image()
+{
+    int v = g_tune_pack.load(std::memory_order_relaxed);
+    if (v == -100) {
+        v = getenv("CGIC_NO_SMALL_KERNELS") || getenv("CGIC_NO_PACK_IMAGE") ? -1 : 0;
+        g_tune_pack.store(v);
+    }
+    return v;
 }
 int tune_fused_decode_ctas()
 {
@@ -220,6 +229,11 @@ int cgic_tune(const char *key, int value)
     if (!strcmp(key, "fused_encode")) {
         CGIC_REQUIRE(value == 0 || value == 1, CGIC_EINVAL, "cgic_tune: fused_encode must be 0 or 1");
         cgic::g_tune_encode.store(value);
+        return CGIC_OK;
+    }
+    if (!strcmp(key, "pack_image")) {
+        CGIC_REQUIRE(value == 0 || value == -1 || value == 1, CGIC_EINVAL, "cgic_tune: pack_image must be -1, 0 or 1");
+        cgic::g_tune_pack.store(value);
         return CGIC_OK;
     }
     cgic::set_error("cgic_tune: unknown key '%s'", key);

@@ -129,6 +129,19 @@ constexpr int DEC_THREADS = 512;
 constexpr int DEC_SUB_BITS = 128;
 constexpr int64_t DEC_STOP = (int64_t)1 << 60;  // "decoding ended": beyond every subsequence
 
+// bulk copy of the decode tables in flight (stage_decode_tables): wait() once, before the first look-up
+struct TableStage {
+    unsigned long long *mbar;
+    bool pending;
+    __device__ __forceinline__ void wait()
+    {
+        if (pending) {
+            pending = false;
+            mbar_wait(mbar, 0);
+        }
+    }
+};
+
 struct BitWindow {
     const uint8_t *in;  // 4-byte aligned stream start (the header byte is bit 0..7)
     int64_t nbytes;
@@ -214,8 +227,9 @@ __device__ __forceinline__ int decode_range(BitWindow &bw, int64_t q, int64_t q_
 // `in` must be 4-byte aligned.
 template <typename Out>
 __device__ int decode_stream_cta(const uint8_t *in, int64_t nbytes, const DevTable &T, const uint32_t *s_lut, const uint32_t *lut2,
-                                 Out *out, int64_t cap)
+                                 Out *out, int64_t cap, TableStage &ts)
 {
+    ts.wait();
     __shared__ int64_t s_start[DEC_THREADS + 1];
     __shared__ int s_wsum[DEC_THREADS / 32];
     if (nbytes <= 0) return -1;
@@ -458,7 +472,7 @@ __device__ __forceinline__ void follow_chains(const uint8_t *s_len, uint16_t *s_
 // bit position of the chunk, 0 = no complete codeword before the payload end), f[ch * D] (uint16)
 template <bool LUT2S, typename Out>
 __device__ int decode_stream_cta_cand(const uint8_t *in, int64_t nbytes, const DevTable &T, const uint32_t *s_lut, const uint32_t *lut2,
-                                      uint32_t *s_words, uint8_t *s_len, uint16_t *s_fn, int ch, Out *out, int64_t cap)
+                                      uint32_t *s_words, uint8_t *s_len, uint16_t *s_fn, int ch, Out *out, int64_t cap, TableStage &ts)
 {
     __shared__ uint8_t s_blockfn[32 * DEC_MAX_D];
     __shared__ uint8_t s_blkstart[32];
@@ -496,6 +510,7 @@ __device__ int decode_stream_cta_cand(const uint8_t *in, int64_t nbytes, const D
                 s_words[wi] = v;
             }
         }
+        ts.wait();  // (first chunk: the tables' bulk copy ran beside the loads above)
         __syncthreads();
         const int64_t rel_end = q_end_abs - c0 * DEC_SUB_BITS;  // payload end, local to the chunk
         const uint32_t q_end = (uint32_t)min(rel_end, (int64_t)(nsub * DEC_SUB_BITS + 8 + DEC_MAX_D + 64));
@@ -626,7 +641,8 @@ __device__ int decode_stream_cta_cand(const uint8_t *in, int64_t nbytes, const D
 // that the single-CTA decoder above stays exactly the code that was tuned on the small-grid batch.
 template <bool LUT2S, bool MULTI, typename Out>
 __device__ int decode_stream_cta_chain(const uint8_t *in, int64_t nbytes, const DevTable &T, const uint32_t *s_lut, const uint32_t *lut2,
-                                      uint32_t *s_words, uint8_t *s_len, uint16_t *s_fn, int ch, Out *out, int64_t cap, const DecChain chain)
+                                      uint32_t *s_words, uint8_t *s_len, uint16_t *s_fn, int ch, Out *out, int64_t cap, const DecChain chain,
+                                      TableStage &ts)
 {
     __shared__ uint8_t s_blockfn[32 * DEC_MAX_D];
     // chained streams only: symbols of a block per candidate start, chunk exit offset / symbol count per candidate start
@@ -675,6 +691,7 @@ __device__ int decode_stream_cta_chain(const uint8_t *in, int64_t nbytes, const 
                 s_words[wi] = v;
             }
         }
+        ts.wait();  // (first chunk: the tables' bulk copy ran beside the loads above)
         __syncthreads();
         const int64_t rel_end = q_end_abs - c0 * DEC_SUB_BITS;  // payload end, local to the chunk
         const uint32_t q_end = (uint32_t)min(rel_end, (int64_t)(nsub * DEC_SUB_BITS + 8 + DEC_MAX_D + 64));
@@ -858,7 +875,8 @@ __host__ __device__ inline int cand_len_bytes(int ch) { return (ch * (DEC_SUB_BI
 
 template <typename Out, bool MULTI = false>
 __device__ __forceinline__ int decode_stream_any(const uint8_t *in, int64_t nbytes, const DevTable &T, const uint32_t *s_dec,
-                                                 const uint32_t *lut2, Out *out, int64_t cap, int ch, const DecChain chain = DecChain{nullptr, 0, 1})
+                                                 const uint32_t *lut2, Out *out, int64_t cap, int ch, TableStage &ts,
+                                                 const DecChain chain = DecChain{nullptr, 0, 1})
 {
     if (T.max_len <= DEC_MAX_D) {
         // f[] lives right behind the staged tables in dynamic shared memory
@@ -867,25 +885,26 @@ __device__ __forceinline__ int decode_stream_any(const uint8_t *in, int64_t nbyt
         uint16_t *s_fn = reinterpret_cast<uint16_t *>(s_len + cand_len_bytes(ch));
         if (MULTI) {
             if (T.dec_stage_words > T.lut_pad)
-                return decode_stream_cta_chain<true, MULTI, Out>(in, nbytes, T, s_dec, lut2, s_words, s_len, s_fn, ch, out, cap, chain);
-            return decode_stream_cta_chain<false, MULTI, Out>(in, nbytes, T, s_dec, lut2, s_words, s_len, s_fn, ch, out, cap, chain);
+                return decode_stream_cta_chain<true, MULTI, Out>(in, nbytes, T, s_dec, lut2, s_words, s_len, s_fn, ch, out, cap, chain, ts);
+            return decode_stream_cta_chain<false, MULTI, Out>(in, nbytes, T, s_dec, lut2, s_words, s_len, s_fn, ch, out, cap, chain, ts);
         }
         if (T.dec_stage_words > T.lut_pad)
-            return decode_stream_cta_cand<true, Out>(in, nbytes, T, s_dec, lut2, s_words, s_len, s_fn, ch, out, cap);
-        return decode_stream_cta_cand<false, Out>(in, nbytes, T, s_dec, lut2, s_words, s_len, s_fn, ch, out, cap);
+            return decode_stream_cta_cand<true, Out>(in, nbytes, T, s_dec, lut2, s_words, s_len, s_fn, ch, out, cap, ts);
+        return decode_stream_cta_cand<false, Out>(in, nbytes, T, s_dec, lut2, s_words, s_len, s_fn, ch, out, cap, ts);
     }
     if (chain.slot != 0) return DEC_NOT_MINE;  // codes longer than a subsequence: one CTA per stream
-    return decode_stream_cta<Out>(in, nbytes, T, s_dec, lut2, out, cap);
+    return decode_stream_cta<Out>(in, nbytes, T, s_dec, lut2, out, cap, ts);
 }
 
-// Stages the decode tables with one TMA bulk copy; every thread of the CTA must call.
+// Stages the decode tables with one TMA bulk copy; every thread of the CTA must call.  The copy is only STARTED here: the
+// decoders wait for it (TableStage::wait) right before their first table look-up, after their own global loads (stream
+// sizes, header byte, the chunk's words) have been issued, so that the two latencies overlap.
 // Returns the second-level table pointer (shared when it was staged, else global).
 __device__ __forceinline__ const uint32_t *stage_decode_tables(const DevTable &T, uint32_t *s_dec, unsigned long long *mbar)
 {
     if (threadIdx.x == 0) mbar_init(mbar);
     __syncthreads();
     if (threadIdx.x == 0) tma_load_1d(s_dec, T.lut, T.dec_stage_words * 4u, mbar);
-    mbar_wait(mbar, 0);
     return T.dec_stage_words > T.lut_pad ? s_dec + T.lut_pad : T.lut2;
 }
 
@@ -1079,7 +1098,11 @@ __device__ __forceinline__ void unpack_decode_cta(const UnpackArgs &a, unsigned 
         // the (immutable) decode tables are staged while the predecessor kernel may still be running
         uint32_t *s_dec = reinterpret_cast<uint32_t *>(dyn);
         const uint32_t *lut2 = nullptr;
-        if (stream_present(a.mode, s)) lut2 = stage_decode_tables(a.T, s_dec, mbar_p);
+        TableStage ts{mbar_p, false};
+        if (stream_present(a.mode, s)) {
+            lut2 = stage_decode_tables(a.T, s_dec, mbar_p);
+            ts.pending = true;
+        }
         pdl_wait();
         int nbytes = stream_present(a.mode, s) ? sz[s] : 0;
         CGIC_STAMP(unpack, 1);
@@ -1092,12 +1115,13 @@ __device__ __forceinline__ void unpack_decode_cta(const UnpackArgs &a, unsigned 
             const DecChain chain{chained ? a.ws.chain + ((int64_t)b * 3 + s) * a.ws.max_chunks : nullptr, chained ? slot : 0, chained ? nslots : 1};
             if (chained || slot == 0)
                 cnt = decode_stream_any<uint16_t, MULTI>(img + a.slot_off[s], nbytes, a.T, s_dec, lut2,
-                                                         a.ws.sym + (int64_t)b * (g.n16 + g.n8 + g.n4) + soff, cap, a.ch, chain);
+                                                         a.ws.sym + (int64_t)b * (g.n16 + g.n8 + g.n4) + soff, cap, a.ch, ts, chain);
             else
                 cnt = DEC_NOT_MINE;
         } else if (slot != 0) {
             cnt = DEC_NOT_MINE;
         }
+        ts.wait();  // never leave with the bulk copy in flight (empty / absent streams decode nothing)
         CGIC_STAMP(unpack, 6);
         if (threadIdx.x == 0) {
             if (cnt == -2) a.ws.flag[b * 5 + s] = CGIC_EFORMAT;  // symbol capacity exceeded (any of the stream's CTAs may see it)
@@ -1209,6 +1233,74 @@ __device__ __forceinline__ bool assemble_quad_core(const UnpackArgs &a, int b, i
     return bad;
 }
 
+// Re-assembly of 4 consecutive fine tokens of a row for the fused kernel: 32-bit arithmetic (the grid has at most 4096
+// cells), tables in shared memory.  Same outputs as assemble_quad_core.
+__device__ __forceinline__ bool assemble_quad_small(const UnpackArgs &a, int b, int quad, const uint32_t *bits, const uint32_t *prefix,
+                                                    const uint16_t *sym, int cnt0, int cnt1, int cnt2)
+{
+    const Geo &g = a.g;
+    const int n4 = (int)g.n4, n8 = (int)g.n8, n16 = (int)g.n16;
+    const int p = quad * 4;
+    const int wq = g.w >> 2;
+    const int y = quad / wq, x = (quad - y * wq) * 4;
+    const int p16 = (y >> 2) * g.w16 + (x >> 2);
+    const int p8 = (y >> 1) * g.w8 + (x >> 1);  // even: p8 and p8 + 1 share a word
+    const uint32_t wc = bits[p16 >> 5], wm = bits[g.nw16 + (p8 >> 5)], wf = bits[g.nw16 + g.nw8 + (p >> 5)];
+    const uint32_t pre_c = prefix[p16 >> 5], pre_m = prefix[g.nw16 + (p8 >> 5)], pre_f = prefix[g.nw16 + g.nw8 + (p >> 5)];
+    const int sc = p16 & 31, sm = p8 & 31, sf = p & 31;
+    const int cbit = (wc >> sc) & 1;
+    int base = 0;
+    if (cbit && cnt0 > 0) {
+        const int r = pre_c + __popc(wc & ((1u << sc) - 1u));
+        if (r < cnt0) base = sym[r];
+    }
+    int mbit[2], mval[2] = {0, 0};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        mbit[j] = (wm >> (sm + j)) & 1;
+        if (mbit[j] && cnt1 > 0) {
+            const int r = pre_m + __popc(wm & ((1u << (sm + j)) - 1u));
+            if (r < cnt1) mval[j] = sym[n16 + r];
+        }
+    }
+    int fbit[4], ind[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        fbit[i] = (wf >> (sf + i)) & 1;
+        int v = base + mval[i >> 1];
+        if (fbit[i] && cnt2 > 0) {
+            const int r = pre_f + __popc(wf & ((1u << (sf + i)) - 1u));
+            if (r < cnt2) v += sym[n16 + n8 + r];
+        }
+        ind[i] = v;
+    }
+    const size_t o4 = (size_t)b * n4 + p;
+    longlong2 *ind_o = reinterpret_cast<longlong2 *>(a.ind_out + o4);
+    ind_o[0] = make_longlong2(ind[0], ind[1]);
+    ind_o[1] = make_longlong2(ind[2], ind[3]);
+    longlong2 *mf_o = reinterpret_cast<longlong2 *>(a.mf_out + o4);
+    mf_o[0] = make_longlong2(fbit[0], fbit[1]);
+    mf_o[1] = make_longlong2(fbit[2], fbit[3]);
+    if ((y & 1) == 0) *reinterpret_cast<longlong2 *>(a.mm_out + (size_t)b * n8 + p8) = make_longlong2(mbit[0], mbit[1]);
+    if ((y & 3) == 0) a.mc_out[(size_t)b * n16 + p16] = cbit;
+    bool bad = false;
+    if (a.quant_out) {
+        float4 e[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            bad |= ind[i] >= a.T.K;  // sums of overlapping levels cannot occur with valid masks
+            e[i] = __ldg(reinterpret_cast<const float4 *>(a.codebook) + (ind[i] < a.T.K ? ind[i] : 0));
+        }
+        float4 *q = reinterpret_cast<float4 *>(a.quant_out + (size_t)b * 4 * n4 + p);
+        const int plane4 = n4 >> 2;
+        q[0] = make_float4(e[0].x, e[1].x, e[2].x, e[3].x);
+        q[plane4] = make_float4(e[0].y, e[1].y, e[2].y, e[3].y);
+        q[2 * plane4] = make_float4(e[0].z, e[1].z, e[2].z, e[3].z);
+        q[3 * plane4] = make_float4(e[0].w, e[1].w, e[2].w, e[3].w);
+    }
+    return bad;
+}
+
 // the reference's masked assignment raises unless #symbols == #set cells (an empty coarse / medium stream stands for
 // zeros, model.py:284-290)
 __device__ __forceinline__ bool counts_mismatch(int mode, const int32_t *cnt, const int32_t *pop)
@@ -1232,9 +1324,15 @@ __device__ __forceinline__ void assemble_quad(const UnpackArgs &a, int b, int64_
         for (int s = 0; s < 5; ++s) bad |= a.ws.flag[b * 5 + s] != 0;
         if (bad) atomicExch(&a.status[b], CGIC_EFORMAT);
     }
-    if (assemble_quad_core(a, b, quad, a.ws.bits + (int64_t)b * nwt, a.ws.prefix + (int64_t)b * nwt,
-                           a.ws.sym + (int64_t)b * (g.n16 + g.n8 + g.n4), cntp[0], cntp[1], cntp[2]))
-        atomicExch(&a.status[b], CGIC_EFORMAT);
+    bool bad;
+    if (g.n4 < ((int64_t)1 << 28)) {  // (always, in practice) 32-bit arithmetic
+        bad = quad * 4 < g.n4 && assemble_quad_small(a, b, (int)quad, a.ws.bits + (int64_t)b * nwt, a.ws.prefix + (int64_t)b * nwt,
+                                                     a.ws.sym + (int64_t)b * (g.n16 + g.n8 + g.n4), cntp[0], cntp[1], cntp[2]);
+    } else {
+        bad = assemble_quad_core(a, b, quad, a.ws.bits + (int64_t)b * nwt, a.ws.prefix + (int64_t)b * nwt,
+                                 a.ws.sym + (int64_t)b * (g.n16 + g.n8 + g.n4), cntp[0], cntp[1], cntp[2]);
+    }
+    if (bad) atomicExch(&a.status[b], CGIC_EFORMAT);
 }
 
 // grid (4, B): one CTA per index stream, then the mask CTA
@@ -1377,74 +1475,6 @@ __device__ __forceinline__ void build_level_warp(int n, int nw, uint32_t *bits, 
         run += __shfl_sync(0xffffffffu, inc, 31);
     }
     if (lane == 0) *pop_out = run;
-}
-
-// Re-assembly of 4 consecutive fine tokens of a row for the fused kernel: 32-bit arithmetic (the grid has at most 4096
-// cells), tables in shared memory.  Same outputs as assemble_quad_core.
-__device__ __forceinline__ bool assemble_quad_small(const UnpackArgs &a, int b, int quad, const uint32_t *bits, const uint32_t *prefix,
-                                                    const uint16_t *sym, int cnt0, int cnt1, int cnt2)
-{
-    const Geo &g = a.g;
-    const int n4 = (int)g.n4, n8 = (int)g.n8, n16 = (int)g.n16;
-    const int p = quad * 4;
-    const int wq = g.w >> 2;
-    const int y = quad / wq, x = (quad - y * wq) * 4;
-    const int p16 = (y >> 2) * g.w16 + (x >> 2);
-    const int p8 = (y >> 1) * g.w8 + (x >> 1);  // even: p8 and p8 + 1 share a word
-    const uint32_t wc = bits[p16 >> 5], wm = bits[g.nw16 + (p8 >> 5)], wf = bits[g.nw16 + g.nw8 + (p >> 5)];
-    const uint32_t pre_c = prefix[p16 >> 5], pre_m = prefix[g.nw16 + (p8 >> 5)], pre_f = prefix[g.nw16 + g.nw8 + (p >> 5)];
-    const int sc = p16 & 31, sm = p8 & 31, sf = p & 31;
-    const int cbit = (wc >> sc) & 1;
-    int base = 0;
-    if (cbit && cnt0 > 0) {
-        const int r = pre_c + __popc(wc & ((1u << sc) - 1u));
-        if (r < cnt0) base = sym[r];
-    }
-    int mbit[2], mval[2] = {0, 0};
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        mbit[j] = (wm >> (sm + j)) & 1;
-        if (mbit[j] && cnt1 > 0) {
-            const int r = pre_m + __popc(wm & ((1u << (sm + j)) - 1u));
-            if (r < cnt1) mval[j] = sym[n16 + r];
-        }
-    }
-    int fbit[4], ind[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        fbit[i] = (wf >> (sf + i)) & 1;
-        int v = base + mval[i >> 1];
-        if (fbit[i] && cnt2 > 0) {
-            const int r = pre_f + __popc(wf & ((1u << (sf + i)) - 1u));
-            if (r < cnt2) v += sym[n16 + n8 + r];
-        }
-        ind[i] = v;
-    }
-    const size_t o4 = (size_t)b * n4 + p;
-    longlong2 *ind_o = reinterpret_cast<longlong2 *>(a.ind_out + o4);
-    ind_o[0] = make_longlong2(ind[0], ind[1]);
-    ind_o[1] = make_longlong2(ind[2], ind[3]);
-    longlong2 *mf_o = reinterpret_cast<longlong2 *>(a.mf_out + o4);
-    mf_o[0] = make_longlong2(fbit[0], fbit[1]);
-    mf_o[1] = make_longlong2(fbit[2], fbit[3]);
-    if ((y & 1) == 0) *reinterpret_cast<longlong2 *>(a.mm_out + (size_t)b * n8 + p8) = make_longlong2(mbit[0], mbit[1]);
-    if ((y & 3) == 0) a.mc_out[(size_t)b * n16 + p16] = cbit;
-    bool bad = false;
-    if (a.quant_out) {
-        float4 e[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            bad |= ind[i] >= a.T.K;  // sums of overlapping levels cannot occur with valid masks
-            e[i] = __ldg(reinterpret_cast<const float4 *>(a.codebook) + (ind[i] < a.T.K ? ind[i] : 0));
-        }
-        float4 *q = reinterpret_cast<float4 *>(a.quant_out + (size_t)b * 4 * n4 + p);
-        const int plane4 = n4 >> 2;
-        q[0] = make_float4(e[0].x, e[1].x, e[2].x, e[3].x);
-        q[plane4] = make_float4(e[0].y, e[1].y, e[2].y, e[3].y);
-        q[2 * plane4] = make_float4(e[0].z, e[1].z, e[2].z, e[3].z);
-        q[3 * plane4] = make_float4(e[0].w, e[1].w, e[2].w, e[3].w);
-    }
-    return bad;
 }
 
 // CL = CTAs per image (a thread-block cluster when > 1).  All CTAs of an image plan the same batches; the 16-word blocks of
@@ -1833,7 +1863,9 @@ huff_decode_single_kernel(const uint8_t *bytes, int64_t nbytes, DevTable T, int3
     __shared__ __align__(8) unsigned long long mbar;
     uint32_t *s_dec = reinterpret_cast<uint32_t *>(dyn);
     const uint32_t *lut2 = stage_decode_tables(T, s_dec, &mbar);
-    const int cnt = decode_stream_any<int32_t>(bytes, nbytes, T, s_dec, lut2, out, cap, ch);
+    TableStage ts{&mbar, true};
+    const int cnt = decode_stream_any<int32_t>(bytes, nbytes, T, s_dec, lut2, out, cap, ch, ts);
+    ts.wait();
     if (threadIdx.x == 0) *count_out = cnt;
 }
 

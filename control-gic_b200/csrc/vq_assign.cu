@@ -469,10 +469,13 @@ constexpr int VQW_THREADS = 256;
 constexpr int VQW_WARPS = VQW_THREADS / 32;
 __host__ __device__ inline size_t vqw_smem_bytes(int K) { return vq_stage_bytes(K) + (size_t)VQW_WARPS * VQW_TILE * (16 + 2 + 1 + 1); }
 
-__global__ void __launch_bounds__(VQW_THREADS, 2)
+#ifndef CGIC_VQW_CTAS
+#define CGIC_VQW_CTAS 2
+#endif
+__global__ void __launch_bounds__(VQW_THREADS, CGIC_VQW_CTAS)
 vq_warp_kernel(const float *__restrict__ z, int h, int w, int tiles_x, int tiles_y, int64_t n_tiles, const unsigned char *__restrict__ blob,
                int K, int64_t *__restrict__ idx_out, float *__restrict__ zq_out, double *__restrict__ partials,
-               int32_t *__restrict__ counters, double *__restrict__ sqerr_out)
+               int32_t *__restrict__ counters, double *__restrict__ sqerr_out, int defer_reduce)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long mbar;
@@ -530,8 +533,14 @@ vq_warp_kernel(const float *__restrict__ z, int h, int w, int tiles_x, int tiles
         double tot = 0.0;
         for (int i = 0; i < VQW_WARPS; ++i) tot += s_red[i];
         partials[blockIdx.x] = tot;
-        __threadfence();
-        s_last = (atomicAdd(&counters[0], 1) == (int)gridDim.x - 1);
+        // defer_reduce: the per-CTA partials are summed (in CTA order) by the kernel that follows in the stream -- the packer of
+        // cgic_encode -- instead of by the last CTA to finish here, whose ~2 us of ticket + reload + reduction would otherwise sit
+        // on the step's critical path
+        s_last = false;
+        if (!defer_reduce) {
+            __threadfence();
+            s_last = (atomicAdd(&counters[0], 1) == (int)gridDim.x - 1);
+        }
     }
     __syncthreads();
     if (s_last) {
@@ -619,9 +628,23 @@ extern "C" int cgic_vq_assign(const float *z, int B, int h, int w, const float *
     return vq_launch("cgic_vq_assign", z, B, h, w, codebook, K, idx_out, zq_out, sqerr_out, workspace, workspace_bytes, stream);
 }
 
+namespace cgic {
+int vq_assign_indexed_launch(const float *z, int B, int h, int w, const cgic_codebook *cb, int64_t *idx_out, float *zq_out, double *sqerr_out,
+                             void *workspace, size_t workspace_bytes, cgic_stream_t stream_, bool defer_reduce, int *grid_out);
+}
+
 extern "C" int cgic_vq_assign_indexed(const float *z, int B, int h, int w, const cgic_codebook *cb, int64_t *idx_out, float *zq_out,
                                       double *sqerr_out, void *workspace, size_t workspace_bytes, cgic_stream_t stream_)
 {
+    return vq_assign_indexed_launch(z, B, h, w, cb, idx_out, zq_out, sqerr_out, workspace, workspace_bytes, stream_, false, nullptr);
+}
+
+// defer_reduce (needs sqerr_out): the kernel leaves one partial per CTA at workspace + 256 ([*grid_out] doubles, CTA order) and
+// does NOT write *sqerr_out; the caller's next kernel sums them.
+int cgic::vq_assign_indexed_launch(const float *z, int B, int h, int w, const cgic_codebook *cb, int64_t *idx_out, float *zq_out, double *sqerr_out,
+                                   void *workspace, size_t workspace_bytes, cgic_stream_t stream_, bool defer_reduce, int *grid_out)
+{
+    if (grid_out) *grid_out = 0;
     const unsigned char *blob = codebook_blob(cb);
     CGIC_REQUIRE(blob, CGIC_EINVAL, "cgic_vq_assign_indexed: no prepared codebook (cgic_codebook_update has not been called)");
     CGIC_REQUIRE(z && idx_out && workspace, CGIC_EINVAL, "cgic_vq_assign_indexed: null argument");
@@ -650,15 +673,16 @@ extern "C" int cgic_vq_assign_indexed(const float *z, int B, int h, int w, const
     // multiple of the SM count so that the round-robin deal leaves every SM with the same load
     const int64_t want = (n_tiles + VQW_WARPS - 1) / VQW_WARPS;
     int64_t per_sm = (want + n_sm - 1) / n_sm;
-    if (per_sm > 2) per_sm = 2;
+    if (per_sm > CGIC_VQW_CTAS) per_sm = CGIC_VQW_CTAS;
     const int64_t full = per_sm * n_sm;
     const int grid = (int)(n_tiles < full ? n_tiles : full);
     {
         CGIC_PROF("vq_warp_kernel", stream);
         CGIC_CUDA_CHECK(launch_pdl(vq_warp_kernel, dim3(grid), dim3(VQW_THREADS), vqw_smem_bytes(K), stream, z, h, w, tiles_x, tiles_y, n_tiles,
-                                   blob, K, idx_out, zq_out, partials, counters, sqerr_out));
+                                   blob, K, idx_out, zq_out, partials, counters, sqerr_out, (int)(defer_reduce && sqerr_out != nullptr)));
     }
     CGIC_LAUNCH_CHECK();
+    if (grid_out) *grid_out = grid;
     return CGIC_OK;
 }
 

@@ -38,7 +38,7 @@ def _stream() -> int:
 
 
 def tune(key: str, value: int) -> None:
-    """Dispatch knobs (cgic_tune): "fused_decode_ctas" in (-1, 0, 1, 2, 4), "fused_encode" in (0, 1).  Which kernels serve a
+    """Dispatch knobs (cgic_tune): "fused_decode_ctas" in (-1, 0, 1, 2, 4), "fused_encode" in (0, 1), "pack_image" in (-1, 0, 1).  Which kernels serve a
     call changes, the results do not."""
     check(lib().cgic_tune(key.encode(), int(value)), "cgic_tune")
 

@@ -56,7 +56,9 @@ CGIC_API int cgic_abi_version(void);
  * CGIC_NO_SMALL_KERNELS, else automatic).  Results never depend on them, only which kernels produce them:
  *   "fused_decode_ctas"  0 automatic (the fused small-grid decoder serves batches larger than the SM count), 1 | 2 | 4 always,
  *                        with that many CTAs per image (a thread-block cluster when > 1), -1 never;
- *   "fused_encode"       0 (default) cgic_encode = two launches, 1 = one CTA per image on grids of at most 4096 cells. */
+ *   "fused_encode"       0 (default) cgic_encode = two launches, 1 = one CTA per image on grids of at most 4096 cells;
+ *   "pack_image"         0 (default) the packer uses one CTA per image on small token grids for batches larger than the SM
+ *                        count, one CTA per stream otherwise; 1 = always one per image (where eligible), -1 = never. */
 CGIC_API int cgic_tune(const char *key, int value);
 CGIC_API const char *cgic_last_error(void);
 

@@ -916,3 +916,47 @@ def test_f1_entropy_route_per_image_batches(cg, orc, B, H, W, c, m):
     # twice in a row: the tickets were left zero
     again = cg.ops.entropy_route(x, c, m)
     assert torch.equal(again[2], m_c) and torch.equal(again[3], m_m) and torch.equal(again[4], near)
+
+
+# ------------------------------------------------- the packer's two shapes: one CTA per image / one CTA per stream
+@pytest.fixture(params=[1, -1], ids=["cta_per_image", "cta_per_stream"])
+def pack_mode(request, cg):
+    cg.ops.tune("pack_image", request.param)
+    yield request.param
+    cg.ops.tune("pack_image", 0)
+
+
+@pytest.mark.parametrize("kind", ["kat5", "short", "flat"])
+@pytest.mark.parametrize("H,W,c,m", [(256, 256, 0.1, 0.8), (256, 256, 0.0, 0.0), (128, 256, 0.05, 0.05), (256, 128, 0.3, 0.6), (64, 128, 0.0, 0.5),
+                                     (128, 128, 1.0, 0.0), (32, 128, 0.2, 0.8), (256, 256, 0.5, 0.0), (64, 64, 0.1, 0.8)])
+def test_pack_kernels_vs_oracle(cg, orc, pack_mode, kind, H, W, c, m):
+    """Both packers against the oracle's five files, every mode, tables with 1-bit to 19-bit codes; a symbol outside the
+    table flags its stream (size -1) in both."""
+    counts = _skew_counts(kind)
+    order = orc.lexicographic_order(1024)
+    t = cg.ops.HuffTable(counts, order)
+    ot = orc.huff_build(counts, order)
+    B, h, w = 3, H // 4, W // 4
+    g = torch.Generator().manual_seed(H + 3 * W + int(100 * c))
+    e16, e8 = torch.rand(B, H // 16, W // 16, generator=g), torch.rand(B, H // 8, W // 8, generator=g)
+    masks = cg.ops.router(e16.cuda(), e8.cuda(), c, m, per_image=True)
+    mode = masks[4]
+    idx = torch.multinomial(torch.from_numpy(counts / counts.sum()), B * h * w, replacement=True, generator=g).cuda()
+    packed, sizes = cg.ops.pack(idx, *masks[:3], mode, t, h, w)
+    torch.cuda.synchronize()
+    offs, _, _ = t.layout(h, w)
+    for b in range(B):
+        streams = orc.pack_image(ot, idx.view(B, h, w)[b].cpu().numpy(), *(mk[b, 0].cpu().numpy() for mk in masks[:3]), mode)
+        blob, sz = packed[b].cpu().numpy(), sizes[b].cpu().numpy()
+        assert sz.tolist() == [len(x) for x in streams], b
+        for s in range(5):
+            assert blob[offs[s]: offs[s] + sz[s]].tobytes() == streams[s], (b, s)
+    if mode == 0:
+        bad = idx.clone().view(B, h, w)
+        mf1 = masks[2][1, 0].nonzero()
+        if len(mf1):
+            y, x = mf1[0].tolist()
+            bad[1, y, x] = 5000                               # outside the table, in image 1's fine stream
+            _, sz_bad = cg.ops.pack(bad.view(-1), *masks[:3], mode, t, h, w)
+            sz_bad = sz_bad.cpu()
+            assert int(sz_bad[1, 2]) == -1 and torch.equal(sz_bad[0], sizes[0].cpu()) and torch.equal(sz_bad[2], sizes[2].cpu())
