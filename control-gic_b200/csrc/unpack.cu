@@ -534,14 +534,36 @@ __device__ int decode_stream_cta_cand(const uint8_t *in, int64_t nbytes, const D
                     e[k] = s_lut[win[k] >> (32 - L)];
                     f[k] = e[k] & 0xFFu;
                 }
-                if ((f[0] | f[1] | f[2] | f[3]) & 0x80u) {  // uncommon: second-level table, rare: tree walk
+                if (LUT2S) {
+                    // second-level codes without a branch (a warp covers 128 positions per pass: "some lane needs the second
+                    // table" is the normal case even at a 1 % share of two-level codes); only flag 0xFF walks the tree
+                    uint32_t e2[4], deep = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const bool two = f[k] >= 0x80u && f[k] != 0xFFu;
+                        const uint32_t hgt = two ? (f[k] & 0x7Fu) : 1u;
+                        e2[k] = lut2[two ? (e[k] >> 8) + ((win[k] << L) >> (32 - hgt)) : 0u];
+                        deep |= f[k] == 0xFFu;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (f[k] >= 0x80u && f[k] != 0xFFu) f[k] = (e2[k] & 0xFFu) + (uint32_t)L;
+                    if (deep) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (f[k] == 0xFFu) {
+                                f[k] = decode_one<LUT2S>(s_words, (uint32_t)wi * 32u + (uint32_t)(p0 + k), s_lut, lut2, T, L) & 0xFFu;
+                                if (f[k] == 0xFFu) f[k] = 0;  // (DEC_MAX_D = 128 < 0xFF)
+                            }
+                    }
+                } else if ((f[0] | f[1] | f[2] | f[3]) & 0x80u) {  // second-level table in global memory / tree walk
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         if (f[k] & 0x80u) {
                             if (f[k] != 0xFFu) {
                                 const uint32_t hgt = f[k] & 0x7Fu;
                                 const uint32_t i2 = (e[k] >> 8) + ((win[k] << L) >> (32 - hgt));  // win holds 32 bits from the position on
-                                f[k] = ((LUT2S ? lut2[i2] : __ldg(&lut2[i2])) & 0xFFu) + (uint32_t)L;
+                                f[k] = (__ldg(&lut2[i2]) & 0xFFu) + (uint32_t)L;
                             } else {
                                 f[k] = decode_one<LUT2S>(s_words, (uint32_t)wi * 32u + (uint32_t)(p0 + k), s_lut, lut2, T, L) & 0xFFu;
                                 if (f[k] == 0xFFu) f[k] = 0;  // (DEC_MAX_D = 128 < 0xFF)
@@ -715,14 +737,36 @@ __device__ int decode_stream_cta_chain(const uint8_t *in, int64_t nbytes, const 
                     e[k] = s_lut[win[k] >> (32 - L)];
                     f[k] = e[k] & 0xFFu;
                 }
-                if ((f[0] | f[1] | f[2] | f[3]) & 0x80u) {  // uncommon: second-level table, rare: tree walk
+                if (LUT2S) {
+                    // second-level codes without a branch (a warp covers 128 positions per pass: "some lane needs the second
+                    // table" is the normal case even at a 1 % share of two-level codes); only flag 0xFF walks the tree
+                    uint32_t e2[4], deep = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const bool two = f[k] >= 0x80u && f[k] != 0xFFu;
+                        const uint32_t hgt = two ? (f[k] & 0x7Fu) : 1u;
+                        e2[k] = lut2[two ? (e[k] >> 8) + ((win[k] << L) >> (32 - hgt)) : 0u];
+                        deep |= f[k] == 0xFFu;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (f[k] >= 0x80u && f[k] != 0xFFu) f[k] = (e2[k] & 0xFFu) + (uint32_t)L;
+                    if (deep) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (f[k] == 0xFFu) {
+                                f[k] = decode_one<LUT2S>(s_words, (uint32_t)wi * 32u + (uint32_t)(p0 + k), s_lut, lut2, T, L) & 0xFFu;
+                                if (f[k] == 0xFFu) f[k] = 0;  // (DEC_MAX_D = 128 < 0xFF)
+                            }
+                    }
+                } else if ((f[0] | f[1] | f[2] | f[3]) & 0x80u) {  // second-level table in global memory / tree walk
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         if (f[k] & 0x80u) {
                             if (f[k] != 0xFFu) {
                                 const uint32_t hgt = f[k] & 0x7Fu;
                                 const uint32_t i2 = (e[k] >> 8) + ((win[k] << L) >> (32 - hgt));  // win holds 32 bits from the position on
-                                f[k] = ((LUT2S ? lut2[i2] : __ldg(&lut2[i2])) & 0xFFu) + (uint32_t)L;
+                                f[k] = (__ldg(&lut2[i2]) & 0xFFu) + (uint32_t)L;
                             } else {
                                 f[k] = decode_one<LUT2S>(s_words, (uint32_t)wi * 32u + (uint32_t)(p0 + k), s_lut, lut2, T, L) & 0xFFu;
                                 if (f[k] == 0xFFu) f[k] = 0;  // (DEC_MAX_D = 128 < 0xFF)
@@ -1678,16 +1722,44 @@ __global__ void __launch_bounds__(DS_THREADS, DS_THREADS <= 512 ? 2 : 1) unpack_
             uint32_t e[8];
 #pragma unroll
             for (int p8 = 0; p8 < 8; ++p8) e[p8] = s_dec[__funnelshift_l(w1, w0, qtr * 8 + p8) >> (32 - L)];
-            uint32_t any = 0;
+            if (lut2_shared) {
+                // second-level codes WITHOUT a branch: a warp covers 256 positions per pass, so even a 1 % share of two-level
+                // codes makes "some lane needs the second table" the normal case -- a divergent slow path would run every time.
+                // The second look-up is always issued (entry 0 when unused); only codes beyond it (flag 0xFF) walk the tree.
+                uint32_t e2[8], deep = 0;
 #pragma unroll
-            for (int p8 = 0; p8 < 8; ++p8) {
-                any |= e[p8];
-                e[p8] &= 0xFFu;
-            }
-            if (any & 0x80u) {  // uncommon: second-level table, rare: tree walk
+                for (int p8 = 0; p8 < 8; ++p8) {
+                    const uint32_t f = e[p8] & 0xFFu;
+                    const bool two = f >= 0x80u;
+                    const uint32_t hgt = two ? (f & 0x7Fu) : 1u;
+                    const uint32_t win = __funnelshift_l(w1, w0, qtr * 8 + p8);
+                    e2[p8] = lut2[two && f != 0xFFu ? (e[p8] >> 8) + ((win << L) >> (32 - hgt)) : 0u];
+                    deep |= f == 0xFFu;
+                }
 #pragma unroll
-                for (int p8 = 0; p8 < 8; ++p8)
-                    if (e[p8] & 0x80u) e[p8] = ds_decode_win(__funnelshift_l(w1, w0, qtr * 8 + p8), s_dec, lut2, a.T, L) & 0xFFu;
+                for (int p8 = 0; p8 < 8; ++p8) {
+                    const uint32_t f = e[p8] & 0xFFu;
+                    e[p8] = f >= 0x80u ? (e2[p8] & 0xFFu) + (uint32_t)L : f;
+                }
+                if (deep) {  // rare: a code deeper than the second level
+#pragma unroll
+                    for (int p8 = 0; p8 < 8; ++p8) {
+                        const uint32_t win = __funnelshift_l(w1, w0, qtr * 8 + p8);
+                        if ((s_dec[win >> (32 - L)] & 0xFFu) == 0xFFu) e[p8] = ds_decode_win(win, s_dec, lut2, a.T, L) & 0xFFu;
+                    }
+                }
+            } else {
+                uint32_t any = 0;
+#pragma unroll
+                for (int p8 = 0; p8 < 8; ++p8) {
+                    any |= e[p8];
+                    e[p8] &= 0xFFu;
+                }
+                if (any & 0x80u) {  // second-level table in global memory / tree walk
+#pragma unroll
+                    for (int p8 = 0; p8 < 8; ++p8)
+                        if (e[p8] & 0x80u) e[p8] = ds_decode_win(__funnelshift_l(w1, w0, qtr * 8 + p8), s_dec, lut2, a.T, L) & 0xFFu;
+                }
             }
 #pragma unroll
             for (int p8 = 0; p8 < 8; ++p8)
