@@ -406,6 +406,9 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    # stdout carries exactly ONE line, the JSON: everything libraries print meanwhile (NCCL's version banner ...) goes to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -445,7 +448,9 @@ def run_b200(args):
     outs = [g_out[0]] if graph is not None else step()
     torch.cuda.synchronize()
     assert torch.equal(outs[0][3].cpu(), sizes_first) and torch.equal(outs[0][4].view(-1), outs[0][0])
-    # the path's only collective: {bytes, pixels, squared error} summed over ranks -- timed, for the job-level figure
+    # the path's only collective: {bytes, pixels, squared error} summed over ranks -- timed, for the job-level figure (one
+    # untimed call first: NCCL builds its channels for a new (dtype, op) pair on first use)
+    cdist.reduce_rate_distortion(0.0, 0.0, 0.0, device=dev)
     ev_r = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     ev_r[0].record()
     tot_bytes, tot_pix, tot_sq, bpp = cdist.reduce_rate_distortion(float(sizes_first.sum()), float(pixels), float(sq.item()), device=dev)
@@ -658,7 +663,8 @@ def run_b200(args):
                          "(bpp bit-exact)")
         line["cpu_baseline"] = cpu
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

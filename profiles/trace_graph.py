@@ -7,48 +7,26 @@ import numpy as np, torch
 import bench, workload
 import cgic_b200 as cg
 B, H, W, c, m = bench.WORKLOADS[bench.DEFAULT_WORKLOAD]
-h, w = H // 4, W // 4
 dev = torch.device("cuda", 0)
-cbk, counts = workload.codebook_and_counts()
-table = cg.ops.HuffTable(counts.numpy(), workload.lexicographic_order()).upload()
-cb = cbk.to(dev)
-prepared = cg.ops.Codebook(cb)
-e16, e8 = workload.entropy_maps(B, H, W, 1000)
-mc, mm, mf, _, mode = cg.ops.router(e16.to(dev), e8.to(dev), c, m, per_image=True)
-hc, hm, hf = (t.to(dev) for t in workload.heads(B, H, W, cbk, 1000))
-z = cg.ops.mask_mix(hc, hm, hf, mc, mm, mf)
-def step():
-    idx, zq, sq = cg.ops.vq_assign(z, prepared)
-    packed, sizes = cg.ops.pack(idx, mc, mm, mf, mode, table, h, w)
-    return cg.ops.unpack(packed, sizes, mode, table, cb, h, w)
-side = torch.cuda.Stream()
-side.wait_stream(torch.cuda.current_stream())
-with torch.cuda.stream(side):
-    for _ in range(3): step()
-torch.cuda.current_stream().wait_stream(side)
-torch.cuda.synchronize()
+hp = bench.HotPath(dev)
+z, masks, mode = hp.inputs(B, H, W, c, m, 0)
+step = hp.step_fn([(z, masks, mode)])
 use_graph = "--eager" not in sys.argv
-if use_graph:
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g, stream=side):
-        out = step()
-    run = g.replay
-else:
-    run = step
+run, g, _ = bench.capture(torch, step, not use_graph)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 for _ in range(5):
     flush.zero_(); ev[0].record(); run(); ev[1].record()
 torch.cuda.synchronize()
 print("step (events):", round(1e3 * ev[0].elapsed_time(ev[1]), 2), "us", "graph" if use_graph else "eager")
-buf = np.zeros(1024 * 8, np.uint64)
+buf = np.zeros(1024 * 16, np.uint64)
 assert ctypes.CDLL(cg._lib.LIB_PATH).cgic_trace_unpack(buf.ctypes.data_as(ctypes.c_void_p)) == 0
-un = buf.reshape(1024, 8)[: 4 * B].astype(np.float64)
-ws = [v for k, v in cg.ops._ws_cache.items() if k[0] == "vq"][-1] if not use_graph else None
+SL = 16
+un = buf.reshape(1024, SL)[: 4 * B].astype(np.float64)
 # the VQ stamps live in the vq workspace of the stream the kernel ran on: take every cached one and keep the latest stamps
 best = None
 for k, v in cg.ops._ws_cache.items():
-    if k[0] != "vq": continue
+    if k[0] not in ("vq", "encode"): continue
     raw = v[256:].view(torch.int64)[512:512 + 300 * 8].cpu().numpy().reshape(300, 8)
     raw = raw[raw[:, 0] > 0]
     if len(raw) and (best is None or raw[:, 0].max() > best[:, 0].max()): best = raw
@@ -67,9 +45,9 @@ for k in range(4):
     print(f"decode {names[k]:6s} start min {rel(s.min()):.2f} median {rel(np.median(s)):.2f} max {rel(s.max()):.2f}{extra}")
 
 def unit(name, n):
-    b_ = np.zeros(1024 * 8, np.uint64)
+    b_ = np.zeros(1024 * 16, np.uint64)
     assert getattr(ctypes.CDLL(cg._lib.LIB_PATH), "cgic_trace_" + name)(b_.ctypes.data_as(ctypes.c_void_p)) == 0
-    return b_.reshape(1024, 8)[:n].astype(np.float64)
+    return b_.reshape(1024, 16)[:n].astype(np.float64)
 pk = unit("pack", 4 * B)
 for k, nm in enumerate(("fine", "medium", "coarse", "masks")):
     r = pk[k * B:(k + 1) * B]
