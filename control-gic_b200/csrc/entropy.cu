@@ -54,8 +54,7 @@ entropy_kernel(const float *__restrict__ x, int H, int W, int regions_x, int reg
 {
     __shared__ __align__(16) float s_rows[EN_WARPS][32 * EN_STRIDE + 4];  // per warp: 32 histogram rows (slice a multiple of 16 bytes)
     __shared__ float s_bins[32];
-    __shared__ uint32_t s_hist[256];
-    __shared__ uint32_t s_state[4];
+    __shared__ uint32_t s_state[RS_STATE];
     __shared__ int s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     pdl_launch_dependents();
@@ -179,7 +178,9 @@ entropy_kernel(const float *__restrict__ x, int H, int W, int regions_x, int reg
     if (!s_last) return;
     __threadfence();
     const int h16 = H / 16, w16 = W / 16, n16 = h16 * w16;
-    uint32_t *s_keys = 4 * n16 <= (int)(sizeof(s_rows) / 4) ? reinterpret_cast<uint32_t *>(&s_rows[0][0]) : nullptr;  // the histogram rows are dead
+    // the histogram rows are dead: the select's histogram (8 KB) and, when it fits behind it, the key cache take their place
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(&s_rows[0][0]);
+    uint32_t *s_keys = RS_BINS + 4 * n16 <= (int)(sizeof(s_rows) / 4) ? s_hist + RS_BINS : nullptr;
     route_image(e16 + (int64_t)b * n16, e8 + (int64_t)b * 4 * n16, h16, w16, rq.mode, rq.k_c, rq.k_m, rq.m_c + (int64_t)b * n16,
                 rq.m_m + (int64_t)b * 4 * n16, rq.near ? rq.near + 2 * b : nullptr, rq.rtol, rq.atol, s_hist, s_state, s_keys);
     if (threadIdx.x == 0) rq.tickets[b] = 0;  // (workspace contract: zero between launches)

@@ -22,8 +22,8 @@ router_select_kernel(const float *__restrict__ e16, const float *__restrict__ e8
                      int32_t *__restrict__ m_f, float *__restrict__ gate, int key_cache)
 {
     extern __shared__ uint32_t s_keys_dyn[];  // key cache (n8 keys) when the launch provided it
-    __shared__ uint32_t s_hist[256];
-    __shared__ uint32_t s_state[4];
+    __shared__ uint32_t s_hist[RS_BINS];
+    __shared__ uint32_t s_state[RS_STATE];
     const int h8 = 2 * h16, w8 = 2 * w16;
     const int64_t n16_img = (int64_t)h16 * w16, n8_img = (int64_t)h8 * w8;
     const int nb = per_image ? 1 : B;
@@ -297,9 +297,9 @@ extern "C" int cgic_router(const float *e16, const float *e8, int B, int h16, in
     {
         CGIC_PROF("router_select_kernel", stream);
         const int64_t n8_cta = (int64_t)(per_image ? 1 : B) * 4 * h16 * w16;
-        // key cache: static (s_hist, s_state) + dynamic shared memory must stay within the 48 KB a kernel gets without
-        // opting in, so 11 776 keys (46 KB) at most -- a 1024 x 768 image has 12 288 medium cells and goes uncached
-        const int key_cache = n8_cta <= 11776;
+        // key cache: static (histogram, state: ~8.5 KB) + dynamic shared memory must stay within the 48 KB a kernel gets without
+        // opting in, so 9 728 keys (38 KB) at most -- larger maps are re-fetched from global memory in every pass
+        const int key_cache = n8_cta <= 9728;
         CGIC_CUDA_CHECK(launch_pdl(router_select_kernel, dim3(per_image ? B : 1), dim3(RT_THREADS), key_cache ? (size_t)n8_cta * 4 : 0, stream, e16, e8, B,
                                    h16, w16, mode, k_c, k_m, per_image, m_c, m_m, fuse_fine ? m_f : (int32_t *)nullptr, gate_out, key_cache));
     }

@@ -17,79 +17,120 @@ __device__ __forceinline__ float key_float(uint32_t k)
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
 }
 
-// value of rank `rank` (0-based) among fetch(0..n-1); whole CTA must call.  s_keys (nullable): room for n keys in
-// shared memory -- the values are fetched and converted once instead of once per pass.
+// Exact select: the value of rank `rank` (0-based, ascending) among fetch(0..n-1); whole CTA must call (any block size that
+// is a multiple of 32, at most 1024 threads).  Order-preserving integer keys; s_keys (nullable): room for n keys in shared
+// memory -- the values are then fetched and converted once.
+//   1. block min / max of the keys: only the bits in which they differ matter (entropies share sign and most of the exponent);
+//   2. a histogram over the top RS_BITS of the remaining range [lo, lo + 2^bits): one shared-memory atomicAdd per key;
+//   3. the bucket that holds the rank (block scan of the histogram);
+//   4. with n keys over 2048 buckets that bucket usually holds a handful of keys: up to 32 are collected and one warp ranks
+//      them directly; a fuller bucket (ties, clusters) goes round again with the bucket as the new range.
+// s_hist: RS_BINS words, s_state: RS_STATE words.
+constexpr int RS_BITS = 11;
+constexpr int RS_BINS = 1 << RS_BITS;
+constexpr int RS_STATE = 48;  // [0] lo, [1] bits, [2] rank in range, [3] keys in bucket, [4] small-list counter, [5] answer, [8..39] small list, [40..] scratch
+
 template <typename Fetch>
 __device__ float select_rank(Fetch fetch, int64_t n, int64_t rank, uint32_t *s_hist, uint32_t *s_state, uint32_t *s_keys)
 {
-    uint32_t prefix = 0, mask = 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
     if (rank > n - 1) rank = n - 1;
     if (rank < 0) rank = 0;
-    if (threadIdx.x == 0) {
-        s_state[0] = 0;
-        s_state[1] = (uint32_t)rank;
-        s_state[2] = (uint32_t)((uint64_t)rank >> 32);
+    auto key_at = [&](int64_t i) { return s_keys ? s_keys[i] : float_key(fetch(i)); };
+    // ---- keys, block min / max
+    uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
+#pragma unroll 4  // (independent global loads: several in flight)
+    for (int64_t i = tid; i < n; i += nthreads) {
+        const uint32_t k = float_key(fetch(i));
+        if (s_keys) s_keys[i] = k;
+        kmin = min(kmin, k);
+        kmax = max(kmax, k);
     }
-    if (s_keys)
-        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = float_key(fetch(i));
-    for (int pass = 0; pass < 4; ++pass) {
-        const int shift = 24 - 8 * pass;
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    __syncthreads();  // (previous users of s_hist / s_state are done)
+    if (lane == 0) {
+        s_hist[warp] = kmin;
+        s_hist[32 + warp] = kmax;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t a = lane < nwarps ? s_hist[lane] : 0xFFFFFFFFu, b = lane < nwarps ? s_hist[32 + lane] : 0u;
+        a = __reduce_min_sync(0xffffffffu, a);
+        b = __reduce_max_sync(0xffffffffu, b);
+        if (lane == 0) {
+            s_state[0] = a;                                              // lo
+            s_state[1] = a == b ? 0u : 32u - (uint32_t)__clz((int)(b - a));  // bits: every key lies in [lo, lo + 2^bits)
+            s_state[2] = (uint32_t)rank;
+        }
+    }
+    __syncthreads();
+    for (;;) {
+        const uint32_t lo = s_state[0], bits = s_state[1], r = s_state[2];
+        if (bits == 0) return key_float(lo);
+        const uint32_t shift = bits > (uint32_t)RS_BITS ? bits - RS_BITS : 0u;
+        // a key belongs to the current range iff (k - lo) >> bits == 0 (and k >= lo); bits == 32 only in the first round: all keys
+        auto in_range = [&](uint32_t k) { return k >= lo && (bits >= 32u || ((k - lo) >> bits) == 0u); };
+        for (int i = tid; i < RS_BINS; i += nthreads) s_hist[i] = 0u;
+        if (tid == 0) s_state[4] = 0u;
         __syncthreads();
-        for (int64_t i0 = 0; i0 < n; i0 += blockDim.x) {  // uniform trip count: the warp votes below need every lane
-            const int64_t i = i0 + threadIdx.x;
-            uint32_t digit = 0xFFFFFFFFu;
-            if (i < n) {
-                const uint32_t k = s_keys ? s_keys[i] : float_key(fetch(i));
-                if ((k & mask) == prefix) digit = (k >> shift) & 255u;
-            }
-            // one atomic per distinct digit and warp (entropies share their exponent: the first pass would otherwise
-            // serialise hundreds of increments on one or two counters)
-            const unsigned same = __match_any_sync(0xffffffffu, digit);
-            if (digit != 0xFFFFFFFFu && (threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&s_hist[digit], (uint32_t)__popc(same));
+        for (int64_t i = tid; i < n; i += nthreads) {
+            const uint32_t k = key_at(i);
+            if (in_range(k)) atomicAdd(&s_hist[(k - lo) >> shift], 1u);
         }
         __syncthreads();
-        if (threadIdx.x < 32) {
-            // the bucket holding the wanted rank: lane l owns buckets 8l .. 8l+7; inclusive scan of the lane totals by
-            // shuffles, then the owning lane walks its 8 buckets (a serial walk over 256 buckets cost 4 us per pass)
-            const int lane = threadIdx.x;
-            uint64_t rk = ((uint64_t)s_state[2] << 32) | s_state[1];
-            uint32_t cnt[8], tot = 0;
+        // ---- the bucket holding rank r: every thread sums its slice of bins, block scan of the slice sums, the owner walks its slice
+        const int per = (RS_BINS + nthreads - 1) / nthreads, b0 = tid * per, b1 = min(RS_BINS, b0 + per);
+        uint32_t mine = 0;
+        for (int i = b0; i < b1; ++i) mine += s_hist[i];
+        uint32_t inc = mine;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                cnt[i] = s_hist[lane * 8 + i];
-                tot += cnt[i];
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        __shared__ uint32_t s_wtot[32];
+        if (lane == 31) s_wtot[warp] = inc;
+        __syncthreads();
+        uint32_t woff = 0;
+        for (int w = 0; w < warp; ++w) woff += s_wtot[w];
+        const uint32_t exc = woff + inc - mine;
+        if (r >= exc && r < exc + mine) {  // exactly one thread (r < number of keys in range)
+            uint32_t rem = r - exc;
+            int i = b0;
+            for (; i < b1 - 1; ++i) {
+                if (rem < s_hist[i]) break;
+                rem -= s_hist[i];
             }
-            uint32_t inc = tot;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += v;
-            }
-            const uint32_t exc = inc - tot;
-            // rank < n always, so exactly one lane has exc <= rk < inc (the last lane takes everything beyond: d <= 255)
-            const bool mine = (rk >= exc && rk < inc) || (lane == 31 && rk >= inc);
-            __syncwarp();  // every lane has read the rank before the owning lane replaces it
-            if (mine) {
-                uint64_t rem = rk - exc;
-                uint32_t d = 0;
-                for (; d < 7; ++d) {
-                    if (rem < cnt[d]) break;
-                    rem -= cnt[d];
-                }
-                s_state[0] = prefix | ((uint32_t)(lane * 8 + d) << shift);
-                s_state[1] = (uint32_t)rem;
-                s_state[2] = (uint32_t)(rem >> 32);
-            }
+            s_state[0] = lo + ((uint32_t)i << shift);
+            s_state[1] = shift;
+            s_state[2] = rem;
+            s_state[3] = s_hist[i];
         }
         __syncthreads();
-        prefix = s_state[0];
-        mask |= 0xFFu << shift;
+        const uint32_t lo2 = s_state[0], bits2 = s_state[1], r2 = s_state[2], cnt = s_state[3];
+        if (bits2 == 0) return key_float(lo2);
+        if (cnt > 32u) continue;  // a full bucket: another round over [lo2, lo2 + 2^bits2)
+        // ---- a handful of keys left: collect them, one warp ranks them
+        for (int64_t i = tid; i < n; i += nthreads) {
+            const uint32_t k = key_at(i);
+            if (k >= lo2 && ((k - lo2) >> bits2) == 0u) s_state[8 + atomicAdd(&s_state[4], 1u)] = k;
+        }
         __syncthreads();
+        if (warp == 0) {
+            const uint32_t k = lane < cnt ? s_state[8 + lane] : 0xFFFFFFFFu;
+            uint32_t less = 0, leq = 0;
+            for (uint32_t j = 0; j < cnt; ++j) {
+                const uint32_t o = s_state[8 + j];
+                less += o < k;
+                leq += o <= k;
+            }
+            if (lane < cnt && less <= r2 && r2 < leq) s_state[5] = k;  // (equal keys write the same value)
+        }
+        __syncthreads();
+        return key_float(s_state[5]);
     }
-    return key_float(prefix);
 }
-
 
 // TripleGrainFixedEntropyRouter.forward for ONE image by the whole CTA (RouterTriple.py:15-96, per-image thresholds =
 // the reference's B == 1 call): thresholds by exact select, then m_c [n16] and m_m [4 n16] (global, int32).  e16 / e8 are
@@ -106,6 +147,7 @@ __device__ __forceinline__ void route_image(const float *e16, const float *e8, i
         const float thr = select_rank([&](int64_t i) { return __ldcg(e16 + i); }, n16, k_c != 0 ? k_c - 1 : 0, s_hist, s_state, s_keys);
         const float tol = rtol * fabsf(thr) + atol;
         int cnt = 0;
+#pragma unroll 4
         for (int i = threadIdx.x; i < n16; i += blockDim.x) {
             const float v = __ldcg(e16 + i);
             c[i] = v < thr;
@@ -123,6 +165,7 @@ __device__ __forceinline__ void route_image(const float *e16, const float *e8, i
                                     : select_rank([&](int64_t i) { return __ldcg(e8 + i); }, n8, k_m != 0 ? k_m - 1 : 0, s_hist, s_state, s_keys);
         const float tol = rtol * fabsf(thr) + atol;
         int cnt = 0;
+#pragma unroll 4
         for (int i = threadIdx.x; i < n8; i += blockDim.x) {
             const float v = __ldcg(e8 + i);
             const bool under = mode == 0 && c[parent(i)];

@@ -6,6 +6,7 @@
 import collections, csv, subprocess, sys, os
 launches, rep, tag = sys.argv[1:4]
 step = (sys.argv[4] if len(sys.argv) > 4 else 'vq_warp_kernel,pack_kernel<8>,unpack_decode_kernel,unpack_assemble_kernel').split(',')
+suffix = sys.argv[5] if len(sys.argv) > 5 else ''
 out_dir = os.path.dirname(os.path.abspath(__file__))
 rows = list(csv.reader(open(launches)))
 hdr_i = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
@@ -21,7 +22,7 @@ for r in rows[hdr_i + 1:]:
         name = r[ki].split('(')[0].split('::')[-1]
         acc.setdefault(name, []).append(float(r[vi].replace(',', '')) / (1000 if r[ui] == 'ns' else 1))
 tot = sum(sum(v) / len(v) for k, v in acc.items() if k in step)
-with open(os.path.join(out_dir, f"{tag}_launches.txt"), "w") as f:
+with open(os.path.join(out_dir, f"{tag}_launches{suffix}.txt"), "w") as f:
     f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised): compare SHARES\n# source: {os.path.basename(launches)}\n")
     for k, v in acc.items():
         if k in step:
@@ -35,12 +36,13 @@ hh = rr[0]
 want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__t_bytes.sum', 'launch__grid_size', 'launch__block_size',
         'launch__registers_per_thread', 'launch__shared_mem_per_block_dynamic', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
-        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__inst_executed.sum']
-with open(os.path.join(out_dir, f"{tag}_kernels.txt"), "w") as f:
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__inst_executed.sum',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'launch__waves_per_multiprocessor', 'launch__cluster_size']
+with open(os.path.join(out_dir, f"{tag}_kernels{suffix}.txt"), "w") as f:
     f.write(f"# ncu --set full --clock-control none --import-source on, one launch per kernel\n# source: {os.path.basename(rep)}\n")
     for r in rr[2:]:
         f.write(r[hh.index('Kernel Name')].split('(')[0].split('::')[-1] + "\n")
         for w in want:
             if w in hh:
                 f.write(f"    {w:70s} {r[hh.index(w)]} {rr[1][hh.index(w)]}\n")
-print(open(os.path.join(out_dir, f"{tag}_launches.txt")).read())
+print(open(os.path.join(out_dir, f"{tag}_launches{suffix}.txt")).read())
