@@ -26,7 +26,10 @@ struct Bins {
 };
 
 constexpr int EN_WIN = 3;
-constexpr int EN_WARPS = 4;              // warps (= regions in flight) per CTA
+#ifndef CGIC_EN_WARPS
+#define CGIC_EN_WARPS 8  // 8: the routing tail of the fused kernel runs on 256 threads (4 warps: 62 us, 8: 54 us, 16: 54 us for entropy + routing of 64 images; the entropy maps alone take 37 us with 4 or 8, 41 us with 16)
+#endif
+constexpr int EN_WARPS = CGIC_EN_WARPS;  // warps (= regions in flight) per CTA
 constexpr int EN_STRIDE = 33;            // words per histogram row: lanes hitting the same bin fall into different banks
 
 __device__ __forceinline__ float ex2_approx(float x)  // no flush-to-zero: denormal results are kept
@@ -48,11 +51,13 @@ struct RouteReq {
 };
 
 // grid (CTAs per image, B): the regions of an image are dealt to its own CTAs, so that an image's last CTA is well defined
-__global__ void __launch_bounds__(EN_WARPS * 32, 8)
+__global__ void __launch_bounds__(EN_WARPS * 32, 32 / EN_WARPS)
 entropy_kernel(const float *__restrict__ x, int H, int W, int regions_x, int regions_img, const Bins bins, float *__restrict__ e8,
                float *__restrict__ e16, const RouteReq rq)
 {
-    __shared__ __align__(16) float s_rows[EN_WARPS][32 * EN_STRIDE + 4];  // per warp: 32 histogram rows (slice a multiple of 16 bytes)
+    extern __shared__ __align__(16) float s_rows_dyn[];                   // per warp: 32 histogram rows (slice a multiple of 16 bytes)
+    float(*s_rows)[32 * EN_STRIDE + 4] = reinterpret_cast<float(*)[32 * EN_STRIDE + 4]>(s_rows_dyn);
+    constexpr int S_ROWS_WORDS = EN_WARPS * (32 * EN_STRIDE + 4);
     __shared__ float s_bins[32];
     __shared__ uint32_t s_state[RS_STATE];
     __shared__ int s_last;
@@ -180,7 +185,7 @@ entropy_kernel(const float *__restrict__ x, int H, int W, int regions_x, int reg
     const int h16 = H / 16, w16 = W / 16, n16 = h16 * w16;
     // the histogram rows are dead: the select's histogram (8 KB) and, when it fits behind it, the key cache take their place
     uint32_t *s_hist = reinterpret_cast<uint32_t *>(&s_rows[0][0]);
-    uint32_t *s_keys = RS_BINS + 4 * n16 <= (int)(sizeof(s_rows) / 4) ? s_hist + RS_BINS : nullptr;
+    uint32_t *s_keys = RS_BINS + 4 * n16 <= S_ROWS_WORDS ? s_hist + RS_BINS : nullptr;
     route_image(e16 + (int64_t)b * n16, e8 + (int64_t)b * 4 * n16, h16, w16, rq.mode, rq.k_c, rq.k_m, rq.m_c + (int64_t)b * n16,
                 rq.m_m + (int64_t)b * 4 * n16, rq.near ? rq.near + 2 * b : nullptr, rq.rtol, rq.atol, s_hist, s_state, s_keys);
     if (threadIdx.x == 0) rq.tickets[b] = 0;  // (workspace contract: zero between launches)
@@ -203,7 +208,10 @@ static int entropy_launch(const char *who, const float *x, int B, int H, int W, 
     for (int i = 0; i < 32; ++i) bins.v[i] = bins32_host[i];
     {
         CGIC_PROF("entropy_kernel", stream);
-        CGIC_CUDA_CHECK(launch_pdl(entropy_kernel, dim3((unsigned)((regions_img + EN_WARPS - 1) / EN_WARPS), (unsigned)B), dim3(EN_WARPS * 32), 0, stream, x,
+        const size_t smem = (size_t)EN_WARPS * (32 * EN_STRIDE + 4) * sizeof(float);
+        const int rc = ensure_smem((const void *)entropy_kernel, smem);
+        if (rc) return rc;
+        CGIC_CUDA_CHECK(launch_pdl(entropy_kernel, dim3((unsigned)((regions_img + EN_WARPS - 1) / EN_WARPS), (unsigned)B), dim3(EN_WARPS * 32), smem, stream, x,
                                    H, W, regions_x, (int)regions_img, bins, e8_out, e16_out, rq));
     }
     CGIC_LAUNCH_CHECK();
