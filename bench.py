@@ -585,7 +585,7 @@ def run_b200(args):
     achieved = alg[top] / (kern[top]["us_per_launch"] * 1e-6) / 1e9
     step_s = dev_ms / args.steps * 1e-3
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_source, "traffic": NCU_TRAFFIC.get(top), "traffic_source": NCU_TRAFFIC_SOURCE if top in NCU_TRAFFIC else None,
+                "peak_source": peak_source, "traffic": _traffic(top, B), "traffic_source": NCU_TRAFFIC_SOURCE if _traffic(top, B) is not None else None,
                 "algorithmic_bytes_per_launch": alg[top],
                 "us_per_launch": kern[top]["us_per_launch"], "kernels": kern,
                 "step_algorithmic_bytes": alg["step"], "step_achieved_gbs": alg["step"] / step_s / 1e9, "step_frac": alg["step"] / step_s / 1e9 / peak}
@@ -671,8 +671,14 @@ def run_b200(args):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/), filled in after
 # each capture; a kernel without an entry reports null.
-NCU_TRAFFIC_SOURCE = "profiles/r2_kernels.txt (ncu --set full, one launch; not re-measured in this run)"
-NCU_TRAFFIC = {}
+NCU_TRAFFIC_SOURCE = ("profiles/r2_kernels.txt: dram__bytes_read.sum + dram__bytes_write.sum of one launch on the 64-image batch under "
+                      "ncu --set full (reads only: the 20 MB working set's writes stay in the 126 MB L2 within a launch); not re-measured in this run")
+NCU_TRAFFIC = {"vq_warp_kernel": 6444800, "pack_kernel": 3525888, "unpack_decode_kernel": 249856, "unpack_assemble_kernel": 295936}
+
+
+def _traffic(top, B):
+    """The committed capture is of the 64-image batch: no figure for other batch sizes / kernels."""
+    return NCU_TRAFFIC.get(top) if B == 64 else None
 
 
 def algorithmic_step_bytes(B, h, w, stream_bytes):
