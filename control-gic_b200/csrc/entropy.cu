@@ -74,6 +74,7 @@ entropy_kernel(const float *__restrict__ x, int H, int W, int regions_x, int reg
     const bool col_ok = gx < W;
     const int64_t plane = (int64_t)H * W;
     const float *xb = x + (int64_t)b * 3 * plane + (int64_t)(ry * 16) * W + gx;
+    const float *xc[3] = {xb, xb + plane, xb + 2 * plane};  // one base pointer per channel: the 48 loads below then need 32-bit offsets only
     float *rows = s_rows[warp];
     float *row = rows + lane * EN_STRIDE;
     // the two halves (upper / lower 8 rows) go through the same 32 histogram rows one after the other; the
@@ -83,9 +84,9 @@ entropy_kernel(const float *__restrict__ x, int H, int W, int regions_x, int reg
     for (int half = 0; half < 2; ++half)
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            const int64_t o = (int64_t)(half * 8 + r) * W;
+            const int o = (half * 8 + r) * W;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) raw[half][r][c] = col_ok ? __ldg(xb + c * plane + o) : 0.f;
+            for (int c = 0; c < 3; ++c) raw[half][r][c] = col_ok ? __ldg(xc[c] + o) : 0.f;
         }
     float acc[2][4];
 #pragma unroll

