@@ -17,6 +17,7 @@ collective, one all-reduce of {bytes, pixels, sqerr} at the end ("scaling": "wea
               unpack + re-assembly): pinned host inputs -> H2D -> kernels -> D2H of every result (streams, sizes, decoded
               indices / masks / latents), wall clock, per step.  `e2e_decoded_on_device` is the same call leaving the decoded
               tensors in HBM for the decoder CNN (what model.py:391-399 does): only streams, sizes, status come back.
+              `e2e_narrow_wire`: every result comes back, but masks travel as bytes and decoded indices as int16.
     configs   the other BASELINE configs through the same step: configs[2] (24 x 512x768 per GPU at its three ratios),
               configs[3] as STRONG scaling (512 images of 256x256 split over the ranks), configs[4] (the six tiles of one
               2032x1344 image, tiles dealt round-robin over the ranks).
@@ -525,20 +526,25 @@ def run_b200(args):
     e2e, e2e_parts = {}, {}
     # image ranges: 8 pipeline the 15 MB of the full copy best; with the decoded tensors left on the device the D2H side is
     # small and per-copy latency dominates: 2 ranges (profiles/e2e_probe.py)
-    for key, on_device, parts in (("full", False, args.e2e_parts or 8), ("decoded_on_device", True, 2)):
+    for key, on_device, narrow, parts in (("full", False, False, args.e2e_parts or 8), ("narrow_wire", False, True, args.e2e_parts or 8),
+                                          ("decoded_on_device", True, False, 2)):
         views = sess.arena(parts)
         e2e_parts[key] = len(views)
         for v in views:
             r = v["images"]
             v["z"].copy_(zh[r.start:r.stop])
-            for name, src in zip(("m_c", "m_m", "m_f"), mh):
-                v[name].copy_(src[r.start:r.stop])
+            for name, src in zip(("m_c8", "m_m8", "m_f8") if narrow else ("m_c", "m_m", "m_f"), mh):
+                v[name].copy_(src[r.start:r.stop].to(v[name].dtype))
             v["sizes"].zero_()
             v["ind"].zero_()
+            v["ind16"].zero_()
         for _ in range(5):
-            sess.roundtrip_arena(decoded_on_device=on_device)
+            sess.roundtrip_arena(decoded_on_device=on_device, narrow=narrow)
         assert torch.equal(torch.cat([v["sizes"] for v in views]), sizes_first) and int(sum(int(v["status"].abs().sum()) for v in views)) == 0
-        if not on_device:
+        if narrow:
+            assert torch.equal(torch.cat([v["ind16"].reshape(-1) for v in views]).long(), idx.cpu())
+            assert torch.equal(torch.cat([v["mf8"].reshape(-1) for v in views]).long(), mh[2].reshape(-1).long())
+        elif not on_device:
             assert torch.equal(torch.cat([v["ind"].reshape(-1) for v in views]), idx.cpu())
         else:
             assert torch.equal(sess.device_tensor("ind").reshape(-1), idx)       # decoded tensors stayed in HBM, and are right
@@ -546,7 +552,7 @@ def run_b200(args):
             dist.barrier()
         t0 = time.perf_counter()
         for _ in range(n_e2e):
-            sess.roundtrip_arena(decoded_on_device=on_device)    # = CGIC.compress: encode + pack + unpack + re-assembly, pinned host in / out
+            sess.roundtrip_arena(decoded_on_device=on_device, narrow=narrow)    # = CGIC.compress: encode + pack + unpack + re-assembly, pinned host in / out
         e2e_s = time.perf_counter() - t0
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         if world > 1:
@@ -596,6 +602,11 @@ def run_b200(args):
             "dtype": "f32", "data": "synthetic", "config": config_of(args, world),
             "e2e": {"value": world * pixels * n_e2e / 1e6 / e2e["full"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": n_e2e, "ms_per_step": 1e3 * e2e["full"] / n_e2e, "call": "cgic_session_roundtrip_arena", "image_ranges": e2e_parts["full"]},
+            "e2e_narrow_wire": {"value": world * pixels * n_e2e / 1e6 / e2e["narrow_wire"], "unit": UNIT, "h2d_bytes_per_step": n4 * 16 + (n4 + n8 + n16),
+                                "d2h_bytes_per_step": d2h_wire + n4 * 2 + n4 * 16 + (n4 + n8 + n16), "ms_per_step": 1e3 * e2e["narrow_wire"] / n_e2e,
+                                "image_ranges": e2e_parts["narrow_wire"],
+                                "call": "cgic_session_roundtrip_arena(flags | 8): every result still comes back, masks as one byte per cell both ways "
+                                        "and decoded indices as int16 (the reference's int32 / int64 tensors exist on the device only)"},
             "e2e_decoded_on_device": {"value": world * pixels * n_e2e / 1e6 / e2e["decoded_on_device"], "unit": UNIT, "h2d_bytes_per_step": h2d,
                                       "d2h_bytes_per_step": d2h_wire, "ms_per_step": 1e3 * e2e["decoded_on_device"] / n_e2e, "image_ranges": e2e_parts["decoded_on_device"],
                                       "call": "cgic_session_roundtrip_arena(flags | 4): streams, sizes, status come back; ind / quant / masks stay "

@@ -32,20 +32,22 @@ struct cgic_session {
     size_t ws_en_bytes = 0, ws_un_bytes = 0;
     // ---- pinned-arena round trip (cgic_session_arena / cgic_session_roundtrip_arena)
     // The batch is cut into `a_parts` image ranges.  Every range has ONE contiguous input block
-    // [z | m_c | m_m | m_f] and ONE contiguous output block [bytes | sizes | status | sqerr | ind | quant |
-    // dmc | dmm | dmf | idx | zq], laid out identically in a pinned host arena and a device arena, so a range
-    // moves with one H2D and one D2H copy; the whole call is a CUDA graph of per-range branches.
+    // [m_c8 | m_m8 | m_f8 | z | m_c | m_m | m_f] and ONE contiguous output block [ind16 | dmc8 | dmm8 | dmf8 | quant |
+    // bytes | sizes | status | sqerr | ind | dmc | dmm | dmf | idx | zq], laid out identically in a pinned host arena
+    // and a device arena.  Whatever the flags ask for is ONE contiguous slice of the block (narrow wire: the head of
+    // either block; reference types: from z / quant on), so a range moves with one H2D and one D2H copy; the whole
+    // call is a CUDA graph of per-range branches.
     int a_parts = 0;
     unsigned char *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr;
     size_t in_bytes = 0, out_bytes = 0;
     struct Part {
         int b0 = 0, nb = 0;
-        size_t in_off = 0, in_len = 0, out_off = 0, out_core = 0, out_idx = 0, out_all = 0;  // D2H lengths by request
+        size_t in_off = 0, in_len = 0, out_off = 0, out_core = 0, out_idx = 0, out_all = 0;  // ends of the D2H slice by request
         size_t o[CGIC_ARENA_COUNT] = {};  // offset of every tensor inside its block
     } part[MAX_PARTS];
-    cudaGraphExec_t graph[8] = {};  // by flags (bit 0: idx, bit 1: zq, bit 2: decoded tensors stay on the device)
+    cudaGraphExec_t graph[16] = {};  // by flags (bit 0: idx, bit 1: zq, bit 2: decoded tensors stay on the device, bit 3: narrow wire)
     cudaEvent_t fork = nullptr, join[MAX_PARTS] = {};
-    bool warmed[8] = {};
+    bool warmed[16] = {};
 };
 
 extern "C" int cgic_session_create(int B, int h, int w, int mode, const cgic_table *t, const float *codebook_host, int K,
@@ -273,8 +275,15 @@ static size_t arena_elem_bytes(int what)
     case CGIC_ARENA_Z: case CGIC_ARENA_QUANT: case CGIC_ARENA_ZQ: return 16;             // per fine token (4 channels)
     case CGIC_ARENA_MC: case CGIC_ARENA_MM: case CGIC_ARENA_MF: return 4;
     case CGIC_ARENA_DMC: case CGIC_ARENA_DMM: case CGIC_ARENA_DMF: case CGIC_ARENA_IND: case CGIC_ARENA_IDX: return 8;
+    case CGIC_ARENA_IND16: return 2;
     default: return 1;
     }
+}
+
+static bool arena_is_input(int what)
+{
+    return what == CGIC_ARENA_Z || what == CGIC_ARENA_MC || what == CGIC_ARENA_MM || what == CGIC_ARENA_MF || what == CGIC_ARENA_MC8 ||
+           what == CGIC_ARENA_MM8 || what == CGIC_ARENA_MF8;
 }
 
 // number of elements of tensor `what` for `nb` images
@@ -283,9 +292,9 @@ static size_t arena_count(const cgic_session *s, int what, int nb)
     const size_t i4 = (size_t)s->h * s->w, i8 = i4 / 4, i16 = i4 / 16;
     switch (what) {
     case CGIC_ARENA_Z: case CGIC_ARENA_QUANT: case CGIC_ARENA_ZQ: case CGIC_ARENA_MF: case CGIC_ARENA_DMF:
-    case CGIC_ARENA_IND: case CGIC_ARENA_IDX: return nb * i4;
-    case CGIC_ARENA_MM: case CGIC_ARENA_DMM: return nb * i8;
-    case CGIC_ARENA_MC: case CGIC_ARENA_DMC: return nb * i16;
+    case CGIC_ARENA_IND: case CGIC_ARENA_IDX: case CGIC_ARENA_IND16: case CGIC_ARENA_MF8: case CGIC_ARENA_DMF8: return nb * i4;
+    case CGIC_ARENA_MM: case CGIC_ARENA_DMM: case CGIC_ARENA_MM8: case CGIC_ARENA_DMM8: return nb * i8;
+    case CGIC_ARENA_MC: case CGIC_ARENA_DMC: case CGIC_ARENA_MC8: case CGIC_ARENA_DMC8: return nb * i16;
     case CGIC_ARENA_BYTES: return (size_t)nb * s->L.stride;
     case CGIC_ARENA_SIZES: return (size_t)nb * 5 * 4;
     case CGIC_ARENA_STATUS: return (size_t)nb * 4;
@@ -305,9 +314,10 @@ extern "C" int cgic_session_arena(cgic_session *s, int parts)
         g = nullptr;
     }
     for (bool &w : s->warmed) w = false;
-    static const int in_order[] = {CGIC_ARENA_Z, CGIC_ARENA_MC, CGIC_ARENA_MM, CGIC_ARENA_MF};
-    static const int out_order[] = {CGIC_ARENA_BYTES, CGIC_ARENA_SIZES, CGIC_ARENA_STATUS, CGIC_ARENA_SQERR, CGIC_ARENA_IND, CGIC_ARENA_QUANT,
-                                    CGIC_ARENA_DMC, CGIC_ARENA_DMM, CGIC_ARENA_DMF, CGIC_ARENA_IDX, CGIC_ARENA_ZQ};
+    static const int in_order[] = {CGIC_ARENA_MC8, CGIC_ARENA_MM8, CGIC_ARENA_MF8, CGIC_ARENA_Z, CGIC_ARENA_MC, CGIC_ARENA_MM, CGIC_ARENA_MF};
+    static const int out_order[] = {CGIC_ARENA_IND16, CGIC_ARENA_DMC8, CGIC_ARENA_DMM8, CGIC_ARENA_DMF8, CGIC_ARENA_QUANT,
+                                    CGIC_ARENA_BYTES, CGIC_ARENA_SIZES, CGIC_ARENA_STATUS, CGIC_ARENA_SQERR,
+                                    CGIC_ARENA_IND,   CGIC_ARENA_DMC,  CGIC_ARENA_DMM,  CGIC_ARENA_DMF,  CGIC_ARENA_IDX, CGIC_ARENA_ZQ};
     auto up = [](size_t v) { return (v + 255) / 256 * 256; };
     size_t in_total = 0, out_total = 0;
     for (int p = 0; p < parts; ++p) {
@@ -365,7 +375,7 @@ extern "C" int cgic_session_arena_tensor(const cgic_session *s, int what, int pa
     CGIC_REQUIRE(what >= 0 && what < CGIC_ARENA_COUNT && part >= 0 && part < s->a_parts && host_ptr, CGIC_EINVAL,
                  "cgic_session_arena_tensor: bad argument what=%d part=%d", what, part);
     const cgic_session::Part &P = s->part[part];
-    const bool is_in = what == CGIC_ARENA_Z || what == CGIC_ARENA_MC || what == CGIC_ARENA_MM || what == CGIC_ARENA_MF;
+    const bool is_in = arena_is_input(what);
     *host_ptr = (is_in ? s->h_in + P.in_off : s->h_out + P.out_off) + P.o[what];
     if (first_image) *first_image = P.b0;
     if (n_images) *n_images = P.nb;
@@ -375,7 +385,7 @@ extern "C" int cgic_session_arena_tensor(const cgic_session *s, int what, int pa
 extern "C" int cgic_session_arena_gather_device(cgic_session *s, int what, void *dst_device)
 {
     CGIC_REQUIRE(s && s->a_parts > 0 && dst_device, CGIC_EINVAL, "cgic_session_arena_gather_device: call cgic_session_arena first");
-    CGIC_REQUIRE(what >= CGIC_ARENA_BYTES && what < CGIC_ARENA_COUNT && what != CGIC_ARENA_SQERR, CGIC_EINVAL,
+    CGIC_REQUIRE(what >= 0 && what < CGIC_ARENA_COUNT && !arena_is_input(what) && what != CGIC_ARENA_SQERR, CGIC_EINVAL,
                  "cgic_session_arena_gather_device: tensor %d is not a per-image output", what);
     unsigned char *dst = static_cast<unsigned char *>(dst_device);
     cudaStream_t s0 = s->streams[0];
@@ -389,11 +399,79 @@ extern "C" int cgic_session_arena_gather_device(cgic_session *s, int what, void 
     return CGIC_OK;
 }
 
+// ---- narrow wire (flags bit 3): masks travel as one byte per cell, decoded indices as int16; the reference's types
+//      (int32 masks in, int64 tensors out) exist on the device only
+namespace {
+struct CastSegs {
+    const void *src[4];
+    void *dst[4];
+    unsigned n[4];  // elements; a thread converts four
+};
+
+__device__ __forceinline__ bool cast_segment(const CastSegs &a, int nseg, unsigned &q, int &seg)
+{
+    for (seg = 0; seg < nseg; ++seg) {
+        const unsigned quads = (a.n[seg] + 3) / 4;
+        if (q < quads) return true;
+        q -= quads;
+    }
+    return false;
+}
+
+// u8 masks of the host arena -> the int32 masks cgic_encode takes
+__global__ void widen_masks_kernel(CastSegs a)
+{
+    unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+    int seg;
+    if (!cast_segment(a, 3, q, seg)) return;
+    const uint8_t *src = static_cast<const uint8_t *>(a.src[seg]);
+    int32_t *dst = static_cast<int32_t *>(a.dst[seg]);
+    const unsigned i = q * 4, n = a.n[seg];
+    if (i + 4 <= n) {
+        const uchar4 v = *reinterpret_cast<const uchar4 *>(src + i);
+        *reinterpret_cast<int4 *>(dst + i) = make_int4(v.x, v.y, v.z, v.w);
+    } else {
+        for (unsigned k = i; k < n; ++k) dst[k] = src[k];
+    }
+}
+
+// decoded int64 tensors -> int16 indices (segment 0) and u8 masks (segments 1..3)
+__global__ void narrow_decoded_kernel(CastSegs a)
+{
+    unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+    int seg;
+    if (!cast_segment(a, 4, q, seg)) return;
+    const int64_t *src = static_cast<const int64_t *>(a.src[seg]);
+    const unsigned i = q * 4, n = a.n[seg];
+    if (i + 4 <= n) {
+        const longlong2 v0 = *reinterpret_cast<const longlong2 *>(src + i), v1 = *reinterpret_cast<const longlong2 *>(src + i + 2);
+        if (seg == 0)
+            *reinterpret_cast<short4 *>(static_cast<int16_t *>(a.dst[0]) + i) = make_short4((short)v0.x, (short)v0.y, (short)v1.x, (short)v1.y);
+        else
+            *reinterpret_cast<uchar4 *>(static_cast<uint8_t *>(a.dst[seg]) + i) =
+                make_uchar4((unsigned char)v0.x, (unsigned char)v0.y, (unsigned char)v1.x, (unsigned char)v1.y);
+    } else {
+        for (unsigned k = i; k < n; ++k) {
+            if (seg == 0)
+                static_cast<int16_t *>(a.dst[0])[k] = (int16_t)src[k];
+            else
+                static_cast<uint8_t *>(a.dst[seg])[k] = (uint8_t)src[k];
+        }
+    }
+}
+
+unsigned cast_blocks(const CastSegs &a, int nseg)
+{
+    unsigned quads = 0;
+    for (int i = 0; i < nseg; ++i) quads += (a.n[i] + 3) / 4;
+    return (quads + 255) / 256;
+}
+}  // namespace
+
 // enqueues the whole round trip of every part (part p on streams[p]); used eagerly once and then under capture
 static int arena_enqueue(cgic_session *s, int flags)
 {
-    const size_t i4 = (size_t)s->h * s->w;
-    (void)i4;
+    const bool narrow = (flags & 8) != 0;
     cudaStream_t s0 = s->streams[0];
     CGIC_CUDA_CHECK(cudaEventRecord(s->fork, s0));
     for (int p = 0; p < s->a_parts; ++p) {
@@ -403,7 +481,20 @@ static int arena_enqueue(cgic_session *s, int flags)
         unsigned char *di = s->d_in + P.in_off, *dout = s->d_out + P.out_off;
         auto in = [&](int what) { return di + P.o[what]; };
         auto out = [&](int what) { return dout + P.o[what]; };
-        CGIC_CUDA_CHECK(cudaMemcpyAsync(di, s->h_in + P.in_off, P.in_len, cudaMemcpyHostToDevice, st));
+        // H2D: one slice of the input block -- [m_c8 m_m8 m_f8 z] (narrow) or [z m_c m_m m_f]
+        const size_t in_lo = narrow ? 0 : P.o[CGIC_ARENA_Z], in_hi = narrow ? P.o[CGIC_ARENA_MC] : P.in_len;
+        CGIC_CUDA_CHECK(cudaMemcpyAsync(di + in_lo, s->h_in + P.in_off + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, st));
+        if (narrow) {
+            CastSegs a = {};
+            const int from[3] = {CGIC_ARENA_MC8, CGIC_ARENA_MM8, CGIC_ARENA_MF8}, to[3] = {CGIC_ARENA_MC, CGIC_ARENA_MM, CGIC_ARENA_MF};
+            for (int i = 0; i < 3; ++i) {
+                a.src[i] = in(from[i]);
+                a.dst[i] = in(to[i]);
+                a.n[i] = (unsigned)arena_count(s, to[i], P.nb);
+            }
+            widen_masks_kernel<<<cast_blocks(a, 3), 256, 0, st>>>(a);
+            CGIC_CUDA_CHECK(cudaGetLastError());
+        }
         int rc = cgic_encode(reinterpret_cast<const float *>(in(CGIC_ARENA_Z)), reinterpret_cast<const int32_t *>(in(CGIC_ARENA_MC)),
                              reinterpret_cast<const int32_t *>(in(CGIC_ARENA_MM)), reinterpret_cast<const int32_t *>(in(CGIC_ARENA_MF)), P.nb, s->h,
                              s->w, s->mode, s->index, s->table, reinterpret_cast<int64_t *>(out(CGIC_ARENA_IDX)),
@@ -417,10 +508,33 @@ static int arena_enqueue(cgic_session *s, int flags)
                          reinterpret_cast<float *>(out(CGIC_ARENA_QUANT)), reinterpret_cast<int32_t *>(out(CGIC_ARENA_STATUS)),
                          s->ws_un + p * s->ws_un_bytes, s->ws_un_bytes, st);
         if (rc) return rc;
-        // D2H: one copy of the block's head.  Bit 2 of flags: the decoded tensors (ind, quant, masks) stay in HBM for the
-        // decoder CNN, as model.py:391-399 hands them over -- only [bytes | sizes | status | sqerr] come back.
-        const size_t len = (flags & 4) ? P.o[CGIC_ARENA_IND] : ((flags & 2) ? P.out_all : ((flags & 1) ? P.out_idx : P.out_core));
-        CGIC_CUDA_CHECK(cudaMemcpyAsync(s->h_out + P.out_off, dout, len, cudaMemcpyDeviceToHost, st));
+        // D2H: one slice of the output block.
+        //   bit 2  the decoded tensors (ind, quant, masks) stay in HBM for the decoder CNN, as model.py:391-399 hands them
+        //          over: only [bytes | sizes | status | sqerr] come back;
+        //   bit 3  narrow wire: [ind16 | masks u8 | quant | bytes | sizes | status | sqerr];
+        //   else   the reference's types: [quant | bytes .. sqerr | ind | masks (int64)] (+ idx, + z_q on request).
+        size_t lo, hi;
+        if (flags & 4) {
+            lo = P.o[CGIC_ARENA_BYTES];
+            hi = P.o[CGIC_ARENA_IND];
+        } else if (narrow) {
+            CastSegs a = {};
+            const int from[4] = {CGIC_ARENA_IND, CGIC_ARENA_DMC, CGIC_ARENA_DMM, CGIC_ARENA_DMF},
+                      to[4] = {CGIC_ARENA_IND16, CGIC_ARENA_DMC8, CGIC_ARENA_DMM8, CGIC_ARENA_DMF8};
+            for (int i = 0; i < 4; ++i) {
+                a.src[i] = out(from[i]);
+                a.dst[i] = out(to[i]);
+                a.n[i] = (unsigned)arena_count(s, to[i], P.nb);
+            }
+            narrow_decoded_kernel<<<cast_blocks(a, 4), 256, 0, st>>>(a);
+            CGIC_CUDA_CHECK(cudaGetLastError());
+            lo = 0;
+            hi = P.o[CGIC_ARENA_IND];
+        } else {
+            lo = P.o[CGIC_ARENA_QUANT];
+            hi = (flags & 2) ? P.out_all : ((flags & 1) ? P.out_idx : P.out_core);
+        }
+        CGIC_CUDA_CHECK(cudaMemcpyAsync(s->h_out + P.out_off + lo, dout + lo, hi - lo, cudaMemcpyDeviceToHost, st));
         if (p) {
             CGIC_CUDA_CHECK(cudaEventRecord(s->join[p], st));
             CGIC_CUDA_CHECK(cudaStreamWaitEvent(s0, s->join[p], 0));
@@ -432,8 +546,9 @@ static int arena_enqueue(cgic_session *s, int flags)
 extern "C" int cgic_session_roundtrip_arena(cgic_session *s, int flags, double *sqerr_out)
 {
     CGIC_REQUIRE(s && s->a_parts > 0, CGIC_EINVAL, "cgic_session_roundtrip_arena: call cgic_session_arena first");
-    CGIC_REQUIRE(flags >= 0 && flags < 8 && (flags & 6) != 6 && (flags & 5) != 5, CGIC_EINVAL,
-                 "cgic_session_roundtrip_arena: flags %d (bit 2 excludes bits 0 and 1: idx / z_q lie behind the decoded tensors)", flags);
+    CGIC_REQUIRE(flags >= 0 && flags < 16 && !((flags & 12) && (flags & 3)), CGIC_EINVAL,
+                 "cgic_session_roundtrip_arena: flags %d (bits 2 and 3 exclude bits 0 and 1: idx / z_q lie behind the decoded tensors)", flags);
+    CGIC_REQUIRE(!(flags & 8) || s->K <= 32768, CGIC_EINVAL, "cgic_session_roundtrip_arena: the narrow wire carries indices as int16 (K = %d)", s->K);
     cudaStream_t s0 = s->streams[0];
     static const bool no_graph = getenv("CGIC_SESSION_NO_GRAPH") != nullptr;  // diagnosis only
     if (!s->warmed[flags] || no_graph) {

@@ -648,18 +648,25 @@ class Session:
     #      ranges pipelined, replayed as a CUDA graph (cgic_session_arena / cgic_session_roundtrip_arena)
     _ARENA = dict(z=(0, torch.float32), m_c=(1, torch.int32), m_m=(2, torch.int32), m_f=(3, torch.int32), bytes=(4, torch.uint8),
                   sizes=(5, torch.int32), status=(6, torch.int32), sqerr=(7, torch.float64), ind=(8, torch.int64), quant=(9, torch.float32),
-                  mc=(10, torch.int64), mm=(11, torch.int64), mf=(12, torch.int64), idx=(13, torch.int64), zq=(14, torch.float32))
+                  mc=(10, torch.int64), mm=(11, torch.int64), mf=(12, torch.int64), idx=(13, torch.int64), zq=(14, torch.float32),
+                  # narrow wire (roundtrip_arena(narrow=True)): masks in as bytes; int16 indices and byte masks out
+                  m_c8=(15, torch.uint8), m_m8=(16, torch.uint8), m_f8=(17, torch.uint8), ind16=(18, torch.int16),
+                  mc8=(19, torch.uint8), mm8=(20, torch.uint8), mf8=(21, torch.uint8))
 
     def arena(self, parts: int = 8):
         """Fixes the number of image ranges and returns a list (one entry per range) of dicts of host tensor
         VIEWS into the session's pinned arenas: inputs z, m_c, m_m, m_f (fill them before roundtrip_arena) and
-        outputs bytes, sizes, status, ind, quant, mc, mm, mf, idx, zq (valid after it), plus `images` = range."""
+        outputs bytes, sizes, status, ind, quant, mc, mm, mf, idx, zq (valid after it), plus `images` = range.
+        Narrow wire: inputs m_c8, m_m8, m_f8 (uint8) replace m_c, m_m, m_f; outputs ind16, mc8, mm8, mf8 replace
+        ind, mc, mm, mf."""
         check(lib().cgic_session_arena(self._s, int(parts)), "cgic_session_arena")
         h, w = self.h, self.w
         shapes = dict(z=lambda n: (n, 4, h, w), m_c=lambda n: (n, 1, h // 4, w // 4), m_m=lambda n: (n, 1, h // 2, w // 2),
                       m_f=lambda n: (n, 1, h, w), bytes=lambda n: (n, self.image_stride), sizes=lambda n: (n, 5), status=lambda n: (n,),
                       sqerr=lambda n: (1,), ind=lambda n: (n, h, w), quant=lambda n: (n, 4, h, w), mc=lambda n: (n, h // 4, w // 4),
                       mm=lambda n: (n, h // 2, w // 2), mf=lambda n: (n, h, w), idx=lambda n: (n * h * w,), zq=lambda n: (n, 4, h, w))
+        shapes.update(m_c8=shapes["m_c"], m_m8=shapes["m_m"], m_f8=shapes["m_f"], ind16=shapes["ind"], mc8=shapes["mc"], mm8=shapes["mm"],
+                      mf8=shapes["mf"])
         views = []
         p = 0
         while True:
@@ -679,11 +686,13 @@ class Session:
         self._arena_views = views
         return views
 
-    def roundtrip_arena(self, want_idx: bool = False, want_zq: bool = False, decoded_on_device: bool = False) -> float:
+    def roundtrip_arena(self, want_idx: bool = False, want_zq: bool = False, decoded_on_device: bool = False, narrow: bool = False) -> float:
         """CGIC.compress on the arena contents; returns sum((e - z)^2) over the batch.  decoded_on_device: the decoded
-        tensors (ind, quant, mc, mm, mf) stay in HBM (fetch them with device_tensor); only bytes / sizes / status return."""
+        tensors (ind, quant, mc, mm, mf) stay in HBM (fetch them with device_tensor); only bytes / sizes / status return.
+        narrow: the masks are taken from m_c8 / m_m8 / m_f8 and the decoded tensors come back as ind16 / mc8 / mm8 / mf8
+        (+ quant); the int64 tensors of the reference stay on the device."""
         sq = C.c_double()
-        flags = 4 if decoded_on_device else int(want_idx) | (int(want_zq) << 1)
+        flags = (4 if decoded_on_device else int(want_idx) | (int(want_zq) << 1)) | (8 if narrow else 0)
         check(lib().cgic_session_roundtrip_arena(self._s, flags, C.byref(sq)), "cgic_session_roundtrip_arena")
         return sq.value
 
@@ -693,7 +702,8 @@ class Session:
         what, dtype = self._ARENA[name]
         B, h, w = self.B, self.h, self.w
         shape = dict(bytes=(B, self.image_stride), sizes=(B, 5), status=(B,), ind=(B, h, w), quant=(B, 4, h, w), mc=(B, h // 4, w // 4),
-                     mm=(B, h // 2, w // 2), mf=(B, h, w), idx=(B * h * w,), zq=(B, 4, h, w))[name]
+                     mm=(B, h // 2, w // 2), mf=(B, h, w), idx=(B * h * w,), zq=(B, 4, h, w), ind16=(B, h, w), mc8=(B, h // 4, w // 4),
+                     mm8=(B, h // 2, w // 2), mf8=(B, h, w))[name]
         out = torch.empty(shape, dtype=dtype, device="cuda")
         check(lib().cgic_session_arena_gather_device(self._s, what, out.data_ptr()), "cgic_session_arena_gather_device")
         return out

@@ -314,16 +314,24 @@ CGIC_API int cgic_session_roundtrip_host(cgic_session *s, const float *z, const 
  *   cgic_session_roundtrip_arena  flags: bit 0 also return idx (VQ indices), bit 1 also z_q; bit 2 (alone): the
  *                             decoded tensors (IND, QUANT, DMC, DMM, DMF) stay in HBM for the decoder CNN, as
  *                             model.py:391-399 hands them over -- only BYTES, SIZES, STATUS, SQERR come back to the host;
+ *                             bit 3 (excludes bits 0, 1; K <= 32768): NARROW WIRE -- the masks are read from MC8 / MM8 / MF8
+ *                             (one byte per cell) instead of MC / MM / MF and widened on the device; the decoded tensors
+ *                             come back as IND16 (int16) and DMC8 / DMM8 / DMF8 (uint8) next to QUANT, BYTES, SIZES,
+ *                             STATUS, SQERR -- the reference's int64 tensors (IND, DMC, DMM, DMF) stay on the device
+ *                             (cgic_session_arena_gather_device).  9.9 MB instead of 15.4 MB per 64 images of 256 x 256;
  *   cgic_session_arena_gather_device  copies output tensor `what` of all ranges, in image order, into one contiguous
  *                             DEVICE buffer of the caller (device to device, then synchronises).
  * Tensor shapes per range of nb images: Z/QUANT/ZQ fp32 [nb,4,h,w]; MC/MM/MF int32 [nb,1,.,.]; BYTES
  * uint8 [nb,image_stride]; SIZES int32 [nb,5]; STATUS int32 [nb]; SQERR double[1]; IND/IDX int64 [nb,h,w];
- * DMC/DMM/DMF int64 [nb,.,.]. */
+ * DMC/DMM/DMF int64 [nb,.,.]; MC8/MM8/MF8/DMC8/DMM8/DMF8 uint8, IND16 int16, same shapes as their wide twins. */
 enum {
     CGIC_ARENA_Z = 0, CGIC_ARENA_MC, CGIC_ARENA_MM, CGIC_ARENA_MF,          /* inputs */
     CGIC_ARENA_BYTES, CGIC_ARENA_SIZES, CGIC_ARENA_STATUS, CGIC_ARENA_SQERR, /* outputs */
     CGIC_ARENA_IND, CGIC_ARENA_QUANT, CGIC_ARENA_DMC, CGIC_ARENA_DMM, CGIC_ARENA_DMF,
-    CGIC_ARENA_IDX, CGIC_ARENA_ZQ, CGIC_ARENA_COUNT
+    CGIC_ARENA_IDX, CGIC_ARENA_ZQ,
+    CGIC_ARENA_MC8, CGIC_ARENA_MM8, CGIC_ARENA_MF8,                          /* narrow wire: masks in, one byte per cell */
+    CGIC_ARENA_IND16, CGIC_ARENA_DMC8, CGIC_ARENA_DMM8, CGIC_ARENA_DMF8,     /* narrow wire: int16 indices, u8 masks out */
+    CGIC_ARENA_COUNT
 };
 CGIC_API int cgic_session_arena(cgic_session *s, int parts);
 CGIC_API int cgic_session_arena_tensor(const cgic_session *s, int what, int part, void **host_ptr, int *first_image,

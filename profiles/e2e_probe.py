@@ -30,10 +30,24 @@ for parts in parts_list:
     for v in views:
         r = v["images"]; v["z"].copy_(zh[r.start:r.stop])
         for name, src in zip(("m_c", "m_m", "m_f"), mh): v[name].copy_(src[r.start:r.stop])
+        for name, src in zip(("m_c8", "m_m8", "m_f8"), mh): v[name].copy_(src[r.start:r.stop].to(torch.uint8))
     print("arena parts", parts, "graph" if not os.environ.get("CGIC_SESSION_NO_GRAPH") else "eager", "us:", round(timeit(sess.roundtrip_arena), 1),
-          "| decoded tensors left on the device us:", round(timeit(lambda: sess.roundtrip_arena(decoded_on_device=True)), 1))
+          "| narrow wire us:", round(timeit(lambda: sess.roundtrip_arena(narrow=True)), 1),
+          "| decoded tensors left on the device us:", round(timeit(lambda: sess.roundtrip_arena(decoded_on_device=True)), 1),
+          "| + byte masks in us:", round(timeit(lambda: sess.roundtrip_arena(decoded_on_device=True, narrow=True)), 1))
 # raw copies of the arena-sized buffers through torch for reference
 a = torch.empty(5570560, dtype=torch.uint8).pin_memory(); d = torch.empty(9878016, dtype=torch.uint8, device=dev); b = torch.empty(9878016, dtype=torch.uint8).pin_memory(); da = torch.empty_like(a, device=dev)
 def cp():
     da.copy_(a, non_blocking=True); b.copy_(d, non_blocking=True); torch.cuda.synchronize()
 print("torch H2D 5.57MB + D2H 9.88MB serial us:", round(timeit(cp), 1))
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+def cp2():
+    with torch.cuda.stream(s1): da.copy_(a, non_blocking=True)
+    with torch.cuda.stream(s2): b.copy_(d, non_blocking=True)
+    torch.cuda.synchronize()
+print("torch H2D 5.57MB + D2H 9.88MB on two streams us:", round(timeit(cp2), 1))
+def h2d():
+    da.copy_(a, non_blocking=True); torch.cuda.synchronize()
+def d2h():
+    b.copy_(d, non_blocking=True); torch.cuda.synchronize()
+print("torch H2D 5.57MB alone us:", round(timeit(h2d), 1), "| D2H 9.88MB alone us:", round(timeit(d2h), 1))

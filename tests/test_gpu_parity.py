@@ -515,6 +515,39 @@ def test_session_host_roundtrip(cg, orc):
             assert np.isclose(sq, float(sq_d), rtol=1e-12)
             if rep == 2:
                 assert torch.equal(torch.cat([v["zq"] for v in views]), zq_d.cpu())
+        # narrow wire: byte masks in, int16 indices + byte masks out (flags bit 3); the wide tensors stay on the device
+        for v in views:
+            r = v["images"]
+            for name, src in zip(("m_c8", "m_m8", "m_f8"), mh):
+                v[name].copy_(src[r.start:r.stop].to(torch.uint8))
+            for name in ("m_c", "m_m", "m_f"):
+                v[name].fill_(7)                 # must not be read
+            for name in ("ind16", "mc8", "mm8", "mf8", "quant", "sizes", "bytes"):
+                v[name].zero_()
+        for rep in range(3):
+            sq_n = sess.roundtrip_arena(narrow=True)
+            assert np.isclose(sq_n, float(sq_d), rtol=1e-12)
+            for v in views:
+                r = v["images"]
+                sl = slice(r.start, r.stop)
+                assert torch.equal(v["sizes"], sizes.cpu()[sl]) and int(v["status"].abs().sum()) == 0, (parts, rep)
+                assert v["ind16"].dtype == torch.int16 and torch.equal(v["ind16"].long().view(len(r), -1), idx_d.cpu().view(B, -1)[sl])
+                assert torch.equal(v["quant"], quant[sl])
+                for got, want in zip((v["mc8"], v["mm8"], v["mf8"]), masks):
+                    assert got.dtype == torch.uint8 and torch.equal(got.long(), want[sl, 0].long().cpu())
+                for i, b in enumerate(r):
+                    for st in range(5):
+                        assert torch.equal(v["bytes"][i, offs[st]: offs[st] + sz[b, st]], packed[b, offs[st]: offs[st] + sz[b, st]].cpu())
+        assert torch.equal(sess.device_tensor("ind").view(-1), idx_d) and torch.equal(sess.device_tensor("ind16").long().view(-1), idx_d)
+        assert torch.equal(sess.device_tensor("mf"), masks[2][:, 0].long())
+        sess.roundtrip_arena(narrow=True, decoded_on_device=True)      # byte masks in, only the streams back
+        assert torch.equal(torch.cat([v["sizes"] for v in views]), sizes.cpu())
+        with pytest.raises(RuntimeError):
+            sess.roundtrip_arena(narrow=True, want_idx=True)
+        for v in views:                          # the wide inputs again for the next `parts`
+            r = v["images"]
+            for name, src in zip(("m_c", "m_m", "m_f"), mh):
+                v[name].copy_(src[r.start:r.stop])
     sess.close()
 
 
