@@ -13,9 +13,10 @@ collective, one all-reduce of {bytes, pixels, sqerr} at the end ("scaling": "wea
 
     value     device-resident: inputs already in HBM, each step timed by a CUDA-event pair on the launching stream, L2
               flushed (256 MiB memset) between steps outside the pairs.
-    e2e       the host-buffer C-ABI call cgic_session_roundtrip_arena (= CGIC.compress, model.py:206-401: encode + pack +
-              unpack + re-assembly): pinned host inputs -> H2D -> kernels -> D2H of every result (streams, sizes, decoded
-              indices / masks / latents), wall clock, per step.  `e2e_decoded_on_device` is the same call leaving the decoded
+    e2e       the host-buffer C-ABI round trip (= CGIC.compress, model.py:206-401: encode + pack + unpack + re-assembly):
+              pinned host inputs -> H2D -> kernels -> D2H of every result (streams, sizes, decoded indices / masks /
+              latents), wall clock per step, two round trips in flight (cgic_session_roundtrip_arena_submit / _wait on the
+              session's two arena sets); `blocking_call_ms` is the single blocking call cgic_session_roundtrip_arena.  `e2e_decoded_on_device` is the same call leaving the decoded
               tensors in HBM for the decoder CNN (what model.py:391-399 does): only streams, sizes, status come back.
               `e2e_narrow_wire`: every result comes back, but masks travel as bytes and decoded indices as int16.
     configs   the other BASELINE configs through the same step: configs[2] (24 x 512x768 per GPU at its three ratios),
@@ -131,7 +132,7 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="headline workload only (skip the configs[2..4] lines)")
-    ap.add_argument("--e2e-parts", type=int, default=0, help="image ranges the pinned-arena round trip is pipelined in (0 = 8)")
+    ap.add_argument("--e2e-parts", type=int, default=0, help="image ranges the pinned-arena round trip is cut in (0 = 4)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -523,41 +524,55 @@ def run_b200(args):
     assert torch.equal(rt[1], sizes_first) and torch.equal(rt[5].view(-1), idx.cpu()) and int(rt[7].abs().sum()) == 0
     # the same call on the session's pinned arenas: one copy per direction and image range, ranges pipelined, CUDA graph
     n_e2e = max(10, args.steps)
-    e2e, e2e_parts = {}, {}
-    # image ranges: 8 pipeline the 15 MB of the full copy best; with the decoded tensors left on the device the D2H side is
-    # small and per-copy latency dominates: 2 ranges (profiles/e2e_probe.py)
-    for key, on_device, narrow, parts in (("full", False, False, args.e2e_parts or 8), ("narrow_wire", False, True, args.e2e_parts or 8),
-                                          ("decoded_on_device", True, False, 2)):
-        views = sess.arena(parts)
-        e2e_parts[key] = len(views)
-        for v in views:
-            r = v["images"]
-            v["z"].copy_(zh[r.start:r.stop])
-            for name, src in zip(("m_c8", "m_m8", "m_f8") if narrow else ("m_c", "m_m", "m_f"), mh):
-                v[name].copy_(src[r.start:r.stop].to(v[name].dtype))
-            v["sizes"].zero_()
-            v["ind"].zero_()
-            v["ind16"].zero_()
-        for _ in range(5):
-            sess.roundtrip_arena(decoded_on_device=on_device, narrow=narrow)
-        assert torch.equal(torch.cat([v["sizes"] for v in views]), sizes_first) and int(sum(int(v["status"].abs().sum()) for v in views)) == 0
-        if narrow:
-            assert torch.equal(torch.cat([v["ind16"].reshape(-1) for v in views]).long(), idx.cpu())
-            assert torch.equal(torch.cat([v["mf8"].reshape(-1) for v in views]).long(), mh[2].reshape(-1).long())
-        elif not on_device:
-            assert torch.equal(torch.cat([v["ind"].reshape(-1) for v in views]), idx.cpu())
-        else:
-            assert torch.equal(sess.device_tensor("ind").reshape(-1), idx)       # decoded tensors stayed in HBM, and are right
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            sess.roundtrip_arena(decoded_on_device=on_device, narrow=narrow)    # = CGIC.compress: encode + pack + unpack + re-assembly, pinned host in / out
-        e2e_s = time.perf_counter() - t0
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e[key] = float(t.item())
+    e2e, e2e_block, e2e_parts = {}, {}, {}
+    # Two round trips in flight (two arena sets, submit / wait): while one batch's results travel back the next one's
+    # inputs travel in.  4 image ranges per round trip: the most robust choice over the boxes probed (profiles/e2e_probe.py;
+    # host<->device copy rates on these VMs vary by up to 2x from box to box and run to run).  The blocking single call
+    # (cgic_session_roundtrip_arena: submit + wait) is timed next to it.
+    for key, on_device, narrow, parts in (("full", False, False, args.e2e_parts or 4), ("narrow_wire", False, True, args.e2e_parts or 4),
+                                          ("decoded_on_device", True, False, args.e2e_parts or 4)):
+        kw = dict(decoded_on_device=on_device, narrow=narrow)
+        sets = [sess.arena(parts, slot=k) for k in (0, 1)]
+        e2e_parts[key] = len(sets[0])
+        for views in sets:
+            for v in views:
+                r = v["images"]
+                v["z"].copy_(zh[r.start:r.stop])
+                for name, src in zip(("m_c8", "m_m8", "m_f8") if narrow else ("m_c", "m_m", "m_f"), mh):
+                    v[name].copy_(src[r.start:r.stop].to(v[name].dtype))
+                v["sizes"].zero_()
+                v["ind"].zero_()
+                v["ind16"].zero_()
+
+        def piped(n):
+            sess.submit_arena(0, **kw)
+            for i in range(1, n):
+                sess.submit_arena(i & 1, **kw)       # the next batch goes in ...
+                sess.wait_arena((i - 1) & 1)         # ... while the previous one comes back
+            sess.wait_arena((n - 1) & 1)
+
+        for _ in range(3):
+            sess.roundtrip_arena(**kw)
+        piped(6)
+        for k, views in enumerate(sets):
+            assert torch.equal(torch.cat([v["sizes"] for v in views]), sizes_first) and int(sum(int(v["status"].abs().sum()) for v in views)) == 0
+            if narrow:
+                assert torch.equal(torch.cat([v["ind16"].reshape(-1) for v in views]).long(), idx.cpu())
+                assert torch.equal(torch.cat([v["mf8"].reshape(-1) for v in views]).long(), mh[2].reshape(-1).long())
+            elif not on_device:
+                assert torch.equal(torch.cat([v["ind"].reshape(-1) for v in views]), idx.cpu())
+            else:
+                assert torch.equal(sess.device_tensor("ind", slot=k).reshape(-1), idx)   # decoded tensors stayed in HBM, and are right
+        for which, fn in (("blocking", lambda: [sess.roundtrip_arena(**kw) for _ in range(n_e2e)]), ("piped", lambda: piped(n_e2e))):
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            fn()                                     # = CGIC.compress n_e2e times: encode + pack + unpack + re-assembly, pinned host in / out
+            e2e_s = time.perf_counter() - t0
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            (e2e_block if which == "blocking" else e2e)[key] = float(t.item())
     t_end = time.time()
     n4, n8, n16 = B * h * w, B * h * w // 4, B * h * w // 16
     blob = B * sess.image_stride
@@ -601,14 +616,18 @@ def run_b200(args):
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config_of(args, world),
             "e2e": {"value": world * pixels * n_e2e / 1e6 / e2e["full"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": n_e2e, "ms_per_step": 1e3 * e2e["full"] / n_e2e, "call": "cgic_session_roundtrip_arena", "image_ranges": e2e_parts["full"]},
+                    "steps": n_e2e, "ms_per_step": 1e3 * e2e["full"] / n_e2e, "image_ranges": e2e_parts["full"], "in_flight": 2,
+                    "call": "cgic_session_roundtrip_arena_submit / _wait on the session's two pinned arena sets; every result comes back in the "
+                            "reference's types (int64 indices and masks, fp32 latents)",
+                    "blocking_call_ms": 1e3 * e2e_block["full"] / n_e2e},
             "e2e_narrow_wire": {"value": world * pixels * n_e2e / 1e6 / e2e["narrow_wire"], "unit": UNIT, "h2d_bytes_per_step": n4 * 16 + (n4 + n8 + n16),
                                 "d2h_bytes_per_step": d2h_wire + n4 * 2 + n4 * 16 + (n4 + n8 + n16), "ms_per_step": 1e3 * e2e["narrow_wire"] / n_e2e,
-                                "image_ranges": e2e_parts["narrow_wire"],
+                                "image_ranges": e2e_parts["narrow_wire"], "in_flight": 2, "blocking_call_ms": 1e3 * e2e_block["narrow_wire"] / n_e2e,
                                 "call": "cgic_session_roundtrip_arena(flags | 8): every result still comes back, masks as one byte per cell both ways "
                                         "and decoded indices as int16 (the reference's int32 / int64 tensors exist on the device only)"},
             "e2e_decoded_on_device": {"value": world * pixels * n_e2e / 1e6 / e2e["decoded_on_device"], "unit": UNIT, "h2d_bytes_per_step": h2d,
                                       "d2h_bytes_per_step": d2h_wire, "ms_per_step": 1e3 * e2e["decoded_on_device"] / n_e2e, "image_ranges": e2e_parts["decoded_on_device"],
+                                      "in_flight": 2, "blocking_call_ms": 1e3 * e2e_block["decoded_on_device"] / n_e2e,
                                       "call": "cgic_session_roundtrip_arena(flags | 4): streams, sizes, status come back; ind / quant / masks stay "
                                               "in HBM for the decoder CNN, as in model.py:391-399"},
             "gpu_launches": kernels_per_step * args.steps, "kernels_per_step": kernels_per_step, "cuda_graph": graph is not None,

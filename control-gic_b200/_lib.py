@@ -85,6 +85,10 @@ _SIGNATURES = {
     "cgic_session_arena_tensor": (c_int, [c_void_p, c_int, c_int, C.POINTER(c_void_p), C.POINTER(c_int), C.POINTER(c_int)]),
     "cgic_session_roundtrip_arena": (c_int, [c_void_p, c_int, c_void_p]),
     "cgic_session_arena_gather_device": (c_int, [c_void_p, c_int, c_void_p]),
+    "cgic_session_arena_slot_tensor": (c_int, [c_void_p, c_int, c_int, c_int, C.POINTER(c_void_p), C.POINTER(c_int), C.POINTER(c_int)]),
+    "cgic_session_roundtrip_arena_submit": (c_int, [c_void_p, c_int, c_int]),
+    "cgic_session_roundtrip_arena_wait": (c_int, [c_void_p, c_int, c_void_p]),
+    "cgic_session_arena_slot_gather_device": (c_int, [c_void_p, c_int, c_int, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -38,16 +38,25 @@ struct cgic_session {
     // either block; reference types: from z / quant on), so a range moves with one H2D and one D2H copy; the whole
     // call is a CUDA graph of per-range branches.
     int a_parts = 0;
-    unsigned char *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr;
-    size_t in_bytes = 0, out_bytes = 0;
+    size_t in_bytes = 0, out_bytes = 0;  // size of one arena set
     struct Part {
         int b0 = 0, nb = 0;
         size_t in_off = 0, in_len = 0, out_off = 0, out_core = 0, out_idx = 0, out_all = 0;  // ends of the D2H slice by request
         size_t o[CGIC_ARENA_COUNT] = {};  // offset of every tensor inside its block
     } part[MAX_PARTS];
-    cudaGraphExec_t graph[16] = {};  // by flags (bit 0: idx, bit 1: zq, bit 2: decoded tensors stay on the device, bit 3: narrow wire)
-    cudaEvent_t fork = nullptr, join[MAX_PARTS] = {};
-    bool warmed[16] = {};
+    // Two independent arena sets ("slots"), so that a caller can keep two round trips in flight: while the results of
+    // slot 0 travel back, the inputs of slot 1 travel in (cgic_session_roundtrip_arena_submit / _wait).  Slot 0 shares
+    // the session's streams and workspaces with the other session calls; slot 1 has its own and is allocated on first use.
+    static constexpr int SLOTS = 2;
+    struct Slot {
+        unsigned char *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr;
+        unsigned char *ws = nullptr;           // slot 1: its own workspaces (MAX_PARTS x ws_en, then MAX_PARTS x ws_un)
+        cudaStream_t streams[MAX_PARTS] = {};  // slot 0: the session's
+        cudaGraphExec_t graph[16] = {};  // by flags (bit 0: idx, bit 1: zq, bit 2: decoded tensors stay on the device, bit 3: narrow wire)
+        bool warmed[16] = {};
+        cudaEvent_t fork = nullptr, join[MAX_PARTS] = {};
+        int in_flight = -1;                    // flags of the submitted, not yet awaited round trip
+    } slot[SLOTS];
 };
 
 extern "C" int cgic_session_create(int B, int h, int w, int mode, const cgic_table *t, const float *codebook_host, int K,
@@ -133,15 +142,22 @@ extern "C" void cgic_session_destroy(cgic_session *s)
     if (!s) return;
     for (cudaStream_t st : s->streams)
         if (st) cudaStreamDestroy(st);
-    for (cudaGraphExec_t g : s->graph)
-        if (g) cudaGraphExecDestroy(g);
-    if (s->fork) cudaEventDestroy(s->fork);
-    for (cudaEvent_t e : s->join)
-        if (e) cudaEventDestroy(e);
-    if (s->h_in) cudaFreeHost(s->h_in);
-    if (s->h_out) cudaFreeHost(s->h_out);
-    if (s->d_in) cudaFree(s->d_in);
-    if (s->d_out) cudaFree(s->d_out);
+    for (int k = 0; k < cgic_session::SLOTS; ++k) {
+        cgic_session::Slot &S = s->slot[k];
+        for (cudaGraphExec_t g : S.graph)
+            if (g) cudaGraphExecDestroy(g);
+        if (S.fork) cudaEventDestroy(S.fork);
+        for (cudaEvent_t e : S.join)
+            if (e) cudaEventDestroy(e);
+        if (k)
+            for (cudaStream_t st : S.streams)
+                if (st) cudaStreamDestroy(st);
+        if (S.h_in) cudaFreeHost(S.h_in);
+        if (S.h_out) cudaFreeHost(S.h_out);
+        if (S.d_in) cudaFree(S.d_in);
+        if (S.d_out) cudaFree(S.d_out);
+        if (S.ws) cudaFree(S.ws);
+    }
     if (s->index) cgic_codebook_free(s->index);
     if (s->packed) cudaEventDestroy(s->packed);
     if (s->arena) cudaFree(s->arena);
@@ -303,17 +319,22 @@ static size_t arena_count(const cgic_session *s, int what, int nb)
     }
 }
 
+static int slot_ready(cgic_session *s, int k);
+
 extern "C" int cgic_session_arena(cgic_session *s, int parts)
 {
     CGIC_REQUIRE(s && parts >= 1 && parts <= cgic_session::MAX_PARTS, CGIC_EINVAL, "cgic_session_arena: parts must be in [1, %d]",
                  cgic_session::MAX_PARTS);
     if (parts > s->B) parts = s->B;
     if (parts == s->a_parts) return CGIC_OK;
-    for (cudaGraphExec_t &g : s->graph) {
-        if (g) cudaGraphExecDestroy(g);
-        g = nullptr;
+    for (cgic_session::Slot &S : s->slot) {
+        CGIC_REQUIRE(S.in_flight < 0, CGIC_EINVAL, "cgic_session_arena: a submitted round trip has not been awaited");
+        for (cudaGraphExec_t &g : S.graph) {
+            if (g) cudaGraphExecDestroy(g);
+            g = nullptr;
+        }
+        for (bool &w : S.warmed) w = false;
     }
-    for (bool &w : s->warmed) w = false;
     static const int in_order[] = {CGIC_ARENA_MC8, CGIC_ARENA_MM8, CGIC_ARENA_MF8, CGIC_ARENA_Z, CGIC_ARENA_MC, CGIC_ARENA_MM, CGIC_ARENA_MF};
     static const int out_order[] = {CGIC_ARENA_IND16, CGIC_ARENA_DMC8, CGIC_ARENA_DMM8, CGIC_ARENA_DMF8, CGIC_ARENA_QUANT,
                                     CGIC_ARENA_BYTES, CGIC_ARENA_SIZES, CGIC_ARENA_STATUS, CGIC_ARENA_SQERR,
@@ -343,60 +364,105 @@ extern "C" int cgic_session_arena(cgic_session *s, int parts)
         P.out_all = o;
         out_total += o;
     }
-    if (in_total > s->in_bytes || out_total > s->out_bytes || !s->h_in) {
-        if (s->h_in) cudaFreeHost(s->h_in);
-        if (s->h_out) cudaFreeHost(s->h_out);
-        if (s->d_in) cudaFree(s->d_in);
-        if (s->d_out) cudaFree(s->d_out);
-        s->h_in = s->h_out = s->d_in = s->d_out = nullptr;
-        cudaError_t e = cudaMallocHost(&s->h_in, in_total);
-        if (e == cudaSuccess) e = cudaMallocHost(&s->h_out, out_total);
-        if (e == cudaSuccess) e = cudaMalloc(&s->d_in, in_total);
-        if (e == cudaSuccess) e = cudaMalloc(&s->d_out, out_total);
-        if (e == cudaSuccess) e = cudaMemset(s->d_out, 0, out_total);
-        if (e != cudaSuccess) {
-            cgic::set_error("cgic_session_arena: %s", cudaGetErrorString(e));
-            return e == cudaErrorMemoryAllocation ? CGIC_ENOMEM : CGIC_ECUDA;
+    if (in_total > s->in_bytes || out_total > s->out_bytes) {
+        for (cgic_session::Slot &S : s->slot) {  // the sets are re-created at the new size (slot 1: on its next use)
+            if (S.h_in) cudaFreeHost(S.h_in);
+            if (S.h_out) cudaFreeHost(S.h_out);
+            if (S.d_in) cudaFree(S.d_in);
+            if (S.d_out) cudaFree(S.d_out);
+            S.h_in = S.h_out = S.d_in = S.d_out = nullptr;
         }
         s->in_bytes = in_total;
         s->out_bytes = out_total;
     }
-    if (!s->fork) {
-        CGIC_CUDA_CHECK(cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming));
-        for (cudaEvent_t &e : s->join) CGIC_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    }
     s->a_parts = parts;
+    return slot_ready(s, 0);
+}
+
+// allocates what slot `k` still lacks (arena set, events; slot 1: streams and workspaces)
+static int slot_ready(cgic_session *s, int k)
+{
+    cgic_session::Slot &S = s->slot[k];
+    if (!S.h_in) {
+        cudaError_t e = cudaMallocHost(&S.h_in, s->in_bytes);
+        if (e == cudaSuccess) e = cudaMallocHost(&S.h_out, s->out_bytes);
+        if (e == cudaSuccess) e = cudaMalloc(&S.d_in, s->in_bytes);
+        if (e == cudaSuccess) e = cudaMalloc(&S.d_out, s->out_bytes);
+        if (e == cudaSuccess) e = cudaMemset(S.d_out, 0, s->out_bytes);
+        if (e != cudaSuccess) {
+            cgic::set_error("cgic_session_arena: %s", cudaGetErrorString(e));
+            return e == cudaErrorMemoryAllocation ? CGIC_ENOMEM : CGIC_ECUDA;
+        }
+    }
+    if (!S.fork) {
+        CGIC_CUDA_CHECK(cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming));
+        for (cudaEvent_t &e : S.join) CGIC_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    if (!S.streams[0]) {
+        if (k == 0) {
+            for (int i = 0; i < cgic_session::MAX_PARTS; ++i) S.streams[i] = s->streams[i];
+        } else {
+            for (cudaStream_t &st : S.streams) CGIC_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            const size_t bytes = (s->ws_en_bytes + s->ws_un_bytes) * cgic_session::MAX_PARTS;
+            CGIC_CUDA_CHECK(cudaMalloc(&S.ws, bytes));
+            CGIC_CUDA_CHECK(cudaMemset(S.ws, 0, bytes));  // workspaces start zeroed (cgic_vq_assign's contract)
+        }
+    }
     return CGIC_OK;
 }
 
-extern "C" int cgic_session_arena_tensor(const cgic_session *s, int what, int part, void **host_ptr, int *first_image, int *n_images)
+static int slot_of(cgic_session *s, int k, const char *who, cgic_session::Slot **out)
 {
-    CGIC_REQUIRE(s && s->a_parts > 0, CGIC_EINVAL, "cgic_session_arena_tensor: call cgic_session_arena first");
+    CGIC_REQUIRE(s && s->a_parts > 0, CGIC_EINVAL, "%s: call cgic_session_arena first", who);
+    CGIC_REQUIRE(k >= 0 && k < cgic_session::SLOTS, CGIC_EINVAL, "%s: slot must be 0 or 1", who);
+    int rc = slot_ready(s, k);
+    if (rc) return rc;
+    *out = &s->slot[k];
+    return CGIC_OK;
+}
+
+extern "C" int cgic_session_arena_slot_tensor(cgic_session *s, int slot, int what, int part, void **host_ptr, int *first_image, int *n_images)
+{
+    cgic_session::Slot *S = nullptr;
+    int rc = slot_of(s, slot, "cgic_session_arena_slot_tensor", &S);
+    if (rc) return rc;
     CGIC_REQUIRE(what >= 0 && what < CGIC_ARENA_COUNT && part >= 0 && part < s->a_parts && host_ptr, CGIC_EINVAL,
-                 "cgic_session_arena_tensor: bad argument what=%d part=%d", what, part);
+                 "cgic_session_arena_slot_tensor: bad argument what=%d part=%d", what, part);
     const cgic_session::Part &P = s->part[part];
-    const bool is_in = arena_is_input(what);
-    *host_ptr = (is_in ? s->h_in + P.in_off : s->h_out + P.out_off) + P.o[what];
+    *host_ptr = (arena_is_input(what) ? S->h_in + P.in_off : S->h_out + P.out_off) + P.o[what];
     if (first_image) *first_image = P.b0;
     if (n_images) *n_images = P.nb;
     return CGIC_OK;
 }
 
-extern "C" int cgic_session_arena_gather_device(cgic_session *s, int what, void *dst_device)
+extern "C" int cgic_session_arena_tensor(const cgic_session *s, int what, int part, void **host_ptr, int *first_image, int *n_images)
 {
-    CGIC_REQUIRE(s && s->a_parts > 0 && dst_device, CGIC_EINVAL, "cgic_session_arena_gather_device: call cgic_session_arena first");
-    CGIC_REQUIRE(what >= 0 && what < CGIC_ARENA_COUNT && !arena_is_input(what) && what != CGIC_ARENA_SQERR, CGIC_EINVAL,
-                 "cgic_session_arena_gather_device: tensor %d is not a per-image output", what);
+    return cgic_session_arena_slot_tensor(const_cast<cgic_session *>(s), 0, what, part, host_ptr, first_image, n_images);
+}
+
+extern "C" int cgic_session_arena_slot_gather_device(cgic_session *s, int slot, int what, void *dst_device)
+{
+    cgic_session::Slot *S = nullptr;
+    int rc = slot_of(s, slot, "cgic_session_arena_slot_gather_device", &S);
+    if (rc) return rc;
+    CGIC_REQUIRE(dst_device && what >= 0 && what < CGIC_ARENA_COUNT && !arena_is_input(what) && what != CGIC_ARENA_SQERR, CGIC_EINVAL,
+                 "cgic_session_arena_slot_gather_device: tensor %d is not a per-image output", what);
+    CGIC_REQUIRE(S->in_flight < 0, CGIC_EINVAL, "cgic_session_arena_slot_gather_device: slot %d has a round trip in flight", slot);
     unsigned char *dst = static_cast<unsigned char *>(dst_device);
-    cudaStream_t s0 = s->streams[0];
+    cudaStream_t s0 = S->streams[0];
     for (int p = 0; p < s->a_parts; ++p) {
         const cgic_session::Part &P = s->part[p];
         const size_t bytes = arena_count(s, what, P.nb) * arena_elem_bytes(what);
-        CGIC_CUDA_CHECK(cudaMemcpyAsync(dst, s->d_out + P.out_off + P.o[what], bytes, cudaMemcpyDeviceToDevice, s0));
+        CGIC_CUDA_CHECK(cudaMemcpyAsync(dst, S->d_out + P.out_off + P.o[what], bytes, cudaMemcpyDeviceToDevice, s0));
         dst += bytes;
     }
     CGIC_CUDA_CHECK(cudaStreamSynchronize(s0));
     return CGIC_OK;
+}
+
+extern "C" int cgic_session_arena_gather_device(cgic_session *s, int what, void *dst_device)
+{
+    return cgic_session_arena_slot_gather_device(s, 0, what, dst_device);
 }
 
 // ---- narrow wire (flags bit 3): masks travel as one byte per cell, decoded indices as int16; the reference's types
@@ -469,21 +535,22 @@ unsigned cast_blocks(const CastSegs &a, int nseg)
 }  // namespace
 
 // enqueues the whole round trip of every part (part p on streams[p]); used eagerly once and then under capture
-static int arena_enqueue(cgic_session *s, int flags)
+static int arena_enqueue(cgic_session *s, cgic_session::Slot &S, int flags)
 {
     const bool narrow = (flags & 8) != 0;
-    cudaStream_t s0 = s->streams[0];
-    CGIC_CUDA_CHECK(cudaEventRecord(s->fork, s0));
+    cudaStream_t s0 = S.streams[0];
+    unsigned char *ws_en = S.ws ? S.ws : s->ws_en, *ws_un = S.ws ? S.ws + s->ws_en_bytes * cgic_session::MAX_PARTS : s->ws_un;
+    CGIC_CUDA_CHECK(cudaEventRecord(S.fork, s0));
     for (int p = 0; p < s->a_parts; ++p) {
         const cgic_session::Part &P = s->part[p];
-        cudaStream_t st = s->streams[p];
-        if (p) CGIC_CUDA_CHECK(cudaStreamWaitEvent(st, s->fork, 0));
-        unsigned char *di = s->d_in + P.in_off, *dout = s->d_out + P.out_off;
+        cudaStream_t st = S.streams[p];
+        if (p) CGIC_CUDA_CHECK(cudaStreamWaitEvent(st, S.fork, 0));
+        unsigned char *di = S.d_in + P.in_off, *dout = S.d_out + P.out_off;
         auto in = [&](int what) { return di + P.o[what]; };
         auto out = [&](int what) { return dout + P.o[what]; };
         // H2D: one slice of the input block -- [m_c8 m_m8 m_f8 z] (narrow) or [z m_c m_m m_f]
         const size_t in_lo = narrow ? 0 : P.o[CGIC_ARENA_Z], in_hi = narrow ? P.o[CGIC_ARENA_MC] : P.in_len;
-        CGIC_CUDA_CHECK(cudaMemcpyAsync(di + in_lo, s->h_in + P.in_off + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, st));
+        CGIC_CUDA_CHECK(cudaMemcpyAsync(di + in_lo, S.h_in + P.in_off + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, st));
         if (narrow) {
             CastSegs a = {};
             const int from[3] = {CGIC_ARENA_MC8, CGIC_ARENA_MM8, CGIC_ARENA_MF8}, to[3] = {CGIC_ARENA_MC, CGIC_ARENA_MM, CGIC_ARENA_MF};
@@ -499,14 +566,14 @@ static int arena_enqueue(cgic_session *s, int flags)
                              reinterpret_cast<const int32_t *>(in(CGIC_ARENA_MM)), reinterpret_cast<const int32_t *>(in(CGIC_ARENA_MF)), P.nb, s->h,
                              s->w, s->mode, s->index, s->table, reinterpret_cast<int64_t *>(out(CGIC_ARENA_IDX)),
                              (flags & 2) ? reinterpret_cast<float *>(out(CGIC_ARENA_ZQ)) : nullptr, reinterpret_cast<double *>(out(CGIC_ARENA_SQERR)),
-                             out(CGIC_ARENA_BYTES), reinterpret_cast<int32_t *>(out(CGIC_ARENA_SIZES)), s->ws_en + p * s->ws_en_bytes,
+                             out(CGIC_ARENA_BYTES), reinterpret_cast<int32_t *>(out(CGIC_ARENA_SIZES)), ws_en + p * s->ws_en_bytes,
                              s->ws_en_bytes, st);
         if (rc) return rc;
         rc = cgic_unpack(out(CGIC_ARENA_BYTES), reinterpret_cast<const int32_t *>(out(CGIC_ARENA_SIZES)), P.nb, s->h, s->w, s->mode, s->table,
                          s->codebook, reinterpret_cast<int64_t *>(out(CGIC_ARENA_DMC)), reinterpret_cast<int64_t *>(out(CGIC_ARENA_DMM)),
                          reinterpret_cast<int64_t *>(out(CGIC_ARENA_DMF)), reinterpret_cast<int64_t *>(out(CGIC_ARENA_IND)),
                          reinterpret_cast<float *>(out(CGIC_ARENA_QUANT)), reinterpret_cast<int32_t *>(out(CGIC_ARENA_STATUS)),
-                         s->ws_un + p * s->ws_un_bytes, s->ws_un_bytes, st);
+                         ws_un + p * s->ws_un_bytes, s->ws_un_bytes, st);
         if (rc) return rc;
         // D2H: one slice of the output block.
         //   bit 2  the decoded tensors (ind, quant, masks) stay in HBM for the decoder CNN, as model.py:391-399 hands them
@@ -534,50 +601,71 @@ static int arena_enqueue(cgic_session *s, int flags)
             lo = P.o[CGIC_ARENA_QUANT];
             hi = (flags & 2) ? P.out_all : ((flags & 1) ? P.out_idx : P.out_core);
         }
-        CGIC_CUDA_CHECK(cudaMemcpyAsync(s->h_out + P.out_off + lo, dout + lo, hi - lo, cudaMemcpyDeviceToHost, st));
+        CGIC_CUDA_CHECK(cudaMemcpyAsync(S.h_out + P.out_off + lo, dout + lo, hi - lo, cudaMemcpyDeviceToHost, st));
         if (p) {
-            CGIC_CUDA_CHECK(cudaEventRecord(s->join[p], st));
-            CGIC_CUDA_CHECK(cudaStreamWaitEvent(s0, s->join[p], 0));
+            CGIC_CUDA_CHECK(cudaEventRecord(S.join[p], st));
+            CGIC_CUDA_CHECK(cudaStreamWaitEvent(s0, S.join[p], 0));
         }
     }
     return CGIC_OK;
 }
 
-extern "C" int cgic_session_roundtrip_arena(cgic_session *s, int flags, double *sqerr_out)
+extern "C" int cgic_session_roundtrip_arena_submit(cgic_session *s, int slot, int flags)
 {
-    CGIC_REQUIRE(s && s->a_parts > 0, CGIC_EINVAL, "cgic_session_roundtrip_arena: call cgic_session_arena first");
+    cgic_session::Slot *Sp = nullptr;
+    int rc = slot_of(s, slot, "cgic_session_roundtrip_arena_submit", &Sp);
+    if (rc) return rc;
+    cgic_session::Slot &S = *Sp;
     CGIC_REQUIRE(flags >= 0 && flags < 16 && !((flags & 12) && (flags & 3)), CGIC_EINVAL,
                  "cgic_session_roundtrip_arena: flags %d (bits 2 and 3 exclude bits 0 and 1: idx / z_q lie behind the decoded tensors)", flags);
     CGIC_REQUIRE(!(flags & 8) || s->K <= 32768, CGIC_EINVAL, "cgic_session_roundtrip_arena: the narrow wire carries indices as int16 (K = %d)", s->K);
-    cudaStream_t s0 = s->streams[0];
+    CGIC_REQUIRE(S.in_flight < 0, CGIC_EINVAL, "cgic_session_roundtrip_arena_submit: slot %d already has a round trip in flight", slot);
+    cudaStream_t s0 = S.streams[0];
     static const bool no_graph = getenv("CGIC_SESSION_NO_GRAPH") != nullptr;  // diagnosis only
-    if (!s->warmed[flags] || no_graph) {
+    if (!S.warmed[flags] || no_graph) {
         // first call: eager (one-time attribute set-up inside the launchers must not happen under capture)
-        int rc = arena_enqueue(s, flags);
+        rc = arena_enqueue(s, S, flags);
         if (rc) return rc;
-        s->warmed[flags] = true;
+        S.warmed[flags] = true;
     } else {
-        if (!s->graph[flags]) {
+        if (!S.graph[flags]) {
             cudaGraph_t g = nullptr;
             CGIC_CUDA_CHECK(cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal));
-            int rc = arena_enqueue(s, flags);
+            rc = arena_enqueue(s, S, flags);
             cudaError_t e = cudaStreamEndCapture(s0, &g);
             if (rc) {
                 if (g) cudaGraphDestroy(g);
                 return rc;
             }
             CGIC_CUDA_CHECK(e);
-            e = cudaGraphInstantiate(&s->graph[flags], g, 0);
+            e = cudaGraphInstantiate(&S.graph[flags], g, 0);
             cudaGraphDestroy(g);
             CGIC_CUDA_CHECK(e);
         }
-        CGIC_CUDA_CHECK(cudaGraphLaunch(s->graph[flags], s0));
+        CGIC_CUDA_CHECK(cudaGraphLaunch(S.graph[flags], s0));
     }
-    CGIC_CUDA_CHECK(cudaStreamSynchronize(s0));
+    S.in_flight = flags;
+    return CGIC_OK;
+}
+
+extern "C" int cgic_session_roundtrip_arena_wait(cgic_session *s, int slot, double *sqerr_out)
+{
+    cgic_session::Slot *Sp = nullptr;
+    int rc = slot_of(s, slot, "cgic_session_roundtrip_arena_wait", &Sp);
+    if (rc) return rc;
+    CGIC_REQUIRE(Sp->in_flight >= 0, CGIC_EINVAL, "cgic_session_roundtrip_arena_wait: nothing was submitted on slot %d", slot);
+    Sp->in_flight = -1;
+    CGIC_CUDA_CHECK(cudaStreamSynchronize(Sp->streams[0]));
     if (sqerr_out) {
         double tot = 0.0;
-        for (int p = 0; p < s->a_parts; ++p) tot += *reinterpret_cast<const double *>(s->h_out + s->part[p].out_off + s->part[p].o[CGIC_ARENA_SQERR]);
+        for (int p = 0; p < s->a_parts; ++p) tot += *reinterpret_cast<const double *>(Sp->h_out + s->part[p].out_off + s->part[p].o[CGIC_ARENA_SQERR]);
         *sqerr_out = tot;  // fixed order: deterministic
     }
     return CGIC_OK;
+}
+
+extern "C" int cgic_session_roundtrip_arena(cgic_session *s, int flags, double *sqerr_out)
+{
+    int rc = cgic_session_roundtrip_arena_submit(s, 0, flags);
+    return rc ? rc : cgic_session_roundtrip_arena_wait(s, 0, sqerr_out);
 }

@@ -653,12 +653,12 @@ class Session:
                   m_c8=(15, torch.uint8), m_m8=(16, torch.uint8), m_f8=(17, torch.uint8), ind16=(18, torch.int16),
                   mc8=(19, torch.uint8), mm8=(20, torch.uint8), mf8=(21, torch.uint8))
 
-    def arena(self, parts: int = 8):
+    def arena(self, parts: int = 8, slot: int = 0):
         """Fixes the number of image ranges and returns a list (one entry per range) of dicts of host tensor
         VIEWS into the session's pinned arenas: inputs z, m_c, m_m, m_f (fill them before roundtrip_arena) and
         outputs bytes, sizes, status, ind, quant, mc, mm, mf, idx, zq (valid after it), plus `images` = range.
         Narrow wire: inputs m_c8, m_m8, m_f8 (uint8) replace m_c, m_m, m_f; outputs ind16, mc8, mm8, mf8 replace
-        ind, mc, mm, mf."""
+        ind, mc, mm, mf.  slot 1 is the second, independent arena set of submit_arena / wait_arena (same `parts`)."""
         check(lib().cgic_session_arena(self._s, int(parts)), "cgic_session_arena")
         h, w = self.h, self.w
         shapes = dict(z=lambda n: (n, 4, h, w), m_c=lambda n: (n, 1, h // 4, w // 4), m_m=lambda n: (n, 1, h // 2, w // 2),
@@ -671,20 +671,27 @@ class Session:
         p = 0
         while True:
             ptr, b0, nb = C.c_void_p(), C.c_int(), C.c_int()
-            rc = lib().cgic_session_arena_tensor(self._s, 0, p, C.byref(ptr), C.byref(b0), C.byref(nb))
+            rc = lib().cgic_session_arena_slot_tensor(self._s, int(slot), 0, p, C.byref(ptr), C.byref(b0), C.byref(nb))
             if rc != 0:
+                if p == 0:
+                    check(rc, "cgic_session_arena_slot_tensor")
                 break
             d = {"images": range(b0.value, b0.value + nb.value)}
             for name, (what, dtype) in self._ARENA.items():
-                check(lib().cgic_session_arena_tensor(self._s, what, p, C.byref(ptr), None, None), "cgic_session_arena_tensor")
+                check(lib().cgic_session_arena_slot_tensor(self._s, int(slot), what, p, C.byref(ptr), None, None), "cgic_session_arena_slot_tensor")
                 shape = shapes[name](nb.value)
                 nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
                 buf = (C.c_uint8 * nbytes).from_address(ptr.value)
                 d[name] = torch.frombuffer(buf, dtype=dtype).view(*shape)
             views.append(d)
             p += 1
-        self._arena_views = views
+        if slot == 0:
+            self._arena_views = views
         return views
+
+    @staticmethod
+    def _arena_flags(want_idx, want_zq, decoded_on_device, narrow) -> int:
+        return (4 if decoded_on_device else int(want_idx) | (int(want_zq) << 1)) | (8 if narrow else 0)
 
     def roundtrip_arena(self, want_idx: bool = False, want_zq: bool = False, decoded_on_device: bool = False, narrow: bool = False) -> float:
         """CGIC.compress on the arena contents; returns sum((e - z)^2) over the batch.  decoded_on_device: the decoded
@@ -692,20 +699,31 @@ class Session:
         narrow: the masks are taken from m_c8 / m_m8 / m_f8 and the decoded tensors come back as ind16 / mc8 / mm8 / mf8
         (+ quant); the int64 tensors of the reference stay on the device."""
         sq = C.c_double()
-        flags = (4 if decoded_on_device else int(want_idx) | (int(want_zq) << 1)) | (8 if narrow else 0)
-        check(lib().cgic_session_roundtrip_arena(self._s, flags, C.byref(sq)), "cgic_session_roundtrip_arena")
+        check(lib().cgic_session_roundtrip_arena(self._s, self._arena_flags(want_idx, want_zq, decoded_on_device, narrow), C.byref(sq)),
+              "cgic_session_roundtrip_arena")
         return sq.value
 
-    def device_tensor(self, name: str) -> torch.Tensor:
-        """Output tensor `name` (ind, quant, mc, mm, mf, bytes, sizes, status, idx, zq) of the last arena round trip for
-        the whole batch, gathered device-to-device into one CUDA tensor."""
+    def submit_arena(self, slot: int, want_idx: bool = False, want_zq: bool = False, decoded_on_device: bool = False, narrow: bool = False) -> None:
+        """Enqueues the round trip of arena set `slot` (0 or 1) and returns at once; wait_arena(slot) blocks until its
+        results are in that set's host tensors.  Alternate the slots to overlap one batch's D2H with the next one's H2D."""
+        check(lib().cgic_session_roundtrip_arena_submit(self._s, int(slot), self._arena_flags(want_idx, want_zq, decoded_on_device, narrow)),
+              "cgic_session_roundtrip_arena_submit")
+
+    def wait_arena(self, slot: int) -> float:
+        sq = C.c_double()
+        check(lib().cgic_session_roundtrip_arena_wait(self._s, int(slot), C.byref(sq)), "cgic_session_roundtrip_arena_wait")
+        return sq.value
+
+    def device_tensor(self, name: str, slot: int = 0) -> torch.Tensor:
+        """Output tensor `name` (ind, quant, mc, mm, mf, bytes, sizes, status, idx, zq, ind16, mc8, mm8, mf8) of the last arena
+        round trip of `slot` for the whole batch, gathered device-to-device into one CUDA tensor."""
         what, dtype = self._ARENA[name]
         B, h, w = self.B, self.h, self.w
         shape = dict(bytes=(B, self.image_stride), sizes=(B, 5), status=(B,), ind=(B, h, w), quant=(B, 4, h, w), mc=(B, h // 4, w // 4),
                      mm=(B, h // 2, w // 2), mf=(B, h, w), idx=(B * h * w,), zq=(B, 4, h, w), ind16=(B, h, w), mc8=(B, h // 4, w // 4),
                      mm8=(B, h // 2, w // 2), mf8=(B, h, w))[name]
         out = torch.empty(shape, dtype=dtype, device="cuda")
-        check(lib().cgic_session_arena_gather_device(self._s, what, out.data_ptr()), "cgic_session_arena_gather_device")
+        check(lib().cgic_session_arena_slot_gather_device(self._s, int(slot), what, out.data_ptr()), "cgic_session_arena_slot_gather_device")
         return out
 
     def roundtrip(self, z, m_c, m_m, m_f, want_idx: bool = False):

@@ -338,6 +338,17 @@ CGIC_API int cgic_session_arena_tensor(const cgic_session *s, int what, int part
                               int *n_images);
 CGIC_API int cgic_session_roundtrip_arena(cgic_session *s, int flags, double *sqerr_out);
 CGIC_API int cgic_session_arena_gather_device(cgic_session *s, int what, void *dst_device);
+/* Two round trips in flight.  The session owns two independent arena sets ("slots" 0 and 1; slot 1 is allocated on first
+ * use; the calls above work on slot 0).  _submit enqueues the round trip of a slot and returns at once; _wait blocks
+ * until its results are in the slot's host arena.  Alternating the slots overlaps the D2H copies of one batch with the
+ * H2D copies and kernels of the next:
+ *     fill(slot 0); submit(0);  loop { fill(slot 1); submit(1); wait(0); use(slot 0);  fill(slot 0); submit(0); wait(1); use(slot 1); }
+ * A slot's tensors must not be touched between its _submit and its _wait; one thread drives a session. */
+CGIC_API int cgic_session_arena_slot_tensor(cgic_session *s, int slot, int what, int part, void **host_ptr, int *first_image,
+                                   int *n_images);
+CGIC_API int cgic_session_roundtrip_arena_submit(cgic_session *s, int slot, int flags);
+CGIC_API int cgic_session_roundtrip_arena_wait(cgic_session *s, int slot, double *sqerr_out);
+CGIC_API int cgic_session_arena_slot_gather_device(cgic_session *s, int slot, int what, void *dst_device);
 
 #ifdef __cplusplus
 }

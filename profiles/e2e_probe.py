@@ -35,6 +35,25 @@ for parts in parts_list:
           "| narrow wire us:", round(timeit(lambda: sess.roundtrip_arena(narrow=True)), 1),
           "| decoded tensors left on the device us:", round(timeit(lambda: sess.roundtrip_arena(decoded_on_device=True)), 1),
           "| + byte masks in us:", round(timeit(lambda: sess.roundtrip_arena(decoded_on_device=True, narrow=True)), 1))
+# two round trips in flight: alternate the two arena sets (submit / wait)
+for parts in parts_list:
+    sets = [sess.arena(parts, slot=k) for k in (0, 1)]
+    for views in sets:
+        for v in views:
+            r = v["images"]; v["z"].copy_(zh[r.start:r.stop])
+            for name, src in zip(("m_c", "m_m", "m_f"), mh): v[name].copy_(src[r.start:r.stop])
+            for name, src in zip(("m_c8", "m_m8", "m_f8"), mh): v[name].copy_(src[r.start:r.stop].to(torch.uint8))
+    def piped(n, **kw):
+        sess.submit_arena(0, **kw)
+        for i in range(1, n):
+            sess.submit_arena(i & 1, **kw)
+            sess.wait_arena((i - 1) & 1)
+        sess.wait_arena((n - 1) & 1)
+    out = []
+    for kw in ({}, dict(narrow=True), dict(decoded_on_device=True), dict(decoded_on_device=True, narrow=True)):
+        piped(20, **kw)
+        t0 = time.perf_counter(); piped(400, **kw); out.append(round(1e6 * (time.perf_counter() - t0) / 400, 1))
+    print("two in flight, parts", parts, "us per round trip: full", out[0], "| narrow wire", out[1], "| decoded on device", out[2], "| + byte masks in", out[3])
 # raw copies of the arena-sized buffers through torch for reference
 a = torch.empty(5570560, dtype=torch.uint8).pin_memory(); d = torch.empty(9878016, dtype=torch.uint8, device=dev); b = torch.empty(9878016, dtype=torch.uint8).pin_memory(); da = torch.empty_like(a, device=dev)
 def cp():

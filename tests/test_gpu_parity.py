@@ -548,6 +548,29 @@ def test_session_host_roundtrip(cg, orc):
             r = v["images"]
             for name, src in zip(("m_c", "m_m", "m_f"), mh):
                 v[name].copy_(src[r.start:r.stop])
+        # two round trips in flight: the second arena set holds the batch in reverse image order
+        views1 = sess.arena(parts, slot=1)
+        rev = torch.arange(B - 1, -1, -1)
+        for v in views1:
+            r = v["images"]
+            v["z"].copy_(zh[rev][r.start:r.stop])
+            for name, src in zip(("m_c", "m_m", "m_f"), mh):
+                v[name].copy_(src[rev][r.start:r.stop])
+        for rep in range(4):
+            sess.submit_arena(0)
+            sess.submit_arena(1)
+            with pytest.raises(RuntimeError):
+                sess.submit_arena(1)             # already in flight
+            sq0, sq1 = sess.wait_arena(0), sess.wait_arena(1)
+            assert np.isclose(sq0, float(sq_d), rtol=1e-12) and np.isclose(sq1, float(sq_d), rtol=1e-9)
+            for vs, order in ((views, torch.arange(B)), (views1, rev)):
+                assert torch.equal(torch.cat([v["sizes"] for v in vs]), sizes.cpu()[order])
+                assert torch.equal(torch.cat([v["ind"].view(len(v["images"]), -1) for v in vs]), idx_d.cpu().view(B, -1)[order])
+                assert torch.equal(torch.cat([v["quant"] for v in vs]), quant[order])
+                assert int(sum(int(v["status"].abs().sum()) for v in vs)) == 0
+        assert torch.equal(sess.device_tensor("ind", slot=1).view(B, -1), idx_d.view(B, -1)[rev.cuda()])
+        with pytest.raises(RuntimeError):
+            sess.wait_arena(1)                   # nothing submitted
     sess.close()
 
 
