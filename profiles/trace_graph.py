@@ -33,7 +33,7 @@ for k, v in cg.ops._ws_cache.items():
 vq = best[:, :7].astype(np.float64)
 t0 = vq[:, 0].min()
 rel = lambda a: (a - t0) / 1e3
-print(f"vq     first start 0.00, last start {rel(vq[:,0].max()):.2f}, searched median {rel(np.median(vq[:,4])):.2f}, end median {rel(np.median(vq[:,6])):.2f} max {rel(vq[:,6].max()):.2f}")
+print(f"vq     first start 0.00, last start {rel(vq[:,0].max()):.2f}, inputs visible (pdl wait) median {rel(np.median(vq[:,1])):.2f}, tiles done median {rel(np.median(vq[:,5])):.2f}, end median {rel(np.median(vq[:,6])):.2f} max {rel(vq[:,6].max()):.2f}")
 names = {0: "medium", 1: "fine", 2: "coarse", 3: "masks"}
 for k in range(4):
     rows = un[k * B:(k + 1) * B]
