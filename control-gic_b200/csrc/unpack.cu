@@ -35,8 +35,9 @@ struct UnpackWs {
     int32_t *count;    // [B][3]  decoded symbols per index stream (-1: empty stream)
     int32_t *pop;      // [B][3]  population of each mask level
     int32_t *flag;     // [B][5]  per decode CTA: 0 or CGIC_EFORMAT (no zeroing needed: every CTA writes its slot)
-    unsigned long long *chain;  // [B][3][max_chunks] chunk hand-over records (zero between launches)
-    int max_chunks;
+    unsigned long long *chain;  // [B][3][max_chunks][chain_row] chunk hand-over tables (zero between launches)
+    int32_t *ticket;            // [B][3] CTAs of a chained stream that are done (zero between launches)
+    int max_chunks, chain_row;
     uint32_t *bits;    // [B][nw16 + nw8 + nw4] bitmaps
     uint32_t *prefix;  // same shape: exclusive popcount prefix
     size_t bytes;
@@ -68,6 +69,9 @@ __host__ __device__ inline Geo make_geo(int h, int w)
 
 // chunk records per stream: enough for a stream of `n4` symbols of 64 bits each in chunks of 128 subsequences
 __host__ __device__ inline int unpack_max_chunks(const Geo &g) { return (int)(g.n4 * 64 / (128 * 128)) + 2; }
+constexpr int DEC_SINGLE_N4 = 4096;  // token grids up to this size: one CTA per stream (no hand-over tables)
+constexpr int DEC_CHAIN_D = 32;      // streams are spread over several CTAs for codes of at most this many bits
+constexpr int DEC_CHAIN_SLOTS = 16;  // at most this many CTAs per stream
 
 UnpackWs carve_unpack(void *ws, int B, const Geo &g)
 {
@@ -76,8 +80,11 @@ UnpackWs carve_unpack(void *ws, int B, const Geo &g)
     unsigned char *p = static_cast<unsigned char *>(ws);
     size_t o = 0;
     c.max_chunks = unpack_max_chunks(g);
+    c.chain_row = g.n4 > DEC_SINGLE_N4 ? DEC_CHAIN_D : 1;       // only large token grids spread a stream over several CTAs
     c.chain = reinterpret_cast<unsigned long long *>(p + o);  // first: the part of the workspace that must start zeroed
-    o += up((size_t)B * 3 * c.max_chunks * 8);
+    o += up((size_t)B * 3 * c.max_chunks * c.chain_row * 8);
+    c.ticket = reinterpret_cast<int32_t *>(p + o);
+    o += up((size_t)B * 3 * 4);
     c.count = reinterpret_cast<int32_t *>(p + o);
     o += up((size_t)B * 3 * 4);
     c.pop = reinterpret_cast<int32_t *>(p + o);
@@ -403,24 +410,27 @@ __device__ __forceinline__ int decode_write_len(const uint32_t *s_words, const u
 }
 
 // Chunks of one stream may be spread over `nslots` CTAs (slot j takes chunks j, j + nslots, ...).  What a chunk
-// needs from its predecessor -- the offset of its first codeword and the number of symbols decoded so far -- travels
-// through one 64-bit record per chunk in global memory: bit 63 = valid, bits 32..39 = start offset of the NEXT chunk,
-// bits 0..31 = symbols up to and including this chunk.  The reader clears the record after use, so the records are
-// all zero again when the kernel ends (workspace contract: zero before the first launch).
+// needs from its predecessors -- the offset of its first codeword and the number of symbols decoded before it -- does
+// NOT travel down a chain of CTAs (one global round trip per chunk): every chunk publishes what it does to EVERY possible
+// start offset, a table of D 64-bit words in global memory (bit 63 = valid, bits 32..39 = start offset of the next chunk,
+// bits 0..31 = symbols of this chunk), as soon as its own phase A is done; a chunk then gathers the tables of the
+// predecessors it has not folded in yet (at most nslots - 1) and composes them locally.  All chunks of a stream thus run
+// at the same time and the serial part is one publish + one gather, whatever the number of chunks.
+// The last CTA of the stream to finish (ticket) zeroes the tables again (workspace contract: zero between launches).
 struct DecChain {
-    unsigned long long *rec;  // [max chunks] of this stream; null = single CTA per stream
-    int slot, nslots;
+    unsigned long long *rec;  // [max chunks][row] tables of this stream; null = single CTA per stream
+    int32_t *ticket;          // CTAs of this stream that are done
+    int slot, nslots, row;
 };
 constexpr int DEC_NOT_MINE = -2147483647 - 1;  // returned by the CTAs that did not decode a stream's last chunk
 
-__device__ __forceinline__ unsigned long long chain_wait_and_clear(unsigned long long *p)
+__device__ __forceinline__ unsigned long long chain_wait(const unsigned long long *p)
 {
     unsigned long long v;
     do {
         asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-        if (!(v >> 63)) __nanosleep(40);
+        if (!(v >> 63)) __nanosleep(20);
     } while (!(v >> 63));
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(0ull) : "memory");
     return v;
 }
 __device__ __forceinline__ void chain_publish(unsigned long long *p, uint32_t next_start, uint32_t symbols)
@@ -661,20 +671,56 @@ __device__ int decode_stream_cta_cand(const uint8_t *in, int64_t nbytes, const D
 
 // The same decoder for streams whose chunks are spread over several CTAs (MULTI) -- kept as a separate function so
 // that the single-CTA decoder above stays exactly the code that was tuned on the small-grid batch.
+// Chunk size and number of chunks of a chained stream of `nsub_total` subsequences: one chunk per CTA whenever the stream
+// allows it (all its chunks are then decoded at the same time and only the gather of the tables is serial), but not
+// below 64 subsequences -- a chunk has fixed costs (staging, barriers) that smaller ones no longer repay.  Every CTA of
+// the stream (and the kernel, for the CTAs that get no chunk) computes the same plan from the stream's length.
+__device__ __forceinline__ int64_t chain_plan(int64_t nsub_total, int nslots, int &ch)
+{
+    const int64_t per = (nsub_total + nslots - 1) / nslots;
+    const int64_t fit = per < 64 ? 64 : ((per + 31) & ~(int64_t)31);
+    if (fit < ch) ch = (int)fit;
+    return (nsub_total + ch - 1) / ch;
+}
+__device__ __forceinline__ int64_t stream_subsequences(const uint8_t *in, int64_t nbytes)
+{
+    const int pad = in[0];
+    int64_t nbits = (nbytes - 1) * 8 - pad;
+    if (pad == 0 || nbits < 0) nbits = 0;
+    return (nbits + DEC_SUB_BITS - 1) / DEC_SUB_BITS;
+}
+
+// Shared memory of decode_stream_cta_chain, ONE instance per kernel (the two table-shape instantiations of the function share
+// it).  Chained streams (MULTI) carry codes of at most DEC_CHAIN_D bits and chunks of at most DEC_CHAIN_CH subsequences, so
+// their kernel's footprint stays small enough for four CTAs per SM.
+constexpr int DEC_CHAIN_CH = 128;
+template <bool MULTI>
+struct ChainShared {
+    static constexpr int MAXD = MULTI ? DEC_CHAIN_D : DEC_MAX_D;
+    uint32_t aggn[MULTI ? MAXD : 1];  // chained streams: symbols of the chunk per candidate start
+    uint32_t tabn[MULTI ? (DEC_CHAIN_SLOTS - 1) * DEC_CHAIN_D : 1];  // tables of the predecessors not folded in yet
+    uint32_t next, start, base, res_st, res_base;  // res_*: state after the last chunk this CTA has resolved
+    int wsum[DEC_THREADS / 32];
+    uint16_t blockcnt[MULTI ? 32 * MAXD : 1];  // chained streams: symbols of a block per candidate start
+    uint8_t blockfn[32 * MAXD];
+    uint8_t aggx[MULTI ? MAXD : 1];   // chained streams: chunk exit offset per candidate start
+    uint8_t tabx[MULTI ? (DEC_CHAIN_SLOTS - 1) * DEC_CHAIN_D : 1];
+    uint8_t blkstart[32];
+    uint8_t substart[MULTI ? DEC_CHAIN_CH : DEC_MAX_CH];
+    bool sweep;
+};
+
 template <bool LUT2S, bool MULTI, typename Out>
 __device__ int decode_stream_cta_chain(const uint8_t *in, int64_t nbytes, const DevTable &T, const uint32_t *s_lut, const uint32_t *lut2,
                                       uint32_t *s_words, uint8_t *s_len, uint16_t *s_fn, int ch, Out *out, int64_t cap, const DecChain chain,
-                                      TableStage &ts)
+                                      TableStage &ts, ChainShared<MULTI> &sh)
 {
-    __shared__ uint8_t s_blockfn[32 * DEC_MAX_D];
-    // chained streams only: symbols of a block per candidate start, chunk exit offset / symbol count per candidate start
-    __shared__ uint16_t s_blockcnt[MULTI ? 32 * DEC_MAX_D : 1];
-    __shared__ uint8_t s_aggx[MULTI ? DEC_MAX_D : 1];
-    __shared__ uint32_t s_aggn[MULTI ? DEC_MAX_D : 1];
-    __shared__ uint8_t s_blkstart[32];
-    __shared__ uint8_t s_substart[DEC_MAX_CH];
-    __shared__ int s_wsum[DEC_THREADS / 32];
-    __shared__ uint32_t s_next, s_start, s_base;
+    uint8_t *s_blockfn = sh.blockfn, *s_aggx = sh.aggx, *s_blkstart = sh.blkstart, *s_substart = sh.substart, *s_tabx = sh.tabx;
+    uint16_t *s_blockcnt = sh.blockcnt;
+    uint32_t *s_aggn = sh.aggn, *s_tabn = sh.tabn;
+    int *s_wsum = sh.wsum;
+    uint32_t &s_next = sh.next, &s_start = sh.start, &s_base = sh.base, &s_res_st = sh.res_st, &s_res_base = sh.res_base;
+    bool &s_sweep = sh.sweep;
     constexpr bool multi = MULTI;
     bool overflow = false;
     if (nbytes <= 0) return chain.slot == 0 ? -1 : DEC_NOT_MINE;
@@ -687,8 +733,15 @@ __device__ int decode_stream_cta_chain(const uint8_t *in, int64_t nbytes, const 
     const int64_t nsub_total = (nbits + DEC_SUB_BITS - 1) / DEC_SUB_BITS;
     uint32_t start_off = 0;
     int64_t total = 0;
-    const int64_t nchunks = (nsub_total + ch - 1) / ch;
     const int nslots = multi ? chain.nslots : 1, slot = multi ? chain.slot : 0;
+    const bool tables = multi && nslots > 1;  // (the predicate is uniform over the CTAs of a stream)
+    // (the shared-memory carve-up is the one of the largest chunk)
+    const int64_t nchunks = tables ? chain_plan(nsub_total, nslots, ch) : (nsub_total + ch - 1) / ch;
+    int64_t res_chunk = -1;                   // last chunk whose outgoing state s_res_* holds
+    if (tables && threadIdx.x == 0) {
+        s_res_st = 0u;
+        s_res_base = 0u;
+    }
     // the CTA that decodes the last chunk reports the stream's symbol count (slot 0 when there is no chunk at all)
     const bool mine_last = nchunks == 0 ? slot == 0 : (int)((nchunks - 1) % nslots) == slot;
     for (int64_t chunk = slot; chunk < nchunks && start_off != DEC_OFF_STOP; chunk += nslots) {
@@ -823,17 +876,33 @@ __device__ int decode_stream_cta_chain(const uint8_t *in, int64_t nbytes, const 
                 s_aggn[tid] = nsym;
             }
             __syncthreads();
-            if (tid == 0) {
-                uint32_t st = 0, base = 0;
-                if (chunk > 0) {
-                    const unsigned long long r = chain_wait_and_clear(chain.rec + (chunk - 1));
-                    st = (uint32_t)(r >> 32) & 0xFFu;
-                    base = (uint32_t)r;
+            if (tables) {
+                // this chunk's table first (nobody waits for us longer than necessary) ...
+                if (tid < D) chain_publish(chain.rec + chunk * chain.row + tid, s_aggx[tid], s_aggn[tid]);
+                // ... then the tables of chunks res_chunk + 1 .. chunk - 1 (at most nslots - 1 of them)
+                const int np = (int)(chunk - 1 - res_chunk);
+                for (int item = tid; item < np * D; item += DEC_THREADS) {
+                    const int p = item / D, d = item - p * D;
+                    const unsigned long long r = chain_wait(chain.rec + (res_chunk + 1 + p) * chain.row + d);
+                    s_tabx[item] = (uint8_t)(r >> 32);
+                    s_tabn[item] = (uint32_t)r;
                 }
-                if (chunk + 1 < nchunks)  // the last chunk has no reader
-                    chain_publish(chain.rec + chunk, st == DEC_OFF_STOP ? DEC_OFF_STOP : s_aggx[st], base + (st == DEC_OFF_STOP ? 0u : s_aggn[st]));
-                s_start = st;
-                s_base = base;
+                __syncthreads();
+                if (tid == 0) {
+                    uint32_t st = s_res_st, base = s_res_base;
+                    for (int p = 0; p < np && st != DEC_OFF_STOP; ++p) {
+                        base += s_tabn[p * D + st];
+                        st = s_tabx[p * D + st];
+                    }
+                    s_start = st;
+                    s_base = base;
+                    s_res_st = st == DEC_OFF_STOP ? DEC_OFF_STOP : s_aggx[st];
+                    s_res_base = base + (st == DEC_OFF_STOP ? 0u : s_aggn[st]);
+                }
+                res_chunk = chunk;
+            } else if (tid == 0) {
+                s_start = start_off;
+                s_base = (uint32_t)total;
             }
             __syncthreads();
             start_off = s_start;
@@ -898,7 +967,22 @@ __device__ int decode_stream_cta_chain(const uint8_t *in, int64_t nbytes, const 
             total += ctot;
             __syncthreads();
         }
-        start_off = multi ? 0u : s_next;
+        start_off = tables ? 0u : s_next;
+    }
+    if (tables && nchunks > 0) {
+        // the stream's last CTA to get here zeroes the hand-over tables for the next launch (every CTA of the stream is
+        // past its last gather when it takes its ticket)
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            s_sweep = atomicAdd(chain.ticket, 1) == (int)min((int64_t)nslots, nchunks) - 1;  // (CTAs without a chunk never get here)
+        }
+        __syncthreads();
+        if (s_sweep) {
+            __threadfence();
+            for (int64_t i = tid; i < nchunks * chain.row; i += DEC_THREADS) chain.rec[i] = 0ull;
+            if (tid == 0) *chain.ticket = 0;
+        }
     }
     if (overflow) return -2;
     return mine_last ? (int)total : DEC_NOT_MINE;
@@ -920,24 +1004,29 @@ __host__ __device__ inline int cand_len_bytes(int ch) { return (ch * (DEC_SUB_BI
 template <typename Out, bool MULTI = false>
 __device__ __forceinline__ int decode_stream_any(const uint8_t *in, int64_t nbytes, const DevTable &T, const uint32_t *s_dec,
                                                  const uint32_t *lut2, Out *out, int64_t cap, int ch, TableStage &ts,
-                                                 const DecChain chain = DecChain{nullptr, 0, 1})
+                                                 const DecChain chain = DecChain{nullptr, nullptr, 0, 1, 1})
 {
     if (T.max_len <= DEC_MAX_D) {
         // f[] lives right behind the staged tables in dynamic shared memory
         uint32_t *s_words = const_cast<uint32_t *>(s_dec) + T.dec_stage_words;
         uint8_t *s_len = reinterpret_cast<uint8_t *>(s_words + cand_words(ch));
         uint16_t *s_fn = reinterpret_cast<uint16_t *>(s_len + cand_len_bytes(ch));
-        if (MULTI) {
+        if constexpr (MULTI) {
+            __shared__ ChainShared<true> sh;
             if (T.dec_stage_words > T.lut_pad)
-                return decode_stream_cta_chain<true, MULTI, Out>(in, nbytes, T, s_dec, lut2, s_words, s_len, s_fn, ch, out, cap, chain, ts);
-            return decode_stream_cta_chain<false, MULTI, Out>(in, nbytes, T, s_dec, lut2, s_words, s_len, s_fn, ch, out, cap, chain, ts);
+                return decode_stream_cta_chain<true, true, Out>(in, nbytes, T, s_dec, lut2, s_words, s_len, s_fn, ch, out, cap, chain, ts, sh);
+            return decode_stream_cta_chain<false, true, Out>(in, nbytes, T, s_dec, lut2, s_words, s_len, s_fn, ch, out, cap, chain, ts, sh);
         }
         if (T.dec_stage_words > T.lut_pad)
             return decode_stream_cta_cand<true, Out>(in, nbytes, T, s_dec, lut2, s_words, s_len, s_fn, ch, out, cap, ts);
         return decode_stream_cta_cand<false, Out>(in, nbytes, T, s_dec, lut2, s_words, s_len, s_fn, ch, out, cap, ts);
     }
-    if (chain.slot != 0) return DEC_NOT_MINE;  // codes longer than a subsequence: one CTA per stream
-    return decode_stream_cta<Out>(in, nbytes, T, s_dec, lut2, out, cap, ts);
+    if constexpr (MULTI) {
+        return chain.slot == 0 ? -2 : DEC_NOT_MINE;  // unreachable: the chained kernel is launched for codes of <= DEC_CHAIN_D bits only
+    } else {
+        if (chain.slot != 0) return DEC_NOT_MINE;  // codes longer than a subsequence: one CTA per stream
+        return decode_stream_cta<Out>(in, nbytes, T, s_dec, lut2, out, cap, ts);
+    }
 }
 
 // Stages the decode tables with one TMA bulk copy; every thread of the CTA must call.  The copy is only STARTED here: the
@@ -1120,7 +1209,19 @@ __device__ __forceinline__ void unpack_decode_cta(const UnpackArgs &a, unsigned 
     const int nslots = MULTI ? a.nslots : 1;
     int s, slot, b;
     if (MULTI) {
-        s = (int)blockIdx.x < 3 * nslots ? (int)blockIdx.x / nslots : 3, slot = (int)blockIdx.x - s * nslots, b = blockIdx.y;
+        // linear block order = hand-out order: slot 0 of every stream of every image first, then slot 1, ...
+        // A short stream leaves its high slots without a chunk: those CTAs come late and leave at once, instead of
+        // holding SM slots that the busy CTAs of later images need.  (A chunk only ever waits for chunks of lower slots or
+        // earlier rounds, all handed out before it.)
+        const int lin = (int)(blockIdx.y * gridDim.x + blockIdx.x), nb = (int)gridDim.y;
+        if (lin < nb) {
+            s = 3, slot = 0, b = lin;  // the mask CTAs (always busy) lead
+        } else {
+            slot = (lin - nb) / (3 * nb);
+            const int r = lin - nb - slot * 3 * nb;
+            b = r / 3;
+            s = r - b * 3;
+        }
     } else {
         // CTAs are handed to the SMs in linear block order, breadth first: the first 148 get an SM of their own.  Long streams
         // first (all medium, then all fine), the short coarse streams and the mask CTAs last, so that at two CTAs per SM a long
@@ -1156,8 +1257,17 @@ __device__ __forceinline__ void unpack_decode_cta(const UnpackArgs &a, unsigned 
         } else if (nbytes > 0) {
             // a stream whose payload may exceed the chain's capacity (only a corrupt size can) is decoded by slot 0 alone
             const bool chained = MULTI && nslots > 1 && ((int64_t)nbytes * 8 + DEC_SUB_BITS - 1) / DEC_SUB_BITS <= (int64_t)a.ws.max_chunks * a.ch;
-            const DecChain chain{chained ? a.ws.chain + ((int64_t)b * 3 + s) * a.ws.max_chunks : nullptr, chained ? slot : 0, chained ? nslots : 1};
-            if (chained || slot == 0)
+            const DecChain chain{chained ? a.ws.chain + ((int64_t)b * 3 + s) * a.ws.max_chunks * a.ws.chain_row : nullptr,
+                                 a.ws.ticket + b * 3 + s, chained ? slot : 0, chained ? nslots : 1, a.ws.chain_row};
+            bool idle = false;  // a chained stream with fewer chunks than slots: the high slots have nothing to do
+            if (chained) {
+                int ch_plan = a.ch;
+                const int64_t nch = chain_plan(stream_subsequences(img + a.slot_off[s], nbytes), nslots, ch_plan);
+                idle = slot >= (nch > 0 ? nch : 1);
+            }
+            if (idle)
+                cnt = DEC_NOT_MINE;
+            else if (chained || slot == 0)
                 cnt = decode_stream_any<uint16_t, MULTI>(img + a.slot_off[s], nbytes, a.T, s_dec, lut2,
                                                          a.ws.sym + (int64_t)b * (g.n16 + g.n8 + g.n4) + soff, cap, a.ch, ts, chain);
             else
@@ -2019,10 +2129,18 @@ extern "C" int cgic_unpack(const uint8_t *bytes, const int32_t *sizes, int B, in
         CGIC_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, CGIC_EINVAL, "cgic_unpack: buffers must be 16-byte aligned");
     // dynamic shared memory: decode tables for the stream CTAs, mask stream bytes for the mask CTAs
     a.ch = cand_chunk_subs(a.T.max_len, a.g.n4);
-    // CTAs per index stream: one chunk holds ch * 128 bits; a fine stream carries up to ~12 bits per token
-    {
-        const int64_t chunks = (a.g.n4 * 12 / DEC_SUB_BITS + a.ch - 1) / a.ch;
-        a.nslots = a.g.n4 <= 4096 || a.T.max_len > DEC_MAX_D ? 1 : (int)std::min<int64_t>(8, std::max<int64_t>(1, chunks));
+    // CTAs per index stream (large token grids, codes of at most DEC_CHAIN_D bits): a fine stream carries up to ~12 bits per
+    // token; chunks of at most 128 subsequences keep five such CTAs on an SM.  The chunk size actually used is chosen per
+    // stream inside the kernel (one chunk per CTA whenever the stream allows it).
+    a.nslots = 1;
+    if (a.g.n4 > DEC_SINGLE_N4 && a.T.max_len <= DEC_CHAIN_D) {
+        static const int ch_env = getenv("CGIC_DEC_CH") ? atoi(getenv("CGIC_DEC_CH")) : 0;        // A-B runs only
+        static const int slots_env = getenv("CGIC_DEC_SLOTS") ? atoi(getenv("CGIC_DEC_SLOTS")) : 0;
+        const int ch_max = ch_env >= 32 && ch_env <= DEC_CHAIN_CH ? (ch_env & ~31) : DEC_CHAIN_CH;
+        a.ch = std::min(a.ch, ch_max);
+        const int slots_max = slots_env >= 1 && slots_env <= DEC_CHAIN_SLOTS ? slots_env : DEC_CHAIN_SLOTS;
+        const int64_t chunks = (a.g.n4 * 12 / DEC_SUB_BITS + 31) / 32;   // 32 subsequences = the smallest chunk
+        a.nslots = (int)std::min<int64_t>(slots_max, std::max<int64_t>(1, chunks));
     }
     // Small token grids, codes of at most 32 bits: decode + re-assembly fused, one CTA per image (unpack_small_kernel) -- once
     // the batch fills the machine.  Measured on B200 (256x256 images, decode + re-assembly per step): 2048 images 175 us

@@ -139,14 +139,16 @@ _WS_PER_OP = 8          # scratch buffers kept per (op, device): one per recentl
 _warned_alias = False
 
 
-def _workspace(tag: str, nbytes: int, device: torch.device) -> torch.Tensor:
-    """Grow-only scratch buffer per (tag, device, stream), zero-filled when it is created (the kernels leave it clean);
-    allocation happens off the hot path after warm-up.
+def _workspace(tag: str, nbytes: int, device: torch.device, geom=()) -> torch.Tensor:
+    """Scratch buffer per (tag, geometry, device, stream), zero-filled when it is created (the kernels leave it clean);
+    allocation happens off the hot path after warm-up.  The geometry is part of the key because the carve-up of a
+    workspace depends on it: the regions one geometry needs zeroed would otherwise lie over another one's scratch data.
 
     Under CUDA-graph capture a miss would put the zero-fill INTO the graph: a ~2 us fill kernel in front of the kernel on
     every replay, which also severs the programmatic (PDL) edge to its predecessor.  So while capturing, a buffer of the
     same tag that a warm-up run created on another stream of this device is reused instead (warm up before capturing, as
     torch asks anyway; do not replay the graph concurrently with eager calls of the same op on that other stream)."""
+    tag = (tag,) + tuple(geom)
     key = (tag, device.index, _stream())
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
@@ -156,7 +158,7 @@ def _workspace(tag: str, nbytes: int, device: torch.device) -> torch.Tensor:
                     global _warned_alias
                     if not _warned_alias:
                         _warned_alias = True
-                        warnings.warn(f"cgic_b200.ops: CUDA-graph capture of '{tag}' reuses the scratch buffer of stream {st:#x}; "
+                        warnings.warn(f"cgic_b200.ops: CUDA-graph capture of '{tag[0]}' reuses the scratch buffer of stream {st:#x}; "
                                       "do not run that stream's eager calls concurrently with replays of this graph "
                                       "(warm up on the capture stream to give the graph a buffer of its own)")
                     _ws_cache[key] = b
@@ -164,7 +166,7 @@ def _workspace(tag: str, nbytes: int, device: torch.device) -> torch.Tensor:
         buf = torch.zeros(max(nbytes, 256), dtype=torch.uint8, device=device)   # cgic_vq_assign wants its ticket zeroed once
         _ws_cache[key] = buf
         # bounded: streams come and go (torch.cuda.Stream() per request, graph captures); keep the newest few per op and device
-        mine = [k for k in _ws_cache if k[0] == tag and k[1] == device.index]
+        mine = [k for k in _ws_cache if k[0][0] == tag[0] and k[1] == device.index]
         for k in mine[:-_WS_PER_OP]:
             del _ws_cache[k]
     return buf
@@ -237,7 +239,7 @@ def vq_assign(z: torch.Tensor, codebook, want_zq: bool = True, want_sqerr: bool 
     zq = torch.empty_like(z) if want_zq else None
     sq = torch.empty(1, dtype=torch.float64, device=z.device) if want_sqerr else None
     nbytes = lib().cgic_vq_workspace_bytes(n)
-    ws = _workspace("vq", nbytes, z.device)
+    ws = _workspace("vq", nbytes, z.device, (n,))
     if indexed:
         check(lib().cgic_vq_assign_indexed(z.data_ptr(), B, h, w, codebook.handle, idx.data_ptr(), _p(zq), _p(sq),
                                            ws.data_ptr(), ws.numel(), _stream()), "cgic_vq_assign_indexed")
@@ -345,7 +347,7 @@ def entropy_route(x: torch.Tensor, coarse_ratio: float, medium_ratio: float, rto
     m_c = torch.empty(B, 1, h16, w16, dtype=torch.int32, device=dev)
     m_m = torch.empty(B, 1, 2 * h16, 2 * w16, dtype=torch.int32, device=dev)
     near = torch.empty(B, 2, dtype=torch.int32, device=dev)
-    ws = _workspace("entropy_route", lib().cgic_entropy_route_workspace_bytes(B), dev)
+    ws = _workspace("entropy_route", lib().cgic_entropy_route_workspace_bytes(B), dev, (B,))
     check(lib().cgic_entropy_route(x.data_ptr(), B, H, W, linspace_bins().ctypes.data, e8.data_ptr(), e16.data_ptr(), mode, k_c, k_m,
                                    float(rtol), float(atol), m_c.data_ptr(), m_m.data_ptr(), near.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
           "cgic_entropy_route")
@@ -424,7 +426,7 @@ def spatial_norm(f: torch.Tensor, zq: torch.Tensor, gn_weight: Optional[torch.Te
     if any(t is not None and t.numel() != Cc for t in vecs):
         raise ValueError(f"spatial_norm: per-channel vectors must have {Cc} elements")
     out = torch.empty_like(f)
-    ws = _workspace("spatial_norm", lib().cgic_spatial_norm_workspace_bytes(B, groups), f.device)
+    ws = _workspace("spatial_norm", lib().cgic_spatial_norm_workspace_bytes(B, groups), f.device, (B, groups))
     check(lib().cgic_spatial_norm(f.data_ptr(), zq.data_ptr(), _p(vecs[0]), _p(vecs[1]), wy.data_ptr(), _p(vecs[2]), wb.data_ptr(), _p(vecs[3]),
                                   B, Cc, H, W, Cz, hz, wz, groups, float(eps), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
           "cgic_spatial_norm")
@@ -444,7 +446,7 @@ def pack(idx: torch.Tensor, m_c, m_m, m_f, mode: int, table: HuffTable, h: int, 
     _, _, stride = table.layout(h, w)
     out = torch.empty(B, stride, dtype=torch.uint8, device=idx.device)
     sizes = torch.empty(B, 5, dtype=torch.int32, device=idx.device)
-    ws = _workspace("pack", lib().cgic_pack_workspace_bytes(B, h, w), idx.device)
+    ws = _workspace("pack", lib().cgic_pack_workspace_bytes(B, h, w), idx.device, (B, h, w))
     check(lib().cgic_pack_ws(idx.data_ptr(), m_c.data_ptr(), m_m.data_ptr(), m_f.data_ptr(), B, h, w, mode, table.handle,
                              out.data_ptr(), sizes.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "cgic_pack_ws")
     return out, sizes
@@ -470,7 +472,7 @@ def encode(z: torch.Tensor, codebook: "Codebook", m_c, m_m, m_f, mode: int, tabl
     sq = torch.empty(1, dtype=torch.float64, device=dev) if want_sqerr else None
     out = torch.empty(B, stride, dtype=torch.uint8, device=dev)
     sizes = torch.empty(B, 5, dtype=torch.int32, device=dev)
-    ws = _workspace("encode", lib().cgic_encode_workspace_bytes(B, h, w), dev)
+    ws = _workspace("encode", lib().cgic_encode_workspace_bytes(B, h, w), dev, (B, h, w))
     check(lib().cgic_encode(z.data_ptr(), m_c.data_ptr(), m_m.data_ptr(), m_f.data_ptr(), B, h, w, mode, codebook.handle, table.handle,
                             idx.data_ptr(), _p(zq), _p(sq), out.data_ptr(), sizes.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
           "cgic_encode")
@@ -480,7 +482,7 @@ def encode(z: torch.Tensor, codebook: "Codebook", m_c, m_m, m_f, mode: int, tabl
 def exhaustive_count(tag: str = "encode") -> int:
     """Running count (since the workspace was created) of latents the indexed search handed to its exhaustive path, summed
     over this op's workspaces (synchronises).  tag: "encode" or "vq"."""
-    return int(sum(int(b[8:12].view(torch.int32).item()) for k, b in _ws_cache.items() if k[0] == tag))
+    return int(sum(int(b[8:12].view(torch.int32).item()) for k, b in _ws_cache.items() if k[0][0] == tag))
 
 
 @_on_tensor_device
@@ -502,7 +504,7 @@ def unpack(bytes_: torch.Tensor, sizes: torch.Tensor, mode: int, table: HuffTabl
     quant = torch.empty(B, 4, h, w, dtype=torch.float32, device=dev)
     status = torch.empty(B, dtype=torch.int32, device=dev)
     nbytes = lib().cgic_unpack_workspace_bytes(B, h, w)
-    ws = _workspace("unpack", nbytes, dev)
+    ws = _workspace("unpack", nbytes, dev, (B, h, w))
     check(lib().cgic_unpack(bytes_.data_ptr(), sizes.data_ptr(), B, h, w, mode, table.handle, cb.data_ptr(), mc.data_ptr(),
                             mm.data_ptr(), mf.data_ptr(), ind.data_ptr(), quant.data_ptr(), status.data_ptr(), ws.data_ptr(),
                             ws.numel(), _stream()), "cgic_unpack")

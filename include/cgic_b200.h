@@ -249,7 +249,9 @@ CGIC_API int cgic_encode(const float *z, const int32_t *m_c, const int32_t *m_m,
  *     status_out int32 [B]: 0 ok, else CGIC_EFORMAT (symbol count != mask population, bad
  *     framing, ...) -- the cases in which the reference raises.
  *     workspace: cgic_unpack_workspace_bytes() bytes, ZERO-filled before the first use (the kernels
- *     leave the chunk hand-over records in it zeroed); one workspace per concurrently running call.
+ *     leave the chunk hand-over tables in it zeroed); one workspace per concurrently running call.
+ *     A workspace belongs to ONE geometry (B, h, w): its carve-up depends on them, so zero-fill it again
+ *     before using it with another geometry (the same holds for cgic_pack / cgic_encode workspaces).
  * ------------------------------------------------------------------------------------------ */
 CGIC_API size_t cgic_unpack_workspace_bytes(int B, int h, int w);
 CGIC_API int cgic_unpack(const uint8_t *bytes, const int32_t *sizes, int B, int h, int w, int mode,

@@ -26,7 +26,7 @@ un = buf.reshape(1024, SL)[: 4 * B].astype(np.float64)
 # the VQ stamps live in the vq workspace of the stream the kernel ran on: take every cached one and keep the latest stamps
 best = None
 for k, v in cg.ops._ws_cache.items():
-    if k[0] not in ("vq", "encode"): continue
+    if k[0][0] not in ("vq", "encode"): continue
     raw = v[256:].view(torch.int64)[512:512 + 300 * 8].cpu().numpy().reshape(300, 8)
     raw = raw[raw[:, 0] > 0]
     if len(raw) and (best is None or raw[:, 0].max() > best[:, 0].max()): best = raw

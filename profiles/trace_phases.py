@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""Phase stamps of the step's kernels for ANY workload (a -DCGIC_TRACE -DCGIC_VQ_TRACE build), without the CTA -> (image,
+stream) mapping of trace_graph.py: per kernel and stamp index, min / median / max over the CTAs that wrote it, in us from
+the first VQ CTA's start.   CGIC_B200_LIB=build/variants/lib_trace.so python profiles/trace_phases.py [workload]"""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bench, workload
+import cgic_b200 as cg
+wl = sys.argv[1] if len(sys.argv) > 1 else bench.DEFAULT_WORKLOAD
+B, H, W, c, m = bench.WORKLOADS[wl]
+dev = torch.device("cuda", 0)
+hp = bench.HotPath(dev)
+z, masks, mode = hp.inputs(B, H, W, c, m, 0)
+step = hp.step_fn([(z, masks, mode)])
+run, g, _ = bench.capture(torch, step, False)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+for _ in range(5):
+    flush.zero_(); ev[0].record(); run(); ev[1].record()
+torch.cuda.synchronize()
+print(wl, "step (events):", round(1e3 * ev[0].elapsed_time(ev[1]), 2), "us")
+best = None
+for k, v in cg.ops._ws_cache.items():
+    if k[0][0] not in ("vq", "encode"): continue
+    raw = v[256:].view(torch.int64)[512:512 + 300 * 8].cpu().numpy().reshape(300, 8)
+    raw = raw[raw[:, 0] > 0]
+    if len(raw) and (best is None or raw[:, 0].max() > best[:, 0].max()): best = raw
+t0 = float(best[:, 0].min())
+def show(name, rows):
+    rows = rows.astype(np.float64)
+    for k in range(rows.shape[1]):
+        col = rows[:, k]; col = col[col > t0 - 1e6]
+        if len(col): print(f"  {name:9s} stamp {k:2d}: n {len(col):4d}  min {(col.min()-t0)/1e3:7.2f}  median {(np.median(col)-t0)/1e3:7.2f}  max {(col.max()-t0)/1e3:7.2f}")
+show("vq", best)
+for name in ("pack", "unpack", "assemble"):
+    b_ = np.zeros(1024 * 16, np.uint64)
+    assert getattr(ctypes.CDLL(cg._lib.LIB_PATH), "cgic_trace_" + name)(b_.ctypes.data_as(ctypes.c_void_p)) == 0
+    r = b_.reshape(1024, 16); show(name, r[r[:, 0] > 0])
