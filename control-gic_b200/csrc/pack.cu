@@ -465,8 +465,10 @@ __device__ void pack_index_stream_chained(const PackArgs &a, int s, int b, int s
             tsum += (int)len[i];
         }
         }  // generic path
+        CGIC_STAMP(pack, 3);  // codes ready
         int tot;
         int o = block_exscan(tsum, s_warp, &tot);  // (its barriers also order the s_bad writes above before the read below)
+        CGIC_STAMP(pack, 4);  // scanned
         if (tid == 0) {
             unsigned long long P = 8, bad = (unsigned long long)(s_bad != 0);
             if (t > 0) {
@@ -479,6 +481,7 @@ __device__ void pack_index_stream_chained(const PackArgs &a, int s, int b, int s
             s_badall = (int)bad;
         }
         __syncthreads();
+        CGIC_STAMP(pack, 5);  // bit position known
         const int64_t P = (int64_t)s_P;
         const int r0 = (int)(P & 31);
         const int nwords = (r0 + tot + 31) >> 5;
@@ -495,6 +498,7 @@ __device__ void pack_index_stream_chained(const PackArgs &a, int s, int b, int s
             }
         }
         __syncthreads();
+        CGIC_STAMP(pack, 6);  // staged
         const int full = (r0 + tot) >> 5;
         const int64_t w0 = P >> 5;
         if (tid == 0) {
@@ -512,6 +516,7 @@ __device__ void pack_index_stream_chained(const PackArgs &a, int s, int b, int s
             for (int j = tid; j < full; j += PK_THREADS) out32[w0 + j] = to_big_endian(stage[j]);
         P_end = P + tot;
         __syncthreads();
+        CGIC_STAMP(pack, 7);  // written
     }
     if (mbar) mbar_wait(mbar, 0);
     if (!mine_last) return;
@@ -643,6 +648,7 @@ __global__ void __launch_bounds__(PK_THREADS) pack_chained_kernel(const PackArgs
     extern __shared__ __align__(128) unsigned char dyn[];
     __shared__ __align__(8) unsigned long long mbar;
     const int s = blockIdx.x / a.nslots, slot = blockIdx.x - s * a.nslots, b = blockIdx.y;
+    CGIC_STAMP(pack, 0);
     pdl_trigger_step<2>();
     if (stream_present(a.mode, s)) {
         const uint32_t bytes = (uint32_t)((a.T.K + 1) / 2 * 2) * 8u;
@@ -650,11 +656,13 @@ __global__ void __launch_bounds__(PK_THREADS) pack_chained_kernel(const PackArgs
         __syncthreads();
         if (threadIdx.x == 0) tma_load_1d(dyn, a.T.enc, bytes, &mbar);
         pdl_wait();
+        CGIC_STAMP(pack, 2);
         pack_index_stream_chained<ITEMS>(a, s, b, slot, reinterpret_cast<uint32_t *>(dyn + bytes), reinterpret_cast<const uint2 *>(dyn), &mbar);
     } else {
         pdl_wait();
         if (threadIdx.x == 0 && slot == 0) a.sizes[b * 5 + s] = 0;
     }
+    CGIC_STAMP(pack, 1);
     if (blockIdx.x != 0) return;
     if (a.sq_out && b == 0) reduce_partials(a.sq_partials, a.sq_n, a.sq_out);
     for (int ms = 3; ms < 5; ++ms) {
@@ -668,6 +676,7 @@ __global__ void __launch_bounds__(PK_THREADS) pack_chained_kernel(const PackArgs
         pack_bit_stream(a.mask[lvl] + (int64_t)b * n, n, a.out + (int64_t)b * a.image_stride + a.slot_off[ms], a.slot_cap[ms],
                         a.sizes + b * 5 + ms);
     }
+    CGIC_STAMP(pack, 8);
 }
 
 template <int ITEMS>

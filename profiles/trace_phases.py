@@ -37,3 +37,13 @@ for name in ("pack", "unpack", "assemble"):
     b_ = np.zeros(1024 * 16, np.uint64)
     assert getattr(ctypes.CDLL(cg._lib.LIB_PATH), "cgic_trace_" + name)(b_.ctypes.data_as(ctypes.c_void_p)) == 0
     r = b_.reshape(1024, 16); show(name, r[r[:, 0] > 0])
+if "--ctas" in sys.argv:  # per-CTA view of the decode kernel: linear block id, start, end (us), "busy" = has a chunk stamp
+    b_ = np.zeros(1024 * 16, np.uint64)
+    ctypes.CDLL(cg._lib.LIB_PATH).cgic_trace_unpack(b_.ctypes.data_as(ctypes.c_void_p))
+    r = b_.reshape(1024, 16).astype(np.float64)
+    k0 = r[:, 0][r[:, 0] > 0].min()
+    for lin in range(0, 1024, 8):
+        row = r[lin]
+        if row[0] <= 0: continue
+        busy = row[2] >= row[0]
+        print(f"  cta {lin:4d}  start {(row[0]-k0)/1e3:6.2f}  end {((row[6] if row[6] >= row[0] else row[0])-k0)/1e3:6.2f}  {'busy' if busy else ''}")
