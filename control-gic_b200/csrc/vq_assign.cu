@@ -519,6 +519,10 @@ vq_warp_kernel(const float *__restrict__ z, int h, int w, int tiles_x, int tiles
                                 staged = true;
                                 mbar_wait(&mbar, 0);
                             }
+                        },
+                        [&](int k) {
+                            (void)k;
+                            if (tile == wid) VQ_STAMP(k);  // the warp's first tile (thread 0 stamps)
                         });
     }
     VQ_STAMP(5);

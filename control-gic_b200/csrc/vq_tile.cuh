@@ -126,10 +126,14 @@ struct VqTileCtx {
 // (NCHW, plane = h*w).  idx_img / zq_img: the image's outputs; idx_s (nullable): the image's indices as u16 in shared
 // memory (fused encoder).  exhaustive_count (nullable): leaders that took the exhaustive path are added there.
 // `staged()` is called once the loads are in flight: it waits for the codebook's bulk copy on first use.
-template <typename Staged>
+struct VqNoStamp {
+    __device__ __forceinline__ void operator()(int) const {}
+};
+// `stamp(k)` (tracing builds): k = 2 tile loaded and classified, 3 cells found, 4 leaders searched.
+template <typename Staged, typename Stamp = VqNoStamp>
 __device__ __forceinline__ void vq_process_tile(const VqTileCtx &c, const float *__restrict__ zb, int h, int w, int gy0, int gx, int lane,
                                                 int64_t *__restrict__ idx_img, float *__restrict__ zq_img, bool want_sq, double &sq,
-                                                uint16_t *idx_s, int32_t *exhaustive_count, Staged staged)
+                                                uint16_t *idx_s, int32_t *exhaustive_count, Staged staged, Stamp stamp = Stamp())
 {
     const int64_t plane = (int64_t)h * w;
     const bool col_ok = gx < w;
@@ -150,33 +154,32 @@ __device__ __forceinline__ void vq_process_tile(const VqTileCtx &c, const float 
 #pragma unroll
         for (int r = 0; r < 4; ++r) zs[r * 32 + lane] = make_float4(zt[r][0], zt[r][1], zt[r][2], zt[r][3]);
     }
+    stamp(7);
     staged();
+    stamp(1);
     __syncwarp();
-    // ---- classify + compact
+    // ---- classify + compact (branch-free: the seven vectors a lane compares are loaded up front)
     int nlead = 0;
     unsigned lmask[4];
+    {
+        const uint4 *zs4 = reinterpret_cast<const uint4 *>(zs);
+        const int t4 = lane & ~3;  // row 0 of the tile is the top row of every 4x4 block
+        const uint4 top4 = zs4[t4], top2a = zs4[lane & ~1], top2b = zs4[64 + (lane & ~1)];
+        uint4 own[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int t = r * 32 + lane;
-        int ld = t;
-        const bool ok = col_ok && gy0 + r < h;
-        if (ok) {
-            const uint4 v = reinterpret_cast<const uint4 *>(zs)[t];
-            const int t4 = lane & ~3;  // row 0 of the tile is the top row of every 4x4 block
-            if (t4 != t) {
-                const uint4 u = reinterpret_cast<const uint4 *>(zs)[t4];
-                if (u.x == v.x && u.y == v.y && u.z == v.z && u.w == v.w) ld = t4;
-            }
-            if (ld == t) {
-                const int t2 = (r & ~1) * 32 + (lane & ~1);
-                if (t2 != t) {
-                    const uint4 u = reinterpret_cast<const uint4 *>(zs)[t2];
-                    if (u.x == v.x && u.y == v.y && u.z == v.z && u.w == v.w) ld = t2;
-                }
-            }
+        for (int r = 0; r < 4; ++r) own[r] = zs4[r * 32 + lane];
+        auto same = [](const uint4 &u, const uint4 &v) { return u.x == v.x && u.y == v.y && u.z == v.z && u.w == v.w; };
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int t = r * 32 + lane;
+            const bool ok = col_ok && gy0 + r < h;
+            const int t2 = (r & ~1) * 32 + (lane & ~1);
+            const bool eq4 = t4 != t && same(top4, own[r]);
+            const bool eq2 = t2 != t && same(r < 2 ? top2a : top2b, own[r]);
+            const int ld = !ok ? t : (eq4 ? t4 : (eq2 ? t2 : t));
+            lead[t] = (uint8_t)ld;
+            lmask[r] = __ballot_sync(0xffffffffu, ok && ld == t);
         }
-        lead[t] = (uint8_t)ld;
-        lmask[r] = __ballot_sync(0xffffffffu, ok && ld == t);
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -184,6 +187,7 @@ __device__ __forceinline__ void vq_process_tile(const VqTileCtx &c, const float 
         nlead += __popc(lmask[r]);
     }
     __syncwarp();
+    stamp(2);
     // ---- search: one lane per leader.  Pass 1 finds every leader's grid cell and prefetches its record, so that
     //      the memory latency of all rounds overlaps; pass 2 evaluates.
     const bool usable = c.hdr->valid != 0;
@@ -204,6 +208,8 @@ __device__ __forceinline__ void vq_process_tile(const VqTileCtx &c, const float 
         res[t] = (uint16_t)cell;  // parked here until pass 2 overwrites it with the code
     }
     __syncwarp();
+    stamp(3);
+    bool unserved = false;  // some leader of this lane must be searched exhaustively
     for (int j = lane; j < nlead; j += 32) {
         const int t = list[j];
         const float4 v = zs[t];
@@ -233,14 +239,16 @@ __device__ __forceinline__ void vq_process_tile(const VqTileCtx &c, const float 
             for (unsigned pc = 4; pc * 8 < count + 1; ++pc) eval_piece(__ldg(rp + pc), v, z2, c.cbs, c.e2s, bd, bk);
         } else {
             bk = 0xffff;  // outside the grid / overflowing cell / no usable index: searched exhaustively by the whole warp below
+            unserved = true;
         }
         res[t] = (uint16_t)bk;
     }
     __syncwarp();
+    stamp(4);
     // ---- leaders the index could not serve: the WARP searches all K codes (lane k, k + 32, ...; per-lane ascending order +
     //      an index tie-break in the reduction = the lowest index among equal minima; no finite distance at all leaves
     //      index 0, like vq_fused_kernel)
-    for (int j0 = 0; j0 < nlead; j0 += 32) {
+    for (int j0 = 0; __any_sync(0xffffffffu, unserved) && j0 < nlead; j0 += 32) {
         const int j = j0 + lane;
         unsigned todo = __ballot_sync(0xffffffffu, j < nlead && res[list[j < nlead ? j : 0]] == 0xffffu);
         if (todo) {
