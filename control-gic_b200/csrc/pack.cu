@@ -799,7 +799,7 @@ __global__ void __launch_bounds__(ES_THREADS, 1) encode_small_kernel(const Encod
     const int64_t plane = (int64_t)h * w;
     const int tiles_x = (w + 31) / 32, tiles_y = (h + 3) / 4, n_tiles = tiles_x * tiles_y;
     double sq = 0.0;
-    const VqTileCtx ctx{hdr, lut, cbs, e2s, recs, K, zs, res, list, lead};
+    const VqTileCtx ctx{hdr, lut, cbs, e2s, recs, K, zs, res, list, lead, nullptr};
     for (int tile = warp; tile < n_tiles; tile += ES_WARPS) {
         const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
         vq_process_tile(ctx, a.z + (int64_t)b * 4 * plane, h, w, ty * 4, tx * 32 + lane, lane, a.idx_out + (int64_t)b * plane,

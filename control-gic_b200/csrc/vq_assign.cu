@@ -467,7 +467,7 @@ vq_fused_kernel(const float *__restrict__ z, int B, int h, int w, const VqTiles 
 //   finalize  idx / z_q row segments, sum((e - z)^2) per lane, reduced per CTA at the end.
 constexpr int VQW_THREADS = 256;
 constexpr int VQW_WARPS = VQW_THREADS / 32;
-__host__ __device__ inline size_t vqw_smem_bytes(int K) { return vq_stage_bytes(K) + (size_t)VQW_WARPS * VQW_TILE * (16 + 2 + 1 + 1); }
+__host__ __device__ inline size_t vqw_smem_bytes(int K) { return vq_stage_bytes(K) + (size_t)VQW_WARPS * (VQW_TILE_BYTES + VQW_REC_BYTES); }
 
 #ifndef CGIC_VQW_CTAS
 #define CGIC_VQW_CTAS 2
@@ -487,7 +487,7 @@ vq_warp_kernel(const float *__restrict__ z, int h, int w, int tiles_x, int tiles
     const float4 *cbs = reinterpret_cast<const float4 *>(smem + CL.cb);
     const float *e2s = reinterpret_cast<const float *>(smem + CL.e2);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned char *wbase = smem + vq_stage_bytes(K) + (size_t)warp * VQW_TILE * (16 + 2 + 1 + 1);
+    unsigned char *wbase = smem + vq_stage_bytes(K) + (size_t)warp * (VQW_TILE_BYTES + VQW_REC_BYTES);
     float4 *zs = reinterpret_cast<float4 *>(wbase);                      // [128] the tile, row-major
     uint16_t *res = reinterpret_cast<uint16_t *>(zs + VQW_TILE);         // [128] code of a leader token
     uint8_t *list = reinterpret_cast<uint8_t *>(res + VQW_TILE);         // [128] leader tokens, compacted
@@ -511,7 +511,7 @@ vq_warp_kernel(const float *__restrict__ z, int h, int w, int tiles_x, int tiles
     for (int64_t tile = wid; tile < n_tiles; tile += nwarps) {
         const int b = (int)(tile / tpi), rt = (int)(tile - (int64_t)b * tpi);
         const int ty = rt / tiles_x, tx = rt - ty * tiles_x;
-        VqTileCtx ctx{hdr, lut, cbs, e2s, recs, K, zs, res, list, lead};
+        VqTileCtx ctx{hdr, lut, cbs, e2s, recs, K, zs, res, list, lead, reinterpret_cast<uint4 *>(wbase + VQW_TILE_BYTES)};
         vq_process_tile(ctx, z + (int64_t)b * 4 * plane, h, w, ty * 4, tx * 32 + lane, lane, idx_out + (int64_t)b * plane,
                         zq_out ? zq_out + (int64_t)b * 4 * plane : nullptr, sqerr_out != nullptr, sq, (uint16_t *)nullptr, counters + 2,
                         [&]() {

@@ -19,6 +19,7 @@ namespace {
 constexpr int VQW_TILE = 128;  // tokens per warp tile
 // per-warp shared memory: the tile (float4 per token), code of a leader token, compacted leaders, leader of every token
 constexpr int VQW_TILE_BYTES = VQW_TILE * (16 + 2 + 1 + 1);
+constexpr int VQW_REC_BYTES = VQW_TILE * 64;  // optional: the first 64 bytes of every leader's cell record, staged with cp.async
 
 __device__ __forceinline__ float sumsq4(float a, float b, float c, float d) { return sumsq4f(a, b, c, d); }
 
@@ -120,6 +121,7 @@ struct VqTileCtx {
     uint16_t *res;               // [128] code of a leader token
     uint8_t *list;               // [128] leader tokens, compacted
     uint8_t *lead;               // [128] leader of every token
+    uint4 *rec_s;                // [128][4] staged head of every leader's record, or null (records are then read from global)
 };
 
 // One tile: rows gy0 .. gy0+3, column gx = tile column 0 + lane of an h x w token grid whose channel planes start at zb
@@ -201,12 +203,21 @@ __device__ __forceinline__ void vq_process_tile(const VqTileCtx &c, const float 
             if ((b0 | b1 | b2 | b3) >= 0) {
                 cell = (((int)c.lut[b0] * CB_G + (int)c.lut[CB_NB + b1]) * CB_G + (int)c.lut[2 * CB_NB + b2]) * CB_G + (int)c.lut[3 * CB_NB + b3];
                 const uint4 *rp = c.recs + (size_t)cell * (CB_RW / 8);
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 2));
+                if (c.rec_s) {
+                    // no registers held, one wait for all rounds: pass 2 reads the records from shared memory
+                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(c.rec_s + j * 4);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * i), "l"(rp + i) : "memory");
+                } else {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 2));
+                }
             }
         }
         res[t] = (uint16_t)cell;  // parked here until pass 2 overwrites it with the code
     }
+    if (c.rec_s) asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
     stamp(3);
     bool unserved = false;  // some leader of this lane must be searched exhaustively
@@ -218,10 +229,18 @@ __device__ __forceinline__ void vq_process_tile(const VqTileCtx &c, const float 
         uint4 q0, q1, q2, q3;
         const uint4 *rp = c.recs + (size_t)max(cell, 0) * (CB_RW / 8);
         if (cell >= 0) {
-            q0 = __ldg(rp);
-            q1 = __ldg(rp + 1);
-            q2 = __ldg(rp + 2);
-            q3 = __ldg(rp + 3);
+            if (c.rec_s) {
+                const uint4 *rs = c.rec_s + j * 4;
+                q0 = rs[0];
+                q1 = rs[1];
+                q2 = rs[2];
+                q3 = rs[3];
+            } else {
+                q0 = __ldg(rp);
+                q1 = __ldg(rp + 1);
+                q2 = __ldg(rp + 2);
+                q3 = __ldg(rp + 3);
+            }
             count = q0.x & 0xffffu;
         }
         const float z2 = sumsq4(v.x, v.y, v.z, v.w);
