@@ -1543,7 +1543,13 @@ __global__ void __launch_bounds__(256) unpack_assemble_kernel(const UnpackArgs a
 #define CGIC_DS_THREADS 512
 #endif
 constexpr int DS_THREADS = CGIC_DS_THREADS;
-constexpr int DS_WORDS = 512;              // stream words (= subsequences) per batch
+#ifndef CGIC_DS_WORDS
+#define CGIC_DS_WORDS 512
+#endif
+#ifndef CGIC_DS_CTAS
+#define CGIC_DS_CTAS 2
+#endif
+constexpr int DS_WORDS = CGIC_DS_WORDS;    // stream words (= subsequences) per batch
 constexpr int DS_BS = 16;                  // words per composition block
 constexpr int DS_NBLK = DS_WORDS / DS_BS;  // 32
 constexpr int DS_WCAP = DS_NBLK * 17 + 1;   // a CTA's blocks as 16 words + the word after them
@@ -1638,7 +1644,7 @@ __device__ __forceinline__ void build_level_warp(int n, int nw, uint32_t *bits, 
 // then does for itself) and the decoded symbols (written into every CTA's symbol list); the re-assembly is split by quads.
 // Small batches thus spread one image over 2 or 4 SMs instead of leaving most of the machine idle.
 template <int G, int CL>
-__global__ void __launch_bounds__(DS_THREADS, DS_THREADS <= 512 ? 2 : 1) unpack_small_kernel(const UnpackArgs a)
+__global__ void __launch_bounds__(DS_THREADS, DS_THREADS <= 512 ? CGIC_DS_CTAS : 1) unpack_small_kernel(const UnpackArgs a)
 {
     namespace cgs = cooperative_groups;
     extern __shared__ __align__(128) unsigned char dyn[];
