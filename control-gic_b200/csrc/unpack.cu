@@ -1543,11 +1543,14 @@ __global__ void __launch_bounds__(256) unpack_assemble_kernel(const UnpackArgs a
 #define CGIC_DS_THREADS 512
 #endif
 constexpr int DS_THREADS = CGIC_DS_THREADS;
+// 448 words per batch and the code lengths overlaid on the fn[] rows keep the kernel's shared memory under 75 KB = three
+// CTAs per SM (40 registers at 512 threads): 167 -> 160 us at 2048 images of 256 x 256; 512 words at two CTAs per SM are as
+// fast at 512 images, smaller batches lose (an image of ~375 words must stay one batch).
 #ifndef CGIC_DS_WORDS
-#define CGIC_DS_WORDS 512
+#define CGIC_DS_WORDS 448
 #endif
 #ifndef CGIC_DS_CTAS
-#define CGIC_DS_CTAS 2
+#define CGIC_DS_CTAS 3
 #endif
 constexpr int DS_WORDS = CGIC_DS_WORDS;    // stream words (= subsequences) per batch
 constexpr int DS_BS = 16;                  // words per composition block
@@ -1574,10 +1577,9 @@ __host__ __device__ inline DsLayout ds_layout(uint32_t dec_stage_words, const Ge
     size_t o = up((size_t)dec_stage_words * 4);
     L.words = o;
     o += up((size_t)(DS_WCAP + 1) * 4);
-    L.len = o;
-    o += up((size_t)DS_WCAP * 36);
-    L.fn = o;
+    L.fn = o;  // (the code lengths of a word occupy the first 32 bytes of its fn[] row until the DP has read them)
     o += up((size_t)DS_WCAP * 68);
+    L.len = L.fn;
     L.sym = o;
     o += up((size_t)(g.n16 + g.n8 + g.n4) * 2);
     L.bits = o;
@@ -1880,7 +1882,7 @@ __global__ void __launch_bounds__(DS_THREADS, DS_THREADS <= 512 ? CGIC_DS_CTAS :
 #pragma unroll
             for (int p8 = 0; p8 < 8; ++p8)
                 if (p8 + (int)e[p8] > lim) e[p8] = 0;
-            uint32_t *dst = reinterpret_cast<uint32_t *>(s_len + 36 * wl + qtr * 8);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(s_len + 68 * wl + qtr * 8);
             dst[0] = e[0] | (e[1] << 8) | (e[2] << 16) | (e[3] << 24);
             dst[1] = e[4] | (e[5] << 8) | (e[6] << 16) | (e[7] << 24);
         }
@@ -1889,8 +1891,8 @@ __global__ void __launch_bounds__(DS_THREADS, DS_THREADS <= 512 ? CGIC_DS_CTAS :
         // ---- DP: fn[q] = (exit offset << 8) | codewords, from the last position of a word to the first
         for (int it = tid; it < nown * DS_BS; it += DS_THREADS) {
             const int wl = 17 * (it >> 4) + (it & 15);
-            const uint32_t *lw = reinterpret_cast<const uint32_t *>(s_len + 36 * wl);
-            uint16_t *fw = s_fn + 34 * wl;
+            const uint32_t *lw = reinterpret_cast<const uint32_t *>(s_len + 68 * wl);  // all 32 lengths are read ...
+            uint16_t *fw = s_fn + 34 * wl;                                            // ... before fn[] overwrites them (same thread)
             uint32_t l8[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) l8[i] = lw[i];
@@ -1999,11 +2001,12 @@ __global__ void __launch_bounds__(DS_THREADS, DS_THREADS <= 512 ? CGIC_DS_CTAS :
             const int ocap = symcap(s);
             int o = (int)min(s_subbase[wl], 0x7FFFFFFFu);
             const uint32_t w0 = s_w[wl], w1 = s_w[wl + 1];
-            const uint8_t *lp = s_len + 36 * wl;
+            const int k = rank + j * CL;
+            const int lim = s_nbits[s] - 32 * (blk_word0(k) + (it & 15));  // a codeword at q is inside the payload iff q + len <= lim
             while (q < 32u) {
-                const uint32_t len = lp[q];
-                if (!len) break;
                 const uint32_t e = ds_decode_win(__funnelshift_l(w1, w0, q), s_dec, lut2, a.T, L);
+                const uint32_t len = e & 0xFFu;
+                if (!len || (int)(q + len) > lim) break;
                 if (o < ocap) {
 #pragma unroll
                     for (int rr = 0; rr < CL; ++rr) remote(out, rr)[o] = (uint16_t)(e >> 8);
