@@ -58,6 +58,7 @@ WORKLOADS = {
     # not BASELINE configs: the c2 workload at larger batches (how the kernels behave once the grid fills the machine)
     "x_b512_256x256_r0.1-0.8-0.1": (512, 256, 256, 0.1, 0.8),
     "x_b2048_256x256_r0.1-0.8-0.1": (2048, 256, 256, 0.1, 0.8),
+    "x_b2_768x768_r0.1-0.8-0.1": (2, 768, 768, 0.1, 0.8),          # the largest tile group of config 5 on its own
 }
 DEFAULT_WORKLOAD = "c2_b64_256x256_r0.1-0.8-0.1"
 C3 = ("c3_b24_512x768_r0.3-0.6-0.1", "c3_b24_512x768_r0.1-0.8-0.1", "c3_b24_512x768_r0.05-0.05-0.9")

@@ -1224,7 +1224,11 @@ static int pack_launch(const int64_t *idx, const int32_t *m_c, const int32_t *m_
     if (items == 8 && fine_tiles > 1 && workspace && workspace_bytes >= cgic_pack_workspace_bytes(B, h, w)) {
         a.chain = static_cast<unsigned long long *>(workspace);
         a.max_tiles = pack_max_tiles(h, w);
-        a.nslots = fine_tiles < 8 ? fine_tiles : 8;
+        // one CTA per tile of the fine stream up to 16 (a 768 x 768 tile has 9: with 8 CTAs one of them packed two tiles in
+        // a row and the stream finished 4 us later)
+        static const int slots_env = getenv("CGIC_PACK_SLOTS") ? atoi(getenv("CGIC_PACK_SLOTS")) : 0;  // A-B runs only
+        const int slots_max = slots_env >= 1 && slots_env <= 32 ? slots_env : 16;
+        a.nslots = fine_tiles < slots_max ? fine_tiles : slots_max;
         rc = ensure_smem((const void *)pack_chained_kernel<8>, smem);
         if (rc) return rc;
         {

@@ -47,3 +47,12 @@ if "--ctas" in sys.argv:  # per-CTA view of the decode kernel: linear block id, 
         if row[0] <= 0: continue
         busy = row[2] >= row[0]
         print(f"  cta {lin:4d}  start {(row[0]-k0)/1e3:6.2f}  end {((row[6] if row[6] >= row[0] else row[0])-k0)/1e3:6.2f}  {'busy' if busy else ''}")
+if "--pack-ctas" in sys.argv:  # per-CTA view of the packer: linear block id and its stamps relative to the first start
+    b_ = np.zeros(1024 * 16, np.uint64)
+    ctypes.CDLL(cg._lib.LIB_PATH).cgic_trace_pack(b_.ctypes.data_as(ctypes.c_void_p))
+    r = b_.reshape(1024, 16).astype(np.float64)
+    k0 = r[:, 0][r[:, 0] > 0].min()
+    for lin in range(1024):
+        row = r[lin]
+        if row[0] <= 0: continue
+        print(f"  pack cta {lin:4d} " + " ".join(f"{k}:{(row[k]-k0)/1e3:5.2f}" if row[k] >= row[0] else f"{k}:  -  " for k in (0, 2, 3, 4, 5, 6, 7, 1)))
