@@ -37,8 +37,9 @@ struct PackArgs {
     int32_t *sizes;
     // large token grids: the tiles of a stream are dealt over `nslots` CTAs and chained through two self-clearing
     // 64-bit records per tile in the workspace (bit position / carry word), see pack_index_stream_chained
-    unsigned long long *chain;  // [B][3][2][max_tiles]
+    unsigned long long *chain;  // [B][3] x (max_tiles x max_tiles + max_tiles) records
     int max_tiles, nslots;
+    int gather;                 // 1: every tile publishes its bit count to all later tiles (long chains), 0: tile-to-tile chain
     // cgic_encode: the per-CTA partial sums of (e - z)^2 the search kernel left behind (its deferred reduction); the mask CTA of
     // image 0 adds them in CTA order and writes *sq_out
     const double *sq_partials;
@@ -351,6 +352,10 @@ __device__ void pack_index_stream(const PackArgs &a, int s, int b, uint32_t *sta
 // two tiles share (known once the predecessor has staged its codes).  Both travel through self-clearing records:
 //   recA[t]: bit 63 valid, bit 62 "a symbol was outside the table so far", bits 0..47 bit position after tile t
 //   recB[t]: bit 63 valid, bits 0..31 the partial last word of tile t (0 when it ended on a word boundary)
+// Long chains (a.gather, >= 8 tiles in the fine stream): the bit position does not travel from tile to tile; every tile
+// publishes its own bit count to ALL later tiles at once (cnt[p][t], t > p: one copy per reader, which clears it) as soon as
+// it has scanned its code lengths, and gathers the counts of all earlier tiles -- one publish + one gather whatever the
+// number of tiles (2032 x 1344 as 768-pixel tiles, 9-tile chains: -2.4 us; on 6-tile chains the plain chain is faster).
 // The boundary word is written by the LATER tile.  The CTA that packs the last tile finishes the stream (pad, header,
 // size).  Tiles are handed out in block-id order, so a CTA only ever waits for CTAs dispatched before it.
 __device__ __forceinline__ unsigned long long pk_wait_clear(unsigned long long *p)
@@ -386,7 +391,9 @@ __device__ void pack_index_stream_chained(const PackArgs &a, int s, int b, int s
     int32_t *size_out = a.sizes + b * 5 + s;
     const int64_t cap = a.slot_cap[s];
     uint32_t *out32 = reinterpret_cast<uint32_t *>(out);
-    unsigned long long *recA = a.chain + (((int64_t)b * 3 + s) * 2) * a.max_tiles, *recB = recA + a.max_tiles;
+    // per stream: recA[max_tiles] (chain) aliasing the first row of cnt[max_tiles][max_tiles] (gather), then recB[max_tiles]
+    unsigned long long *cnt = a.chain + ((int64_t)b * 3 + s) * ((int64_t)a.max_tiles * a.max_tiles + a.max_tiles);
+    unsigned long long *recA = cnt, *recB = cnt + (int64_t)a.max_tiles * a.max_tiles;
     const int n_tiles = (int)((n_pos + TILE - 1) / TILE);
     const bool mine_last = (n_tiles - 1) % a.nslots == slot;
     if (tid == 0) {
@@ -469,7 +476,30 @@ __device__ void pack_index_stream_chained(const PackArgs &a, int s, int b, int s
         int tot;
         int o = block_exscan(tsum, s_warp, &tot);  // (its barriers also order the s_bad writes above before the read below)
         CGIC_STAMP(pack, 4);  // scanned
-        if (tid == 0) {
+        if (a.gather) {
+            if (tid < 32) {
+                // this tile's count to every later tile first (nobody waits for it longer than necessary) ...
+                const unsigned long long mine = ((unsigned long long)(s_bad != 0) << 62) | (unsigned long long)tot;
+                for (int r = t + 1 + tid; r < n_tiles; r += 32) pk_publish(cnt + (int64_t)t * a.max_tiles + r, mine);
+                // ... then the counts of all earlier tiles (each record is this tile's own copy: cleared after reading)
+                unsigned long long sum = 0;
+                unsigned bad = 0;
+                for (int p = tid; p < t; p += 32) {
+                    const unsigned long long r = pk_wait_clear(cnt + (int64_t)p * a.max_tiles + t);
+                    sum += r & 0xFFFFFFFFFFFFull;
+                    bad |= (unsigned)(r >> 62) & 1u;
+                }
+#pragma unroll
+                for (int o2 = 16; o2 > 0; o2 >>= 1) {
+                    sum += __shfl_xor_sync(0xffffffffu, sum, o2);
+                    bad |= __shfl_xor_sync(0xffffffffu, bad, o2);
+                }
+                if (tid == 0) {
+                    s_P = 8ull + sum;
+                    if (bad || s_bad) s_badall = 1;
+                }
+            }
+        } else if (tid == 0) {
             unsigned long long P = 8, bad = (unsigned long long)(s_bad != 0);
             if (t > 0) {
                 const unsigned long long r = pk_wait_clear(recA + (t - 1));
@@ -1136,7 +1166,8 @@ static int pack_max_tiles(int h, int w) { return (int)(((int64_t)h * w + PK_THRE
 extern "C" size_t cgic_pack_workspace_bytes(int B, int h, int w)
 {
     if (B <= 0 || h <= 0 || w <= 0) return 256;
-    return ((size_t)B * 3 * 2 * pack_max_tiles(h, w) * 8 + 255) / 256 * 256;
+    const size_t mt = (size_t)pack_max_tiles(h, w);
+    return ((size_t)B * 3 * (mt * mt + mt) * 8 + 255) / 256 * 256;  // count records (one per ordered pair of tiles) + carry records
 }
 
 extern "C" int cgic_pack(const int64_t *idx, const int32_t *m_c, const int32_t *m_m, const int32_t *m_f, int B, int h, int w,
@@ -1229,6 +1260,8 @@ static int pack_launch(const int64_t *idx, const int32_t *m_c, const int32_t *m_
         static const int slots_env = getenv("CGIC_PACK_SLOTS") ? atoi(getenv("CGIC_PACK_SLOTS")) : 0;  // A-B runs only
         const int slots_max = slots_env >= 1 && slots_env <= 32 ? slots_env : 16;
         a.nslots = fine_tiles < slots_max ? fine_tiles : slots_max;
+        static const int gather_env = getenv("CGIC_PACK_GATHER") ? atoi(getenv("CGIC_PACK_GATHER")) : -1;        // A-B runs only
+        a.gather = gather_env >= 0 ? (gather_env != 0) : fine_tiles >= 8;
         rc = ensure_smem((const void *)pack_chained_kernel<8>, smem);
         if (rc) return rc;
         {
