@@ -491,22 +491,18 @@ __device__ int decode_stream_cta_cand(const uint8_t *in, int64_t nbytes, const D
     __shared__ uint32_t s_next;
     if (nbytes <= 0) return -1;
     const int tid = threadIdx.x;
-    const int pad = in[0];
-    int64_t nbits = (nbytes - 1) * 8 - pad;
-    if (pad == 0 || nbits < 0) nbits = 0;
-    const int64_t q_end_abs = 8 + nbits;  // stream bit coordinates (header byte = bits 0..7)
+    const int pad = in[0];  // (consumed after the first chunk's loads have been issued: one global round trip, not two)
+    const int64_t nsub_ub = ((nbytes - 1) * 8 + DEC_SUB_BITS - 1) / DEC_SUB_BITS;  // the pad byte takes at most one subsequence off
     const int D = T.max_len, L = T.lut_bits;
-    const int64_t nsub_total = (nbits + DEC_SUB_BITS - 1) / DEC_SUB_BITS;
     uint32_t start_off = 0;
     int64_t total = 0;
+    int64_t nbits = 0, q_end_abs = 8, nsub_total = nsub_ub;
     for (int64_t c0 = 0; c0 < nsub_total && start_off != DEC_OFF_STOP; c0 += ch) {
-        const int nsub = (int)min((int64_t)ch, nsub_total - c0);
         CGIC_STAMP(unpack, 2);
         // ---- stage the chunk: bytes [c0 * 16, ...) of the stream as big-endian words, zero past the end
-        const int npos_words = nsub * (DEC_SUB_BITS / 32) + (DEC_MAX_D + 8 + 31) / 32;  // positions a chain can visit
         {
             const int64_t byte0 = c0 * (DEC_SUB_BITS / 8);
-            const int nw = nsub * (DEC_SUB_BITS / 32) + DEC_LOOKAHEAD_WORDS;
+            const int nw = (int)min((int64_t)ch, nsub_total - c0) * (DEC_SUB_BITS / 32) + DEC_LOOKAHEAD_WORDS;
             for (int wi = tid; wi < nw; wi += DEC_THREADS) {
                 const int64_t bo = byte0 + (int64_t)wi * 4;
                 uint32_t v = 0;
@@ -520,6 +516,15 @@ __device__ int decode_stream_cta_cand(const uint8_t *in, int64_t nbytes, const D
                 s_words[wi] = v;
             }
         }
+        if (c0 == 0) {  // now the header byte: payload bits, exact number of subsequences
+            nbits = (nbytes - 1) * 8 - pad;
+            if (pad == 0 || nbits < 0) nbits = 0;
+            q_end_abs = 8 + nbits;  // stream bit coordinates (header byte = bits 0..7)
+            nsub_total = (nbits + DEC_SUB_BITS - 1) / DEC_SUB_BITS;
+            if (nsub_total == 0) break;
+        }
+        const int nsub = (int)min((int64_t)ch, nsub_total - c0);
+        const int npos_words = nsub * (DEC_SUB_BITS / 32) + (DEC_MAX_D + 8 + 31) / 32;  // positions a chain can visit
         ts.wait();  // (first chunk: the tables' bulk copy ran beside the loads above)
         __syncthreads();
         const int64_t rel_end = q_end_abs - c0 * DEC_SUB_BITS;  // payload end, local to the chunk
