@@ -16,6 +16,24 @@
 // fp32 throughout, denormals kept (eps = 1e-40 is a denormal; flush-to-zero would turn every entropy into
 // NaN).  Float-tolerance parity (rtol 2e-5 in the tests): the summation order is ours, and
 // exp(-0.5 ((v - bin) / 0.01)^2) is evaluated as ex2.approx(-((v - bin) * c)^2), c = 100 sqrt(log2(e) / 2).
+#include "common.cuh"
+#ifdef CGIC_TRACE
+// phases of the routing tail, one row per image: 0 tail starts (the image's last entropy CTA), 1 routing starts, 2 coarse
+// threshold, 3 coarse mask written, 4 medium threshold, 5 done   (profiles/trace_phases.py --route)
+static __device__ unsigned long long g_trace_route[1024 * 8];
+extern "C" __attribute__((visibility("default"))) int cgic_trace_route(unsigned long long *host)
+{
+    return (int)cudaMemcpyFromSymbol(host, g_trace_route, sizeof(g_trace_route));
+}
+#define RS_STAMP(k)                                                       \
+    do {                                                                  \
+        if (threadIdx.x == 0 && blockIdx.y < 1024) {                      \
+            unsigned long long t__;                                       \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));       \
+            g_trace_route[blockIdx.y * 8 + (k)] = t__;                    \
+        }                                                                 \
+    } while (0)
+#endif
 #include "router_select.cuh"
 
 namespace cgic {
@@ -182,6 +200,7 @@ entropy_kernel(const float *__restrict__ x, int H, int W, int regions_x, int reg
     }
     __syncthreads();
     if (!s_last) return;
+    RS_STAMP(0);
     __threadfence();
     const int h16 = H / 16, w16 = W / 16, n16 = h16 * w16;
     // the histogram rows are dead: the select's histogram (8 KB) and, when it fits behind it, the key cache take their place
@@ -189,6 +208,7 @@ entropy_kernel(const float *__restrict__ x, int H, int W, int regions_x, int reg
     uint32_t *s_keys = RS_BINS + 4 * n16 <= S_ROWS_WORDS ? s_hist + RS_BINS : nullptr;
     route_image(e16 + (int64_t)b * n16, e8 + (int64_t)b * 4 * n16, h16, w16, rq.mode, rq.k_c, rq.k_m, rq.m_c + (int64_t)b * n16,
                 rq.m_m + (int64_t)b * 4 * n16, rq.near ? rq.near + 2 * b : nullptr, rq.rtol, rq.atol, s_hist, s_state, s_keys);
+    RS_STAMP(5);
     if (threadIdx.x == 0) rq.tickets[b] = 0;  // (workspace contract: zero between launches)
 }
 

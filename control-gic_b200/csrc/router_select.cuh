@@ -2,6 +2,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef RS_STAMP
+#define RS_STAMP(k)  // (tracing builds of entropy.cu stamp the phases of the routing tail)
+#endif
+
 namespace cgic {
 namespace {
 
@@ -25,10 +29,12 @@ __device__ __forceinline__ float key_float(uint32_t k)
 //   3. the bucket that holds the rank (block scan of the histogram);
 //   4. with n keys over 2048 buckets that bucket usually holds a handful of keys: up to 32 are collected and one warp ranks
 //      them directly; a fuller bucket (ties, clusters) goes round again with the bucket as the new range.
-// s_hist: RS_BINS words, s_state: RS_STATE words.
+// s_hist: RS_BINS words, s_state: RS_STATE words.  Five block barriers in the common case (one round): the histogram is zeroed
+// before the keys are fetched, every thread derives the range from the per-warp minima / maxima itself, and every warp ranks
+// the final handful of keys for itself.
 constexpr int RS_BITS = 11;
 constexpr int RS_BINS = 1 << RS_BITS;
-constexpr int RS_STATE = 48;  // [0] lo, [1] bits, [2] rank in range, [3] keys in bucket, [4] small-list counter, [5] answer, [8..39] small list, [40..] scratch
+constexpr int RS_STATE = 176;  // [0] lo, [1] bits, [2] rank in range, [3] keys in bucket, [4] small-list counter, [8..39] small list, [48..79] per-warp min, [80..111] per-warp max, [112..143] per-warp min over keys > key(+0), [144..175] per-warp count of keys <= key(+0)
 
 template <typename Fetch>
 __device__ float select_rank(Fetch fetch, int64_t n, int64_t rank, uint32_t *s_hist, uint32_t *s_state, uint32_t *s_keys)
@@ -37,43 +43,64 @@ __device__ float select_rank(Fetch fetch, int64_t n, int64_t rank, uint32_t *s_h
     if (rank > n - 1) rank = n - 1;
     if (rank < 0) rank = 0;
     auto key_at = [&](int64_t i) { return s_keys ? s_keys[i] : float_key(fetch(i)); };
-    // ---- keys, block min / max
-    uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
+    // (a previous select's readers of s_hist are behind its last barriers; its answer, read after them, lives in a register)
+    for (int i = tid; i < RS_BINS; i += nthreads) s_hist[i] = 0u;
+    // ---- keys, block min / max; the values <= +0 are counted apart: order-preserving keys are dense in the exponent, so a
+    //      range that reaches from 0 up to the entropies (the router zeroes the cells under a coarse patch) would spend almost
+    //      all histogram bins on the empty stretch in between and need two or three rounds
+    constexpr uint32_t KZ = 0x80000000u;  // float_key(+0.0f)
+    uint32_t kmin = 0xFFFFFFFFu, kmax = 0u, kminp = 0xFFFFFFFFu, nle = 0u;
 #pragma unroll 4  // (independent global loads: several in flight)
     for (int64_t i = tid; i < n; i += nthreads) {
         const uint32_t k = float_key(fetch(i));
         if (s_keys) s_keys[i] = k;
         kmin = min(kmin, k);
         kmax = max(kmax, k);
+        if (k > KZ) kminp = min(kminp, k);
+        else ++nle;
     }
     kmin = __reduce_min_sync(0xffffffffu, kmin);
     kmax = __reduce_max_sync(0xffffffffu, kmax);
-    __syncthreads();  // (previous users of s_hist / s_state are done)
+    kminp = __reduce_min_sync(0xffffffffu, kminp);
+    nle = __reduce_add_sync(0xffffffffu, nle);
     if (lane == 0) {
-        s_hist[warp] = kmin;
-        s_hist[32 + warp] = kmax;
+        s_state[48 + warp] = kmin;
+        s_state[80 + warp] = kmax;
+        s_state[112 + warp] = kminp;
+        s_state[144 + warp] = nle;
     }
+    if (tid == 0) s_state[4] = 0u;
     __syncthreads();
-    if (warp == 0) {
-        uint32_t a = lane < nwarps ? s_hist[lane] : 0xFFFFFFFFu, b = lane < nwarps ? s_hist[32 + lane] : 0u;
+    // the answer lies in [lo, lo + 2^bits) at rank r of that range: derived by every warp for itself
+    uint32_t lo, bits, r = (uint32_t)rank;
+    {
+        uint32_t a = lane < nwarps ? s_state[48 + lane] : 0xFFFFFFFFu, b = lane < nwarps ? s_state[80 + lane] : 0u;
+        uint32_t ap = lane < nwarps ? s_state[112 + lane] : 0xFFFFFFFFu, c = lane < nwarps ? s_state[144 + lane] : 0u;
         a = __reduce_min_sync(0xffffffffu, a);
         b = __reduce_max_sync(0xffffffffu, b);
-        if (lane == 0) {
-            s_state[0] = a;                                              // lo
-            s_state[1] = a == b ? 0u : 32u - (uint32_t)__clz((int)(b - a));  // bits: every key lies in [lo, lo + 2^bits)
-            s_state[2] = (uint32_t)rank;
+        ap = __reduce_min_sync(0xffffffffu, ap);
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c != 0u && (int64_t)c != n) {
+            if (r >= c) {  // among the positive values: the c smaller keys lie below the range
+                a = ap;
+                r -= c;
+            } else {       // among the values <= +0: the range starts at the global minimum, so ranks in it are global ranks
+                b = KZ;
+            }
         }
+        lo = a;
+        bits = a == b ? 0u : 32u - (uint32_t)__clz((int)(b - a));
     }
-    __syncthreads();
-    for (;;) {
-        const uint32_t lo = s_state[0], bits = s_state[1], r = s_state[2];
+    for (bool first = true;; first = false) {
         if (bits == 0) return key_float(lo);
         const uint32_t shift = bits > (uint32_t)RS_BITS ? bits - RS_BITS : 0u;
         // a key belongs to the current range iff (k - lo) >> bits == 0 (and k >= lo); bits == 32 only in the first round: all keys
         auto in_range = [&](uint32_t k) { return k >= lo && (bits >= 32u || ((k - lo) >> bits) == 0u); };
-        for (int i = tid; i < RS_BINS; i += nthreads) s_hist[i] = 0u;
-        if (tid == 0) s_state[4] = 0u;
-        __syncthreads();
+        if (!first) {  // (the first round's histogram was zeroed before the keys were fetched)
+            for (int i = tid; i < RS_BINS; i += nthreads) s_hist[i] = 0u;
+            if (tid == 0) s_state[4] = 0u;
+            __syncthreads();
+        }
         for (int64_t i = tid; i < n; i += nthreads) {
             const uint32_t k = key_at(i);
             if (in_range(k)) atomicAdd(&s_hist[(k - lo) >> shift], 1u);
@@ -108,27 +135,30 @@ __device__ float select_rank(Fetch fetch, int64_t n, int64_t rank, uint32_t *s_h
             s_state[3] = s_hist[i];
         }
         __syncthreads();
-        const uint32_t lo2 = s_state[0], bits2 = s_state[1], r2 = s_state[2], cnt = s_state[3];
-        if (bits2 == 0) return key_float(lo2);
-        if (cnt > 32u) continue;  // a full bucket: another round over [lo2, lo2 + 2^bits2)
-        // ---- a handful of keys left: collect them, one warp ranks them
+        lo = s_state[0];
+        bits = s_state[1];
+        r = s_state[2];
+        const uint32_t cnt = s_state[3];
+        if (bits == 0) return key_float(lo);
+        if (cnt > 32u) {  // a full bucket: another round over [lo, lo + 2^bits)
+            __syncthreads();  // (everybody has read the state before the next round rewrites it)
+            continue;
+        }
+        // ---- a handful of keys left: collect them, every warp ranks them for itself
         for (int64_t i = tid; i < n; i += nthreads) {
             const uint32_t k = key_at(i);
-            if (k >= lo2 && ((k - lo2) >> bits2) == 0u) s_state[8 + atomicAdd(&s_state[4], 1u)] = k;
+            if (k >= lo && ((k - lo) >> bits) == 0u) s_state[8 + atomicAdd(&s_state[4], 1u)] = k;
         }
         __syncthreads();
-        if (warp == 0) {
-            const uint32_t k = lane < cnt ? s_state[8 + lane] : 0xFFFFFFFFu;
-            uint32_t less = 0, leq = 0;
-            for (uint32_t j = 0; j < cnt; ++j) {
-                const uint32_t o = s_state[8 + j];
-                less += o < k;
-                leq += o <= k;
-            }
-            if (lane < cnt && less <= r2 && r2 < leq) s_state[5] = k;  // (equal keys write the same value)
+        const uint32_t k = lane < cnt ? s_state[8 + lane] : 0xFFFFFFFFu;
+        uint32_t less = 0, leq = 0;
+        for (uint32_t j = 0; j < cnt; ++j) {
+            const uint32_t o = s_state[8 + j];
+            less += o < k;
+            leq += o <= k;
         }
-        __syncthreads();
-        return key_float(s_state[5]);
+        const unsigned hit = __ballot_sync(0xffffffffu, lane < cnt && less <= r && r < leq);  // (equal keys: any of them)
+        return key_float(__shfl_sync(0xffffffffu, k, __ffs(hit) - 1));
     }
 }
 
@@ -143,8 +173,10 @@ __device__ __forceinline__ void route_image(const float *e16, const float *e8, i
     const int n16 = h16 * w16, n8 = 4 * n16, w8 = 2 * w16;
     const bool use_c = mode == 0 || mode == 2 || mode == 3;
     auto parent = [&](int i) { return ((i / w8) >> 1) * w16 + ((i % w8) >> 1); };  // coarse cell above medium cell i
+    RS_STAMP(1);
     if (use_c) {
         const float thr = select_rank([&](int64_t i) { return __ldcg(e16 + i); }, n16, k_c != 0 ? k_c - 1 : 0, s_hist, s_state, s_keys);
+        RS_STAMP(2);
         const float tol = rtol * fabsf(thr) + atol;
         int cnt = 0;
 #pragma unroll 4
@@ -158,11 +190,13 @@ __device__ __forceinline__ void route_image(const float *e16, const float *e8, i
         for (int i = threadIdx.x; i < n16; i += blockDim.x) c[i] = (mode == 4);
     }
     __syncthreads();  // c[] (global) is re-read below by other threads of this CTA
+    RS_STAMP(3);
     if (mode == 0 || mode == 1) {
         // mode 0: the entropy of cells under a coarse patch is zeroed before the sort (RouterTriple.py:27)
         const float thr = mode == 0 ? select_rank([&](int64_t i) { return __fmul_rn(__ldcg(e8 + i), __fsub_rn(1.0f, (float)c[parent((int)i)])); }, n8,
                                                   k_m != 0 ? k_m - 1 : 0, s_hist, s_state, s_keys)
                                     : select_rank([&](int64_t i) { return __ldcg(e8 + i); }, n8, k_m != 0 ? k_m - 1 : 0, s_hist, s_state, s_keys);
+        RS_STAMP(4);
         const float tol = rtol * fabsf(thr) + atol;
         int cnt = 0;
 #pragma unroll 4

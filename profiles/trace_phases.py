@@ -56,3 +56,16 @@ if "--pack-ctas" in sys.argv:  # per-CTA view of the packer: linear block id and
         row = r[lin]
         if row[0] <= 0: continue
         print(f"  pack cta {lin:4d} " + " ".join(f"{k}:{(row[k]-k0)/1e3:5.2f}" if row[k] >= row[0] else f"{k}:  -  " for k in (0, 2, 3, 4, 5, 6, 7, 1)))
+if "--route" in sys.argv:  # routing tail of the fused entropy kernel, per image (needs an image-in run: profiles/bench_image_in.py style)
+    x = workload.images(B, H, W, 1000).to(dev) if hasattr(workload, "images") else torch.rand(B, 3, H, W, device=dev)
+    for _ in range(3):
+        cg.ops.entropy_route(x, c, m)
+    torch.cuda.synchronize()
+    b_ = np.zeros(1024 * 8, np.uint64)
+    ctypes.CDLL(cg._lib.LIB_PATH).cgic_trace_route(b_.ctypes.data_as(ctypes.c_void_p))
+    r = b_.reshape(1024, 8)[:B].astype(np.float64)
+    k0 = r[:, 0].min()
+    for k in range(6):
+        print(f"  route stamp {k}: min {(r[:,k].min()-k0)/1e3:6.2f} median {(np.median(r[:,k])-k0)/1e3:6.2f} max {(r[:,k].max()-k0)/1e3:6.2f}")
+    d = r[:, 1:6] - r[:, 0:5]
+    print("  per image, median us per phase (start, coarse select, coarse mask, medium select, medium mask):", np.round(np.median(d, 0) / 1e3, 2))
