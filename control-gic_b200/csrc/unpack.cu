@@ -117,7 +117,7 @@ struct UnpackArgs {
     int32_t *status;
     int mask_stage;  // 1: mask CTAs copy the mask streams to shared memory first
     int ch;          // subsequences per chunk of the candidate decoder (shared-memory budget)
-    int nslots;      // CTAs per index stream (chunks dealt round-robin, chained through ws.chain)
+    int nslots;      // CTAs per index stream (chunks dealt round-robin; hand-over tables in ws.chain)
 };
 
 // ---- parallel prefix decoder (whole CTA, one stream) ------------------------------------------
@@ -913,7 +913,7 @@ __device__ int decode_stream_cta_chain(const uint8_t *in, int64_t nbytes, const 
             start_off = s_start;
             total = s_base;
             if (start_off == DEC_OFF_STOP) {  // decoding ended in an earlier chunk: nothing here (and nothing after)
-                start_off = 0;                // (keeps the loop going so that this slot's later chunks pass the chain on)
+                start_off = 0;                // (keeps the loop going: this slot's later chunks must still publish their tables)
                 continue;
             }
         }
@@ -963,7 +963,7 @@ __device__ int decode_stream_cta_chain(const uint8_t *in, int64_t nbytes, const 
             }
             if (total + ctot > cap) {
                 if (!multi) return -2;
-                overflow = true;  // a chained CTA must keep passing the chain on; the stream's last CTA sees the overflow too
+                overflow = true;  // a chained CTA keeps going (later chunks must still publish); the stream's last CTA sees the overflow too
             }
             if (cnt && !overflow) {
                 const uint32_t sub0 = 8u + (uint32_t)i * DEC_SUB_BITS;
