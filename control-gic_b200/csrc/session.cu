@@ -394,19 +394,25 @@ static int slot_ready(cgic_session *s, int k)
             return e == cudaErrorMemoryAllocation ? CGIC_ENOMEM : CGIC_ECUDA;
         }
     }
-    if (!S.fork) {
-        CGIC_CUDA_CHECK(cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming));
-        for (cudaEvent_t &e : S.join) CGIC_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    // (every item is created on its own test, so a call that failed half-way is completed by the next one)
+    if (!S.fork) CGIC_CUDA_CHECK(cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming));
+    for (cudaEvent_t &e : S.join)
+        if (!e) CGIC_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (int i = 0; i < cgic_session::MAX_PARTS; ++i) {
+        if (S.streams[i]) continue;
+        if (k == 0) S.streams[i] = s->streams[i];
+        else CGIC_CUDA_CHECK(cudaStreamCreateWithFlags(&S.streams[i], cudaStreamNonBlocking));
     }
-    if (!S.streams[0]) {
-        if (k == 0) {
-            for (int i = 0; i < cgic_session::MAX_PARTS; ++i) S.streams[i] = s->streams[i];
-        } else {
-            for (cudaStream_t &st : S.streams) CGIC_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-            const size_t bytes = (s->ws_en_bytes + s->ws_un_bytes) * cgic_session::MAX_PARTS;
-            CGIC_CUDA_CHECK(cudaMalloc(&S.ws, bytes));
-            CGIC_CUDA_CHECK(cudaMemset(S.ws, 0, bytes));  // workspaces start zeroed (cgic_vq_assign's contract)
+    if (k && !S.ws) {  // (never fall back to slot 0's workspaces: the two slots run at the same time)
+        const size_t bytes = (s->ws_en_bytes + s->ws_un_bytes) * cgic_session::MAX_PARTS;
+        unsigned char *ws = nullptr;
+        CGIC_CUDA_CHECK(cudaMalloc(&ws, bytes));
+        cudaError_t e = cudaMemset(ws, 0, bytes);  // workspaces start zeroed (cgic_vq_assign's contract)
+        if (e != cudaSuccess) {
+            cudaFree(ws);
+            CGIC_CUDA_CHECK(e);
         }
+        S.ws = ws;
     }
     return CGIC_OK;
 }
