@@ -205,10 +205,13 @@ __device__ __forceinline__ void vq_process_tile(const VqTileCtx &c, const float 
                 const uint4 *rp = c.recs + (size_t)cell * (CB_RW / 8);
                 if (c.rec_s) {
                     // no registers held, one wait for all rounds: pass 2 reads the records from shared memory
+                    // piece i of leader j sits in slot i ^ ((j >> 1) & 3) of its 64-byte row: the eight lanes of a quarter warp,
+                    // which read piece i of eight consecutive leaders together, then touch eight different 16-byte bank groups
                     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(c.rec_s + j * 4);
+                    const int sw = (j >> 1) & 3;
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * i), "l"(rp + i) : "memory");
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * (i ^ sw)), "l"(rp + i) : "memory");
                 } else {
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 2));
@@ -231,10 +234,11 @@ __device__ __forceinline__ void vq_process_tile(const VqTileCtx &c, const float 
         if (cell >= 0) {
             if (c.rec_s) {
                 const uint4 *rs = c.rec_s + j * 4;
-                q0 = rs[0];
-                q1 = rs[1];
-                q2 = rs[2];
-                q3 = rs[3];
+                const int sw = (j >> 1) & 3;
+                q0 = rs[sw];
+                q1 = rs[1 ^ sw];
+                q2 = rs[2 ^ sw];
+                q3 = rs[3 ^ sw];
             } else {
                 q0 = __ldg(rp);
                 q1 = __ldg(rp + 1);
