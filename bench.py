@@ -704,7 +704,7 @@ def run_b200(args):
 # each capture; a kernel without an entry reports null.
 NCU_TRAFFIC_SOURCE = ("profiles/r2_kernels.txt: dram__bytes_read.sum + dram__bytes_write.sum of one launch on the 64-image batch under "
                       "ncu --set full (reads only: the 20 MB working set's writes stay in the 126 MB L2 within a launch); not re-measured in this run")
-NCU_TRAFFIC = {"vq_warp_kernel": 6446336, "pack_kernel": 3525888, "unpack_decode_kernel": 249344, "unpack_assemble_kernel": 296192}
+NCU_TRAFFIC = {"vq_warp_kernel": 6447104, "pack_kernel": 3525632, "unpack_decode_kernel": 249600, "unpack_assemble_kernel": 296704}
 
 
 def _traffic(top, B):
